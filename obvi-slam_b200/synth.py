@@ -1,0 +1,360 @@
+"""Seeded synthetic factor graphs S(K, P, O, seed) of the shape BASELINE.json names.
+
+This is input generation only (no solver arithmetic): a serpentine planar trajectory sampled
+every 0.2 m (the reference's sparsifier spacing, config/base7a_2_fallback.json:460-463), a
+stereo pair with the intrinsics of data/vslam_set7/calibration/camera_matrix.txt (400 400 320 240),
+points observed in 5..15 consecutive keyframes by both cameras, upright ellipsoids drawn from the
+six shape priors of config/base7a_2_fallback.json:151-316, bounding boxes with the covariance rule
+of bounding_box_front_end_creation_utils.h:56-102, and relative-pose factors with generateOdomCov
+(relative_pose_factor_utils.h:17-36).  See SURVEY.md section 8(d).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+K_DIM_REG = float(np.float32(1e-3))
+
+# (mean dims, covariance diag) -- config/base7a_2_fallback.json:151-316
+SHAPE_PRIORS = [
+    ((0.62, 0.62, 0.975), (0.0025, 0.0025, 0.0025)),  # chair
+    ((1.0, 2.5, 1.5), (2.25, 4.0, 2.25)),  # bench
+    ((0.29, 0.29, 0.48), (1e-6, 1e-6, 1e-4)),  # roadblock
+    ((0.4, 0.4, 2.0), (0.04, 0.04, 9.0)),  # treetrunk
+    ((0.3, 0.3, 4.0), (0.0225, 0.0225, 9.0)),  # lamppost
+    ((1.0, 1.0, 1.5), (1.0, 1.0, 2.25)),  # trashcan
+]
+
+IMG_W, IMG_H = 640.0, 480.0
+INTR = (400.0, 400.0, 320.0, 240.0)
+# camera (x right, y down, z forward) expressed in the robot frame (x forward, y left, z up)
+R_EXTR = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+T_EXTR = [np.array([0.0, 0.06, 0.0]), np.array([0.0, -0.06, 0.0])]
+
+
+class FactorGraph:
+    """Plain-NumPy factor graph (see oracle/py_oracle.py:Graph for the field list)."""
+
+    def copy(self):
+        g = FactorGraph()
+        for k, v in self.__dict__.items():
+            if isinstance(v, np.ndarray):
+                setattr(g, k, v.copy())
+            elif isinstance(v, dict):
+                setattr(g, k, {kk: (vv.copy() if isinstance(vv, np.ndarray) else vv) for kk, vv in v.items()})
+            else:
+                setattr(g, k, v)
+        return g
+
+    def counts(self):
+        return dict(poses=len(self.poses), points=len(self.points), objects=len(self.objects),
+                    reproj=len(self.reproj["pose"]), bbox=len(self.bbox["obj"]), shape=len(self.shape["obj"]),
+                    relpose=len(self.relpose["p1"]), ltm=len(self.ltm["obj"]))
+
+
+# ----------------------------------------------------------------------------- rotations (vectorised)
+def rotvec_to_mat(w):
+    w = np.asarray(w, dtype=np.float64)
+    th = np.linalg.norm(w, axis=-1)
+    small = th < 1e-12
+    ths = np.where(small, 1.0, th)
+    a = w / ths[..., None]
+    c, s = np.cos(th), np.sin(th)
+    t = 1.0 - c
+    x, y, z = a[..., 0], a[..., 1], a[..., 2]
+    R = np.stack([
+        np.stack([t * x * x + c, t * x * y - s * z, t * x * z + s * y], -1),
+        np.stack([t * x * y + s * z, t * y * y + c, t * y * z - s * x], -1),
+        np.stack([t * x * z - s * y, t * y * z + s * x, t * z * z + c], -1)], -2)
+    R[small] = np.eye(3)
+    return R
+
+
+def mat_to_rotvec(R):
+    """Log map of rotation matrices (..., 3, 3) -> (..., 3), robust away from pi."""
+    R = np.asarray(R, dtype=np.float64)
+    v = np.stack([R[..., 2, 1] - R[..., 1, 2], R[..., 0, 2] - R[..., 2, 0], R[..., 1, 0] - R[..., 0, 1]], -1)
+    s = 0.5 * np.linalg.norm(v, axis=-1)
+    c = 0.5 * (np.trace(R, axis1=-2, axis2=-1) - 1.0)
+    th = np.arctan2(s, c)
+    k = np.where(s > 1e-12, th / np.where(s > 1e-12, 2.0 * s, 1.0), 0.5)
+    return v * k[..., None]
+
+
+def _euler_zyx(yaw, pitch, roll):
+    cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+    R = np.empty(yaw.shape + (3, 3))
+    R[..., 0, 0] = cy * cp
+    R[..., 0, 1] = cy * sp * sr - sy * cr
+    R[..., 0, 2] = cy * sp * cr + sy * sr
+    R[..., 1, 0] = sy * cp
+    R[..., 1, 1] = sy * sp * sr + cy * cr
+    R[..., 1, 2] = sy * sp * cr - cy * sr
+    R[..., 2, 0] = -sp
+    R[..., 2, 1] = cp * sr
+    R[..., 2, 2] = cp * cr
+    return R
+
+
+def _project(R_wr, t_wr, cam, X):
+    """Camera-frame coordinates of world points X for robot poses (R_wr, t_wr) and camera index cam."""
+    Xr = np.einsum("nji,nj->ni", R_wr, X - t_wr)  # R^T (X - t)
+    Xc = (Xr - T_EXTR[cam][None, :]) @ R_EXTR  # R_e^T (.)
+    return Xc
+
+
+def _bbox_exact(ell, R_wr, t_wr, cam):
+    """Exact dual-quadric bounding box (pixels; xmin,xmax,ymin,ymax) + validity, vectorised."""
+    n = ell.shape[0]
+    Rz = np.zeros((n, 3, 3))
+    c, s = np.cos(ell[:, 3]), np.sin(ell[:, 3])
+    Rz[:, 0, 0], Rz[:, 0, 1], Rz[:, 1, 0], Rz[:, 1, 1], Rz[:, 2, 2] = c, -s, s, c, 1.0
+    R_cw = np.einsum("ji,nkj->nik", R_EXTR, R_wr)  # R_e^T R^T
+    t_cw = -np.einsum("nij,nj->ni", R_cw, t_wr) - (R_EXTR.T @ T_EXTR[cam])[None, :]
+    A = R_cw @ Rz
+    tau = np.einsum("nij,nj->ni", R_cw, ell[:, 0:3]) + t_cw
+    d = (ell[:, 4:7] / 2.0) ** 2 + K_DIM_REG
+    Q = np.einsum("nik,nk,njk->nij", A, d, A) - tau[:, :, None] * tau[:, None, :]
+    xin = Q[:, 0, 2] ** 2 - Q[:, 0, 0] * Q[:, 2, 2]
+    yin = Q[:, 1, 2] ** 2 - Q[:, 1, 1] * Q[:, 2, 2]
+    ok = (xin > 0) & (yin > 0) & (Q[:, 2, 2] < 0) & (tau[:, 2] > 0)
+    xs, ys = np.sqrt(np.where(ok, xin, 1.0)), np.sqrt(np.where(ok, yin, 1.0))
+    q33 = np.where(ok, Q[:, 2, 2], -1.0)
+    cr = np.stack([Q[:, 0, 2] + xs, Q[:, 0, 2] - xs, Q[:, 1, 2] + ys, Q[:, 1, 2] - ys], -1) / q33[:, None]
+    fx, fy, cx, cy = INTR
+    px = np.stack([fx * cr[:, 0] + cx, fx * cr[:, 1] + cx, fy * cr[:, 2] + cy, fy * cr[:, 3] + cy], -1)
+    return px, ok, tau[:, 2]
+
+
+def odom_cov(t, R, k=0.025):
+    """generateOdomCov with all four multipliers = k (config :449-454); vectorised over the first axis."""
+    rv = mat_to_rotvec(R)
+    ang = np.linalg.norm(rv, axis=-1)
+    sd = np.empty(t.shape[:-1] + (6,))
+    sd[..., 0:3] = np.abs(t) * k + (ang * k)[..., None]
+    sd[..., 3:6] = np.abs(rv) * k + (np.linalg.norm(t, axis=-1) * k)[..., None]
+    var = np.maximum(sd ** 2, 1e-6)
+    cov = np.zeros(t.shape[:-1] + (6, 6))
+    for i in range(6):
+        cov[..., i, i] = var[..., i]
+    return cov
+
+
+# ----------------------------------------------------------------------------- generator
+def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_poses=1,
+               sigma_px=1.5, outlier_frac=0.05, min_point_obs=5, min_obj_obs=10, ltm_frac=0.0,
+               pose_noise=True):
+    """Build S(K, P, O, seed).
+
+    relpose: "starved" -> rel-pose factors only into feature-starved keyframes (reference rule,
+             object_pose_graph_optimizer.h:240-299; every 20th keyframe is starved), "all" -> every
+             consecutive pair, "none".
+    n_const_poses: number of leading poses held constant (1 for a window starting at frame 0, 5 for a
+             local window; object_pose_graph_optimizer.h:440-459).
+    ltm_frac: fraction of objects that carry a long-term-map prior factor.
+    """
+    rng = np.random.default_rng(seed)
+    g = FactorGraph()
+    g.cams = [dict(intr=INTR, R=R_EXTR.copy(), t=T_EXTR[c].copy()) for c in range(2)]
+
+    # --- trajectory: serpentine, 0.2 m per keyframe, |dyaw| <= 0.04 rad per keyframe
+    k = np.arange(K)
+    yaw = 1.2 * np.sin(2.0 * np.pi * k / 200.0)
+    pitch = rng.normal(0.0, 0.01, K)
+    roll = rng.normal(0.0, 0.01, K)
+    yaw[0], pitch[0], roll[0] = 0.0, 0.0, 0.0
+    step = 0.2 * np.stack([np.cos(yaw), np.sin(yaw), np.zeros(K)], -1)
+    t_gt = np.concatenate([np.zeros((1, 3)), np.cumsum(step[:-1], axis=0)], axis=0)
+    R_gt = _euler_zyx(yaw, pitch, roll)
+    poses_gt = np.concatenate([t_gt, mat_to_rotvec(R_gt)], axis=1)
+
+    # --- points: anchored to a keyframe, inside camera 0's frustum there
+    anchor = rng.integers(0, K, P)
+    L = rng.integers(5, 16, P)
+    depth = rng.uniform(2.0, 30.0, P)
+    upx = rng.uniform(20.0, IMG_W - 20.0, P)
+    vpx = rng.uniform(20.0, IMG_H - 20.0, P)
+    fx, fy, cx, cy = INTR
+    Xc = np.stack([(upx - cx) / fx * depth, (vpx - cy) / fy * depth, depth], -1)
+    Xr = Xc @ R_EXTR.T + T_EXTR[0][None, :]
+    X_gt = np.einsum("nij,nj->ni", R_gt[anchor], Xr) + t_gt[anchor]
+
+    # candidate observations: point p at keyframes anchor..anchor+L-1, both cameras
+    rep = np.repeat(np.arange(P), L)
+    offs = np.arange(L.sum()) - np.repeat(np.cumsum(L) - L, L)
+    kf = anchor[rep] + offs
+    keep = kf < K
+    rep, kf = rep[keep], kf[keep]
+    obs_pose, obs_point, obs_cam, obs_px = [], [], [], []
+    for cam in range(2):
+        Xc_o = _project(R_gt[kf], t_gt[kf], cam, X_gt[rep])
+        z = Xc_o[:, 2]
+        zz = np.where(z > 0.1, z, 1.0)
+        u = fx * Xc_o[:, 0] / zz + cx
+        v = fy * Xc_o[:, 1] / zz + cy
+        ok = (z > 0.1) & (u >= 0) & (u < IMG_W) & (v >= 0) & (v < IMG_H)
+        obs_pose.append(kf[ok]); obs_point.append(rep[ok]); obs_cam.append(np.full(ok.sum(), cam))
+        obs_px.append(np.stack([u[ok], v[ok]], -1))
+    obs_pose = np.concatenate(obs_pose); obs_point = np.concatenate(obs_point)
+    obs_cam = np.concatenate(obs_cam); obs_px = np.concatenate(obs_px)
+    # feature-starved keyframes (every 20th): keep at most 30 observations
+    starved = np.zeros(K, dtype=bool)
+    if relpose == "starved":
+        starved[np.arange(19, K, 20)] = True
+        drop = np.zeros(len(obs_pose), dtype=bool)
+        for kk in np.nonzero(starved)[0]:
+            idx = np.nonzero(obs_pose == kk)[0]
+            if len(idx) > 30:
+                drop[rng.permutation(idx)[30:]] = True
+        obs_pose, obs_point, obs_cam, obs_px = obs_pose[~drop], obs_point[~drop], obs_cam[~drop], obs_px[~drop]
+    # points need >= min_point_obs factors (object_pose_graph_optimizer.h:234-237)
+    cnt = np.bincount(obs_point, minlength=P)
+    good = cnt[obs_point] >= min_point_obs
+    obs_pose, obs_point, obs_cam, obs_px = obs_pose[good], obs_point[good], obs_cam[good], obs_px[good]
+    n_obs = len(obs_pose)
+    obs_px = obs_px + rng.normal(0.0, 1.0, (n_obs, 2))
+    outl = rng.random(n_obs) < outlier_frac
+    obs_px[outl] += rng.uniform(-50.0, 50.0, (int(outl.sum()), 2))
+    # canonical order: by pose, camera, point
+    order = np.lexsort((obs_point, obs_cam, obs_pose))
+    g.reproj = dict(pose=obs_pose[order].astype(np.int64), point=obs_point[order].astype(np.int64),
+                    cam=obs_cam[order].astype(np.int64), px=np.ascontiguousarray(obs_px[order]),
+                    sigma=np.full(n_obs, sigma_px), huber=1.0)
+
+    # --- objects
+    g.bbox = dict(obj=np.zeros(0, np.int64), pose=np.zeros(0, np.int64), cam=np.zeros(0, np.int64),
+                  corners=np.zeros((0, 4)), cov=np.zeros((0, 4, 4)), huber=0.5, invalid_err=1000.0)
+    g.shape = dict(obj=np.zeros(0, np.int64), mean=np.zeros((0, 3)), cov=np.zeros((0, 3, 3)), huber=10.0)
+    g.ltm = dict(obj=np.zeros(0, np.int64), mean=np.zeros((0, 7)), cov=np.zeros((0, 7, 7)), huber=1.0)
+    obj_gt = np.zeros((O, 7))
+    if O > 0:
+        cls = rng.integers(0, len(SHAPE_PRIORS), O)
+        okf = rng.integers(0, K, O)
+        side = rng.choice([-1.0, 1.0], O)
+        lat = rng.uniform(3.0, 15.0, O) * side
+        fwd = rng.uniform(4.0, 12.0, O)
+        mean = np.array([SHAPE_PRIORS[c][0] for c in cls])
+        var = np.array([SHAPE_PRIORS[c][1] for c in cls])
+        dims = np.clip(mean + rng.normal(0.0, 1.0, (O, 3)) * np.minimum(np.sqrt(var), 0.15 * mean), 0.1, None)
+        ca, sa = np.cos(yaw[okf]), np.sin(yaw[okf])
+        obj_gt[:, 0] = t_gt[okf, 0] + ca * fwd - sa * lat
+        obj_gt[:, 1] = t_gt[okf, 1] + sa * fwd + ca * lat
+        obj_gt[:, 2] = dims[:, 2] / 2.0 - 0.3  # standing on the ground, robot origin 0.3 m above it
+        obj_gt[:, 3] = rng.uniform(-np.pi, np.pi, O)
+        obj_gt[:, 4:7] = dims
+    if O > 0 and objects_on:
+        bo, bp, bc, bcr, bcv = [], [], [], [], []
+        for o in range(O):
+            d2 = np.sum((t_gt[:, :2] - obj_gt[o, :2]) ** 2, axis=1)
+            near = np.nonzero(d2 < 20.0 ** 2)[0]
+            if len(near) == 0:
+                continue
+            ell = np.repeat(obj_gt[o][None, :], len(near), axis=0)
+            vis = []
+            for cam in range(2):
+                px, ok, zc = _bbox_exact(ell, R_gt[near], t_gt[near], cam)
+                ctr_u, ctr_v = 0.5 * (px[:, 0] + px[:, 1]), 0.5 * (px[:, 2] + px[:, 3])
+                ok &= (zc > 1.5) & (ctr_u > 0) & (ctr_u < IMG_W) & (ctr_v > 0) & (ctr_v < IMG_H)
+                ok &= (np.abs(px[:, 1] - px[:, 0]) < 2.0 * IMG_W) & (np.abs(px[:, 3] - px[:, 2]) < 2.0 * IMG_H)
+                vis.append((px, ok))
+            both = vis[0][1] & vis[1][1]
+            sel = np.nonzero(both)[0][:40]  # cap: 40 keyframes x 2 cameras
+            if 2 * len(sel) < min_obj_obs:
+                continue
+            for cam in range(2):
+                px = vis[cam][0][sel]
+                # reference corner order is (xmin, xmax, ymin, ymax); the functor's prediction order is
+                # (q13+sqrt, q13-sqrt, ...)/q33 which equals that order for q33 < 0.
+                lo_x, hi_x = np.minimum(px[:, 0], px[:, 1]), np.maximum(px[:, 0], px[:, 1])
+                lo_y, hi_y = np.minimum(px[:, 2], px[:, 3]), np.maximum(px[:, 2], px[:, 3])
+                c4 = np.stack([lo_x, hi_x, lo_y, hi_y], -1) + rng.normal(0.0, 10.0, (len(sel), 4))
+                c4 = np.stack([np.clip(c4[:, 0], 0, IMG_W - 1), np.clip(c4[:, 1], 0, IMG_W - 1),
+                               np.clip(c4[:, 2], 0, IMG_H - 1), np.clip(c4[:, 3], 0, IMG_H - 1)], -1)
+                cov = np.zeros((len(sel), 4, 4))
+                cov[:, 0, 0] = np.where(c4[:, 0] < 25.0, 40000.0, 900.0)
+                cov[:, 1, 1] = np.where(c4[:, 1] > IMG_W - 25.0, 40000.0, 900.0)
+                cov[:, 2, 2] = np.where(c4[:, 2] < 25.0, 40000.0, 900.0)
+                cov[:, 3, 3] = np.where(c4[:, 3] > IMG_H - 25.0, 40000.0, 900.0)
+                bo.append(np.full(len(sel), o)); bp.append(near[sel]); bc.append(np.full(len(sel), cam))
+                bcr.append(c4); bcv.append(cov)
+        if bo:
+            g.bbox.update(obj=np.concatenate(bo).astype(np.int64), pose=np.concatenate(bp).astype(np.int64),
+                          cam=np.concatenate(bc).astype(np.int64), corners=np.concatenate(bcr),
+                          cov=np.concatenate(bcv))
+        seen = np.unique(g.bbox["obj"])
+        g.shape.update(obj=seen.astype(np.int64), mean=np.array([SHAPE_PRIORS[cls[o]][0] for o in seen]).reshape(-1, 3),
+                       cov=np.array([np.diag(SHAPE_PRIORS[cls[o]][1]) for o in seen]).reshape(-1, 3, 3))
+        if ltm_frac > 0 and len(seen):
+            nl = max(1, int(len(seen) * ltm_frac))
+            lo = seen[:nl]
+            A = rng.normal(0.0, 1.0, (nl, 7, 7)) * 0.02
+            cov7 = A @ np.transpose(A, (0, 2, 1)) + np.diag([0.04, 0.04, 0.04, 0.02, 0.02, 0.02, 0.02])[None]
+            g.ltm.update(obj=lo.astype(np.int64), mean=obj_gt[lo] + rng.normal(0, 0.05, (nl, 7)), cov=cov7)
+
+    # --- initial values
+    if pose_noise:
+        # integrate noisy odometry: 0.2 % translation, 0.03 deg per keyframe (a trajectory that local
+        # windows have already cleaned up, as when the reference enters its global BA)
+        R_i = np.empty_like(R_gt); t_i = np.empty_like(t_gt)
+        R_i[0], t_i[0] = R_gt[0], t_gt[0]
+        dR = np.einsum("nji,njk->nik", R_gt[:-1], R_gt[1:])
+        dt = np.einsum("nji,nj->ni", R_gt[:-1], t_gt[1:] - t_gt[:-1])
+        nR = rotvec_to_mat(rng.normal(0.0, np.deg2rad(0.03), (K - 1, 3)))
+        nt = dt * (1.0 + rng.normal(0.0, 0.002, (K - 1, 3)))
+        for i in range(K - 1):
+            R_i[i + 1] = R_i[i] @ dR[i] @ nR[i]
+            t_i[i + 1] = t_i[i] + R_i[i] @ nt[i]
+        poses0 = np.concatenate([t_i, mat_to_rotvec(R_i)], axis=1)
+    else:
+        R_i, t_i, poses0 = R_gt, t_gt, poses_gt.copy()
+    g.poses = np.ascontiguousarray(poses0)
+    g.poses_gt = poses_gt
+    # map entities are initialised relative to the (drifted) estimate of the keyframe that first saw
+    # them -- the map is locally consistent, as after triangulation from the current pose estimates
+    X_loc = np.einsum("nji,nj->ni", R_gt[anchor], X_gt - t_gt[anchor])
+    X0 = np.einsum("nij,nj->ni", R_i[anchor], X_loc) + t_i[anchor]
+    g.points = np.ascontiguousarray(X0 + rng.normal(0.0, 0.1, (P, 3)))
+    g.points_gt = X_gt
+    obj0 = obj_gt.copy()
+    if O > 0:
+        c_loc = np.einsum("nji,nj->ni", R_gt[okf], obj_gt[:, 0:3] - t_gt[okf])
+        obj0[:, 0:3] = np.einsum("nij,nj->ni", R_i[okf], c_loc) + t_i[okf]
+        obj0[:, 3] += mat_to_rotvec(np.einsum("nij,nkj->nik", R_i[okf], R_gt[okf]))[:, 2]
+        obj0[:, 0:3] += rng.normal(0.0, 0.3, (O, 3))
+        obj0[:, 3] += rng.normal(0.0, 0.2, O)
+        obj0[:, 4:7] *= 1.0 + rng.uniform(-0.2, 0.2, (O, 3))
+    g.objects = np.ascontiguousarray(obj0)
+    g.objects_gt = obj_gt
+
+    # --- relative-pose factors from the *initial* poses (pose_graph_frame_data_adder.h:48-55)
+    if relpose == "none" or K < 2:
+        p1 = np.zeros(0, np.int64)
+    elif relpose == "all":
+        p1 = np.arange(K - 1)
+    else:
+        p1 = np.nonzero(starved[1:])[0]  # factor (k-1, k) for every starved keyframe k
+    p2 = p1 + 1
+    Rm = np.einsum("nji,njk->nik", R_i[p1], R_i[p2]) if len(p1) else np.zeros((0, 3, 3))
+    tm = np.einsum("nji,nj->ni", R_i[p1], t_i[p2] - t_i[p1]) if len(p1) else np.zeros((0, 3))
+    g.relpose = dict(p1=p1.astype(np.int64), p2=p2.astype(np.int64), t=tm, Rm=Rm,
+                     cov=odom_cov(tm, Rm) if len(p1) else np.zeros((0, 6, 6)), huber=1.0)
+
+    g.const_pose = np.zeros(K, dtype=bool)
+    g.const_pose[:n_const_poses] = True
+    g.const_point = np.zeros(P, dtype=bool)
+    g.const_obj = np.zeros(O, dtype=bool)
+    return g
+
+
+# Named configs of BASELINE.json
+CONFIGS = {
+    "C1": dict(K=50, P=2000, O=20, objects_on=False, relpose="starved", n_const_poses=5),
+    "C1obj": dict(K=50, P=2000, O=20, objects_on=True, relpose="starved", n_const_poses=5),
+    "C2": dict(K=500, P=50000, O=100, objects_on=False, relpose="all", n_const_poses=1),
+    "C3": dict(K=2000, P=200000, O=500, objects_on=True, relpose="starved", n_const_poses=1),
+}
+
+
+def make_config(name, seed=0, **over):
+    kw = dict(CONFIGS[name])
+    kw.update(over)
+    return make_graph(seed=seed, **kw)
