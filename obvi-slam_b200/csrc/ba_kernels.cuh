@@ -1,0 +1,897 @@
+// CUDA kernels (sm_100a) of the bundle-adjustment hot path: residual + Jacobian evaluation, J^T J block
+// accumulation, Schur elimination of points / objects, the reduced-camera-system PCG, back-substitution
+// and the candidate-cost evaluation.  Everything is float64 (the reference is all-double).
+//
+// Data layout:
+//   * reprojection observations are sorted pose-major; the Jacobian kernel writes one 160-byte chunk per
+//     observation  [Jp 2x6 | Jl 2x3 | r 2]  (row-major, loss-corrected), so a keyframe's Jacobian tile is one
+//     contiguous range;
+//   * bbox observations are sorted object-major with 448-byte chunks [Jp 4x6 | Jo 4x7 | r 4];
+//   * every e-block (point or object) has a CSR list of its observations (position, f index, merged pose slot)
+//     and the precomputed index of the reduced-matrix block of every slot pair;
+//   * the reduced camera system is accumulated into an upper block-CSR (6x6 blocks) in "pose-unscaled" form,
+//     then `finish_kernel` applies Jacobi scaling + LM damping and mirrors it into a full symmetric BSR whose
+//     scalar rows are contiguous for the PCG SpMV.
+#pragma once
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "factors.cuh"
+#include "problem.hpp"
+
+namespace obvi {
+namespace cg = cooperative_groups;
+
+// scalar slots in the device `scalars` array
+enum : int {
+  // 0-2 are produced by linearize (), 3-6 by take_step () / candidate_cost (): the two groups are reduced
+  // across ranks separately in a sharded run
+  SC_COST = 0, SC_FIXED = 1, SC_XNORM2 = 2, SC_CAND = 3, SC_CAND_FIXED = 4, SC_MODEL = 5, SC_STEP2 = 6,
+  SC_GMAX = 7 /* u64 bits of a non-negative double */, SC_FAIL = 8, SC_PCG_IT = 9, SC_PCG_RES = 10, SC_PCG_BB = 11,
+  SC_PCG_BREAK = 12, SC_COUNT = 16
+};
+
+struct LMParams { double radius, min_diag, max_diag; int compute_scale; };
+
+// ------------------------------------------------------------------------------------------ reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum over the block; result valid in every thread.  `red` needs >= 33 doubles of shared memory.
+template <int T>
+__device__ __forceinline__ double block_sum_all(double v, double* red) {
+  v = warp_sum(v);
+  if (T <= 32) return v;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < T / 32; i++) s += red[i];
+  return s;
+}
+__device__ __forceinline__ void atomic_max_nonneg(double* slot, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(slot), (unsigned long long)__double_as_longlong(v));
+}
+
+// ------------------------------------------------------------------------------------------ pose / camera table
+// One thread per (pose, camera): R_cw, t_cw and the rotation-derivative matrices shared by every
+// observation of that pose (the reference recomputes them per observation on 9-wide Jets).
+__global__ void pose_cam_kernel(const double* __restrict__ poses, int K, const Camera* __restrict__ cams, int C, int jac,
+                                PoseCam* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * C) return;
+  const int k = i / C, c = i % C;
+  double p[6];
+#pragma unroll
+  for (int a = 0; a < 6; a++) p[a] = poses[6 * k + a];
+  PoseCam pc;
+  make_pose_cam(p, cams[c].Rinv, cams[c].tinv, jac != 0, &pc);
+  if (jac) { out[i] = pc; }
+  else {
+#pragma unroll
+    for (int a = 0; a < 9; a++) out[i].Rcw[a] = pc.Rcw[a];
+#pragma unroll
+    for (int a = 0; a < 3; a++) out[i].tcw[a] = pc.tcw[a];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ reprojection: residual + Jacobian
+// THE Jacobian-evaluation kernel.  One thread per observation.  Reads the 32-byte record (coalesced 2 x 16 B),
+// the pose/camera entry (uniform across most of a warp: observations are pose-major), the point (gather through
+// L2), writes the 160-byte chunk [Jp | Jl | r] with the Huber corrector applied, and reduces the cost.
+constexpr int kJacThreads = 256;
+constexpr int kChunk = 20;  // doubles per reprojection observation
+
+__global__ void __launch_bounds__(kJacThreads) reproj_jac_kernel(const ObsRec* __restrict__ obs, int64_t n,
+                                                                  const PoseCam* __restrict__ pcam, int C,
+                                                                  const CalibClass* __restrict__ cls,
+                                                                  const double* __restrict__ points, int apply_loss,
+                                                                  double* __restrict__ J, double* __restrict__ scalars) {
+  __shared__ double red[33];
+  const int64_t i = (int64_t)blockIdx.x * kJacThreads + threadIdx.x;
+  double cost = 0.0, fixed = 0.0;
+  if (i < n) {
+    const double2 uv = reinterpret_cast<const double2*>(obs)[2 * i];
+    const uint4 id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];  // pose, point, cls, flags
+    const CalibClass cc = cls[id.z];
+    const PoseCam& pc = pcam[(size_t)id.x * C + cc.cam];
+    const double X[3] = {points[3 * (size_t)id.y], points[3 * (size_t)id.y + 1], points[3 * (size_t)id.y + 2]};
+    double r[2], Jp[12], Jl[6];
+    reproj_residual_jacobian(pc, X, uv.x, uv.y, cc.mx, cc.my, r, Jp, Jl);
+    const double s = r[0] * r[0] + r[1] * r[1];
+    double sc = 1.0, c = 0.5 * s;
+    if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
+    if (id.w == 3u) fixed = c; else cost = c;
+    double2* out = reinterpret_cast<double2*>(J + (size_t)i * kChunk);
+#pragma unroll
+    for (int a = 0; a < 6; a++) out[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) out[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
+    out[9] = make_double2(sc * r[0], sc * r[1]);
+  }
+  cost = block_sum_all<kJacThreads>(cost, red);
+  fixed = block_sum_all<kJacThreads>(fixed, red);
+  if (threadIdx.x == 0) {
+    if (cost != 0.0) atomicAdd(&scalars[SC_COST], cost);
+    if (fixed != 0.0) atomicAdd(&scalars[SC_FIXED], fixed);
+  }
+}
+
+// Residual-only evaluation at the candidate point (cost only; nothing is stored).
+__global__ void __launch_bounds__(kJacThreads) reproj_cost_kernel(const ObsRec* __restrict__ obs, int64_t n,
+                                                                   const PoseCam* __restrict__ pcam, int C,
+                                                                   const CalibClass* __restrict__ cls,
+                                                                   const double* __restrict__ points,
+                                                                   double* __restrict__ scalars) {
+  __shared__ double red[33];
+  const int64_t i = (int64_t)blockIdx.x * kJacThreads + threadIdx.x;
+  double cost = 0.0, fixed = 0.0;
+  if (i < n) {
+    const double2 uv = reinterpret_cast<const double2*>(obs)[2 * i];
+    const uint4 id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];
+    const CalibClass cc = cls[id.z];
+    const PoseCam& pc = pcam[(size_t)id.x * C + cc.cam];
+    const double X[3] = {points[3 * (size_t)id.y], points[3 * (size_t)id.y + 1], points[3 * (size_t)id.y + 2]};
+    double r[2];
+    reproj_residual(pc, X, uv.x, uv.y, cc.mx, cc.my, r);
+    const double s = r[0] * r[0] + r[1] * r[1];
+    double sc, c = 0.5 * s;
+    if (cc.huber > 0.0) c = huber(cc.huber, s, &sc);
+    if (id.w == 3u) fixed = c; else cost = c;
+  }
+  cost = block_sum_all<kJacThreads>(cost, red);
+  fixed = block_sum_all<kJacThreads>(fixed, red);
+  if (threadIdx.x == 0) {
+    if (cost != 0.0) atomicAdd(&scalars[SC_CAND], cost);
+    if (fixed != 0.0) atomicAdd(&scalars[SC_CAND_FIXED], fixed);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ pose-side J^T J accumulation
+// One CTA per keyframe: the keyframe's Jacobian tile is contiguous (pose-major order).  Accumulates
+// H_pp = sum Jp^T Jp (6x6), g_p = sum Jp^T r and the column square norms with warp-shuffle reductions;
+// one set of atomics per CTA.
+constexpr int kPoseAccThreads = 256;
+__global__ void __launch_bounds__(kPoseAccThreads) pose_accum_kernel(const double* __restrict__ J,
+                                                                      const uint32_t* __restrict__ pose_ptr,
+                                                                      const int32_t* __restrict__ f_of_pose,
+                                                                      const uint32_t* __restrict__ su_ptr,
+                                                                      double* __restrict__ S_upper, double* __restrict__ gp,
+                                                                      double* __restrict__ hpp_diag) {
+  const int k = blockIdx.x;
+  const int f = f_of_pose[k];
+  if (f < 0) return;
+  const uint32_t b0 = pose_ptr[k], b1 = pose_ptr[k + 1];
+  if (b0 == b1) return;
+  double acc[27];
+#pragma unroll
+  for (int a = 0; a < 27; a++) acc[a] = 0.0;
+  for (uint32_t i = b0 + threadIdx.x; i < b1; i += kPoseAccThreads) {
+    const double2* ch = reinterpret_cast<const double2*>(J + (size_t)i * kChunk);
+    double jp[12];
+#pragma unroll
+    for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
+    const double2 r = ch[9];
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+#pragma unroll
+      for (int b = a; b < 6; b++) acc[t++] += jp[a] * jp[b] + jp[6 + a] * jp[6 + b];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) acc[21 + a] += jp[a] * r.x + jp[6 + a] * r.y;
+  }
+  __shared__ double red[27][kPoseAccThreads / 32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int a = 0; a < 27; a++) {
+    const double v = warp_sum(acc[a]);
+    if (l == 0) red[a][w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < kPoseAccThreads / 32; i++) s += red[threadIdx.x][i];
+    double* Sd = S_upper + (size_t)su_ptr[f] * 36;
+    if (threadIdx.x < 21) {
+      int a = 0, t = threadIdx.x;
+      while (t >= 6 - a) { t -= 6 - a; a++; }
+      const int b = a + t;
+      atomicAdd(&Sd[a * 6 + b], s);
+      if (a != b) atomicAdd(&Sd[b * 6 + a], s);
+      else atomicAdd(&hpp_diag[6 * f + a], s);
+    } else {
+      atomicAdd(&gp[6 * f + (threadIdx.x - 21)], s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ e-block elimination
+struct EArgs {
+  const uint32_t* ptr; const uint32_t* pos; const int32_t* f; const uint16_t* slot;
+  const uint32_t* pair_ptr; const uint16_t* nslots; const uint32_t* pair_blk;
+  const uint8_t* cst;
+  const double* J;          // chunks [Jp KRx6 | Je KRxNE | r KR]
+  double* escale;           // NE per e-block (Jacobi scaling, written when compute_scale)
+  double* einv;             // NE*NE per e-block: S_e (S_e H S_e + D^2)^-1 S_e
+  double* eg;               // NE per e-block: E^T r
+  const double* prior_H;    // NE*NE per e-block or null (unary factors on the e-block)
+  const double* prior_g;    // NE per e-block or null
+  double* overflow;         // staging for e-blocks with more than MAXS slots
+  const uint32_t* overflow_off;  // per e-block offset (in doubles) into overflow, valid when nslots > MAXS
+  int ne;
+};
+
+// One CTA (T threads) per e-block.  Phase A: H_ee, g_e (shuffle reductions), damping, inverse.
+// Phase B: per merged pose slot W = sum Jp^T Je and Z = W Hinv, staged in shared memory.
+// Phase C: S_ab -= Z_a W_b^T for every slot pair, spread over the threads by block row.
+template <int NE, int KR, int T, int MAXS, bool POSE_SIDE>
+__global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, const uint32_t* __restrict__ su_ptr,
+                                                          double* __restrict__ S_upper, double* __restrict__ gp,
+                                                          double* __restrict__ hpp_diag, double* __restrict__ b_schur,
+                                                          double* __restrict__ scalars) {
+  constexpr int CH = KR * (6 + NE + 1);
+  constexpr int NH = NE * (NE + 1) / 2;
+  constexpr int SL = 12 * NE;  // doubles per slot in the staging buffer: Z (6xNE) then W (6xNE)
+  __shared__ double red[33];
+  __shared__ double stage_s[MAXS * SL];
+  const int e = blockIdx.x;
+  if (A.cst[e]) return;
+  const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
+  if (b0 == b1 && A.prior_H == nullptr) return;
+  // ---- phase A
+  double H[NH], g[NE];
+#pragma unroll
+  for (int a = 0; a < NH; a++) H[a] = 0.0;
+#pragma unroll
+  for (int a = 0; a < NE; a++) g[a] = 0.0;
+  for (uint32_t q = b0 + threadIdx.x; q < b1; q += T) {
+    const double* ch = A.J + (size_t)A.pos[q] * CH;
+    const double* Je = ch + KR * 6;
+    const double* r = ch + KR * (6 + NE);
+#pragma unroll
+    for (int k = 0; k < KR; k++) {
+      double je[NE];
+#pragma unroll
+      for (int a = 0; a < NE; a++) je[a] = Je[k * NE + a];
+      const double rk = r[k];
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < NE; a++) {
+        g[a] += je[a] * rk;
+#pragma unroll
+        for (int b = a; b < NE; b++) H[t++] += je[a] * je[b];
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NH; a++) H[a] = block_sum_all<T>(H[a], red);
+#pragma unroll
+  for (int a = 0; a < NE; a++) g[a] = block_sum_all<T>(g[a], red);
+  if (A.prior_H) {
+    const double* ph = A.prior_H + (size_t)e * NE * NE;
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < NE; a++) {
+      g[a] += A.prior_g[(size_t)e * NE + a];
+#pragma unroll
+      for (int b = a; b < NE; b++) H[t++] += ph[a * NE + b];
+    }
+  }
+  double s[NE], Hs[NE * NE], hinv[NE * NE];
+  {
+    int t = 0;
+    double gm = 0.0;
+#pragma unroll
+    for (int a = 0; a < NE; a++) {
+      const double haa = H[t];
+      t += NE - a;
+      s[a] = lm.compute_scale ? 1.0 / (1.0 + sqrt(haa)) : A.escale[(size_t)e * NE + a];
+      gm = fmax(gm, fabs(g[a]));
+    }
+    if (threadIdx.x == 0) {
+      if (lm.compute_scale) {
+#pragma unroll
+        for (int a = 0; a < NE; a++) A.escale[(size_t)e * NE + a] = s[a];
+      }
+      atomic_max_nonneg(&scalars[SC_GMAX], gm);
+    }
+    t = 0;
+#pragma unroll
+    for (int a = 0; a < NE; a++) {
+#pragma unroll
+      for (int b = a; b < NE; b++) {
+        const double v = s[a] * H[t++] * s[b];
+        Hs[a * NE + b] = v;
+        Hs[b * NE + a] = v;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NE; a++) Hs[a * NE + a] += fmin(fmax(Hs[a * NE + a], lm.min_diag), lm.max_diag) / lm.radius;
+  }
+  if (!spd_inverse<NE>(Hs, hinv)) {
+    if (threadIdx.x == 0) atomicAdd(&scalars[SC_FAIL], 1.0);
+    return;
+  }
+#pragma unroll
+  for (int a = 0; a < NE; a++) {
+#pragma unroll
+    for (int b = 0; b < NE; b++) hinv[a * NE + b] *= s[a] * s[b];
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int a = 0; a < NE * NE; a++) A.einv[(size_t)e * NE * NE + a] = hinv[a];
+#pragma unroll
+    for (int a = 0; a < NE; a++) A.eg[(size_t)e * NE + a] = g[a];
+  }
+  // ---- phase B
+  const int ns = A.nslots[e];
+  if (ns == 0) return;
+  double* stage = (ns <= MAXS) ? stage_s : (A.overflow + A.overflow_off[e]);
+  for (uint32_t q = b0 + threadIdx.x; q < b1; q += T) {
+    const uint16_t sl = A.slot[q];
+    if (sl == 0xFFFF) continue;
+    if (q > b0 && A.slot[q - 1] == sl) continue;  // not the head of its run
+    double Wm[6 * NE];
+#pragma unroll
+    for (int a = 0; a < 6 * NE; a++) Wm[a] = 0.0;
+    double hp[21], gq[6];
+    if (POSE_SIDE) {
+#pragma unroll
+      for (int a = 0; a < 21; a++) hp[a] = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; a++) gq[a] = 0.0;
+    }
+    for (uint32_t q2 = q; q2 < b1 && A.slot[q2] == sl; q2++) {
+      const double* ch = A.J + (size_t)A.pos[q2] * CH;
+#pragma unroll
+      for (int k = 0; k < KR; k++) {
+        double jp[6], je[NE];
+#pragma unroll
+        for (int a = 0; a < 6; a++) jp[a] = ch[k * 6 + a];
+#pragma unroll
+        for (int a = 0; a < NE; a++) je[a] = ch[KR * 6 + k * NE + a];
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+#pragma unroll
+          for (int c = 0; c < NE; c++) Wm[a * NE + c] += jp[a] * je[c];
+        }
+        if (POSE_SIDE) {
+          const double rk = ch[KR * (6 + NE) + k];
+          int t = 0;
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+            gq[a] += jp[a] * rk;
+#pragma unroll
+            for (int b = a; b < 6; b++) hp[t++] += jp[a] * jp[b];
+          }
+        }
+      }
+    }
+    const int fi = A.f[q];
+    double* st = stage + (size_t)sl * SL;
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+      double zg = 0.0;
+#pragma unroll
+      for (int c = 0; c < NE; c++) {
+        double z = 0.0;
+#pragma unroll
+        for (int d = 0; d < NE; d++) z += Wm[a * NE + d] * hinv[d * NE + c];
+        st[a * NE + c] = z;
+        st[6 * NE + a * NE + c] = Wm[a * NE + c];
+        zg += z * g[c];
+      }
+      atomicAdd(&b_schur[6 * fi + a], -zg);
+    }
+    if (POSE_SIDE) {
+      double* Sd = S_upper + (size_t)su_ptr[fi] * 36;
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+        atomicAdd(&gp[6 * fi + a], gq[a]);
+#pragma unroll
+        for (int b = a; b < 6; b++) {
+          const double v = hp[t++];
+          atomicAdd(&Sd[a * 6 + b], v);
+          if (a != b) atomicAdd(&Sd[b * 6 + a], v);
+          else atomicAdd(&hpp_diag[6 * fi + a], v);
+        }
+      }
+    }
+  }
+  if (ns > MAXS) __threadfence_block();
+  __syncthreads();
+  // ---- phase C
+  const int items = ns * (ns + 1) / 2 * 6;
+  const uint32_t* pb = A.pair_blk + A.pair_ptr[e];
+  for (int it = threadIdx.x; it < items; it += T) {
+    const int pr = it / 6, row = it - 6 * pr;
+    int a = 0, t = pr;
+    while (t >= ns - a) { t -= ns - a; a++; }
+    const int b = a + t;
+    const double* Za = stage + (size_t)a * SL + row * NE;
+    const double* Wb = stage + (size_t)b * SL + 6 * NE;
+    double z[NE];
+#pragma unroll
+    for (int d = 0; d < NE; d++) z[d] = Za[d];
+    double* Sb = S_upper + (size_t)pb[pr] * 36 + row * 6;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      double v = 0.0;
+#pragma unroll
+      for (int d = 0; d < NE; d++) v += z[d] * Wb[c * NE + d];
+      atomicAdd(&Sb[c], -v);
+    }
+  }
+}
+
+// Back-substitution for one e-block + its share of the model cost change and of the candidate point:
+//   delta_e = -Hinv (g_e + sum_obs Je^T (Jp delta_p)),  model += sum m (r + m/2), m = Jp delta_p + Je delta_e
+template <int NE, int KR, int T>
+__global__ void __launch_bounds__(T) backsub_eblock_kernel(EArgs A, const double* __restrict__ dpose,
+                                                            const double* __restrict__ x, double* __restrict__ x_cand,
+                                                            double* __restrict__ delta_e, double* __restrict__ scalars) {
+  constexpr int CH = KR * (6 + NE + 1);
+  __shared__ double red[33];
+  const int e = blockIdx.x;
+  const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
+  const bool cst = A.cst[e] != 0;
+  double de[NE];
+#pragma unroll
+  for (int a = 0; a < NE; a++) de[a] = 0.0;
+  if (!cst) {
+    if (b0 == b1 && A.prior_H == nullptr) return;
+    double t[NE];
+#pragma unroll
+    for (int a = 0; a < NE; a++) t[a] = 0.0;
+    for (uint32_t q = b0 + threadIdx.x; q < b1; q += T) {
+      const int fi = A.f[q];
+      if (fi < 0) continue;
+      const double* ch = A.J + (size_t)A.pos[q] * CH;
+      double dp[6];
+#pragma unroll
+      for (int a = 0; a < 6; a++) dp[a] = dpose[6 * fi + a];
+#pragma unroll
+      for (int k = 0; k < KR; k++) {
+        double jd = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) jd += ch[k * 6 + a] * dp[a];
+#pragma unroll
+        for (int c = 0; c < NE; c++) t[c] += ch[KR * 6 + k * NE + c] * jd;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NE; a++) t[a] = block_sum_all<T>(t[a], red) + A.eg[(size_t)e * NE + a];
+    const double* hinv = A.einv + (size_t)e * NE * NE;
+#pragma unroll
+    for (int a = 0; a < NE; a++) {
+      double v = 0.0;
+#pragma unroll
+      for (int b = 0; b < NE; b++) v += hinv[a * NE + b] * t[b];
+      de[a] = -v;
+    }
+    if (threadIdx.x == 0) {
+      double s2 = 0.0;
+#pragma unroll
+      for (int a = 0; a < NE; a++) {
+        delta_e[(size_t)e * NE + a] = de[a];
+        x_cand[(size_t)e * NE + a] = x[(size_t)e * NE + a] + de[a];
+        s2 += de[a] * de[a];
+      }
+      atomicAdd(&scalars[SC_STEP2], s2);
+    }
+  }
+  double mc = 0.0;
+  for (uint32_t q = b0 + threadIdx.x; q < b1; q += T) {
+    const int fi = A.f[q];
+    if (cst && fi < 0) continue;
+    const double* ch = A.J + (size_t)A.pos[q] * CH;
+    double dp[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) dp[a] = fi >= 0 ? dpose[6 * fi + a] : 0.0;
+#pragma unroll
+    for (int k = 0; k < KR; k++) {
+      double m = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; a++) m += ch[k * 6 + a] * dp[a];
+#pragma unroll
+      for (int c = 0; c < NE; c++) m += ch[KR * 6 + k * NE + c] * de[c];
+      mc += m * (ch[KR * (6 + NE) + k] + 0.5 * m);
+    }
+  }
+  mc = block_sum_all<T>(mc, red);
+  if (threadIdx.x == 0 && mc != 0.0) atomicAdd(&scalars[SC_MODEL], mc);
+}
+
+// ------------------------------------------------------------------------------------------ bbox observations
+constexpr int kBBoxChunk = 56;
+// mode 0: residual + Jacobians into the chunk, cost; mode 1: candidate cost only
+__global__ void bbox_kernel(const BBoxRec* __restrict__ rec, int64_t n, const PoseCam* __restrict__ pcam, int C,
+                            const double* __restrict__ objs, int mode, int apply_loss, double* __restrict__ J,
+                            double* __restrict__ scalars) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const BBoxRec& R = rec[i];
+  const PoseCam& pc = pcam[(size_t)R.pose * C + R.cam];
+  double ell[7];
+#pragma unroll
+  for (int a = 0; a < 7; a++) ell[a] = objs[7 * (size_t)R.obj + a];
+  double r[4];
+  double* ch = J + (size_t)i * kBBoxChunk;
+  if (mode == 0) bbox_residual_jacobian(pc, ell, R.A4, R.brect, R.invalid_err, r, ch + 24, ch);
+  else bbox_residual_jacobian(pc, ell, R.A4, R.brect, R.invalid_err, r, nullptr, nullptr);
+  const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+  double sc = 1.0, c = 0.5 * s;
+  if (apply_loss && R.huber > 0.0) c = huber(R.huber, s, &sc);
+  if (mode == 0) {
+    for (int a = 0; a < 52; a++) ch[a] *= sc;
+    for (int a = 0; a < 4; a++) ch[52 + a] = sc * r[a];
+    atomicAdd(&scalars[R.flags == 3u ? SC_FIXED : SC_COST], c);
+  } else {
+    atomicAdd(&scalars[R.flags == 3u ? SC_CAND_FIXED : SC_CAND], c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ unary factors
+// r = A (x[off:off+k] - mean).  mode 0: evaluate at x (store r, scale; cost); 1: accumulate J^T J / J^T r into the
+// block's prior arrays (e-blocks) or the reduced system (poses); 2: model cost change; 3: candidate cost.
+struct UnaryOut { double r[7]; double sc; };
+__global__ void unary_kernel(const UnaryRec* __restrict__ rec, int64_t n, int mode, int apply_loss,
+                             const double* __restrict__ poses, const double* __restrict__ points,
+                             const double* __restrict__ objs, UnaryOut* __restrict__ out,
+                             const int32_t* __restrict__ f_of_pose, const uint32_t* __restrict__ su_ptr,
+                             double* __restrict__ S_upper, double* __restrict__ gp, double* __restrict__ hpp_diag,
+                             double* __restrict__ prior_H_pt, double* __restrict__ prior_g_pt,
+                             double* __restrict__ prior_H_obj, double* __restrict__ prior_g_obj,
+                             const double* __restrict__ dpose, const double* __restrict__ dpoint,
+                             const double* __restrict__ dobj, double* __restrict__ scalars) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const UnaryRec& R = rec[i];
+  const int k = R.k, off = R.off;
+  const int bs = R.kind == 0 ? 6 : (R.kind == 1 ? 3 : 7);
+  if (mode == 0 || mode == 3) {
+    const double* x = (R.kind == 0 ? poses + 6 * (size_t)R.idx : (R.kind == 1 ? points + 3 * (size_t)R.idx : objs + 7 * (size_t)R.idx));
+    double r[7], s = 0.0;
+    for (int a = 0; a < k; a++) {
+      double v = 0.0;
+      for (int c = 0; c < k; c++) v += R.A[a * k + c] * (x[off + c] - R.mean[c]);
+      r[a] = v;
+      s += v * v;
+    }
+    double sc = 1.0, c = 0.5 * s;
+    if (apply_loss && R.huber > 0.0) c = huber(R.huber, s, &sc);
+    if (mode == 0) {
+      for (int a = 0; a < k; a++) out[i].r[a] = sc * r[a];
+      out[i].sc = sc;
+      atomicAdd(&scalars[R.flags ? SC_FIXED : SC_COST], c);
+    } else {
+      atomicAdd(&scalars[R.flags ? SC_CAND_FIXED : SC_CAND], c);
+    }
+    return;
+  }
+  if (R.flags) return;  // constant block: no columns
+  const double sc = out[i].sc;
+  if (mode == 1) {
+    // J = sc * A on columns off..off+k-1
+    double* Hd; double* gd; int ld;
+    if (R.kind == 0) { const int f = f_of_pose[R.idx]; Hd = S_upper + (size_t)su_ptr[f] * 36; gd = gp + 6 * f; ld = 6; }
+    else if (R.kind == 1) { Hd = prior_H_pt + 9 * (size_t)R.idx; gd = prior_g_pt + 3 * (size_t)R.idx; ld = 3; }
+    else { Hd = prior_H_obj + 49 * (size_t)R.idx; gd = prior_g_obj + 7 * (size_t)R.idx; ld = 7; }
+    for (int a = 0; a < k; a++) {
+      double gv = 0.0;
+      for (int m = 0; m < k; m++) gv += sc * R.A[m * k + a] * out[i].r[m];
+      atomicAdd(&gd[off + a], gv);
+      for (int c = 0; c < k; c++) {
+        double hv = 0.0;
+        for (int m = 0; m < k; m++) hv += R.A[m * k + a] * R.A[m * k + c];
+        hv *= sc * sc;
+        atomicAdd(&Hd[(off + a) * ld + off + c], hv);
+        if (R.kind == 0 && a == c) atomicAdd(&hpp_diag[6 * f_of_pose[R.idx] + off + a], hv);
+      }
+    }
+    (void)bs;
+    return;
+  }
+  // mode 2
+  const double* d = (R.kind == 0 ? dpose + 6 * (size_t)f_of_pose[R.idx] : (R.kind == 1 ? dpoint + 3 * (size_t)R.idx : dobj + 7 * (size_t)R.idx));
+  double mc = 0.0;
+  for (int a = 0; a < k; a++) {
+    double m = 0.0;
+    for (int c = 0; c < k; c++) m += sc * R.A[a * k + c] * d[off + c];
+    mc += m * (out[i].r[a] + 0.5 * m);
+  }
+  atomicAdd(&scalars[SC_MODEL], mc);
+}
+
+// ------------------------------------------------------------------------------------------ relative-pose factors
+struct RelOut { double r[6]; double J1[36]; double J2[36]; };
+// mode 0 evaluate (+cost), 1 accumulate into the reduced system, 2 model cost change, 3 candidate cost
+__global__ void relpose_kernel(const RelRec* __restrict__ rec, int64_t n, int mode, int apply_loss,
+                               const double* __restrict__ poses, RelOut* __restrict__ out,
+                               double* __restrict__ S_upper, double* __restrict__ gp, double* __restrict__ hpp_diag,
+                               const double* __restrict__ dpose, double* __restrict__ scalars) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RelRec& R = rec[i];
+  const bool fixed = R.f1 < 0 && R.f2 < 0;
+  if (mode == 0 || mode == 3) {
+    double p1[6], p2[6];
+    for (int a = 0; a < 6; a++) { p1[a] = poses[6 * (size_t)R.p1 + a]; p2[a] = poses[6 * (size_t)R.p2 + a]; }
+    RelOut o;
+    relpose_residual_jacobian(p1, p2, R.tm, R.Rm_inv, R.A6, o.r, mode == 0 ? o.J1 : nullptr, mode == 0 ? o.J2 : nullptr);
+    double s = 0.0;
+    for (int a = 0; a < 6; a++) s += o.r[a] * o.r[a];
+    double sc = 1.0, c = 0.5 * s;
+    if (apply_loss && R.huber > 0.0) c = huber(R.huber, s, &sc);
+    if (mode == 0) {
+      for (int a = 0; a < 6; a++) out[i].r[a] = sc * o.r[a];
+      for (int a = 0; a < 36; a++) { out[i].J1[a] = sc * o.J1[a]; out[i].J2[a] = sc * o.J2[a]; }
+      atomicAdd(&scalars[fixed ? SC_FIXED : SC_COST], c);
+    } else {
+      atomicAdd(&scalars[fixed ? SC_CAND_FIXED : SC_CAND], c);
+    }
+    return;
+  }
+  if (fixed) return;
+  const RelOut& o = out[i];
+  if (mode == 1) {
+    const int fs[2] = {R.f1, R.f2};
+    const double* Js[2] = {o.J1, o.J2};
+    const int blk[2] = {R.blk11, R.blk22};
+    for (int u = 0; u < 2; u++) {
+      if (fs[u] < 0) continue;
+      double* Sd = S_upper + (size_t)blk[u] * 36;
+      for (int a = 0; a < 6; a++) {
+        double gv = 0.0;
+        for (int k = 0; k < 6; k++) gv += Js[u][k * 6 + a] * o.r[k];
+        atomicAdd(&gp[6 * fs[u] + a], gv);
+        for (int b = 0; b < 6; b++) {
+          double hv = 0.0;
+          for (int k = 0; k < 6; k++) hv += Js[u][k * 6 + a] * Js[u][k * 6 + b];
+          atomicAdd(&Sd[a * 6 + b], hv);
+          if (a == b) atomicAdd(&hpp_diag[6 * fs[u] + a], hv);
+        }
+      }
+    }
+    if (R.blk12 >= 0) {
+      // upper block (min f, max f): rows from the smaller-f pose
+      const double* Ja = R.swap12 ? o.J2 : o.J1;
+      const double* Jb = R.swap12 ? o.J1 : o.J2;
+      double* Sd = S_upper + (size_t)R.blk12 * 36;
+      for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) {
+          double hv = 0.0;
+          for (int k = 0; k < 6; k++) hv += Ja[k * 6 + a] * Jb[k * 6 + b];
+          atomicAdd(&Sd[a * 6 + b], hv);
+        }
+    }
+    return;
+  }
+  double mc = 0.0;
+  for (int k = 0; k < 6; k++) {
+    double m = 0.0;
+    if (R.f1 >= 0) for (int a = 0; a < 6; a++) m += o.J1[k * 6 + a] * dpose[6 * R.f1 + a];
+    if (R.f2 >= 0) for (int a = 0; a < 6; a++) m += o.J2[k * 6 + a] * dpose[6 * R.f2 + a];
+    mc += m * (o.r[k] + 0.5 * m);
+  }
+  atomicAdd(&scalars[SC_MODEL], mc);
+}
+
+// ------------------------------------------------------------------------------------------ reduced system: finish
+// Jacobi scaling of the pose columns from the first Jacobian (Ceres: 1 / (1 + column norm)).
+__global__ void pose_scale_kernel(const double* __restrict__ hpp_diag, int n, double* __restrict__ pscale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pscale[i] = 1.0 / (1.0 + sqrt(hpp_diag[i]));
+}
+
+// One warp per block row: S~ = S_p S_raw S_p + D_p^2 mirrored into the full BSR (scalar rows contiguous),
+// b~ = S_p (g_p + b_schur), block-Jacobi preconditioner = inverse of the diagonal block, |g_p|_inf.
+__global__ void finish_kernel(int nf, const uint32_t* __restrict__ sf_ptr, const uint32_t* __restrict__ sf_col,
+                              const uint32_t* __restrict__ sf_src, const double* __restrict__ S_upper,
+                              const double* __restrict__ pscale, const double* __restrict__ hpp_diag,
+                              const double* __restrict__ gp, const double* __restrict__ b_schur, LMParams lm,
+                              double* __restrict__ Sf, double* __restrict__ rhs, double* __restrict__ Minv,
+                              double* __restrict__ scalars) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= nf) return;
+  const uint32_t p0 = sf_ptr[i], nb = sf_ptr[i + 1] - p0;
+  double* row = Sf + (size_t)p0 * 36;
+  const uint32_t total = nb * 36;
+  for (uint32_t t = lane; t < total; t += 32) {
+    // destination layout: [a][k][c] -> a * (nb*6) + k*6 + c
+    const uint32_t a = t / (nb * 6), rem = t - a * nb * 6, k = rem / 6, c = rem - 6 * k;
+    const uint32_t src = sf_src[p0 + k];
+    const uint32_t j = sf_col[p0 + k];
+    const double* sb = S_upper + (size_t)(src & 0x7fffffffu) * 36;
+    double v = (src >> 31) ? sb[c * 6 + a] : sb[a * 6 + c];
+    v *= pscale[6 * i + a] * pscale[6 * j + c];
+    if (j == (uint32_t)i && a == c) {
+      const double sd = pscale[6 * i + a] * pscale[6 * i + a] * hpp_diag[6 * i + a];
+      v += fmin(fmax(sd, lm.min_diag), lm.max_diag) / lm.radius;
+    }
+    row[t] = v;
+  }
+  __syncwarp();
+  if (lane < 6) {
+    const double g = gp[6 * i + lane];
+    rhs[6 * i + lane] = pscale[6 * i + lane] * (g + b_schur[6 * i + lane]);
+    atomic_max_nonneg(&scalars[SC_GMAX], fabs(g));
+  }
+  if (lane == 0) {
+    // locate the diagonal block in this row
+    uint32_t kd = 0;
+    for (uint32_t k = 0; k < nb; k++) if (sf_col[p0 + k] == (uint32_t)i) { kd = k; break; }
+    double D[36], inv[36];
+    for (int a = 0; a < 6; a++)
+      for (int c = 0; c < 6; c++) D[a * 6 + c] = row[a * nb * 6 + kd * 6 + c];
+    if (!spd_inverse<6>(D, inv)) {
+      atomicAdd(&scalars[SC_FAIL], 1.0);
+      for (int a = 0; a < 36; a++) inv[a] = (a % 7 == 0) ? 1.0 / D[a] : 0.0;
+    }
+    for (int a = 0; a < 36; a++) Minv[(size_t)i * 36 + a] = inv[a];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ reduced system: PCG
+// Persistent cooperative kernel: the whole preconditioned conjugate-gradient solve of S~ y = b~ runs in ONE launch
+// (three grid barriers per iteration, no host round trips).  One warp owns a block row: it multiplies the row's
+// 6 scalar rows (contiguous, coalesced) against p gathered from L2 and then updates its 6 entries of x, r, z, p.
+constexpr int kPcgThreads = 512;
+__global__ void __launch_bounds__(kPcgThreads) pcg_kernel(int nf, const uint32_t* __restrict__ sf_ptr,
+                                                          const uint32_t* __restrict__ sf_col,
+                                                          const double* __restrict__ Sf, const double* __restrict__ rhs,
+                                                          const double* __restrict__ Minv, double* __restrict__ y,
+                                                          double* r, double* z, double* p, double* q, double* acc /*4x4*/,
+                                                          int max_iter, double tol, double* __restrict__ scalars) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[3][kPcgThreads / 32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int gw = (blockIdx.x * kPcgThreads + threadIdx.x) >> 5;
+  const int GW = (gridDim.x * kPcgThreads) >> 5;
+  volatile double* vacc = acc;
+
+  auto block_acc = [&](double a0, double a1, double a2, double* dst) {
+    if (lane == 0) { red[0][wib] = a0; red[1][wib] = a1; red[2][wib] = a2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double s = 0.0;
+      for (int i = 0; i < kPcgThreads / 32; i++) s += red[threadIdx.x][i];
+      if (s != 0.0) atomicAdd(&dst[threadIdx.x], s);
+    }
+    __syncthreads();
+  };
+
+  // init: y = 0, r = b, z = Minv r, p = z; acc[0] = {rz, bb}
+  if (blockIdx.x == 0 && threadIdx.x < 16) acc[threadIdx.x] = 0.0;
+  grid.sync();
+  {
+    double rz = 0.0, bb = 0.0;
+    for (int i = gw; i < nf; i += GW) {
+      const double rv = lane < 6 ? rhs[6 * i + lane] : 0.0;
+      double zv = 0.0;
+      for (int c = 0; c < 6; c++) {
+        const double rc = __shfl_sync(0xffffffffu, rv, c);
+        if (lane < 6) zv += Minv[(size_t)i * 36 + lane * 6 + c] * rc;
+      }
+      if (lane < 6) { y[6 * i + lane] = 0.0; r[6 * i + lane] = rv; z[6 * i + lane] = zv; p[6 * i + lane] = zv; rz += rv * zv; bb += rv * rv; }
+    }
+    rz = warp_sum(rz); bb = warp_sum(bb);
+    block_acc(rz, bb, 0.0, acc);
+  }
+  grid.sync();
+  double rho = vacc[0];
+  const double bb = vacc[1];
+  int it = 0;
+  double rr = bb;
+  int brk = 0;
+  if (bb > 0.0) {
+    for (it = 0; it < max_iter;) {
+      double* A = acc + 4 * ((it + 1) & 3);      // this iteration's accumulators
+      double* Z = acc + 4 * ((it + 3) & 3);      // cleared for iteration it+2
+      if (blockIdx.x == 0 && threadIdx.x < 4) Z[threadIdx.x] = 0.0;
+      // q = S p, pq
+      double pq = 0.0;
+      for (int i = gw; i < nf; i += GW) {
+        const uint32_t p0 = sf_ptr[i], nb = sf_ptr[i + 1] - p0;
+        const uint32_t len = nb * 6;
+        const double* row = Sf + (size_t)p0 * 36;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+        for (uint32_t e = lane; e < len; e += 32) {
+          const uint32_t k = e / 6, c = e - 6 * k;
+          const double xv = p[6 * sf_col[p0 + k] + c];
+          a0 += row[e] * xv; a1 += row[len + e] * xv; a2 += row[2 * len + e] * xv;
+          a3 += row[3 * len + e] * xv; a4 += row[4 * len + e] * xv; a5 += row[5 * len + e] * xv;
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4); a5 = warp_sum(a5);
+        if (lane < 6) {
+          const double qv = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : lane == 3 ? a3 : lane == 4 ? a4 : a5;
+          q[6 * i + lane] = qv;
+          pq += qv * p[6 * i + lane];
+        }
+      }
+      pq = warp_sum(pq);
+      block_acc(pq, 0.0, 0.0, A);
+      grid.sync();
+      const double pqs = ((volatile double*)A)[0];
+      if (!(pqs > 0.0)) { brk = 1; break; }
+      const double alpha = rho / pqs;
+      double rz = 0.0, r2 = 0.0;
+      for (int i = gw; i < nf; i += GW) {
+        double rv = 0.0;
+        if (lane < 6) {
+          y[6 * i + lane] += alpha * p[6 * i + lane];
+          rv = r[6 * i + lane] - alpha * q[6 * i + lane];
+          r[6 * i + lane] = rv;
+        }
+        double zv = 0.0;
+        for (int c = 0; c < 6; c++) {
+          const double rc = __shfl_sync(0xffffffffu, rv, c);
+          if (lane < 6) zv += Minv[(size_t)i * 36 + lane * 6 + c] * rc;
+        }
+        if (lane < 6) { z[6 * i + lane] = zv; rz += rv * zv; r2 += rv * rv; }
+      }
+      rz = warp_sum(rz); r2 = warp_sum(r2);
+      block_acc(0.0, rz, r2, A);
+      grid.sync();
+      const double rho_new = ((volatile double*)A)[1];
+      rr = ((volatile double*)A)[2];
+      it++;
+      if (rr <= tol * tol * bb) break;
+      const double beta = rho_new / rho;
+      rho = rho_new;
+      for (int i = gw; i < nf; i += GW)
+        if (lane < 6) p[6 * i + lane] = z[6 * i + lane] + beta * p[6 * i + lane];
+      grid.sync();
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scalars[SC_PCG_IT] = (double)it;
+    scalars[SC_PCG_RES] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+    scalars[SC_PCG_BB] = bb;
+    scalars[SC_PCG_BREAK] = (double)brk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ step / norms
+// delta_p = -s_p * y (undo the Jacobi scaling), candidate pose, |delta|^2
+__global__ void pose_step_kernel(int nf, const int32_t* __restrict__ pose_of_f, const double* __restrict__ pscale,
+                                 const double* __restrict__ y, const double* __restrict__ poses,
+                                 double* __restrict__ poses_cand, double* __restrict__ dpose, int contribute,
+                                 double* __restrict__ scalars) {
+  __shared__ double red[33];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s2 = 0.0;
+  if (i < 6 * nf) {
+    const int f = i / 6, a = i - 6 * f;
+    const double d = -pscale[i] * y[i];
+    dpose[i] = d;
+    const size_t k = (size_t)pose_of_f[f];
+    poses_cand[6 * k + a] = poses[6 * k + a] + d;
+    s2 = d * d;
+  }
+  s2 = block_sum_all<256>(s2, red);
+  if (threadIdx.x == 0 && s2 != 0.0 && contribute) atomicAdd(&scalars[SC_STEP2], s2);
+}
+
+// |x|^2 over the variable blocks: `mask` (per block, nonzero = skip), block size bs
+__global__ void xnorm_kernel(const double* __restrict__ x, const uint8_t* __restrict__ skip, int64_t nblocks, int bs,
+                             double* __restrict__ scalars) {
+  __shared__ double red[33];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (i < nblocks * bs && !skip[i / bs]) s = x[i] * x[i];
+  s = block_sum_all<256>(s, red);
+  if (threadIdx.x == 0 && s != 0.0) atomicAdd(&scalars[SC_XNORM2], s);
+}
+
+}  // namespace obvi

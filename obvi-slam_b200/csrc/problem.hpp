@@ -1,0 +1,445 @@
+// Host-side problem container: parameter blocks keyed by host pointer, factor records, and the
+// structure build that turns them into the flat, sorted device layout (DESIGN.md "Data layout").
+// Mirrors what ceres::Problem + the reference's residual_creator hold on the host
+// (include/refactoring/optimization/residual_creator.h:20-436,
+//  include/refactoring/optimization/object_pose_graph_optimizer.h:126-632).
+#pragma once
+
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/obvi_ba.h"
+#include "host_math.hpp"
+
+namespace obvi {
+
+struct ParamBlock {
+  double* host;
+  int32_t size;
+  uint8_t constant;
+  uint8_t alive;
+};
+
+struct ParamArray { double* base; int32_t size; int64_t count; int64_t first_id; };
+
+struct Camera { double intr[4]; double Rinv[9]; double tinv[3]; };
+
+struct ReprojFactor { int32_t pose, point, cam; uint8_t alive; double px, py, sigma, huber; };
+struct BBoxFactor { int32_t obj, pose, cam; uint8_t alive; double brect[4]; double A4[16]; double invalid_err, huber; };
+// unary factor on one block: r = A (x[off:off+k] - mean), k rows (shape 3, ltm 7, param prior 1)
+struct UnaryFactor { int32_t block; int32_t type; int32_t k; int32_t off; uint8_t alive; double A[49]; double mean[7]; double huber; };
+struct RelPoseFactor { int32_t p1, p2; uint8_t alive; double tm[3]; double Rm_inv[9]; double A6[36]; double huber; };
+
+inline obvi_factor_id make_id(int type, uint64_t index) { return ((uint64_t)type << 56) | index; }
+inline int id_type(obvi_factor_id id) { return (int)(id >> 56); }
+inline uint64_t id_index(obvi_factor_id id) { return id & ((1ull << 56) - 1); }
+
+// ---- device-facing records -------------------------------------------------------------------------
+struct ObsRec {       // 32 B, one per reprojection observation, pose-major order
+  double ur, vr;      // rectified feature
+  uint32_t pose;      // pose index
+  uint32_t point;     // internal point index
+  uint32_t cls;       // calibration class (camera, sigma, huber)
+  uint32_t flags;     // bit0: pose constant, bit1: point constant
+};
+struct CalibClass { double mx, my, huber; int32_t cam; int32_t pad; };  // 32 B
+struct BBoxRec {      // one per bbox observation, object-major order
+  double brect[4];
+  double A4[16];
+  double invalid_err, huber;
+  uint32_t obj, pose, cam, flags;  // bit0: pose constant, bit1: object constant
+};
+struct UnaryRec { double A[49]; double mean[7]; double huber; int32_t kind /*0 pose 1 point 2 obj*/, idx, k, off; uint32_t flags, pad; };
+struct RelRec { double tm[3]; double Rm_inv[9]; double A6[36]; double huber; int32_t p1, p2, f1, f2; int32_t blk11, blk12, blk22, swap12; };
+
+// Flat structure produced by the build (host copies; the solver uploads them).
+struct Structure {
+  int K = 0, P = 0, O = 0, C = 0;   // poses, points, objects (referenced by live factors), cameras
+  int nf = 0;                        // variable poses (f-blocks)
+  int64_t n_obs = 0, n_bbox = 0, n_unary = 0, n_rel = 0;
+  int64_t num_residual_blocks_reduced = 0, num_residuals_reduced = 0;
+  int num_param_blocks_reduced = 0, num_params_reduced = 0;
+  std::vector<int32_t> pose_block, point_block, obj_block;  // internal index -> param block id
+  std::vector<int32_t> f_of_pose;                           // pose index -> f index or -1
+  std::vector<uint8_t> point_const, obj_const;
+  // reprojection observations, pose-major
+  std::vector<ObsRec> obs;
+  std::vector<uint32_t> obs_user;          // internal obs -> index in Problem::reproj
+  std::vector<uint32_t> pose_ptr;          // K+1: obs segment of each pose
+  std::vector<CalibClass> classes;
+  // e-block lists (points then objects share the same layout)
+  struct EList {
+    std::vector<uint32_t> ptr;       // ne+1
+    std::vector<uint32_t> pos;       // obs position (index into the J array) per list entry
+    std::vector<int32_t> f;          // f index of the entry's pose (-1 constant)
+    std::vector<uint16_t> slot;      // merged pose slot within the e-block (0xFFFF: constant pose)
+    std::vector<uint32_t> pair_ptr;  // ne+1: offset into pair_blk (ns (ns+1)/2 entries per e-block)
+    std::vector<uint16_t> nslots;    // ne
+    std::vector<uint32_t> pair_blk;  // S_upper block index of slot pair (a<=b), row-major upper
+    std::vector<int32_t> slot_f;     // per e-block slot -> f index (offset by slot_ptr)
+    std::vector<uint32_t> slot_ptr;  // ne+1
+    int max_slots = 0;
+  } pts, objs;
+  std::vector<BBoxRec> bbox;
+  std::vector<uint32_t> bbox_user;
+  std::vector<UnaryRec> unary;
+  std::vector<uint32_t> unary_user;        // index into Problem::unary
+  std::vector<RelRec> rel;
+  std::vector<uint32_t> rel_user;
+  // reduced camera system
+  int64_t n_upper = 0;                      // blocks in the upper triangle (incl. diagonal)
+  std::vector<uint32_t> su_ptr, su_col;     // upper BSR (row i: cols >= i)
+  std::vector<uint32_t> sf_ptr, sf_col, sf_src;  // full symmetric BSR; sf_src = upper block index | (transposed << 31)
+};
+
+struct Problem {
+  int device = 0;
+  std::string error;
+  std::vector<ParamBlock> blocks;
+  std::vector<ParamArray> arrays;            // sorted by base
+  std::unordered_map<const double*, int32_t> single;
+  std::vector<Camera> cams;
+  std::vector<ReprojFactor> reproj;
+  std::vector<BBoxFactor> bbox;
+  std::vector<UnaryFactor> unary;
+  std::vector<RelPoseFactor> rel;
+  std::vector<obvi_factor_id> order;         // addition order (dead ids skipped lazily)
+  int64_t n_live = 0;
+  bool dirty = true;                         // structure must be rebuilt
+  uint64_t const_epoch = 0;
+
+  int32_t find_block(const double* ptr) const {
+    if (!arrays.empty()) {
+      auto it = std::upper_bound(arrays.begin(), arrays.end(), ptr, [](const double* p, const ParamArray& a) { return p < a.base; });
+      if (it != arrays.begin()) {
+        const ParamArray& a = *(it - 1);
+        const ptrdiff_t d = ptr - a.base;
+        if (d >= 0 && d < a.count * a.size && d % a.size == 0) return (int32_t)(a.first_id + d / a.size);
+      }
+    }
+    auto it = single.find(ptr);
+    return it == single.end() ? -1 : it->second;
+  }
+  int32_t add_block(double* ptr, int size) {
+    int32_t id = find_block(ptr);
+    if (id >= 0) {
+      if (blocks[id].size != size) return -2;
+      if (!blocks[id].alive) { blocks[id].alive = 1; blocks[id].constant = 0; dirty = true; }
+      return id;
+    }
+    id = (int32_t)blocks.size();
+    blocks.push_back({ptr, size, 0, 1});
+    single.emplace(ptr, id);
+    dirty = true;
+    return id;
+  }
+  int add_array(double* base, int size, int64_t count) {
+    ParamArray a{base, size, count, (int64_t)blocks.size()};
+    for (int64_t i = 0; i < count; i++) blocks.push_back({base + i * size, size, 0, 1});
+    arrays.insert(std::upper_bound(arrays.begin(), arrays.end(), a, [](const ParamArray& x, const ParamArray& y) { return x.base < y.base; }), a);
+    dirty = true;
+    return 0;
+  }
+};
+
+// ---- structure build ---------------------------------------------------------------------------
+// rank/world: e-blocks (points, objects) are dealt to ranks in contiguous ranges of the internal
+// (first-observing-keyframe) order, balanced by observation count; rank 0 also owns the pose-only factors.
+inline bool build_structure(const Problem& pb, Structure& S, int rank, int world, std::string& err) {
+  S = Structure();
+  const int nb = (int)pb.blocks.size();
+  std::vector<int32_t> pose_of_block(nb, -1), point_of_block(nb, -1), obj_of_block(nb, -1);
+  std::vector<uint8_t> used(nb, 0);
+  for (const auto& f : pb.reproj) if (f.alive) { used[f.pose] = 1; used[f.point] = 1; }
+  for (const auto& f : pb.bbox) if (f.alive) { used[f.obj] = 1; used[f.pose] = 1; }
+  for (const auto& f : pb.unary) if (f.alive) used[f.block] = 1;
+  for (const auto& f : pb.rel) if (f.alive) { used[f.p1] = 1; used[f.p2] = 1; }
+  for (int b = 0; b < nb; b++) {
+    if (!used[b]) continue;
+    if (!pb.blocks[b].alive) { err = "a live factor references a removed parameter block"; return false; }
+    if (pb.blocks[b].size == 6) { pose_of_block[b] = S.K++; S.pose_block.push_back(b); }
+  }
+  S.C = (int)pb.cams.size();
+  S.f_of_pose.assign(S.K, -1);
+  for (int k = 0; k < S.K; k++) if (!pb.blocks[S.pose_block[k]].constant) S.f_of_pose[k] = S.nf++;
+
+  // points: internal order = (first observing pose, block id)
+  {
+    std::vector<int32_t> first(nb, INT32_MAX);
+    for (const auto& f : pb.reproj) if (f.alive) first[f.point] = std::min(first[f.point], pose_of_block[f.pose]);
+    std::vector<int32_t> ids;
+    for (int b = 0; b < nb; b++) if (used[b] && pb.blocks[b].size == 3) ids.push_back(b);
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return first[a] < first[b]; });
+    S.P = (int)ids.size();
+    S.point_block = ids;
+    S.point_const.resize(S.P);
+    for (int i = 0; i < S.P; i++) { point_of_block[ids[i]] = i; S.point_const[i] = pb.blocks[ids[i]].constant; }
+  }
+  for (int b = 0; b < nb; b++) if (used[b] && pb.blocks[b].size == 7) { obj_of_block[b] = S.O++; S.obj_block.push_back(b); }
+  S.obj_const.resize(S.O);
+  for (int i = 0; i < S.O; i++) S.obj_const[i] = pb.blocks[S.obj_block[i]].constant;
+
+  // ownership ranges (multi-GPU): by cumulative observation count
+  std::vector<uint32_t> pt_cnt(S.P, 0), ob_cnt(S.O, 0);
+  for (const auto& f : pb.reproj) if (f.alive) pt_cnt[point_of_block[f.point]]++;
+  for (const auto& f : pb.bbox) if (f.alive) ob_cnt[obj_of_block[f.obj]]++;
+  auto owner_range = [&](const std::vector<uint32_t>& cnt, int& lo, int& hi) {
+    const int n = (int)cnt.size();
+    if (world <= 1) { lo = 0; hi = n; return; }
+    uint64_t total = 0; for (uint32_t c : cnt) total += c + 1;
+    uint64_t acc = 0; lo = n; hi = n; bool lo_set = false;
+    for (int i = 0; i < n; i++) {
+      const int r = (int)std::min<uint64_t>(world - 1, acc * world / std::max<uint64_t>(total, 1));
+      if (r == rank && !lo_set) { lo = i; lo_set = true; }
+      if (r > rank) { hi = i; break; }
+      acc += cnt[i] + 1;
+    }
+    if (!lo_set) lo = hi;
+  };
+  int p_lo, p_hi, o_lo, o_hi;
+  owner_range(pt_cnt, p_lo, p_hi);
+  owner_range(ob_cnt, o_lo, o_hi);
+  const bool owns_pose_factors = (rank == 0);
+
+  // calibration classes
+  auto class_of = [&](int cam, double sigma, double huber) {
+    const double mx = pb.cams[cam].intr[0] / sigma, my = pb.cams[cam].intr[1] / sigma;
+    for (size_t i = 0; i < S.classes.size(); i++)
+      if (S.classes[i].cam == cam && S.classes[i].mx == mx && S.classes[i].my == my && S.classes[i].huber == huber) return (uint32_t)i;
+    S.classes.push_back({mx, my, huber, cam, 0});
+    return (uint32_t)(S.classes.size() - 1);
+  };
+
+  // ---- reprojection observations: counting sort by pose, then (camera, point) inside each pose
+  {
+    std::vector<uint32_t> cnt(S.K + 1, 0);
+    for (const auto& f : pb.reproj) {
+      if (!f.alive) continue;
+      const int pt = point_of_block[f.point];
+      if (pt < p_lo || pt >= p_hi) continue;
+      cnt[pose_of_block[f.pose] + 1]++;
+    }
+    for (int k = 0; k < S.K; k++) cnt[k + 1] += cnt[k];
+    S.pose_ptr = cnt;
+    S.n_obs = cnt[S.K];
+    S.obs.resize(S.n_obs); S.obs_user.resize(S.n_obs);
+    std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
+    uint32_t last_cls = 0; int last_cam = -1; double last_sigma = 0, last_huber = 0;
+    for (size_t n = 0; n < pb.reproj.size(); n++) {
+      const ReprojFactor& f = pb.reproj[n];
+      if (!f.alive) continue;
+      const int pt = point_of_block[f.point];
+      if (pt < p_lo || pt >= p_hi) continue;
+      const int k = pose_of_block[f.pose];
+      if (f.cam != last_cam || f.sigma != last_sigma || f.huber != last_huber) { last_cls = class_of(f.cam, f.sigma, f.huber); last_cam = f.cam; last_sigma = f.sigma; last_huber = f.huber; }
+      const Camera& c = pb.cams[f.cam];
+      ObsRec& o = S.obs[cur[k]];
+      o.ur = (f.px - c.intr[2]) / c.intr[0]; o.vr = (f.py - c.intr[3]) / c.intr[1];
+      o.pose = k; o.point = pt; o.cls = last_cls;
+      o.flags = (S.f_of_pose[k] < 0 ? 1u : 0u) | (S.point_const[pt] ? 2u : 0u);
+      S.obs_user[cur[k]] = (uint32_t)n;
+      cur[k]++;
+    }
+    // sort inside each pose segment by (camera, point)
+    std::vector<uint32_t> idx;
+    std::vector<ObsRec> tmp; std::vector<uint32_t> tmpu;
+    for (int k = 0; k < S.K; k++) {
+      const uint32_t b = S.pose_ptr[k], e = S.pose_ptr[k + 1];
+      if (e - b < 2) continue;
+      idx.resize(e - b); std::iota(idx.begin(), idx.end(), 0u);
+      const ObsRec* ob = &S.obs[b];
+      std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {
+        const int cx = S.classes[ob[x].cls].cam, cy = S.classes[ob[y].cls].cam;
+        if (cx != cy) return cx < cy;
+        if (ob[x].point != ob[y].point) return ob[x].point < ob[y].point;
+        return x < y; });
+      tmp.assign(S.obs.begin() + b, S.obs.begin() + e); tmpu.assign(S.obs_user.begin() + b, S.obs_user.begin() + e);
+      for (uint32_t i = 0; i < e - b; i++) { S.obs[b + i] = tmp[idx[i]]; S.obs_user[b + i] = tmpu[idx[i]]; }
+    }
+  }
+
+  // ---- bbox observations, object-major (object, pose, camera)
+  {
+    std::vector<uint32_t> ids;
+    for (size_t n = 0; n < pb.bbox.size(); n++) {
+      const BBoxFactor& f = pb.bbox[n];
+      if (!f.alive) continue;
+      const int o = obj_of_block[f.obj];
+      if (o < o_lo || o >= o_hi) continue;
+      ids.push_back((uint32_t)n);
+    }
+    std::stable_sort(ids.begin(), ids.end(), [&](uint32_t x, uint32_t y) {
+      const BBoxFactor &a = pb.bbox[x], &b = pb.bbox[y];
+      const int oa = obj_of_block[a.obj], ob = obj_of_block[b.obj];
+      if (oa != ob) return oa < ob;
+      const int pa = pose_of_block[a.pose], pb2 = pose_of_block[b.pose];
+      if (pa != pb2) return pa < pb2;
+      return a.cam < b.cam; });
+    S.n_bbox = (int64_t)ids.size();
+    S.bbox.resize(ids.size()); S.bbox_user = ids;
+    for (size_t i = 0; i < ids.size(); i++) {
+      const BBoxFactor& f = pb.bbox[ids[i]];
+      BBoxRec& r = S.bbox[i];
+      std::memcpy(r.brect, f.brect, sizeof(r.brect)); std::memcpy(r.A4, f.A4, sizeof(r.A4));
+      r.invalid_err = f.invalid_err; r.huber = f.huber;
+      r.obj = obj_of_block[f.obj]; r.pose = pose_of_block[f.pose]; r.cam = f.cam;
+      r.flags = (S.f_of_pose[r.pose] < 0 ? 1u : 0u) | (S.obj_const[r.obj] ? 2u : 0u);
+    }
+  }
+
+  // ---- unary factors (shape / LTM / parameter priors)
+  for (size_t n = 0; n < pb.unary.size(); n++) {
+    const UnaryFactor& f = pb.unary[n];
+    if (!f.alive) continue;
+    UnaryRec r; std::memset(&r, 0, sizeof(r));
+    std::memcpy(r.A, f.A, sizeof(r.A)); std::memcpy(r.mean, f.mean, sizeof(r.mean));
+    r.huber = f.huber; r.k = f.k; r.off = f.off;
+    const int sz = pb.blocks[f.block].size;
+    if (sz == 6) { r.kind = 0; r.idx = pose_of_block[f.block]; r.flags = S.f_of_pose[r.idx] < 0 ? 1u : 0u; if (!owns_pose_factors) continue; }
+    else if (sz == 3) { r.kind = 1; r.idx = point_of_block[f.block]; r.flags = S.point_const[r.idx] ? 1u : 0u; if (r.idx < p_lo || r.idx >= p_hi) continue; }
+    else { r.kind = 2; r.idx = obj_of_block[f.block]; r.flags = S.obj_const[r.idx] ? 1u : 0u; if (r.idx < o_lo || r.idx >= o_hi) continue; }
+    S.unary.push_back(r); S.unary_user.push_back((uint32_t)n);
+  }
+  S.n_unary = (int64_t)S.unary.size();
+
+  // ---- e-block lists + reduced-system structure (bitmap over f x f)
+  const int nf = S.nf;
+  const int W = (nf + 63) / 64;
+  std::vector<uint64_t> bits((size_t)nf * W, 0);
+  auto setbit = [&](int i, int j) { bits[(size_t)i * W + (j >> 6)] |= 1ull << (j & 63); };
+  for (int i = 0; i < nf; i++) setbit(i, i);
+
+  auto build_elist = [&](Structure::EList& L, int ne, auto entry_e, auto entry_pose, int64_t n_entries) {
+    L.ptr.assign(ne + 1, 0);
+    for (int64_t q = 0; q < n_entries; q++) L.ptr[entry_e(q) + 1]++;
+    for (int e = 0; e < ne; e++) L.ptr[e + 1] += L.ptr[e];
+    L.pos.resize(n_entries); L.f.resize(n_entries); L.slot.resize(n_entries);
+    std::vector<uint32_t> cur(L.ptr.begin(), L.ptr.end() - 1);
+    for (int64_t q = 0; q < n_entries; q++) { const uint32_t d = cur[entry_e(q)]++; L.pos[d] = (uint32_t)q; L.f[d] = S.f_of_pose[entry_pose(q)]; }
+    L.nslots.assign(ne, 0); L.pair_ptr.assign(ne + 1, 0); L.slot_ptr.assign(ne + 1, 0);
+    for (int e = 0; e < ne; e++) {
+      int ns = 0, lastf = -1;
+      for (uint32_t d = L.ptr[e]; d < L.ptr[e + 1]; d++) {
+        if (L.f[d] < 0) { L.slot[d] = 0xFFFF; continue; }
+        if (L.f[d] != lastf) { ns++; lastf = L.f[d]; }
+        L.slot[d] = (uint16_t)(ns - 1);
+      }
+      L.nslots[e] = (uint16_t)ns;
+      L.max_slots = std::max(L.max_slots, ns);
+      L.pair_ptr[e + 1] = L.pair_ptr[e] + (uint32_t)(ns * (ns + 1) / 2);
+      L.slot_ptr[e + 1] = L.slot_ptr[e] + ns;
+    }
+    L.slot_f.resize(L.slot_ptr[ne]);
+    for (int e = 0; e < ne; e++) {
+      uint32_t w = L.slot_ptr[e]; int lastf = -1;
+      for (uint32_t d = L.ptr[e]; d < L.ptr[e + 1]; d++) if (L.f[d] >= 0 && L.f[d] != lastf) { L.slot_f[w++] = L.f[d]; lastf = L.f[d]; }
+    }
+  };
+  // list entries of one e-block are visited in obs order = (pose, camera): equal poses are adjacent
+  build_elist(S.pts, S.P, [&](int64_t q) { return (int)S.obs[q].point; }, [&](int64_t q) { return (int)S.obs[q].pose; }, S.n_obs);
+  build_elist(S.objs, S.O, [&](int64_t q) { return (int)S.bbox[q].obj; }, [&](int64_t q) { return (int)S.bbox[q].pose; }, S.n_bbox);
+  for (Structure::EList* L : {&S.pts, &S.objs}) {
+    const int ne = (int)L->nslots.size();
+    const std::vector<uint8_t>& cst = (L == &S.pts) ? S.point_const : S.obj_const;
+    for (int e = 0; e < ne; e++) {
+      if (cst[e]) continue;
+      const int32_t* sf = &L->slot_f[L->slot_ptr[e]]; const int ns = L->nslots[e];
+      for (int a = 0; a < ns; a++) for (int b = a; b < ns; b++) setbit(sf[a], sf[b]);
+    }
+  }
+  // relative-pose factors
+  for (size_t n = 0; n < pb.rel.size(); n++) {
+    const RelPoseFactor& f = pb.rel[n];
+    if (!f.alive || !owns_pose_factors) continue;
+    RelRec r; std::memset(&r, 0, sizeof(r));
+    std::memcpy(r.tm, f.tm, sizeof(r.tm)); std::memcpy(r.Rm_inv, f.Rm_inv, sizeof(r.Rm_inv)); std::memcpy(r.A6, f.A6, sizeof(r.A6));
+    r.huber = f.huber; r.p1 = pose_of_block[f.p1]; r.p2 = pose_of_block[f.p2];
+    r.f1 = S.f_of_pose[r.p1]; r.f2 = S.f_of_pose[r.p2];
+    if (r.f1 >= 0 && r.f2 >= 0) setbit(std::min(r.f1, r.f2), std::max(r.f1, r.f2));
+    S.rel.push_back(r); S.rel_user.push_back((uint32_t)n);
+  }
+  S.n_rel = (int64_t)S.rel.size();
+  // In a multi-rank run every rank must hold the SAME S structure (it is all-reduced): the structure is
+  // the union over all ranks' e-blocks, so ranks > 1 rebuild the bitmap from the full graph.
+  if (world > 1) {
+    // pairs induced by points / objects owned by other ranks, and by the pose-only factors
+    std::vector<std::vector<int32_t>> fl_pt(S.P), fl_ob(S.O);
+    for (const auto& f : pb.reproj) if (f.alive) { const int fi = S.f_of_pose[pose_of_block[f.pose]]; const int pt = point_of_block[f.point]; if (fi >= 0 && !S.point_const[pt]) fl_pt[pt].push_back(fi); }
+    for (const auto& f : pb.bbox) if (f.alive) { const int fi = S.f_of_pose[pose_of_block[f.pose]]; const int ob = obj_of_block[f.obj]; if (fi >= 0 && !S.obj_const[ob]) fl_ob[ob].push_back(fi); }
+    for (auto* fl : {&fl_pt, &fl_ob}) for (auto& v : *fl) {
+      std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end());
+      for (size_t a = 0; a < v.size(); a++) for (size_t b = a; b < v.size(); b++) setbit(v[a], v[b]);
+    }
+    for (const auto& f : pb.rel) if (f.alive) { const int f1 = S.f_of_pose[pose_of_block[f.p1]], f2 = S.f_of_pose[pose_of_block[f.p2]]; if (f1 >= 0 && f2 >= 0) setbit(std::min(f1, f2), std::max(f1, f2)); }
+  }
+  // upper BSR + O(1) rank lookup
+  std::vector<uint32_t> wpre((size_t)nf * W + 1, 0);  // blocks before word w of row i (global)
+  S.su_ptr.assign(nf + 1, 0);
+  {
+    uint32_t acc = 0;
+    for (int i = 0; i < nf; i++) {
+      S.su_ptr[i] = acc;
+      for (int w = 0; w < W; w++) { wpre[(size_t)i * W + w] = acc; acc += (uint32_t)__builtin_popcountll(bits[(size_t)i * W + w]); }
+    }
+    S.su_ptr[nf] = acc; S.n_upper = acc;
+  }
+  S.su_col.resize(S.n_upper);
+  for (int i = 0; i < nf; i++) {
+    uint32_t w0 = S.su_ptr[i];
+    for (int w = 0; w < W; w++) { uint64_t m = bits[(size_t)i * W + w]; while (m) { S.su_col[w0++] = (uint32_t)(w * 64 + __builtin_ctzll(m)); m &= m - 1; } }
+  }
+  auto blk_of = [&](int i, int j) -> uint32_t {  // i <= j, bit must be set
+    const uint64_t word = bits[(size_t)i * W + (j >> 6)];
+    return wpre[(size_t)i * W + (j >> 6)] + (uint32_t)__builtin_popcountll(word & ((1ull << (j & 63)) - 1));
+  };
+  for (Structure::EList* L : {&S.pts, &S.objs}) {
+    const int ne = (int)L->nslots.size();
+    L->pair_blk.resize(L->pair_ptr[ne]);
+    for (int e = 0; e < ne; e++) {
+      const int32_t* sf = &L->slot_f[L->slot_ptr[e]]; const int ns = L->nslots[e];
+      uint32_t w = L->pair_ptr[e];
+      const std::vector<uint8_t>& cst = (L == &S.pts) ? S.point_const : S.obj_const;
+      for (int a = 0; a < ns; a++) for (int b = a; b < ns; b++) L->pair_blk[w++] = cst[e] ? 0u : blk_of(sf[a], sf[b]);
+    }
+  }
+  for (RelRec& r : S.rel) {
+    r.blk11 = r.f1 >= 0 ? (int32_t)blk_of(r.f1, r.f1) : -1;
+    r.blk22 = r.f2 >= 0 ? (int32_t)blk_of(r.f2, r.f2) : -1;
+    r.blk12 = -1; r.swap12 = 0;
+    if (r.f1 >= 0 && r.f2 >= 0 && r.f1 != r.f2) { r.swap12 = r.f1 > r.f2; r.blk12 = (int32_t)blk_of(std::min(r.f1, r.f2), std::max(r.f1, r.f2)); }
+  }
+  // full symmetric BSR
+  {
+    std::vector<uint32_t> cnt(nf + 1, 0);
+    for (int i = 0; i < nf; i++) for (uint32_t q = S.su_ptr[i]; q < S.su_ptr[i + 1]; q++) { cnt[i + 1]++; if ((int)S.su_col[q] != i) cnt[S.su_col[q] + 1]++; }
+    for (int i = 0; i < nf; i++) cnt[i + 1] += cnt[i];
+    S.sf_ptr = cnt; S.sf_col.resize(cnt[nf]); S.sf_src.resize(cnt[nf]);
+    std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
+    // lower part first (cols < i, ascending), produced by scanning rows in order
+    for (int i = 0; i < nf; i++) for (uint32_t q = S.su_ptr[i]; q < S.su_ptr[i + 1]; q++) {
+      const int j = (int)S.su_col[q];
+      if (j == i) continue;
+      S.sf_col[cur[j]] = (uint32_t)i; S.sf_src[cur[j]] = q | 0x80000000u; cur[j]++;
+    }
+    for (int i = 0; i < nf; i++) for (uint32_t q = S.su_ptr[i]; q < S.su_ptr[i + 1]; q++) { S.sf_col[cur[i]] = S.su_col[q]; S.sf_src[cur[i]] = q; cur[i]++; }
+  }
+  // reduced-program bookkeeping (Summary::num_*_reduced): over the whole graph, not just this rank
+  {
+    std::vector<uint8_t> touched(nb, 0);
+    auto var = [&](int b) { return !pb.blocks[b].constant; };
+    for (const auto& f : pb.reproj) if (f.alive && (var(f.pose) || var(f.point))) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += 2; touched[f.pose] = touched[f.point] = 1; }
+    for (const auto& f : pb.bbox) if (f.alive && (var(f.pose) || var(f.obj))) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += 4; touched[f.pose] = touched[f.obj] = 1; }
+    for (const auto& f : pb.unary) if (f.alive && var(f.block)) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += f.k; touched[f.block] = 1; }
+    for (const auto& f : pb.rel) if (f.alive && (var(f.p1) || var(f.p2))) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += 6; touched[f.p1] = touched[f.p2] = 1; }
+    for (int b = 0; b < nb; b++) if (touched[b] && var(b)) { S.num_param_blocks_reduced++; S.num_params_reduced += pb.blocks[b].size; }
+  }
+  return true;
+}
+
+}  // namespace obvi

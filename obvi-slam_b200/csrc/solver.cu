@@ -1,0 +1,970 @@
+// LM driver + C ABI (include/obvi_ba.h).  Host C++ orchestrates; all arithmetic is in ba_kernels.cuh.
+// Replaces ceres::Solve(options, problem, &summary) as configured by
+// ObjectPoseGraphOptimizer::solveOptimization (include/refactoring/optimization/object_pose_graph_optimizer.h:634-707)
+// with Ceres' TrustRegionMinimizer / LevenbergMarquardtStrategy semantics (SURVEY.md Appendix B -- external
+// knowledge of upstream Ceres): Jacobi scaling from the first Jacobian, clamped LM diagonal, exact-enough Schur
+// solve, rho-based radius update, non-monotonic acceptance, the three tolerance tests, min-cost iterate returned.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ba_kernels.cuh"
+
+namespace obvi {
+
+static thread_local std::string g_create_error;
+
+#define CUDA_OK(expr)                                                                                          \
+  do {                                                                                                         \
+    cudaError_t e__ = (expr);                                                                                  \
+    if (e__ != cudaSuccess) {                                                                                  \
+      char buf__[512];                                                                                         \
+      snprintf(buf__, sizeof(buf__), "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__,  \
+               cudaGetErrorString(e__));                                                                       \
+      throw std::runtime_error(buf__);                                                                         \
+    }                                                                                                          \
+  } while (0)
+
+// ---- NCCL through dlopen: the library loads without NCCL; only obvi_comm_* need it -------------------------
+struct Nccl {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string& err) {
+    if (h) return true;
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { err = std::string("cannot load NCCL: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+    Broadcast = (decltype(Broadcast))dlsym(h, "ncclBroadcast");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !Broadcast || !CommDestroy) { err = "NCCL symbols missing"; return false; }
+    return true;
+  }
+};
+static Nccl g_nccl;
+
+// ---- small RAII device buffer ---------------------------------------------------------------------------
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    free();
+    if (count == 0) count = 1;
+    CUDA_OK(cudaMalloc((void**)&p, count * sizeof(T)));
+    n = count;
+  }
+  void upload(const std::vector<T>& v, cudaStream_t s) {
+    alloc(v.size());
+    if (!v.empty()) CUDA_OK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void zero(cudaStream_t s) { if (p) CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DBuf() { free(); }
+};
+
+struct EListDev {
+  DBuf<uint32_t> ptr, pos, pair_ptr, pair_blk, overflow_off;
+  DBuf<int32_t> f;
+  DBuf<uint16_t> slot, nslots;
+  DBuf<uint8_t> cst;
+  DBuf<double> escale, einv, eg, prior_H, prior_g, overflow, delta;
+  int ne = 0;
+  bool has_prior = false;
+};
+
+struct Solver {
+  Problem pb;
+  Structure st;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  bool uploaded = false;
+  int num_sms = 0;
+  int pcg_blocks_per_sm = 0;
+  // communicator
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  // device structure
+  DBuf<Camera> cams;
+  DBuf<CalibClass> classes;
+  DBuf<ObsRec> obs;
+  DBuf<uint32_t> pose_ptr, su_ptr, sf_ptr, sf_col, sf_src;
+  DBuf<int32_t> f_of_pose, pose_of_f;
+  DBuf<uint8_t> pose_skip, point_skip, obj_skip;
+  DBuf<BBoxRec> bbox;
+  DBuf<UnaryRec> unary;
+  DBuf<RelRec> rel;
+  EListDev pts, objs;
+  // state
+  DBuf<double> poses[3], points[3], objects[3];  // cur, cand, best
+  int cur = 0;
+  DBuf<PoseCam> pcam, pcam_cand;
+  DBuf<double> J, Jb;
+  DBuf<UnaryOut> unary_out;
+  DBuf<RelOut> rel_out;
+  DBuf<double> redbuf;  // [S_upper | gp | b_schur | hpp_diag]
+  double *S_upper = nullptr, *gp = nullptr, *b_schur = nullptr, *hpp_diag = nullptr;
+  DBuf<double> pscale, Sf, rhs, Minv, y, cg_r, cg_z, cg_p, cg_q, cg_acc, dpose, scalars;
+  double* h_scalars = nullptr;  // pinned
+  std::vector<double> h_poses, h_points, h_objects;
+  int64_t launches = 0;
+
+  ~Solver() {
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    if (h_scalars) cudaFreeHost(h_scalars);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  void init_device() {
+    CUDA_OK(cudaSetDevice(pb.device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, pb.device));
+    if (prop.major < 10) throw std::runtime_error(std::string("obvi_ba is built for sm_100a (B200); found ") + prop.name);
+    num_sms = prop.multiProcessorCount;
+    CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+    CUDA_OK(cudaMallocHost((void**)&h_scalars, SC_COUNT * sizeof(double)));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_blocks_per_sm, pcg_kernel, kPcgThreads, 0));
+    if (pcg_blocks_per_sm < 1) throw std::runtime_error("pcg_kernel cannot be made resident");
+  }
+
+  void upload_elist(EListDev& D, const Structure::EList& L, const std::vector<uint8_t>& cst, int NE, int maxs) {
+    D.ne = (int)cst.size();
+    D.ptr.upload(L.ptr, stream); D.pos.upload(L.pos, stream); D.f.upload(L.f, stream); D.slot.upload(L.slot, stream);
+    D.pair_ptr.upload(L.pair_ptr, stream); D.nslots.upload(L.nslots, stream); D.pair_blk.upload(L.pair_blk, stream);
+    D.cst.upload(cst, stream);
+    D.escale.alloc((size_t)D.ne * NE); D.einv.alloc((size_t)D.ne * NE * NE); D.eg.alloc((size_t)D.ne * NE);
+    D.delta.alloc((size_t)D.ne * NE); D.delta.zero(stream);
+    std::vector<uint32_t> off(D.ne, 0);
+    size_t tot = 0;
+    for (int e = 0; e < D.ne; e++) if (L.nslots[e] > maxs) { off[e] = (uint32_t)tot; tot += (size_t)L.nslots[e] * 12 * NE; }
+    D.overflow_off.upload(off, stream); D.overflow.alloc(tot);
+  }
+
+  void upload_structure() {
+    const Structure& S = st;
+    cams.upload(pb.cams, stream); classes.upload(S.classes, stream); obs.upload(S.obs, stream);
+    pose_ptr.upload(S.pose_ptr, stream); f_of_pose.upload(S.f_of_pose, stream);
+    std::vector<int32_t> pof(S.nf);
+    for (int k = 0; k < S.K; k++) if (S.f_of_pose[k] >= 0) pof[S.f_of_pose[k]] = k;
+    pose_of_f.upload(pof, stream);
+    su_ptr.upload(S.su_ptr, stream); sf_ptr.upload(S.sf_ptr, stream); sf_col.upload(S.sf_col, stream); sf_src.upload(S.sf_src, stream);
+    bbox.upload(S.bbox, stream); unary.upload(S.unary, stream); rel.upload(S.rel, stream);
+    upload_elist(pts, S.pts, S.point_const, 3, 16);
+    upload_elist(objs, S.objs, S.obj_const, 7, 64);
+    pts.has_prior = objs.has_prior = false;
+    for (const UnaryRec& u : S.unary) { if (u.kind == 1) pts.has_prior = true; if (u.kind == 2) objs.has_prior = true; }
+    if (pts.has_prior) { pts.prior_H.alloc((size_t)S.P * 9); pts.prior_g.alloc((size_t)S.P * 3); }
+    if (objs.has_prior) { objs.prior_H.alloc((size_t)S.O * 49); objs.prior_g.alloc((size_t)S.O * 7); }
+    // x-norm masks: a block counts iff it is variable and (multi-GPU) this rank contributes it
+    std::vector<uint8_t> ps(S.K), pt(S.P), ob(S.O);
+    for (int k = 0; k < S.K; k++) ps[k] = (S.f_of_pose[k] < 0) || rank != 0;
+    for (int i = 0; i < S.P; i++) pt[i] = S.point_const[i] || S.pts.ptr[i] == S.pts.ptr[i + 1];
+    for (int i = 0; i < S.O; i++) ob[i] = S.obj_const[i] || !owns_object(i);
+    pose_skip.upload(ps, stream); point_skip.upload(pt, stream); obj_skip.upload(ob, stream);
+    for (int b = 0; b < 3; b++) { poses[b].alloc((size_t)S.K * 6); points[b].alloc((size_t)S.P * 3); objects[b].alloc((size_t)S.O * 7); }
+    pcam.alloc((size_t)S.K * std::max(S.C, 1)); pcam_cand.alloc((size_t)S.K * std::max(S.C, 1));
+    J.alloc((size_t)S.n_obs * kChunk); Jb.alloc((size_t)S.n_bbox * kBBoxChunk);
+    unary_out.alloc(S.n_unary); rel_out.alloc(S.n_rel);
+    const size_t nf6 = (size_t)S.nf * 6;
+    redbuf.alloc((size_t)S.n_upper * 36 + 3 * nf6);
+    S_upper = redbuf.p; gp = S_upper + (size_t)S.n_upper * 36; b_schur = gp + nf6; hpp_diag = b_schur + nf6;
+    pscale.alloc(nf6); Sf.alloc((size_t)S.sf_col.size() * 36); rhs.alloc(nf6); Minv.alloc((size_t)S.nf * 36);
+    y.alloc(nf6); cg_r.alloc(nf6); cg_z.alloc(nf6); cg_p.alloc(nf6); cg_q.alloc(nf6); cg_acc.alloc(16); dpose.alloc(nf6);
+    scalars.alloc(SC_COUNT);
+    uploaded = true;
+  }
+  bool owns_object(int o) const {
+    // an object is "owned" when this rank holds its observations or (no observations) rank 0
+    if (world <= 1) return true;
+    if (st.objs.ptr[o] != st.objs.ptr[o + 1]) return true;
+    for (const UnaryRec& u : st.unary) if (u.kind == 2 && u.idx == o) return true;
+    return false;
+  }
+
+  // ---- parameter gather / scatter --------------------------------------------------------------------
+  void gather_params() {
+    const Structure& S = st;
+    h_poses.resize((size_t)S.K * 6); h_points.resize((size_t)S.P * 3); h_objects.resize((size_t)S.O * 7);
+    for (int k = 0; k < S.K; k++) std::memcpy(&h_poses[6 * (size_t)k], pb.blocks[S.pose_block[k]].host, 48);
+    for (int i = 0; i < S.P; i++) std::memcpy(&h_points[3 * (size_t)i], pb.blocks[S.point_block[i]].host, 24);
+    for (int i = 0; i < S.O; i++) std::memcpy(&h_objects[7 * (size_t)i], pb.blocks[S.obj_block[i]].host, 56);
+    for (int b = 0; b < 3; b++) {
+      if (S.K) CUDA_OK(cudaMemcpyAsync(poses[b].p, h_poses.data(), h_poses.size() * 8, cudaMemcpyHostToDevice, stream));
+      if (S.P) CUDA_OK(cudaMemcpyAsync(points[b].p, h_points.data(), h_points.size() * 8, cudaMemcpyHostToDevice, stream));
+      if (S.O) CUDA_OK(cudaMemcpyAsync(objects[b].p, h_objects.data(), h_objects.size() * 8, cudaMemcpyHostToDevice, stream));
+    }
+    cur = 0;
+  }
+  void scatter_params(int buf) {
+    const Structure& S = st;
+    if (world > 1) {
+      // every rank owns a slice of the e-blocks: zero what it does not own and sum across ranks
+      // (poses are replicated: rank 0 contributes them)
+      merge_sharded(poses[buf].p, pose_skip.p, S.K, 6);
+      merge_sharded(points[buf].p, point_skip.p, S.P, 3);
+      merge_sharded(objects[buf].p, obj_skip.p, S.O, 7);
+    }
+    if (S.K) CUDA_OK(cudaMemcpyAsync(h_poses.data(), poses[buf].p, h_poses.size() * 8, cudaMemcpyDeviceToHost, stream));
+    if (S.P) CUDA_OK(cudaMemcpyAsync(h_points.data(), points[buf].p, h_points.size() * 8, cudaMemcpyDeviceToHost, stream));
+    if (S.O) CUDA_OK(cudaMemcpyAsync(h_objects.data(), objects[buf].p, h_objects.size() * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    for (int k = 0; k < S.K; k++) if (S.f_of_pose[k] >= 0) std::memcpy(pb.blocks[S.pose_block[k]].host, &h_poses[6 * (size_t)k], 48);
+    for (int i = 0; i < S.P; i++) if (!S.point_const[i]) std::memcpy(pb.blocks[S.point_block[i]].host, &h_points[3 * (size_t)i], 24);
+    for (int i = 0; i < S.O; i++) if (!S.obj_const[i]) std::memcpy(pb.blocks[S.obj_block[i]].host, &h_objects[7 * (size_t)i], 56);
+  }
+  void merge_sharded(double* x, const uint8_t* skip, int nblocks, int bs);
+
+  // ---- kernel sequences -------------------------------------------------------------------------------
+  static int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
+  EArgs eargs(EListDev& D, const double* Jp) {
+    EArgs a;
+    a.ptr = D.ptr.p; a.pos = D.pos.p; a.f = D.f.p; a.slot = D.slot.p; a.pair_ptr = D.pair_ptr.p; a.nslots = D.nslots.p;
+    a.pair_blk = D.pair_blk.p; a.cst = D.cst.p; a.J = Jp; a.escale = D.escale.p; a.einv = D.einv.p; a.eg = D.eg.p;
+    a.prior_H = D.has_prior ? D.prior_H.p : nullptr; a.prior_g = D.has_prior ? D.prior_g.p : nullptr;
+    a.overflow = D.overflow.p; a.overflow_off = D.overflow_off.p; a.ne = D.ne;
+    return a;
+  }
+  void zero_scalars(int first, int count) { CUDA_OK(cudaMemsetAsync(scalars.p + first, 0, count * sizeof(double), stream)); }
+
+  // residuals + Jacobians at the current point
+  void linearize(int apply_loss) {
+    const Structure& S = st;
+    zero_scalars(SC_COST, 3);
+    if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p); launches++; }
+    if (S.n_obs) { reproj_jac_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, points[cur].p, apply_loss, J.p, scalars.p); launches++; }
+    if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, stream>>>(bbox.p, S.n_bbox, pcam.p, S.C, objects[cur].p, 0, apply_loss, Jb.p, scalars.p); launches++; }
+    if (S.n_unary) { launch_unary(0, apply_loss, cur); }
+    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, stream>>>(rel.p, S.n_rel, 0, apply_loss, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    if (S.K) { xnorm_kernel<<<nblk((int64_t)S.K * 6, 256), 256, 0, stream>>>(poses[cur].p, pose_skip.p, S.K, 6, scalars.p); launches++; }
+    if (S.P) { xnorm_kernel<<<nblk((int64_t)S.P * 3, 256), 256, 0, stream>>>(points[cur].p, point_skip.p, S.P, 3, scalars.p); launches++; }
+    if (S.O) { xnorm_kernel<<<nblk((int64_t)S.O * 7, 256), 256, 0, stream>>>(objects[cur].p, obj_skip.p, S.O, 7, scalars.p); launches++; }
+  }
+  void launch_unary(int mode, int apply_loss, int buf) {
+    const Structure& S = st;
+    unary_kernel<<<nblk(S.n_unary, 64), 64, 0, stream>>>(unary.p, S.n_unary, mode, apply_loss, poses[buf].p, points[buf].p, objects[buf].p,
+                                                         unary_out.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag, pts.prior_H.p,
+                                                         pts.prior_g.p, objs.prior_H.p, objs.prior_g.p, dpose.p, pts.delta.p,
+                                                         objs.delta.p, scalars.p);
+    launches++;
+  }
+  // Schur complement + rhs for the given radius (J fixed)
+  void build_reduced(const LMParams& lm) {
+    const Structure& S = st;
+    redbuf.zero(stream);
+    zero_scalars(SC_GMAX, 2);  // gmax + fail
+    if (pts.has_prior) { pts.prior_H.zero(stream); pts.prior_g.zero(stream); }
+    if (objs.has_prior) { objs.prior_H.zero(stream); objs.prior_g.zero(stream); }
+    if (S.n_obs && S.nf) { pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag); launches++; }
+    if (S.n_unary) launch_unary(1, 1, cur);
+    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, stream>>>(rel.p, S.n_rel, 1, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    if (S.P) { schur_eblock_kernel<3, 2, 32, 16, false><<<S.P, 32, 0, stream>>>(eargs(pts, J.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
+    if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, stream>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
+    if (world > 1) allreduce_sum(redbuf.p, redbuf.n);
+    if (S.nf) {
+      if (lm.compute_scale) { pose_scale_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(hpp_diag, S.nf * 6, pscale.p); launches++; }
+      finish_kernel<<<nblk((int64_t)S.nf * 32, 256), 256, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, sf_src.p, S_upper, pscale.p, hpp_diag, gp, b_schur, lm, Sf.p, rhs.p, Minv.p, scalars.p);
+      launches++;
+    }
+  }
+  void solve_reduced(const obvi_solver_options& o) {
+    const Structure& S = st;
+    if (!S.nf) return;
+    int nf = S.nf, max_iter = o.pcg_max_iterations;
+    double tol = o.pcg_relative_tolerance;
+    int grid = std::min(num_sms * pcg_blocks_per_sm, std::max(1, nblk(nf, kPcgThreads / 32)));
+    const uint32_t *a1 = sf_ptr.p, *a2 = sf_col.p;
+    const double *a3 = Sf.p, *a4 = rhs.p, *a5 = Minv.p;
+    double *a6 = y.p, *a7 = cg_r.p, *a8 = cg_z.p, *a9 = cg_p.p, *a10 = cg_q.p, *a11 = cg_acc.p, *a14 = scalars.p;
+    void* args[] = {&nf, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11, &max_iter, &tol, &a14};
+    CUDA_OK(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(grid), dim3(kPcgThreads), args, 0, stream));
+    launches++;
+    if (world > 1) broadcast0(y.p, (size_t)nf * 6);
+  }
+  // step, model cost change, candidate point
+  void take_step() {
+    const Structure& S = st;
+    const int cand = 1 - cur;
+    zero_scalars(SC_MODEL, 2);
+    if (S.nf) { pose_step_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(S.nf, pose_of_f.p, pscale.p, y.p, poses[cur].p, poses[cand].p, dpose.p, rank == 0, scalars.p); launches++; }
+    if (S.P) { backsub_eblock_kernel<3, 2, 32><<<S.P, 32, 0, stream>>>(eargs(pts, J.p), dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p); launches++; }
+    if (S.O) { backsub_eblock_kernel<7, 4, 128><<<S.O, 128, 0, stream>>>(eargs(objs, Jb.p), dpose.p, objects[cur].p, objects[cand].p, objs.delta.p, scalars.p); launches++; }
+    if (S.n_unary) launch_unary(2, 1, cur);
+    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, stream>>>(rel.p, S.n_rel, 2, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+  }
+  void candidate_cost() {
+    const Structure& S = st;
+    const int cand = 1 - cur;
+    zero_scalars(SC_CAND, 2);
+    if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cand].p, S.K, cams.p, S.C, 0, pcam_cand.p); launches++; }
+    if (S.n_obs) { reproj_cost_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam_cand.p, S.C, classes.p, points[cand].p, scalars.p); launches++; }
+    if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, stream>>>(bbox.p, S.n_bbox, pcam_cand.p, S.C, objects[cand].p, 1, 1, Jb.p, scalars.p); launches++; }
+    if (S.n_unary) launch_unary(3, 1, cand);
+    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, stream>>>(rel.p, S.n_rel, 3, 1, poses[cand].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+  }
+  // scalars -> host (with the cross-rank reduction when sharded)
+  // stage 0: after linearize () + build_reduced (); stage 1: after take_step () + candidate_cost ()
+  void fetch_scalars(int stage) {
+    if (world > 1) {
+      // replicated pose contributions (|x|^2, |delta|^2) are added by rank 0 only
+      if (stage == 0) allreduce_sum(scalars.p + SC_COST, 3); else allreduce_sum(scalars.p + SC_CAND, 4);
+      allreduce_max(scalars.p + SC_GMAX, 2);
+    }
+    CUDA_OK(cudaMemcpyAsync(h_scalars, scalars.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaGetLastError());
+  }
+  void allreduce_sum(double* p, size_t n) {
+    ncclResult_t r = g_nccl.AllReduce(p, p, n, ncclDouble, ncclSum, comm, stream);
+    if (r != ncclSuccess) throw std::runtime_error(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
+  }
+  void allreduce_max(double* p, size_t n) {
+    ncclResult_t r = g_nccl.AllReduce(p, p, n, ncclDouble, ncclMax, comm, stream);
+    if (r != ncclSuccess) throw std::runtime_error(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
+  }
+  void broadcast0(double* p, size_t n) {
+    ncclResult_t r = g_nccl.Broadcast(p, p, n, ncclDouble, 0, comm, stream);
+    if (r != ncclSuccess) throw std::runtime_error(std::string("ncclBroadcast: ") + g_nccl.GetErrorString(r));
+  }
+
+  void ensure_structure(double* preprocess_seconds) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (pb.dirty || !uploaded) {
+      std::string err;
+      if (!build_structure(pb, st, rank, world, err)) throw std::runtime_error(err);
+      upload_structure();
+      pb.dirty = false;
+    }
+    if (preprocess_seconds) *preprocess_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+
+  int solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteration_summary* its, int cap);
+};
+
+__global__ void mask_blocks_kernel(double* x, const uint8_t* skip, int64_t n, int bs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * bs && skip[i / bs]) x[i] = 0.0;
+}
+void Solver::merge_sharded(double* x, const uint8_t* skip, int nblocks, int bs) {
+  if (!nblocks) return;
+  // constant blocks are skipped by every rank: they are never written back, so zeros are harmless
+  mask_blocks_kernel<<<nblk((int64_t)nblocks * bs, 256), 256, 0, stream>>>(x, skip, nblocks, bs);
+  allreduce_sum(x, (size_t)nblocks * bs);
+}
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteration_summary* its, int cap) {
+  const double t_start = now_s();
+  std::memset(sum, 0, sizeof(*sum));
+  launches = 0;
+  double prep = 0;
+  ensure_structure(&prep);
+  const Structure& S = st;
+  sum->preprocessor_time_in_seconds = prep;
+  sum->num_parameter_blocks_reduced = S.num_param_blocks_reduced;
+  sum->num_parameters_reduced = S.num_params_reduced;
+  sum->num_residual_blocks_reduced = (int32_t)S.num_residual_blocks_reduced;
+  sum->num_residuals_reduced = (int32_t)S.num_residuals_reduced;
+  gather_params();
+
+  int n_log = 0;
+  auto push = [&](int iter, bool valid, bool ok, int lin_it, double cost, double cc, double gmax, double sn, double rd, double radius) {
+    if (its && n_log < cap) {
+      obvi_iteration_summary& s = its[n_log];
+      s.iteration = iter; s.step_is_valid = valid; s.step_is_successful = ok; s.linear_solver_iterations = lin_it;
+      s.cost = cost; s.cost_change = cc; s.gradient_max_norm = gmax; s.step_norm = sn; s.relative_decrease = rd; s.trust_region_radius = radius;
+    }
+    n_log++;
+  };
+  float ms = 0;
+  double t_jac = 0, t_lin = 0, t_res = 0;
+  LMParams lm;
+  lm.radius = o.initial_trust_region_radius; lm.min_diag = o.min_lm_diagonal; lm.max_diag = o.max_lm_diagonal; lm.compute_scale = 1;
+
+  CUDA_OK(cudaEventRecord(ev[6], stream));
+  // ---- iteration 0
+  CUDA_OK(cudaEventRecord(ev[0], stream));
+  linearize(1);
+  CUDA_OK(cudaEventRecord(ev[1], stream));
+  build_reduced(lm);
+  CUDA_OK(cudaEventRecord(ev[2], stream));
+  fetch_scalars(0);
+  lm.compute_scale = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, ev[0], ev[1])); t_jac += ms * 1e-3;
+  CUDA_OK(cudaEventElapsedTime(&ms, ev[1], ev[2])); t_lin += ms * 1e-3;
+  double x_cost = h_scalars[SC_COST];
+  const double fixed_cost = h_scalars[SC_FIXED];
+  double gmax = h_scalars[SC_GMAX];
+  double x_norm = std::sqrt(h_scalars[SC_XNORM2]);
+  bool build_failed = h_scalars[SC_FAIL] != 0.0;
+  sum->initial_cost = x_cost + fixed_cost; sum->fixed_cost = fixed_cost;
+  push(0, false, false, 0, x_cost + fixed_cost, 0, gmax, 0, 0, lm.radius);
+  double minimum_cost = x_cost;
+  int best = cur;  // buffer index holding the minimum-cost iterate (buffer 2 once it diverges from `cur`)
+  int termination = OBVI_NO_CONVERGENCE;
+  const int max_nonmono = o.use_nonmonotonic_steps ? o.max_consecutive_nonmonotonic_steps : 0;
+  double ev_min = x_cost, ev_cur = x_cost, ev_ref = x_cost, ev_cand = x_cost, acc_ref = 0, acc_cand = 0;
+  int n_nonmono = 0, n_invalid = 0, iter = 0, lm_steps = 0, n_ok = 0, n_bad = 0;
+  double decrease = 2.0;
+  bool need_build = false;
+  int64_t pcg_total = 0;
+  const bool finite0 = std::isfinite(x_cost);
+  if (!finite0) termination = OBVI_FAILURE;
+  else if (S.num_params_reduced == 0 || gmax <= o.gradient_tolerance) termination = OBVI_CONVERGENCE;
+  else while (true) {
+    if (iter >= o.max_num_iterations) { termination = OBVI_NO_CONVERGENCE; break; }
+    iter++; lm_steps++;
+    CUDA_OK(cudaEventRecord(ev[2], stream));
+    if (need_build) { build_reduced(lm); need_build = false; }
+    solve_reduced(o);
+    take_step();
+    CUDA_OK(cudaEventRecord(ev[3], stream));
+    candidate_cost();
+    CUDA_OK(cudaEventRecord(ev[4], stream));
+    fetch_scalars(1);
+    CUDA_OK(cudaEventElapsedTime(&ms, ev[2], ev[3])); t_lin += ms * 1e-3;
+    CUDA_OK(cudaEventElapsedTime(&ms, ev[3], ev[4])); t_res += ms * 1e-3;
+    const int pcg_it = (int)h_scalars[SC_PCG_IT];
+    pcg_total += pcg_it;
+    const double model_change = -h_scalars[SC_MODEL];
+    bool valid = !build_failed && h_scalars[SC_FAIL] == 0.0 && h_scalars[SC_PCG_BREAK] == 0.0 && std::isfinite(model_change) &&
+                 std::isfinite(h_scalars[SC_STEP2]) && model_change > 0.0;
+    build_failed = false;
+    if (!valid) {
+      if (++n_invalid >= o.max_num_consecutive_invalid_steps) { termination = OBVI_FAILURE; break; }
+      lm.radius *= 0.5;  // LevenbergMarquardtStrategy::StepIsInvalid
+      need_build = true;
+      n_bad++;
+      push(iter, false, false, pcg_it, x_cost + fixed_cost, 0, gmax, 0, 0, lm.radius);
+      continue;
+    }
+    n_invalid = 0;
+    double cand_cost = h_scalars[SC_CAND];
+    if (!std::isfinite(cand_cost)) cand_cost = std::numeric_limits<double>::max();
+    const double step_norm = std::sqrt(h_scalars[SC_STEP2]);
+    if (step_norm <= o.parameter_tolerance * (x_norm + o.parameter_tolerance)) { termination = OBVI_CONVERGENCE; break; }
+    const double cost_change = x_cost - cand_cost;
+    if (std::fabs(cost_change) <= o.function_tolerance * x_cost) { termination = OBVI_CONVERGENCE; break; }
+    double rho;
+    if (cand_cost >= std::numeric_limits<double>::max()) rho = std::numeric_limits<double>::lowest();
+    else rho = std::max((ev_cur - cand_cost) / model_change, (ev_ref - cand_cost) / (acc_ref + model_change));
+    if (rho > o.min_relative_decrease) {
+      // keep the minimum-cost iterate alive in buffer 2 before the buffers rotate
+      if (best == cur) { /* current is the best so far: nothing to save yet */ }
+      const int old = cur;
+      cur = 1 - cur;
+      if (best == old) {
+        // `old` becomes the candidate buffer of the next step and will be overwritten: save it
+        const size_t np = (size_t)S.K * 6 * 8, nq = (size_t)S.P * 3 * 8, no = (size_t)S.O * 7 * 8;
+        if (np) CUDA_OK(cudaMemcpyAsync(poses[2].p, poses[old].p, np, cudaMemcpyDeviceToDevice, stream));
+        if (nq) CUDA_OK(cudaMemcpyAsync(points[2].p, points[old].p, nq, cudaMemcpyDeviceToDevice, stream));
+        if (no) CUDA_OK(cudaMemcpyAsync(objects[2].p, objects[old].p, no, cudaMemcpyDeviceToDevice, stream));
+        best = 2;
+      }
+      lm.radius = std::min(o.max_trust_region_radius, lm.radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
+      decrease = 2.0;
+      CUDA_OK(cudaEventRecord(ev[0], stream));
+      linearize(1);
+      CUDA_OK(cudaEventRecord(ev[1], stream));
+      build_reduced(lm);
+      CUDA_OK(cudaEventRecord(ev[5], stream));
+      fetch_scalars(0);
+      CUDA_OK(cudaEventElapsedTime(&ms, ev[0], ev[1])); t_jac += ms * 1e-3;
+      CUDA_OK(cudaEventElapsedTime(&ms, ev[1], ev[5])); t_lin += ms * 1e-3;
+      x_cost = h_scalars[SC_COST];
+      gmax = h_scalars[SC_GMAX];
+      x_norm = std::sqrt(h_scalars[SC_XNORM2]);
+      build_failed = h_scalars[SC_FAIL] != 0.0;
+      ev_cur = cand_cost; acc_cand += model_change; acc_ref += model_change;
+      if (ev_cur < ev_min) { ev_min = ev_cur; n_nonmono = 0; ev_cand = ev_cur; acc_cand = 0; }
+      else { n_nonmono++; if (ev_cur > ev_cand) { ev_cand = ev_cur; acc_cand = 0; } }
+      if (n_nonmono == max_nonmono) { ev_ref = ev_cand; acc_ref = acc_cand; }
+      n_ok++;
+      if (x_cost < minimum_cost) { minimum_cost = x_cost; best = cur; }
+      push(iter, true, true, pcg_it, x_cost + fixed_cost, cost_change, gmax, step_norm, rho, lm.radius);
+      if (gmax <= o.gradient_tolerance) { termination = OBVI_CONVERGENCE; break; }
+    } else {
+      lm.radius /= decrease; decrease *= 2.0;
+      need_build = true;
+      n_bad++;
+      push(iter, true, false, pcg_it, cand_cost + fixed_cost, cost_change, gmax, step_norm, rho, lm.radius);
+    }
+    if (lm.radius <= o.min_trust_region_radius) { termination = OBVI_CONVERGENCE; break; }
+  }
+  CUDA_OK(cudaEventRecord(ev[7], stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  CUDA_OK(cudaEventElapsedTime(&ms, ev[6], ev[7]));
+  sum->minimizer_device_time_in_seconds = ms * 1e-3;
+  // write the minimum-cost iterate back to the caller's blocks (on FAILURE the initial values stay)
+  if (termination != OBVI_FAILURE) scatter_params(best);
+  sum->termination_type = termination;
+  sum->is_solution_usable = termination == OBVI_CONVERGENCE || termination == OBVI_NO_CONVERGENCE;
+  sum->num_iterations = n_log; sum->num_lm_steps = lm_steps; sum->num_successful_steps = n_ok; sum->num_unsuccessful_steps = n_bad;
+  sum->final_cost = minimum_cost + fixed_cost;
+  sum->linear_solver_time_in_seconds = t_lin; sum->jacobian_evaluation_time_in_seconds = t_jac; sum->residual_evaluation_time_in_seconds = t_res;
+  sum->pcg_iterations_total = pcg_total; sum->kernel_launches = launches;
+  sum->total_time_in_seconds = now_s() - t_start;
+  return OBVI_OK;
+}
+
+}  // namespace obvi
+
+// =========================================================================================== C ABI
+using namespace obvi;
+
+struct obvi_problem { Solver s; };
+
+#define API_BEGIN try {
+#define API_END(p)                                                                   \
+  }                                                                                  \
+  catch (const std::exception& e) {                                                  \
+    if (p) (p)->s.pb.error = e.what(); else g_create_error = e.what();               \
+    return OBVI_ERR_CUDA;                                                            \
+  }
+
+static int fail(obvi_problem* p, int code, const char* msg) { p->s.pb.error = msg; return code; }
+
+extern "C" {
+
+const char* obvi_version(void) { return "obvi_ba 0.1 (sm_100a, fp64)"; }
+
+int obvi_problem_create(int device, obvi_problem** out) {
+  if (!out) return OBVI_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  obvi_problem* p = nullptr;
+  try {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { g_create_error = std::string("no usable CUDA device: ") + cudaGetErrorString(e) + " (this backend has no CPU fallback)"; return OBVI_ERR_CUDA; }
+    if (device < 0 || device >= n) { g_create_error = "cuda_device out of range"; return OBVI_ERR_INVALID_ARGUMENT; }
+    p = new obvi_problem();
+    p->s.pb.device = device;
+    p->s.init_device();
+    *out = p;
+    return OBVI_OK;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    delete p;
+    return OBVI_ERR_CUDA;
+  }
+}
+void obvi_problem_destroy(obvi_problem* p) { if (p) { cudaSetDevice(p->s.pb.device); delete p; } }
+const char* obvi_last_error(const obvi_problem* p) { return p ? p->s.pb.error.c_str() : g_create_error.c_str(); }
+
+int obvi_param_add(obvi_problem* p, double* host, int size) {
+  if (!p || !host || (size != 3 && size != 6 && size != 7)) return p ? fail(p, OBVI_ERR_INVALID_ARGUMENT, "parameter block size must be 3, 6 or 7") : OBVI_ERR_INVALID_ARGUMENT;
+  const int id = p->s.pb.add_block(host, size);
+  if (id == -2) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "parameter block already registered with another size");
+  return OBVI_OK;
+}
+int obvi_param_add_array(obvi_problem* p, double* base, int size, int64_t count) {
+  if (!p || !base || count < 0 || (size != 3 && size != 6 && size != 7)) return OBVI_ERR_INVALID_ARGUMENT;
+  if (count == 0) return OBVI_OK;
+  if (p->s.pb.find_block(base) >= 0 || p->s.pb.find_block(base + (count - 1) * size) >= 0) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "array overlaps registered blocks");
+  p->s.pb.add_array(base, size, count);
+  return OBVI_OK;
+}
+int obvi_param_remove(obvi_problem* p, double* host) {
+  if (!p) return OBVI_ERR_INVALID_ARGUMENT;
+  const int id = p->s.pb.find_block(host);
+  if (id < 0 || !p->s.pb.blocks[id].alive) return fail(p, OBVI_ERR_NOT_FOUND, "unknown parameter block");
+  // Ceres removes the residual blocks that depend on the parameter block as well
+  Problem& pb = p->s.pb;
+  for (auto& f : pb.reproj) if (f.alive && (f.pose == id || f.point == id)) { f.alive = 0; pb.n_live--; }
+  for (auto& f : pb.bbox) if (f.alive && (f.pose == id || f.obj == id)) { f.alive = 0; pb.n_live--; }
+  for (auto& f : pb.unary) if (f.alive && f.block == id) { f.alive = 0; pb.n_live--; }
+  for (auto& f : pb.rel) if (f.alive && (f.p1 == id || f.p2 == id)) { f.alive = 0; pb.n_live--; }
+  pb.blocks[id].alive = 0;
+  pb.dirty = true;
+  return OBVI_OK;
+}
+int obvi_param_set_constant(obvi_problem* p, double* host, int c) {
+  if (!p) return OBVI_ERR_INVALID_ARGUMENT;
+  const int id = p->s.pb.find_block(host);
+  if (id < 0 || !p->s.pb.blocks[id].alive) return fail(p, OBVI_ERR_NOT_FOUND, "unknown parameter block");
+  if (p->s.pb.blocks[id].constant != (uint8_t)(c != 0)) { p->s.pb.blocks[id].constant = c != 0; p->s.pb.dirty = true; }
+  return OBVI_OK;
+}
+int obvi_param_is_constant(const obvi_problem* p, const double* host, int* out) {
+  if (!p || !out) return OBVI_ERR_INVALID_ARGUMENT;
+  const int id = p->s.pb.find_block(host);
+  if (id < 0 || !p->s.pb.blocks[id].alive) return OBVI_ERR_NOT_FOUND;
+  *out = p->s.pb.blocks[id].constant;
+  return OBVI_OK;
+}
+
+int obvi_camera_add(obvi_problem* p, const double intr[4], const double R[9], const double t[3], int* cam_id) {
+  if (!p || !intr || !R || !t || !cam_id) return OBVI_ERR_INVALID_ARGUMENT;
+  Camera c;
+  std::memcpy(c.intr, intr, sizeof(c.intr));
+  invert_extrinsics(R, t, c.Rinv, c.tinv);
+  for (size_t i = 0; i < p->s.pb.cams.size(); i++)
+    if (std::memcmp(&p->s.pb.cams[i], &c, sizeof(Camera)) == 0) { *cam_id = (int)i; return OBVI_OK; }
+  p->s.pb.cams.push_back(c);
+  *cam_id = (int)p->s.pb.cams.size() - 1;
+  p->s.pb.dirty = true;
+  return OBVI_OK;
+}
+
+static int add_id(Problem& pb, int type, size_t index, obvi_factor_id* id) {
+  const obvi_factor_id v = make_id(type, index);
+  pb.order.push_back(v);
+  pb.n_live++;
+  pb.dirty = true;
+  if (id) *id = v;
+  return OBVI_OK;
+}
+
+int obvi_factor_add_reproj(obvi_problem* p, double* pose, double* point, int cam, const double px[2], double sigma, double huber, obvi_factor_id* id) {
+  if (!p || !pose || !point || !px) return OBVI_ERR_INVALID_ARGUMENT;
+  Problem& pb = p->s.pb;
+  if (cam < 0 || cam >= (int)pb.cams.size()) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "unknown camera id");
+  if (!(sigma > 0)) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "reprojection_error_std_dev must be positive");
+  const int a = pb.add_block(pose, 6), b = pb.add_block(point, 3);
+  if (a < 0 || b < 0) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "parameter block size mismatch");
+  pb.reproj.push_back({a, b, cam, 1, px[0], px[1], sigma, huber});
+  return add_id(pb, OBVI_FACTOR_REPROJECTION, pb.reproj.size() - 1, id);
+}
+int obvi_factor_add_reproj_batch(obvi_problem* p, int64_t n, double* const* poses, double* const* points, const int32_t* cams,
+                                 const double* px, const double* sig, double huber, obvi_factor_id* ids) {
+  if (!p || n < 0 || (n && (!poses || !points || !cams || !px || !sig))) return OBVI_ERR_INVALID_ARGUMENT;
+  Problem& pb = p->s.pb;
+  pb.reproj.reserve(pb.reproj.size() + n); pb.order.reserve(pb.order.size() + n);
+  for (int64_t i = 0; i < n; i++) {
+    const int rc = obvi_factor_add_reproj(p, poses[i], points[i], cams[i], px + 2 * i, sig[i], huber, ids ? ids + i : nullptr);
+    if (rc != OBVI_OK) return rc;
+  }
+  return OBVI_OK;
+}
+int obvi_factor_add_bbox(obvi_problem* p, double* ell, double* pose, int cam, const double corners[4], const double cov[16],
+                         double invalid_err, double huber, obvi_factor_id* id) {
+  if (!p || !ell || !pose || !corners || !cov) return OBVI_ERR_INVALID_ARGUMENT;
+  Problem& pb = p->s.pb;
+  if (cam < 0 || cam >= (int)pb.cams.size()) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "unknown camera id");
+  const int a = pb.add_block(ell, 7), b = pb.add_block(pose, 6);
+  if (a < 0 || b < 0) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "parameter block size mismatch");
+  BBoxFactor f;
+  f.obj = a; f.pose = b; f.cam = cam; f.alive = 1; f.invalid_err = invalid_err; f.huber = huber;
+  const Camera& c = pb.cams[cam];
+  double sq[16];
+  if (!sqrt_information(cov, 4, sq)) return fail(p, OBVI_ERR_NUMERIC, "bounding-box information matrix has NaN");
+  const double sc[4] = {c.intr[0], c.intr[0], c.intr[1], c.intr[1]};
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) f.A4[4 * i + j] = sq[4 * i + j] * sc[j];
+  f.brect[0] = (corners[0] - c.intr[2]) / c.intr[0]; f.brect[1] = (corners[1] - c.intr[2]) / c.intr[0];
+  f.brect[2] = (corners[2] - c.intr[3]) / c.intr[1]; f.brect[3] = (corners[3] - c.intr[3]) / c.intr[1];
+  pb.bbox.push_back(f);
+  return add_id(pb, OBVI_FACTOR_BBOX, pb.bbox.size() - 1, id);
+}
+int obvi_factor_add_bbox_batch(obvi_problem* p, int64_t n, double* const* ells, double* const* poses, const int32_t* cams,
+                               const double* corners, const double* covs, double invalid_err, double huber, obvi_factor_id* ids) {
+  if (!p || n < 0 || (n && (!ells || !poses || !cams || !corners || !covs))) return OBVI_ERR_INVALID_ARGUMENT;
+  for (int64_t i = 0; i < n; i++) {
+    const int rc = obvi_factor_add_bbox(p, ells[i], poses[i], cams[i], corners + 4 * i, covs + 16 * i, invalid_err, huber, ids ? ids + i : nullptr);
+    if (rc != OBVI_OK) return rc;
+  }
+  return OBVI_OK;
+}
+static int add_unary(obvi_problem* p, double* block, int bs, int type, int k, int off, const double* A, const double* mean, double huber, obvi_factor_id* id) {
+  Problem& pb = p->s.pb;
+  const int a = pb.add_block(block, bs);
+  if (a < 0) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "parameter block size mismatch");
+  UnaryFactor f; std::memset(&f, 0, sizeof(f));
+  f.block = a; f.type = type; f.k = k; f.off = off; f.alive = 1; f.huber = huber;
+  std::memcpy(f.A, A, sizeof(double) * k * k); std::memcpy(f.mean, mean, sizeof(double) * k);
+  pb.unary.push_back(f);
+  return add_id(pb, type, pb.unary.size() - 1, id);
+}
+int obvi_factor_add_shape_prior(obvi_problem* p, double* ell, const double mean[3], const double cov[9], double huber, obvi_factor_id* id) {
+  if (!p || !ell || !mean || !cov) return OBVI_ERR_INVALID_ARGUMENT;
+  double A[9];
+  if (!sqrt_information(cov, 3, A)) return fail(p, OBVI_ERR_NUMERIC, "shape-prior information matrix has NaN");
+  return add_unary(p, ell, 7, OBVI_FACTOR_SHAPE_PRIOR, 3, 4, A, mean, huber, id);
+}
+int obvi_factor_add_ltm_prior(obvi_problem* p, double* ell, const double mean[7], const double cov[49], double huber, obvi_factor_id* id) {
+  if (!p || !ell || !mean || !cov) return OBVI_ERR_INVALID_ARGUMENT;
+  double A[49];
+  if (!sqrt_information(cov, 7, A)) return fail(p, OBVI_ERR_NUMERIC, "LTM-prior information matrix has NaN");
+  return add_unary(p, ell, 7, OBVI_FACTOR_LTM_PRIOR, 7, 0, A, mean, huber, id);
+}
+int obvi_factor_add_param_prior(obvi_problem* p, double* block, int idx, double mean, double sd, double huber, obvi_factor_id* id) {
+  if (!p || !block) return OBVI_ERR_INVALID_ARGUMENT;
+  const int b = p->s.pb.find_block(block);
+  if (b < 0) return fail(p, OBVI_ERR_NOT_FOUND, "parameter prior on an unknown block (add the block first)");
+  const int bs = p->s.pb.blocks[b].size;
+  if (idx < 0 || idx >= bs || !(sd > 0)) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "bad parameter prior");
+  const double A = 1.0 / sd;
+  return add_unary(p, block, bs, OBVI_FACTOR_PARAM_PRIOR, 1, idx, &A, &mean, huber, id);
+}
+int obvi_factor_add_rel_pose(obvi_problem* p, double* p1, double* p2, const double tm[3], const double Rm[9], const double cov[36], double huber, obvi_factor_id* id) {
+  if (!p || !p1 || !p2 || !tm || !Rm || !cov) return OBVI_ERR_INVALID_ARGUMENT;
+  Problem& pb = p->s.pb;
+  const int a = pb.add_block(p1, 6), b = pb.add_block(p2, 6);
+  if (a < 0 || b < 0) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "parameter block size mismatch");
+  RelPoseFactor f;
+  f.p1 = a; f.p2 = b; f.alive = 1; f.huber = huber;
+  std::memcpy(f.tm, tm, sizeof(f.tm));
+  inverse3(Rm, f.Rm_inv);
+  if (!sqrt_information(cov, 6, f.A6)) return fail(p, OBVI_ERR_NUMERIC, "Relative pose factor had NaN information matrix");
+  pb.rel.push_back(f);
+  return add_id(pb, OBVI_FACTOR_REL_POSE, pb.rel.size() - 1, id);
+}
+int obvi_factor_remove(obvi_problem* p, obvi_factor_id id) {
+  if (!p) return OBVI_ERR_INVALID_ARGUMENT;
+  Problem& pb = p->s.pb;
+  const int t = id_type(id); const uint64_t i = id_index(id);
+  uint8_t* alive = nullptr;
+  if (t == OBVI_FACTOR_REPROJECTION && i < pb.reproj.size()) alive = &pb.reproj[i].alive;
+  else if (t == OBVI_FACTOR_BBOX && i < pb.bbox.size()) alive = &pb.bbox[i].alive;
+  else if ((t == OBVI_FACTOR_SHAPE_PRIOR || t == OBVI_FACTOR_LTM_PRIOR || t == OBVI_FACTOR_PARAM_PRIOR) && i < pb.unary.size() && pb.unary[i].type == t) alive = &pb.unary[i].alive;
+  else if (t == OBVI_FACTOR_REL_POSE && i < pb.rel.size()) alive = &pb.rel[i].alive;
+  if (!alive || !*alive) return fail(p, OBVI_ERR_NOT_FOUND, "unknown residual block id");
+  *alive = 0; pb.n_live--; pb.dirty = true;
+  return OBVI_OK;
+}
+int64_t obvi_num_factors(const obvi_problem* p) { return p ? p->s.pb.n_live : 0; }
+
+static bool id_alive(const Problem& pb, obvi_factor_id id, int* size) {
+  const int t = id_type(id); const uint64_t i = id_index(id);
+  switch (t) {
+    case OBVI_FACTOR_REPROJECTION: *size = 2; return pb.reproj[i].alive;
+    case OBVI_FACTOR_BBOX: *size = 4; return pb.bbox[i].alive;
+    case OBVI_FACTOR_REL_POSE: *size = 6; return pb.rel[i].alive;
+    default: *size = pb.unary[i].k; return pb.unary[i].alive;
+  }
+}
+int obvi_residual_blocks(const obvi_problem* p, obvi_factor_id* ids, int32_t* types, int32_t* sizes, int64_t cap, int64_t* n) {
+  if (!p || !n) return OBVI_ERR_INVALID_ARGUMENT;
+  int64_t c = 0;
+  for (obvi_factor_id id : p->s.pb.order) {
+    int sz;
+    if (!id_alive(p->s.pb, id, &sz)) continue;
+    if (c < cap) { if (ids) ids[c] = id; if (types) types[c] = id_type(id); if (sizes) sizes[c] = sz; }
+    c++;
+  }
+  *n = c;
+  return OBVI_OK;
+}
+
+void obvi_solver_options_init(obvi_solver_options* o) {
+  if (!o) return;
+  o->max_num_iterations = 50; o->use_nonmonotonic_steps = 0;
+  o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32; o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+  o->max_consecutive_nonmonotonic_steps = 5; o->max_num_consecutive_invalid_steps = 5;
+  o->pcg_max_iterations = 2000; o->pcg_relative_tolerance = 1e-12;
+}
+
+int obvi_solve(obvi_problem* p, const obvi_solver_options* o, obvi_summary* sum, obvi_iteration_summary* its, int32_t cap) {
+  if (!p || !o || !sum) return OBVI_ERR_INVALID_ARGUMENT;
+  API_BEGIN
+  CUDA_OK(cudaSetDevice(p->s.pb.device));
+  return p->s.solve(*o, sum, its, cap);
+  API_END(p)
+}
+
+// evaluate every type at the current host values; results land in the Solver's device buffers
+static void evaluate_all(Solver& s, int apply_loss) {
+  s.ensure_structure(nullptr);
+  s.gather_params();
+  s.linearize(apply_loss);
+  s.fetch_scalars(0);
+}
+
+int obvi_evaluate_factor_type(obvi_problem* p, int type, int apply_loss, double* r, double* J0, double* J1) {
+  if (!p) return OBVI_ERR_INVALID_ARGUMENT;
+  API_BEGIN
+  Solver& s = p->s;
+  CUDA_OK(cudaSetDevice(s.pb.device));
+  if (s.world > 1) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "obvi_evaluate_factor_type is single-rank only");
+  evaluate_all(s, apply_loss);
+  const Structure& S = s.st;
+  if (type == OBVI_FACTOR_REPROJECTION) {
+    std::vector<double> h((size_t)S.n_obs * kChunk);
+    if (S.n_obs) CUDA_OK(cudaMemcpy(h.data(), s.J.p, h.size() * 8, cudaMemcpyDeviceToHost));
+    // user order = position among live reprojection factors in order of addition
+    std::vector<int64_t> live_rank(s.pb.reproj.size(), -1);
+    int64_t c = 0;
+    for (size_t i = 0; i < s.pb.reproj.size(); i++) if (s.pb.reproj[i].alive) live_rank[i] = c++;
+    for (int64_t q = 0; q < S.n_obs; q++) {
+      const int64_t u = live_rank[S.obs_user[q]];
+      const double* ch = &h[(size_t)q * kChunk];
+      if (J0) std::memcpy(J0 + 12 * u, ch, 96);
+      if (J1) std::memcpy(J1 + 6 * u, ch + 12, 48);
+      if (r) std::memcpy(r + 2 * u, ch + 18, 16);
+    }
+  } else if (type == OBVI_FACTOR_BBOX) {
+    std::vector<double> h((size_t)S.n_bbox * kBBoxChunk);
+    if (S.n_bbox) CUDA_OK(cudaMemcpy(h.data(), s.Jb.p, h.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<int64_t> live_rank(s.pb.bbox.size(), -1);
+    int64_t c = 0;
+    for (size_t i = 0; i < s.pb.bbox.size(); i++) if (s.pb.bbox[i].alive) live_rank[i] = c++;
+    for (int64_t q = 0; q < S.n_bbox; q++) {
+      const int64_t u = live_rank[S.bbox_user[q]];
+      const double* ch = &h[(size_t)q * kBBoxChunk];
+      if (J1) std::memcpy(J1 + 24 * u, ch, 192);       // pose
+      if (J0) std::memcpy(J0 + 28 * u, ch + 24, 224);  // ellipsoid
+      if (r) std::memcpy(r + 4 * u, ch + 52, 32);
+    }
+  } else if (type == OBVI_FACTOR_REL_POSE) {
+    std::vector<RelOut> h(S.n_rel);
+    if (S.n_rel) CUDA_OK(cudaMemcpy(h.data(), s.rel_out.p, h.size() * sizeof(RelOut), cudaMemcpyDeviceToHost));
+    std::vector<int64_t> live_rank(s.pb.rel.size(), -1);
+    int64_t c = 0;
+    for (size_t i = 0; i < s.pb.rel.size(); i++) if (s.pb.rel[i].alive) live_rank[i] = c++;
+    for (int64_t q = 0; q < S.n_rel; q++) {
+      const int64_t u = live_rank[S.rel_user[q]];
+      if (r) std::memcpy(r + 6 * u, h[q].r, 48);
+      if (J0) std::memcpy(J0 + 36 * u, h[q].J1, 288);
+      if (J1) std::memcpy(J1 + 36 * u, h[q].J2, 288);
+    }
+  } else if (type == OBVI_FACTOR_SHAPE_PRIOR || type == OBVI_FACTOR_LTM_PRIOR || type == OBVI_FACTOR_PARAM_PRIOR) {
+    std::vector<UnaryOut> h(S.n_unary);
+    if (S.n_unary) CUDA_OK(cudaMemcpy(h.data(), s.unary_out.p, h.size() * sizeof(UnaryOut), cudaMemcpyDeviceToHost));
+    std::vector<int64_t> live_rank(s.pb.unary.size(), -1);
+    int64_t c = 0;
+    for (size_t i = 0; i < s.pb.unary.size(); i++) if (s.pb.unary[i].alive && s.pb.unary[i].type == type) live_rank[i] = c++;
+    for (int64_t q = 0; q < S.n_unary; q++) {
+      const UnaryFactor& f = s.pb.unary[S.unary_user[q]];
+      if (f.type != type) continue;
+      const int64_t u = live_rank[S.unary_user[q]];
+      const int k = f.k, bs = s.pb.blocks[f.block].size;
+      const int ld = type == OBVI_FACTOR_PARAM_PRIOR ? 7 : bs;
+      if (r) std::memcpy(r + (size_t)k * u, h[q].r, 8 * k);
+      if (J0) {
+        double* Jd = J0 + (size_t)k * ld * u;
+        for (int a = 0; a < k * ld; a++) Jd[a] = 0.0;
+        for (int a = 0; a < k; a++) for (int c2 = 0; c2 < k; c2++) Jd[a * ld + f.off + c2] = h[q].sc * f.A[a * k + c2];
+      }
+    }
+  } else {
+    return fail(p, OBVI_ERR_INVALID_ARGUMENT, "unknown factor type");
+  }
+  return OBVI_OK;
+  API_END(p)
+}
+
+int obvi_evaluate(obvi_problem* p, int apply_loss, double* cost, double* residuals, int64_t cap, int64_t* nres) {
+  if (!p) return OBVI_ERR_INVALID_ARGUMENT;
+  API_BEGIN
+  Solver& s = p->s;
+  CUDA_OK(cudaSetDevice(s.pb.device));
+  evaluate_all(s, apply_loss);
+  if (cost) *cost = s.h_scalars[SC_COST] + s.h_scalars[SC_FIXED];
+  if (!residuals && !nres) return OBVI_OK;
+  if (s.world > 1) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "residual export is single-rank only");
+  const Structure& S = s.st;
+  // per-type residuals in internal order -> per factor index
+  std::vector<double> hJ((size_t)S.n_obs * kChunk), hB((size_t)S.n_bbox * kBBoxChunk);
+  std::vector<RelOut> hR(S.n_rel); std::vector<UnaryOut> hU(S.n_unary);
+  if (S.n_obs) CUDA_OK(cudaMemcpy(hJ.data(), s.J.p, hJ.size() * 8, cudaMemcpyDeviceToHost));
+  if (S.n_bbox) CUDA_OK(cudaMemcpy(hB.data(), s.Jb.p, hB.size() * 8, cudaMemcpyDeviceToHost));
+  if (S.n_rel) CUDA_OK(cudaMemcpy(hR.data(), s.rel_out.p, hR.size() * sizeof(RelOut), cudaMemcpyDeviceToHost));
+  if (S.n_unary) CUDA_OK(cudaMemcpy(hU.data(), s.unary_out.p, hU.size() * sizeof(UnaryOut), cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> inv_rp(s.pb.reproj.size(), 0), inv_bb(s.pb.bbox.size(), 0), inv_un(s.pb.unary.size(), 0), inv_rl(s.pb.rel.size(), 0);
+  for (int64_t q = 0; q < S.n_obs; q++) inv_rp[S.obs_user[q]] = (uint32_t)q;
+  for (int64_t q = 0; q < S.n_bbox; q++) inv_bb[S.bbox_user[q]] = (uint32_t)q;
+  for (int64_t q = 0; q < S.n_unary; q++) inv_un[S.unary_user[q]] = (uint32_t)q;
+  for (int64_t q = 0; q < S.n_rel; q++) inv_rl[S.rel_user[q]] = (uint32_t)q;
+  int64_t w = 0;
+  for (obvi_factor_id id : s.pb.order) {
+    int sz;
+    if (!id_alive(s.pb, id, &sz)) continue;
+    const uint64_t i = id_index(id);
+    const double* src;
+    switch (id_type(id)) {
+      case OBVI_FACTOR_REPROJECTION: src = &hJ[(size_t)inv_rp[i] * kChunk + 18]; break;
+      case OBVI_FACTOR_BBOX: src = &hB[(size_t)inv_bb[i] * kBBoxChunk + 52]; break;
+      case OBVI_FACTOR_REL_POSE: src = hR[inv_rl[i]].r; break;
+      default: src = hU[inv_un[i]].r; break;
+    }
+    if (residuals && w + sz <= cap) std::memcpy(residuals + w, src, 8 * sz);
+    w += sz;
+  }
+  if (nres) *nres = w;
+  return OBVI_OK;
+  API_END(p)
+}
+
+// Two-phase outlier rejection support (offline_problem_runner.h:752-801): per block sum r^2 from the raw
+// residuals, inserted into std::map<double, id, std::greater<double>> (equal keys overwrite), then the first
+// (size_t)(map.size() * fraction) entries.
+int obvi_topk_outliers(obvi_problem* p, int type, double fraction, obvi_factor_id* ids, int64_t cap, int64_t* n) {
+  if (!p || !n) return OBVI_ERR_INVALID_ARGUMENT;
+  API_BEGIN
+  Solver& s = p->s;
+  CUDA_OK(cudaSetDevice(s.pb.device));
+  int64_t nres = 0;
+  int rc = obvi_evaluate(p, 0, nullptr, nullptr, 0, &nres);
+  if (rc != OBVI_OK) return rc;
+  std::vector<double> res(nres);
+  rc = obvi_evaluate(p, 0, nullptr, res.data(), nres, &nres);
+  if (rc != OBVI_OK) return rc;
+  std::map<double, obvi_factor_id, std::greater<double>> by_err;
+  int64_t w = 0;
+  for (obvi_factor_id id : s.pb.order) {
+    int sz;
+    if (!id_alive(s.pb, id, &sz)) continue;
+    if (id_type(id) == type) {
+      double e = 0;
+      for (int a = 0; a < sz; a++) e += res[w + a] * res[w + a];
+      by_err[e] = id;
+    }
+    w += sz;
+  }
+  const size_t k = (size_t)(by_err.size() * fraction);
+  int64_t c = 0;
+  for (auto it = by_err.begin(); it != by_err.end() && (size_t)c < k; ++it, ++c) if (ids && c < cap) ids[c] = it->second;
+  *n = (int64_t)k;
+  return OBVI_OK;
+  API_END(p)
+}
+
+int obvi_comm_unique_id(void* out) {
+  if (!out) return OBVI_ERR_INVALID_ARGUMENT;
+  std::string err;
+  if (!g_nccl.load(err)) { g_create_error = err; return OBVI_ERR_COMM; }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return OBVI_ERR_COMM; }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  std::memcpy(out, &id, 128);
+  return OBVI_OK;
+}
+int obvi_comm_init(obvi_problem* p, const void* uid, int rank, int world) {
+  if (!p || !uid || world < 1 || rank < 0 || rank >= world) return OBVI_ERR_INVALID_ARGUMENT;
+  API_BEGIN
+  Solver& s = p->s;
+  CUDA_OK(cudaSetDevice(s.pb.device));
+  std::string err;
+  if (!g_nccl.load(err)) return fail(p, OBVI_ERR_COMM, err.c_str());
+  ncclUniqueId id;
+  std::memcpy(&id, uid, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&s.comm, world, id, rank);
+  if (r != ncclSuccess) return fail(p, OBVI_ERR_COMM, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclCommInitRank failed");
+  s.rank = rank; s.world = world; s.pb.dirty = true;
+  return OBVI_OK;
+  API_END(p)
+}
+
+}  // extern "C"

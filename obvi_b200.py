@@ -1,0 +1,14 @@
+"""Import helper: the package directory is `obvi-slam_b200/` (hyphenated, as the task names it), which the
+`import` statement cannot spell.  `import obvi_b200 as ob` gives the package; `ob.synth` the generator."""
+import importlib
+import os
+import sys
+
+_ROOT = os.path.dirname(os.path.abspath(__file__))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+_pkg = importlib.import_module("obvi-slam_b200")
+synth = importlib.import_module("obvi-slam_b200.synth")
+
+globals().update({k: v for k, v in vars(_pkg).items() if not k.startswith("__")})

@@ -1,0 +1,116 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances: residuals / Jacobians 1e-9 relative (float64, different operation order); LM trajectories: the
+north-star bar -- final cost within 1e-5 relative, pose translations within 1e-4.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+OPTS = dict(max_num_iterations=12, function_tolerance=1e-6, gradient_tolerance=1e-10, parameter_tolerance=1e-8,
+            initial_trust_region_radius=100.0, max_trust_region_radius=1e4, use_nonmonotonic_steps=1)
+
+
+def oracle_opts(o):
+    return dict(max_num_iterations=o["max_num_iterations"], function_tolerance=o["function_tolerance"],
+                gradient_tolerance=o["gradient_tolerance"], parameter_tolerance=o["parameter_tolerance"],
+                initial_radius=o["initial_trust_region_radius"], max_radius=o["max_trust_region_radius"],
+                use_nonmonotonic_steps=bool(o["use_nonmonotonic_steps"]))
+
+
+def small_graph(ob, seed=1, **kw):
+    args = dict(K=12, P=300, O=5, seed=seed, objects_on=True, relpose="all", n_const_poses=1, min_obj_obs=4, ltm_frac=0.5)
+    args.update(kw)
+    return ob.synth.make_graph(**args)
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / (1.0 + np.abs(b).max())) if a.size else 0.0
+
+
+@pytest.mark.parametrize("apply_loss", [False, True])
+def test_evaluate_matches_oracle(ob, oracle, apply_loss):
+    g = small_graph(ob)
+    # adversarial poses: rotation norm on both sides of the 1e-8 branch, and near pi
+    g.poses[3, 3:6] = [3e-9, 0, 0]
+    g.poses[4, 3:6] = [2e-8, 1e-9, 0]
+    g.poses[5, 3:6] = 0.0
+    ref = oracle.evaluate(g, apply_loss=apply_loss)
+    p = ob.problem_from_graph(g)
+    n = g.counts()
+    r, jp, jl = p.evaluate_factor_type(ob.FACTOR_REPROJECTION, n["reproj"], apply_loss)
+    assert rel_err(r, ref["r_reproj"]) < 1e-9 and rel_err(jp, ref["jp_reproj"]) < 1e-9 and rel_err(jl, ref["jl_reproj"]) < 1e-9
+    r, jo, jp = p.evaluate_factor_type(ob.FACTOR_BBOX, n["bbox"], apply_loss)
+    assert n["bbox"] > 0
+    assert rel_err(r, ref["r_bbox"]) < 1e-9 and rel_err(jo, ref["jo_bbox"]) < 1e-9 and rel_err(jp, ref["jp_bbox"]) < 1e-9
+    r, j, _ = p.evaluate_factor_type(ob.FACTOR_SHAPE_PRIOR, n["shape"], apply_loss)
+    assert rel_err(r, ref["r_shape"]) < 1e-9 and rel_err(j, ref["j_shape"]) < 1e-9
+    r, j, _ = p.evaluate_factor_type(ob.FACTOR_LTM_PRIOR, n["ltm"], apply_loss)
+    assert n["ltm"] > 0
+    assert rel_err(r, ref["r_ltm"]) < 1e-9 and rel_err(j, ref["j_ltm"]) < 1e-9
+    r, j1, j2 = p.evaluate_factor_type(ob.FACTOR_REL_POSE, n["relpose"], apply_loss)
+    assert rel_err(r, ref["r_rel"]) < 1e-9 and rel_err(j1, ref["j1_rel"]) < 1e-9 and rel_err(j2, ref["j2_rel"]) < 1e-9
+    cost, res = p.evaluate(apply_loss_function=apply_loss)
+    assert abs(cost - ref["cost"]) <= 1e-10 * abs(ref["cost"])
+    # concatenated residuals follow the order of addition: reproj, bbox, shape, ltm, relpose
+    cat = np.concatenate([ref[k].ravel() for k in ("r_reproj", "r_bbox", "r_shape", "r_ltm", "r_rel")])
+    assert res.shape == cat.shape and rel_err(res, cat) < 1e-9
+
+
+def check_solve(ob, oracle, g, opts, cost_tol=1e-5, transl_tol=1e-4):
+    g_ref = g.copy()
+    p = ob.problem_from_graph(g)
+    s = p.solve(**opts)
+    ref = oracle.solve(g_ref, **oracle_opts(opts))
+    its = s.iterations
+    msg = "\n".join(f"{a['iteration']:3d} gpu {a['cost']:.10e} ok={int(a['successful'])} pcg={a['linear_solver_iterations']:4d} | "
+                    f"cpu {b['cost']:.10e} ok={int(b['successful'])}" for a, b in zip(its, ref["iterations"]))
+    print(msg)
+    assert s.termination == ref["termination"], msg
+    assert s.num_iterations == len(ref["iterations"]) and s.num_lm_steps == ref["lm_steps"], msg
+    for a, b in zip(its, ref["iterations"]):
+        assert a["successful"] == b["successful"], msg
+        assert abs(a["cost"] - b["cost"]) <= cost_tol * abs(b["cost"]), msg
+    assert abs(s.final_cost - ref["final_cost"]) <= cost_tol * ref["final_cost"], msg
+    assert abs(s.initial_cost - ref["initial_cost"]) <= 1e-10 * ref["initial_cost"]
+    assert s.num_parameters_reduced == ref["num_parameters_reduced"]
+    assert np.abs(g.poses[:, :3] - g_ref.poses[:, :3]).max() < transl_tol
+    assert s.kernel_launches > 0
+    return s, ref
+
+
+def test_solve_small_all_factors(ob, oracle):
+    check_solve(ob, oracle, small_graph(ob, seed=2), OPTS)
+
+
+def test_solve_reproj_only(ob, oracle):
+    g = ob.synth.make_graph(K=16, P=500, O=0, seed=3, objects_on=False, relpose="none", n_const_poses=1)
+    check_solve(ob, oracle, g, OPTS)
+
+
+def test_solve_monotonic_default_radius(ob, oracle):
+    o = dict(OPTS, use_nonmonotonic_steps=0, initial_trust_region_radius=1e4, max_trust_region_radius=1e16)
+    check_solve(ob, oracle, small_graph(ob, seed=4), o)
+
+
+def test_solve_local_window_c1(ob, oracle):
+    """BASELINE config 1 shape: 50 keyframes / 2k points / 20 objects, 5 leading poses constant, LBA options."""
+    g = ob.synth.make_config("C1obj")
+    o = dict(OPTS, max_num_iterations=50, function_tolerance=1e-3)
+    check_solve(ob, oracle, g, o)
+
+
+def test_points_only_ba(ob, oracle):
+    """fix_poses_ (pose_graph_plus_objects_optimizer.h:301): every pose constant, only points move."""
+    g = ob.synth.make_graph(K=10, P=200, O=0, seed=6, objects_on=False, relpose="none", n_const_poses=10)
+    check_solve(ob, oracle, g, OPTS)
+
+
+def test_zero_iterations_is_evaluation_only(ob, oracle):
+    """max_num_iterations = 0 (long_term_object_map_extraction.cpp:118-120): evaluate and return."""
+    g = small_graph(ob, seed=7)
+    before = g.poses.copy()
+    p = ob.problem_from_graph(g)
+    s = p.solve(**dict(OPTS, max_num_iterations=0))
+    assert s.num_iterations == 1 and s.termination == "NO_CONVERGENCE" and np.array_equal(before, g.poses)
