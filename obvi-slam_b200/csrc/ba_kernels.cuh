@@ -30,7 +30,7 @@ enum : int {
   // across ranks separately in a sharded run
   SC_COST = 0, SC_FIXED = 1, SC_XNORM2 = 2, SC_CAND = 3, SC_CAND_FIXED = 4, SC_MODEL = 5, SC_STEP2 = 6,
   SC_GMAX = 7 /* u64 bits of a non-negative double */, SC_FAIL = 8, SC_PCG_IT = 9, SC_PCG_RES = 10, SC_PCG_BB = 11,
-  SC_PCG_BREAK = 12, SC_COUNT = 16
+  SC_PCG_BREAK = 12, SC_BT_FAIL = 13, SC_COUNT = 16
 };
 
 struct LMParams { double radius, min_diag, max_diag; int compute_scale; };

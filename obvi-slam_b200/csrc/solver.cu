@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -19,6 +20,7 @@
 #include <vector>
 
 #include "ba_kernels.cuh"
+#include "bt_precond.cuh"
 
 namespace obvi {
 
@@ -124,6 +126,15 @@ struct Solver {
   DBuf<double> redbuf;  // [S_upper | gp | b_schur | hpp_diag]
   double *S_upper = nullptr, *gp = nullptr, *b_schur = nullptr, *hpp_diag = nullptr;
   DBuf<double> pscale, Sf, rhs, Minv, y, cg_r, cg_z, cg_p, cg_q, cg_acc, dpose, scalars;
+  // block-tridiagonal preconditioner (bt_precond.cuh)
+  int nsb = 0, nlev = 0, pcg_bt_blocks_per_sm = 0;
+  DBuf<double> bt_D, bt_Dinv, bt_GaT, bt_GcT, bt_C, bt_w, bt_z;
+  DBuf<GemmTask> bt_tasks;
+  DBuf<int> bt_idx;
+  struct BtLevel { int inv_off, inv_n, g_off, g_n, u_off, u_n; };
+  std::vector<BtLevel> bt_levels;
+  int bt_last_inv_off = 0;
+  bool use_bt = true;
   double* h_scalars = nullptr;  // pinned
   std::vector<double> h_poses, h_points, h_objects;
   int64_t launches = 0;
@@ -146,6 +157,11 @@ struct Solver {
     CUDA_OK(cudaMallocHost((void**)&h_scalars, SC_COUNT * sizeof(double)));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_blocks_per_sm, pcg_kernel, kPcgThreads, 0));
     if (pcg_blocks_per_sm < 1) throw std::runtime_error("pcg_kernel cannot be made resident");
+    CUDA_OK(cudaFuncSetAttribute(bt_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBB * 8));
+    CUDA_OK(cudaFuncSetAttribute(bt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBB * 8));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_bt_blocks_per_sm, pcg_bt_kernel, kPcgThreads, 0));
+    if (pcg_bt_blocks_per_sm < 1) throw std::runtime_error("pcg_bt_kernel cannot be made resident");
+    if (const char* e = getenv("OBVI_PRECOND")) use_bt = std::string(e) != "jacobi";
   }
 
   void upload_elist(EListDev& D, const Structure::EList& L, const std::vector<uint8_t>& cst, int NE, int maxs) {
@@ -192,7 +208,76 @@ struct Solver {
     pscale.alloc(nf6); Sf.alloc((size_t)S.sf_col.size() * 36); rhs.alloc(nf6); Minv.alloc((size_t)S.nf * 36);
     y.alloc(nf6); cg_r.alloc(nf6); cg_z.alloc(nf6); cg_p.alloc(nf6); cg_q.alloc(nf6); cg_acc.alloc(16); dpose.alloc(nf6);
     scalars.alloc(SC_COUNT);
+    setup_bt();
     uploaded = true;
+  }
+  // level tables + GEMM task lists of the cyclic-reduction factorisation (static per structure)
+  void setup_bt() {
+    const Structure& S = st;
+    nsb = (S.nf + kSbPoses - 1) / kSbPoses;
+    nlev = 0;
+    while ((1 << nlev) < nsb) nlev++;
+    bt_levels.clear();
+    if (nsb == 0) return;
+    bt_D.alloc((size_t)nsb * kBB); bt_Dinv.alloc((size_t)nsb * kBB); bt_GaT.alloc((size_t)nsb * kBB); bt_GcT.alloc((size_t)nsb * kBB);
+    bt_w.alloc((size_t)nsb * kB); bt_z.alloc((size_t)nsb * kB);
+    // couplings: level l holds n_l - 1 blocks
+    std::vector<size_t> coff(nlev + 1, 0);
+    size_t ctot = 0;
+    for (int l = 0; l <= nlev; l++) { const int s = 1 << l, nl = (nsb + s - 1) / s; coff[l] = ctot; ctot += (size_t)std::max(nl - 1, 0); }
+    bt_C.alloc(std::max<size_t>(ctot, 1) * kBB);
+    std::vector<GemmTask> tasks;
+    std::vector<int> idx;
+    auto Cl = [&](int l, int k) { return bt_C.p + (coff[l] + (size_t)k) * kBB; };
+    for (int l = 0; l < nlev; l++) {
+      const int s = 1 << l, nl = (nsb + s - 1) / s;
+      BtLevel L;
+      L.inv_off = (int)idx.size();
+      for (int k = 1; k < nl; k += 2) idx.push_back(k * s);
+      L.inv_n = (int)idx.size() - L.inv_off;
+      L.g_off = (int)tasks.size();
+      for (int k = 1; k < nl; k += 2) {
+        const size_t i = (size_t)k * s;
+        GemmTask t{}; t.C = bt_GaT.p + i * kBB; t.A1 = Cl(l, k - 1); t.tA1 = 1; t.B1 = bt_Dinv.p + i * kBB; t.alpha1 = 1.0; t.beta = 0.0;
+        tasks.push_back(t);
+        if (k + 1 < nl) { GemmTask u{}; u.C = bt_GcT.p + i * kBB; u.A1 = Cl(l, k); u.B1 = bt_Dinv.p + i * kBB; u.alpha1 = 1.0; u.beta = 0.0; tasks.push_back(u); }
+      }
+      L.g_n = (int)tasks.size() - L.g_off;
+      L.u_off = (int)tasks.size();
+      for (int k = 0; k < nl; k += 2) {
+        const size_t a = (size_t)k * s;
+        GemmTask t{}; t.C = bt_D.p + a * kBB; t.beta = 1.0;
+        int nt = 0;
+        if (k + 1 < nl) { t.A1 = bt_GaT.p + (size_t)(k + 1) * s * kBB; t.B1 = Cl(l, k); t.alpha1 = -1.0; nt = 1; }
+        if (k >= 1) {
+          const double* A = bt_GcT.p + (size_t)(k - 1) * s * kBB; const double* Bm = Cl(l, k - 1);
+          if (nt == 0) { t.A1 = A; t.B1 = Bm; t.tB1 = 1; t.alpha1 = -1.0; } else { t.A2 = A; t.B2 = Bm; t.tB2 = 1; t.alpha2 = -1.0; }
+          nt++;
+        }
+        if (nt) tasks.push_back(t);
+        if (k + 2 < nl) { GemmTask c{}; c.C = Cl(l + 1, k / 2); c.A1 = bt_GcT.p + (size_t)(k + 1) * s * kBB; c.B1 = Cl(l, k); c.alpha1 = -1.0; c.beta = 0.0; tasks.push_back(c); }
+      }
+      L.u_n = (int)tasks.size() - L.u_off;
+      bt_levels.push_back(L);
+    }
+    bt_last_inv_off = (int)idx.size();
+    idx.push_back(0);
+    bt_tasks.upload(tasks, stream); bt_idx.upload(idx, stream);
+  }
+  void factor_bt() {
+    const Structure& S = st;
+    if (!use_bt || nsb == 0) return;
+    bt_D.zero(stream);
+    if (nsb > 1) CUDA_OK(cudaMemsetAsync(bt_C.p, 0, (size_t)(nsb - 1) * kBB * 8, stream));
+    bt_assemble_kernel<<<nblk((int64_t)nsb * kSbPoses * 32, 256), 256, 0, stream>>>(S.nf, nsb, sf_ptr.p, sf_col.p, Sf.p, bt_D.p, bt_C.p);
+    launches++;
+    for (const BtLevel& L : bt_levels) {
+      if (L.inv_n) { bt_invert_kernel<<<L.inv_n, 256, kBB * 8, stream>>>(bt_idx.p + L.inv_off, bt_D.p, bt_Dinv.p, scalars.p); launches++; }
+      if (L.g_n) { bt_gemm_kernel<<<L.g_n, 256, 2 * kBB * 8, stream>>>(bt_tasks.p + L.g_off); launches++; }
+      if (L.u_n) { bt_gemm_kernel<<<L.u_n, 256, 2 * kBB * 8, stream>>>(bt_tasks.p + L.u_off); launches++; }
+    }
+    bt_invert_kernel<<<1, 256, kBB * 8, stream>>>(bt_idx.p + bt_last_inv_off, bt_D.p, bt_Dinv.p, scalars.p);
+    launches++;
   }
   bool owns_object(int o) const {
     // an object is "owned" when this rank holds its observations or (no observations) rank 0
@@ -273,6 +358,7 @@ struct Solver {
     const Structure& S = st;
     redbuf.zero(stream);
     zero_scalars(SC_GMAX, 2);  // gmax + fail
+    zero_scalars(SC_BT_FAIL, 1);
     if (pts.has_prior) { pts.prior_H.zero(stream); pts.prior_g.zero(stream); }
     if (objs.has_prior) { objs.prior_H.zero(stream); objs.prior_g.zero(stream); }
     if (S.n_obs && S.nf) { pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag); launches++; }
@@ -285,13 +371,26 @@ struct Solver {
       if (lm.compute_scale) { pose_scale_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(hpp_diag, S.nf * 6, pscale.p); launches++; }
       finish_kernel<<<nblk((int64_t)S.nf * 32, 256), 256, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, sf_src.p, S_upper, pscale.p, hpp_diag, gp, b_schur, lm, Sf.p, rhs.p, Minv.p, scalars.p);
       launches++;
+      factor_bt();
     }
   }
-  void solve_reduced(const obvi_solver_options& o) {
+  void solve_reduced(const obvi_solver_options& o, bool force_jacobi = false) {
     const Structure& S = st;
     if (!S.nf) return;
     int nf = S.nf, max_iter = o.pcg_max_iterations;
     double tol = o.pcg_relative_tolerance;
+    if (use_bt && !force_jacobi) {
+      BtApply P; P.nsb = nsb; P.nlev = nlev; P.Dinv = bt_Dinv.p; P.GaT = bt_GaT.p; P.GcT = bt_GcT.p; P.w = bt_w.p; P.z = bt_z.p;
+      int grid = std::min(num_sms * pcg_bt_blocks_per_sm, std::max(1, nblk(nf, kPcgThreads / 32)));
+      const uint32_t *a1 = sf_ptr.p, *a2 = sf_col.p;
+      const double *a3 = Sf.p, *a4 = rhs.p;
+      double *a6 = y.p, *a7 = cg_r.p, *a9 = cg_p.p, *a10 = cg_q.p, *a11 = cg_acc.p, *a14 = scalars.p;
+      void* args[] = {&nf, &a1, &a2, &a3, &a4, &P, &a6, &a7, &a9, &a10, &a11, &max_iter, &tol, &a14};
+      CUDA_OK(cudaLaunchCooperativeKernel((void*)pcg_bt_kernel, dim3(grid), dim3(kPcgThreads), args, 0, stream));
+      launches++;
+      if (world > 1) broadcast0(y.p, (size_t)nf * 6);
+      return;
+    }
     int grid = std::min(num_sms * pcg_blocks_per_sm, std::max(1, nblk(nf, kPcgThreads / 32)));
     const uint32_t *a1 = sf_ptr.p, *a2 = sf_col.p;
     const double *a3 = Sf.p, *a4 = rhs.p, *a5 = Minv.p;
@@ -445,6 +544,13 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
     fetch_scalars(1);
     CUDA_OK(cudaEventElapsedTime(&ms, ev[2], ev[3])); t_lin += ms * 1e-3;
     CUDA_OK(cudaEventElapsedTime(&ms, ev[3], ev[4])); t_res += ms * 1e-3;
+    if (h_scalars[SC_PCG_BREAK] == 2.0) {
+      // the block-tridiagonal factorisation hit a non-positive pivot: redo this step with block-Jacobi PCG
+      solve_reduced(o, true);
+      take_step();
+      candidate_cost();
+      fetch_scalars(1);
+    }
     const int pcg_it = (int)h_scalars[SC_PCG_IT];
     pcg_total += pcg_it;
     const double model_change = -h_scalars[SC_MODEL];

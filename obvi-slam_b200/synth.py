@@ -142,7 +142,7 @@ def odom_cov(t, R, k=0.025):
 # ----------------------------------------------------------------------------- generator
 def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_poses=1,
                sigma_px=1.5, outlier_frac=0.05, min_point_obs=5, min_obj_obs=10, ltm_frac=0.0,
-               pose_noise=True):
+               pose_noise=True, min_parallax_deg=1.0, symmetric_priors=False, min_bbox_px=30.0):
     """Build S(K, P, O, seed).
 
     relpose: "starved" -> rel-pose factors only into feature-starved keyframes (reference rule,
@@ -151,6 +151,7 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
     n_const_poses: number of leading poses held constant (1 for a window starting at frame 0, 5 for a
              local window; object_pose_graph_optimizer.h:440-459).
     ltm_frac: fraction of objects that carry a long-term-map prior factor.
+    min_parallax_deg: tracks whose first/last rays subtend less than this at the point are dropped.
     """
     rng = np.random.default_rng(seed)
     g = FactorGraph()
@@ -206,6 +207,21 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
             if len(idx) > 30:
                 drop[rng.permutation(idx)[30:]] = True
         obs_pose, obs_point, obs_cam, obs_px = obs_pose[~drop], obs_point[~drop], obs_cam[~drop], obs_px[~drop]
+    # parallax gate (the reference's visual front end only admits tracks with enough parallax,
+    # visual_feature_front_end.h:214-802): angle subtended at the point by the first and last observing
+    # camera centres must exceed min_parallax_deg, otherwise the depth is unobservable
+    if min_parallax_deg > 0 and len(obs_pose):
+        first = np.full(P, K, dtype=np.int64); last = np.full(P, -1, dtype=np.int64)
+        np.minimum.at(first, obs_point, obs_pose); np.maximum.at(last, obs_point, obs_pose)
+        seen = last >= 0
+        fi, la = np.where(seen, first, 0), np.where(seen, last, 0)
+        c0 = t_gt[fi] + np.einsum("nij,j->ni", R_gt[fi], T_EXTR[0])
+        c1 = t_gt[la] + np.einsum("nij,j->ni", R_gt[la], T_EXTR[1])
+        v0, v1 = X_gt - c0, X_gt - c1
+        cosang = np.einsum("ni,ni->n", v0, v1) / (np.linalg.norm(v0, axis=1) * np.linalg.norm(v1, axis=1))
+        ok_par = seen & (np.degrees(np.arccos(np.clip(cosang, -1.0, 1.0))) >= min_parallax_deg)
+        keep_o = ok_par[obs_point]
+        obs_pose, obs_point, obs_cam, obs_px = obs_pose[keep_o], obs_point[keep_o], obs_cam[keep_o], obs_px[keep_o]
     # points need >= min_point_obs factors (object_pose_graph_optimizer.h:234-237)
     cnt = np.bincount(obs_point, minlength=P)
     good = cnt[obs_point] >= min_point_obs
@@ -230,10 +246,16 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
         cls = rng.integers(0, len(SHAPE_PRIORS), O)
         okf = rng.integers(0, K, O)
         side = rng.choice([-1.0, 1.0], O)
-        lat = rng.uniform(3.0, 15.0, O) * side
-        fwd = rng.uniform(4.0, 12.0, O)
+        lat = rng.uniform(2.5, 7.0, O) * side
+        fwd = rng.uniform(3.0, 8.0, O)
         mean = np.array([SHAPE_PRIORS[c][0] for c in cls])
         var = np.array([SHAPE_PRIORS[c][1] for c in cls])
+        if not symmetric_priors:
+            # Five of the six class means have dx == dy, which makes the ellipsoid's yaw a pure gauge freedom
+            # (the tight dimension priors pull dx, dy back to the symmetric mean): LM -- Ceres' too -- then takes
+            # yaw steps of thousands of radians and the iteration sequence becomes chaotic, useless for parity
+            # checks.  The synthetic classes therefore use the config's means with dy scaled by 1.5.
+            mean = mean * np.array([1.0, 1.5, 1.0])
         dims = np.clip(mean + rng.normal(0.0, 1.0, (O, 3)) * np.minimum(np.sqrt(var), 0.15 * mean), 0.1, None)
         ca, sa = np.cos(yaw[okf]), np.sin(yaw[okf])
         obj_gt[:, 0] = t_gt[okf, 0] + ca * fwd - sa * lat
@@ -255,6 +277,8 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
                 ctr_u, ctr_v = 0.5 * (px[:, 0] + px[:, 1]), 0.5 * (px[:, 2] + px[:, 3])
                 ok &= (zc > 1.5) & (ctr_u > 0) & (ctr_u < IMG_W) & (ctr_v > 0) & (ctr_v < IMG_H)
                 ok &= (np.abs(px[:, 1] - px[:, 0]) < 2.0 * IMG_W) & (np.abs(px[:, 3] - px[:, 2]) < 2.0 * IMG_H)
+                # detections smaller than min_bbox_px carry no shape information at 10 px noise
+                ok &= (np.abs(px[:, 1] - px[:, 0]) >= min_bbox_px) & (np.abs(px[:, 3] - px[:, 2]) >= min_bbox_px)
                 vis.append((px, ok))
             both = vis[0][1] & vis[1][1]
             sel = np.nonzero(both)[0][:40]  # cap: 40 keyframes x 2 cameras
@@ -281,7 +305,7 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
                           cam=np.concatenate(bc).astype(np.int64), corners=np.concatenate(bcr),
                           cov=np.concatenate(bcv))
         seen = np.unique(g.bbox["obj"])
-        g.shape.update(obj=seen.astype(np.int64), mean=np.array([SHAPE_PRIORS[cls[o]][0] for o in seen]).reshape(-1, 3),
+        g.shape.update(obj=seen.astype(np.int64), mean=mean[seen].reshape(-1, 3),
                        cov=np.array([np.diag(SHAPE_PRIORS[cls[o]][1]) for o in seen]).reshape(-1, 3, 3))
         if ltm_frac > 0 and len(seen):
             nl = max(1, int(len(seen) * ltm_frac))
