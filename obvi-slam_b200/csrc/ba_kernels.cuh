@@ -123,6 +123,112 @@ __global__ void __launch_bounds__(kJacThreads) reproj_jac_kernel(const ObsRec* _
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ TMA helpers (sm_90+ PTX)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA, completes on the mbarrier); size multiple of 16, 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// 1-D bulk copy shared -> global (TMA store)
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------ reprojection Jacobians, TMA-staged
+// Same arithmetic as reproj_jac_kernel, restructured around the memory system:
+//   * observations are pose-major, so the pose/camera entries a 256-observation tile needs are a short CONTIGUOUS range
+//     of the table: one 1-D TMA bulk copy stages them in shared memory (no per-thread 384-byte reloads);
+//   * each thread writes its 160-byte chunk into a shared-memory image of the output tile, and one elected thread
+//     stores the whole contiguous 40 KB tile with a single TMA bulk store: full-line HBM writes, no LSU store traffic.
+constexpr int kJacMaxPc = 6;                       // staged pose/camera entries per tile
+constexpr int kJacTileBytes = kJacThreads * kChunk * 8;
+constexpr int kJacSmemBytes = kJacTileBytes + kJacMaxPc * (int)sizeof(PoseCam) + 16;
+
+__global__ void __launch_bounds__(kJacThreads, 3) reproj_jac_tma_kernel(const ObsRec* __restrict__ obs, int64_t n,
+                                                                         const PoseCam* __restrict__ pcam, int C,
+                                                                         const CalibClass* __restrict__ cls,
+                                                                         const double* __restrict__ points, int apply_loss,
+                                                                         const uint2* __restrict__ tile_pc,
+                                                                         double* __restrict__ J, double* __restrict__ scalars) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ double red[33];
+  double* out_tile = reinterpret_cast<double*>(smem);
+  PoseCam* pc_s = reinterpret_cast<PoseCam*>(smem + kJacTileBytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kJacTileBytes + kJacMaxPc * sizeof(PoseCam));
+  const int64_t i0 = (int64_t)blockIdx.x * kJacThreads;
+  const int nt = (int)min((int64_t)kJacThreads, n - i0);
+  const uint2 tp = tile_pc[blockIdx.x];  // first pose/camera entry of the tile, number of entries staged
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, tp.y * (uint32_t)sizeof(PoseCam));
+    tma_load_1d(pc_s, pcam + tp.x, tp.y * (uint32_t)sizeof(PoseCam), bar);
+  }
+  const int64_t i = i0 + threadIdx.x;
+  double cost = 0.0, fixed = 0.0;
+  double2 uv = make_double2(0.0, 0.0);
+  uint4 id = make_uint4(0, 0, 0, 0);
+  CalibClass cc;
+  double X[3] = {0.0, 0.0, 0.0};
+  const bool active = (int)threadIdx.x < nt;
+  if (active) {
+    uv = reinterpret_cast<const double2*>(obs)[2 * i];
+    id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];
+    cc = cls[id.z];
+    X[0] = points[3 * (size_t)id.y]; X[1] = points[3 * (size_t)id.y + 1]; X[2] = points[3 * (size_t)id.y + 2];
+  }
+  mbar_wait(bar, 0);
+  if (active) {
+    const uint32_t pci = id.x * (uint32_t)C + (uint32_t)cc.cam;
+    const uint32_t rel = pci - tp.x;
+    const PoseCam& pc = rel < tp.y ? pc_s[rel] : pcam[pci];
+    double r[2], Jp[12], Jl[6];
+    reproj_residual_jacobian(pc, X, uv.x, uv.y, cc.mx, cc.my, r, Jp, Jl);
+    const double s = r[0] * r[0] + r[1] * r[1];
+    double sc = 1.0, c = 0.5 * s;
+    if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
+    if (id.w == 3u) fixed = c; else cost = c;
+    double2* out = reinterpret_cast<double2*>(out_tile + (size_t)threadIdx.x * kChunk);
+#pragma unroll
+    for (int a = 0; a < 6; a++) out[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) out[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
+    out[9] = make_double2(sc * r[0], sc * r[1]);
+  }
+  fence_proxy_async_smem();
+  cost = block_sum_all<kJacThreads>(cost, red);     // contains __syncthreads: the tile image is complete after it
+  fixed = block_sum_all<kJacThreads>(fixed, red);
+  if (threadIdx.x == 0) {
+    tma_store_1d(J + (size_t)i0 * kChunk, out_tile, (uint32_t)nt * kChunk * 8);
+    if (cost != 0.0) atomicAdd(&scalars[SC_COST], cost);
+    if (fixed != 0.0) atomicAdd(&scalars[SC_FIXED], fixed);
+    tma_store_wait_read();
+  }
+}
+
 // Residual-only evaluation at the candidate point (cost only; nothing is stored).
 __global__ void __launch_bounds__(kJacThreads) reproj_cost_kernel(const ObsRec* __restrict__ obs, int64_t n,
                                                                    const PoseCam* __restrict__ pcam, int C,
@@ -226,6 +332,7 @@ struct EArgs {
   const double* prior_g;    // NE per e-block or null
   double* overflow;         // staging for e-blocks with more than MAXS slots
   const uint32_t* overflow_off;  // per e-block offset (in doubles) into overflow, valid when nslots > MAXS
+  const uint32_t* elist;         // optional: process e-block elist[blockIdx.x] instead of blockIdx.x
   int ne;
 };
 
@@ -242,7 +349,7 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
   constexpr int SL = 12 * NE;  // doubles per slot in the staging buffer: Z (6xNE) then W (6xNE)
   __shared__ double red[33];
   __shared__ double stage_s[MAXS * SL];
-  const int e = blockIdx.x;
+  const int e = A.elist ? (int)A.elist[blockIdx.x] : (int)blockIdx.x;
   if (A.cst[e]) return;
   const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
   if (b0 == b1 && A.prior_H == nullptr) return;
@@ -433,6 +540,197 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ points: batched elimination
+// Owner-computes Schur elimination of points.  A CTA takes a batch of consecutive points (they are ordered by
+// first-observing keyframe, so the batch touches a narrow window of <= 64 poses) and every thread OWNS one 6x6
+// block of the reduced matrix for the whole batch: the per-point products Z_a W_b^T are accumulated in registers
+// and flushed with one set of atomics per batch instead of one per point (40x fewer global atomics).
+//   phase 1 (a warp per point, 16 points per pass): H_ll, g_l by warp-shuffle reduction, damping, 3x3 inverse,
+//            W = sum Jp^T Jl and Z = W Hinv per merged pose slot, staged in shared memory;
+//   phase 2 (a thread per block pair): for every staged point that observes both poses of the pair, acc += Z_a W_b^T.
+struct BatchArgs {
+  const uint32_t* first; const uint32_t* count; const int32_t* win_f; const uint32_t* nwin; const uint64_t* mask;
+  const uint32_t* pair_ptr; const uint32_t* pair_info; const uint32_t* pair_blk;
+};
+constexpr int kBatchThreads = 512;
+constexpr int kSubPts = kBatchThreads / 32;   // 16 points per pass
+constexpr int kStageSlots = 16;
+constexpr int kSlotStride = 37;               // 36 doubles (Z 6x3, W 6x3) + 1 pad: conflict-free across slots
+constexpr int kPtStride = kStageSlots * kSlotStride;
+
+__global__ void __launch_bounds__(kBatchThreads) schur_points_batched_kernel(EArgs A, BatchArgs B, LMParams lm,
+                                                                              double* __restrict__ S_upper,
+                                                                              double* __restrict__ b_schur,
+                                                                              double* __restrict__ scalars) {
+  extern __shared__ double stage[];          // [kSubPts][kStageSlots][kSlotStride]
+  __shared__ unsigned long long s_mask[kSubPts];
+  __shared__ double s_g[kSubPts][3];
+  __shared__ double s_gmax[kSubPts];
+  const int batch = blockIdx.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t p_first = B.first[batch], np = B.count[batch];
+  const uint32_t pr0 = B.pair_ptr[batch];
+  const int npairs = (int)(B.pair_ptr[batch + 1] - pr0);
+  const int nwin = (int)B.nwin[batch];
+  int wa = 0, wb = 0;
+  const bool own_pair = (int)threadIdx.x < npairs;
+  if (own_pair) { const uint32_t info = B.pair_info[pr0 + threadIdx.x]; wa = info & 0xff; wb = (info >> 8) & 0xff; }
+  const bool own_b = (int)threadIdx.x < nwin * 6;
+  const int bw = threadIdx.x / 6, brow = threadIdx.x - 6 * bw;
+  double acc[36];
+#pragma unroll
+  for (int a = 0; a < 36; a++) acc[a] = 0.0;
+  double bacc = 0.0, gmax = 0.0;
+
+  for (uint32_t s0 = 0; s0 < np; s0 += kSubPts) {
+    // ---------------- phase 1: warp `wib` handles point p_first + s0 + wib
+    {
+      const uint32_t pi = s0 + wib;
+      unsigned long long mk = 0ull;
+      double g[3] = {0.0, 0.0, 0.0};
+      if (pi < np) {
+        const int e = (int)(p_first + pi);
+        const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
+        if (!A.cst[e] && b1 > b0) {
+          double H[6] = {0, 0, 0, 0, 0, 0};
+          for (uint32_t q = b0 + lane; q < b1; q += 32) {
+            const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)A.pos[q] * kChunk);
+            const double2 l0 = ch[6], l1 = ch[7], l2 = ch[8], rr = ch[9];  // Jl rows (3+3), r
+            const double je0[3] = {l0.x, l0.y, l1.x}, je1[3] = {l1.y, l2.x, l2.y};
+            int t = 0;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+              g[a] += je0[a] * rr.x + je1[a] * rr.y;
+#pragma unroll
+              for (int b = a; b < 3; b++) H[t++] += je0[a] * je0[b] + je1[a] * je1[b];
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < 6; a++) H[a] = warp_sum(H[a]);
+#pragma unroll
+          for (int a = 0; a < 3; a++) g[a] = warp_sum(g[a]);
+          if (A.prior_H) {
+            const double* ph = A.prior_H + (size_t)e * 9;
+            H[0] += ph[0]; H[1] += ph[1]; H[2] += ph[2]; H[3] += ph[4]; H[4] += ph[5]; H[5] += ph[8];
+#pragma unroll
+            for (int a = 0; a < 3; a++) g[a] += A.prior_g[(size_t)e * 3 + a];
+          }
+          const double hd[3] = {H[0], H[3], H[5]};
+          double s[3];
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            s[a] = lm.compute_scale ? 1.0 / (1.0 + sqrt(hd[a])) : A.escale[(size_t)e * 3 + a];
+            gmax = fmax(gmax, fabs(g[a]));
+          }
+          double Hs[9], hinv[9];
+          Hs[0] = s[0] * H[0] * s[0]; Hs[1] = Hs[3] = s[0] * H[1] * s[1]; Hs[2] = Hs[6] = s[0] * H[2] * s[2];
+          Hs[4] = s[1] * H[3] * s[1]; Hs[5] = Hs[7] = s[1] * H[4] * s[2]; Hs[8] = s[2] * H[5] * s[2];
+#pragma unroll
+          for (int a = 0; a < 3; a++) Hs[4 * a] += fmin(fmax(Hs[4 * a], lm.min_diag), lm.max_diag) / lm.radius;
+          const bool ok = spd_inverse<3>(Hs, hinv);
+          if (!ok) {
+            if (lane == 0) atomicAdd(&scalars[SC_FAIL], 1.0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+              for (int b = 0; b < 3; b++) hinv[3 * a + b] *= s[a] * s[b];
+            if (lane == 0) {
+              if (lm.compute_scale) { A.escale[(size_t)e * 3] = s[0]; A.escale[(size_t)e * 3 + 1] = s[1]; A.escale[(size_t)e * 3 + 2] = s[2]; }
+#pragma unroll
+              for (int a = 0; a < 9; a++) A.einv[(size_t)e * 9 + a] = hinv[a];
+#pragma unroll
+              for (int a = 0; a < 3; a++) A.eg[(size_t)e * 3 + a] = g[a];
+            }
+            mk = B.mask[e];
+            double* st_pt = stage + (size_t)wib * kPtStride;
+            for (uint32_t q = b0 + lane; q < b1; q += 32) {
+              const uint16_t sl = A.slot[q];
+              if (sl == 0xFFFF) continue;
+              if (q > b0 && A.slot[q - 1] == sl) continue;  // not the head of its run
+              double Wm[18];
+#pragma unroll
+              for (int a = 0; a < 18; a++) Wm[a] = 0.0;
+              for (uint32_t q2 = q; q2 < b1 && A.slot[q2] == sl; q2++) {
+                const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)A.pos[q2] * kChunk);
+                double jp[12];
+#pragma unroll
+                for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
+                const double2 l0 = ch[6], l1 = ch[7], l2 = ch[8];
+                const double je0[3] = {l0.x, l0.y, l1.x}, je1[3] = {l1.y, l2.x, l2.y};
+#pragma unroll
+                for (int a = 0; a < 6; a++)
+#pragma unroll
+                  for (int c = 0; c < 3; c++) Wm[3 * a + c] += jp[a] * je0[c] + jp[6 + a] * je1[c];
+              }
+              double* st = st_pt + (size_t)sl * kSlotStride;
+#pragma unroll
+              for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                  st[3 * a + c] = Wm[3 * a] * hinv[c] + Wm[3 * a + 1] * hinv[3 + c] + Wm[3 * a + 2] * hinv[6 + c];
+                  st[18 + 3 * a + c] = Wm[3 * a + c];
+                }
+            }
+          }
+        }
+      }
+      if (lane == 0) { s_mask[wib] = mk; s_g[wib][0] = g[0]; s_g[wib][1] = g[1]; s_g[wib][2] = g[2]; }
+    }
+    __syncthreads();
+    // ---------------- phase 2: owner-computes accumulation over the staged points
+    if (own_pair) {
+#pragma unroll 1
+      for (int pt = 0; pt < kSubPts; pt++) {
+        const unsigned long long m = s_mask[pt];
+        if (((m >> wa) & (m >> wb) & 1ull) == 0ull) continue;
+        const int sa = __popcll(m & ((1ull << wa) - 1ull)), sb = __popcll(m & ((1ull << wb) - 1ull));
+        const double* Za = stage + (size_t)pt * kPtStride + (size_t)sa * kSlotStride;
+        const double* Wb = stage + (size_t)pt * kPtStride + (size_t)sb * kSlotStride + 18;
+        double wv[18];
+#pragma unroll
+        for (int a = 0; a < 18; a++) wv[a] = Wb[a];
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+          const double z0 = Za[3 * a], z1 = Za[3 * a + 1], z2 = Za[3 * a + 2];
+#pragma unroll
+          for (int c = 0; c < 6; c++) acc[6 * a + c] += z0 * wv[3 * c] + z1 * wv[3 * c + 1] + z2 * wv[3 * c + 2];
+        }
+      }
+    }
+    if (own_b) {
+#pragma unroll 1
+      for (int pt = 0; pt < kSubPts; pt++) {
+        const unsigned long long m = s_mask[pt];
+        if (((m >> bw) & 1ull) == 0ull) continue;
+        const int sa = __popcll(m & ((1ull << bw) - 1ull));
+        const double* Za = stage + (size_t)pt * kPtStride + (size_t)sa * kSlotStride + 3 * brow;
+        bacc += Za[0] * s_g[pt][0] + Za[1] * s_g[pt][1] + Za[2] * s_g[pt][2];
+      }
+    }
+    __syncthreads();
+  }
+  // ---------------- flush: one set of atomics per batch
+  if (own_pair) {
+    double* Sb = S_upper + (size_t)B.pair_blk[pr0 + threadIdx.x] * 36;
+#pragma unroll
+    for (int a = 0; a < 36; a++) atomicAdd(&Sb[a], -acc[a]);
+  }
+  if (own_b) {
+    const int f = B.win_f[(size_t)batch * 64 + bw];
+    if (bacc != 0.0) atomicAdd(&b_schur[6 * f + brow], -bacc);
+  }
+  gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 16));  // every lane of a warp holds the same value already
+  if (lane == 0) s_gmax[wib] = gmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int i = 0; i < kSubPts; i++) m = fmax(m, s_gmax[i]);
+    atomic_max_nonneg(&scalars[SC_GMAX], m);
+  }
+}
+
 // Back-substitution for one e-block + its share of the model cost change and of the candidate point:
 //   delta_e = -Hinv (g_e + sum_obs Je^T (Jp delta_p)),  model += sum m (r + m/2), m = Jp delta_p + Je delta_e
 template <int NE, int KR, int T>
@@ -509,6 +807,101 @@ __global__ void __launch_bounds__(T) backsub_eblock_kernel(EArgs A, const double
   }
   mc = block_sum_all<T>(mc, red);
   if (threadIdx.x == 0 && mc != 0.0) atomicAdd(&scalars[SC_MODEL], mc);
+}
+
+// Back-substitution for points, one warp per point, lane = observation, the 160-byte chunk held in registers
+// between the two passes (10 x 16-byte loads per observation).
+__global__ void __launch_bounds__(128) backsub_points_kernel(EArgs A, const double* __restrict__ dpose,
+                                                             const double* __restrict__ x, double* __restrict__ x_cand,
+                                                             double* __restrict__ delta_e, double* __restrict__ scalars) {
+  __shared__ double s_mc[4], s_s2[4];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * 4 + wib;
+  double mc = 0.0, s2 = 0.0;
+  if (e < A.ne) {
+    const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
+    const bool cst = A.cst[e] != 0;
+    if (b1 > b0 || (!cst && A.prior_H != nullptr)) {
+      double t[3] = {0.0, 0.0, 0.0};
+      // first 32 observations stay in registers; longer tracks loop (second pass re-reads)
+      double jp[12], jl[6], r[2], dp[6];
+      int fi = -1;
+      const bool have = b0 + lane < b1;
+      if (have) {
+        const uint32_t q = b0 + lane;
+        fi = A.f[q];
+        const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)A.pos[q] * kChunk);
+#pragma unroll
+        for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
+#pragma unroll
+        for (int a = 0; a < 3; a++) { const double2 v = ch[6 + a]; jl[2 * a] = v.x; jl[2 * a + 1] = v.y; }
+        const double2 rv = ch[9]; r[0] = rv.x; r[1] = rv.y;
+#pragma unroll
+        for (int a = 0; a < 6; a++) dp[a] = fi >= 0 ? dpose[6 * fi + a] : 0.0;
+      }
+      auto accum_t = [&](const double* jpq, const double* jlq, const double* dpq) {
+        const double jd0 = jpq[0] * dpq[0] + jpq[1] * dpq[1] + jpq[2] * dpq[2] + jpq[3] * dpq[3] + jpq[4] * dpq[4] + jpq[5] * dpq[5];
+        const double jd1 = jpq[6] * dpq[0] + jpq[7] * dpq[1] + jpq[8] * dpq[2] + jpq[9] * dpq[3] + jpq[10] * dpq[4] + jpq[11] * dpq[5];
+#pragma unroll
+        for (int c = 0; c < 3; c++) t[c] += jlq[c] * jd0 + jlq[3 + c] * jd1;
+      };
+      if (!cst) {
+        if (have && fi >= 0) accum_t(jp, jl, dp);
+        for (uint32_t q = b0 + 32 + lane; q < b1; q += 32) {
+          const int f2 = A.f[q];
+          if (f2 < 0) continue;
+          const double* ch = A.J + (size_t)A.pos[q] * kChunk;
+          double d2[6];
+#pragma unroll
+          for (int a = 0; a < 6; a++) d2[a] = dpose[6 * f2 + a];
+          accum_t(ch, ch + 12, d2);
+        }
+      }
+      double de[3] = {0.0, 0.0, 0.0};
+      if (!cst) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) t[a] = warp_sum(t[a]) + A.eg[(size_t)e * 3 + a];
+        const double* hinv = A.einv + (size_t)e * 9;
+#pragma unroll
+        for (int a = 0; a < 3; a++) de[a] = -(hinv[3 * a] * t[0] + hinv[3 * a + 1] * t[1] + hinv[3 * a + 2] * t[2]);
+        if (lane == 0) {
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            delta_e[(size_t)e * 3 + a] = de[a];
+            x_cand[(size_t)e * 3 + a] = x[(size_t)e * 3 + a] + de[a];
+            s2 += de[a] * de[a];
+          }
+        }
+      }
+      auto accum_m = [&](const double* jpq, const double* jlq, const double* rq, const double* dpq) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          double m = jlq[3 * k] * de[0] + jlq[3 * k + 1] * de[1] + jlq[3 * k + 2] * de[2];
+#pragma unroll
+          for (int a = 0; a < 6; a++) m += jpq[6 * k + a] * dpq[a];
+          mc += m * (rq[k] + 0.5 * m);
+        }
+      };
+      if (have && !(cst && fi < 0)) accum_m(jp, jl, r, dp);
+      for (uint32_t q = b0 + 32 + lane; q < b1; q += 32) {
+        const int f2 = A.f[q];
+        if (cst && f2 < 0) continue;
+        const double* ch = A.J + (size_t)A.pos[q] * kChunk;
+        double d2[6];
+#pragma unroll
+        for (int a = 0; a < 6; a++) d2[a] = f2 >= 0 ? dpose[6 * f2 + a] : 0.0;
+        accum_m(ch, ch + 12, ch + 18, d2);
+      }
+    }
+  }
+  mc = warp_sum(mc);
+  if (lane == 0) { s_mc[wib] = mc; s_s2[wib] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double m = s_mc[0] + s_mc[1] + s_mc[2] + s_mc[3], s = s_s2[0] + s_s2[1] + s_s2[2] + s_s2[3];
+    if (m != 0.0) atomicAdd(&scalars[SC_MODEL], m);
+    if (s != 0.0) atomicAdd(&scalars[SC_STEP2], s);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ bbox observations

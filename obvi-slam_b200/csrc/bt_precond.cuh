@@ -46,41 +46,42 @@ __global__ void bt_assemble_kernel(int nf, int nsb, const uint32_t* __restrict__
 }
 
 // In-place Gauss-Jordan inverse (no pivoting: the blocks are SPD) of 96 x 96 matrices in shared memory.
-// One CTA of 256 threads per matrix; thread (ty, tx) owns rows ty + 16 m and columns tx + 16 n.
-__global__ void __launch_bounds__(256) bt_invert_kernel(const int* __restrict__ idx, const double* __restrict__ D,
-                                                         double* __restrict__ Dinv, double* __restrict__ scalars) {
+// One CTA of 1024 threads per matrix; thread (ty, tx) owns rows ty + 32 m and columns tx + 32 n (m, n < 3), so a
+// warp touches 32 consecutive columns of one row: conflict-free shared-memory traffic, 2 barriers per pivot.
+constexpr int kInvThreads = 1024;
+__global__ void __launch_bounds__(kInvThreads) bt_invert_kernel(const int* __restrict__ idx, const double* __restrict__ D,
+                                                                 double* __restrict__ Dinv, double* __restrict__ scalars) {
   extern __shared__ double sm[];
   const int blk = idx[blockIdx.x];
   const double* src = D + (size_t)blk * kBB;
   double* dst = Dinv + (size_t)blk * kBB;
-  for (int t = threadIdx.x; t < kBB; t += 256) sm[t] = src[t];
+  for (int t = threadIdx.x; t < kBB; t += kInvThreads) sm[t] = src[t];
   __syncthreads();
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
   bool bad = false;
   for (int p = 0; p < kB; p++) {
     const double piv = sm[p * kB + p];
     if (!(piv > 0.0)) bad = true;
     const double d = 1.0 / piv;
-    double f[6], g[6];
+    double f[3], g[3], v[3][3];
 #pragma unroll
-    for (int m = 0; m < 6; m++) { f[m] = sm[(ty + 16 * m) * kB + p]; g[m] = sm[p * kB + tx + 16 * m] * d; }
+    for (int m = 0; m < 3; m++) { f[m] = sm[(ty + 32 * m) * kB + p]; g[m] = sm[p * kB + tx + 32 * m] * d; }
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+      for (int n = 0; n < 3; n++) {
+        const int i = ty + 32 * m, j = tx + 32 * n;
+        const double cur = sm[i * kB + j];
+        v[m][n] = (i == p) ? ((j == p) ? d : g[n]) : ((j == p) ? -f[m] * d : cur - f[m] * g[n]);
+      }
     __syncthreads();
 #pragma unroll
-    for (int m = 0; m < 6; m++) {
-      const int i = ty + 16 * m;
+    for (int m = 0; m < 3; m++)
 #pragma unroll
-      for (int n = 0; n < 6; n++) {
-        const int j = tx + 16 * n;
-        double v;
-        if (i == p) v = (j == p) ? d : g[n];
-        else if (j == p) v = -f[m] * d;
-        else v = sm[i * kB + j] - f[m] * g[n];
-        sm[i * kB + j] = v;
-      }
-    }
+      for (int n = 0; n < 3; n++) sm[(ty + 32 * m) * kB + tx + 32 * n] = v[m][n];
     __syncthreads();
   }
-  for (int t = threadIdx.x; t < kBB; t += 256) dst[t] = sm[t];
+  for (int t = threadIdx.x; t < kBB; t += kInvThreads) dst[t] = sm[t];
   if (bad && threadIdx.x == 0) atomicAdd(&scalars[SC_BT_FAIL], 1.0);
 }
 

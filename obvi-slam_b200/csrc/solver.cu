@@ -112,10 +112,17 @@ struct Solver {
   DBuf<uint32_t> pose_ptr, su_ptr, sf_ptr, sf_col, sf_src;
   DBuf<int32_t> f_of_pose, pose_of_f;
   DBuf<uint8_t> pose_skip, point_skip, obj_skip;
+  DBuf<uint2> jac_tile;  // per 256-observation tile: first pose/camera entry, entries staged by TMA
+  bool use_tma_jac = true;
   DBuf<BBoxRec> bbox;
   DBuf<UnaryRec> unary;
   DBuf<RelRec> rel;
   EListDev pts, objs;
+  // point batches (schur_points_batched_kernel)
+  DBuf<uint32_t> pb_first, pb_count, pb_nwin, pb_pair_ptr, pb_pair_info, pb_pair_blk, pb_fallback;
+  DBuf<int32_t> pb_win_f;
+  DBuf<uint64_t> pb_mask;
+  int n_batches = 0, n_fallback = 0;
   // state
   DBuf<double> poses[3], points[3], objects[3];  // cur, cand, best
   int cur = 0;
@@ -157,11 +164,14 @@ struct Solver {
     CUDA_OK(cudaMallocHost((void**)&h_scalars, SC_COUNT * sizeof(double)));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_blocks_per_sm, pcg_kernel, kPcgThreads, 0));
     if (pcg_blocks_per_sm < 1) throw std::runtime_error("pcg_kernel cannot be made resident");
+    CUDA_OK(cudaFuncSetAttribute(schur_points_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubPts * kPtStride * 8));
     CUDA_OK(cudaFuncSetAttribute(bt_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBB * 8));
     CUDA_OK(cudaFuncSetAttribute(bt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBB * 8));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_bt_blocks_per_sm, pcg_bt_kernel, kPcgThreads, 0));
     if (pcg_bt_blocks_per_sm < 1) throw std::runtime_error("pcg_bt_kernel cannot be made resident");
     if (const char* e = getenv("OBVI_PRECOND")) use_bt = std::string(e) != "jacobi";
+    if (const char* e = getenv("OBVI_JAC")) use_tma_jac = std::string(e) != "plain";
+    CUDA_OK(cudaFuncSetAttribute(reproj_jac_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes));
   }
 
   void upload_elist(EListDev& D, const Structure::EList& L, const std::vector<uint8_t>& cst, int NE, int maxs) {
@@ -186,8 +196,26 @@ struct Solver {
     pose_of_f.upload(pof, stream);
     su_ptr.upload(S.su_ptr, stream); sf_ptr.upload(S.sf_ptr, stream); sf_col.upload(S.sf_col, stream); sf_src.upload(S.sf_src, stream);
     bbox.upload(S.bbox, stream); unary.upload(S.unary, stream); rel.upload(S.rel, stream);
+    {
+      const int64_t ntiles = (S.n_obs + kJacThreads - 1) / kJacThreads;
+      std::vector<uint2> tp(ntiles);
+      for (int64_t t = 0; t < ntiles; t++) {
+        const ObsRec& a = S.obs[t * kJacThreads];
+        const ObsRec& b = S.obs[std::min<int64_t>(S.n_obs, (t + 1) * kJacThreads) - 1];
+        const uint32_t lo = a.pose * (uint32_t)S.C + (uint32_t)S.classes[a.cls].cam, hi = b.pose * (uint32_t)S.C + (uint32_t)S.classes[b.cls].cam;
+        tp[t] = make_uint2(lo, std::min<uint32_t>(hi - lo + 1, kJacMaxPc));
+      }
+      jac_tile.upload(tp, stream);
+    }
     upload_elist(pts, S.pts, S.point_const, 3, 16);
     upload_elist(objs, S.objs, S.obj_const, 7, 64);
+    {
+      const Structure::PointBatches& B = S.pbatch;
+      n_batches = (int)B.first.size(); n_fallback = (int)B.fallback.size();
+      pb_first.upload(B.first, stream); pb_count.upload(B.count, stream); pb_nwin.upload(B.nwin, stream); pb_win_f.upload(B.win_f, stream);
+      pb_mask.upload(B.mask, stream); pb_pair_ptr.upload(B.pair_ptr, stream); pb_pair_info.upload(B.pair_info, stream);
+      pb_pair_blk.upload(B.pair_blk, stream); pb_fallback.upload(B.fallback, stream);
+    }
     pts.has_prior = objs.has_prior = false;
     for (const UnaryRec& u : S.unary) { if (u.kind == 1) pts.has_prior = true; if (u.kind == 2) objs.has_prior = true; }
     if (pts.has_prior) { pts.prior_H.alloc((size_t)S.P * 9); pts.prior_g.alloc((size_t)S.P * 3); }
@@ -272,11 +300,11 @@ struct Solver {
     bt_assemble_kernel<<<nblk((int64_t)nsb * kSbPoses * 32, 256), 256, 0, stream>>>(S.nf, nsb, sf_ptr.p, sf_col.p, Sf.p, bt_D.p, bt_C.p);
     launches++;
     for (const BtLevel& L : bt_levels) {
-      if (L.inv_n) { bt_invert_kernel<<<L.inv_n, 256, kBB * 8, stream>>>(bt_idx.p + L.inv_off, bt_D.p, bt_Dinv.p, scalars.p); launches++; }
+      if (L.inv_n) { bt_invert_kernel<<<L.inv_n, kInvThreads, kBB * 8, stream>>>(bt_idx.p + L.inv_off, bt_D.p, bt_Dinv.p, scalars.p); launches++; }
       if (L.g_n) { bt_gemm_kernel<<<L.g_n, 256, 2 * kBB * 8, stream>>>(bt_tasks.p + L.g_off); launches++; }
       if (L.u_n) { bt_gemm_kernel<<<L.u_n, 256, 2 * kBB * 8, stream>>>(bt_tasks.p + L.u_off); launches++; }
     }
-    bt_invert_kernel<<<1, 256, kBB * 8, stream>>>(bt_idx.p + bt_last_inv_off, bt_D.p, bt_Dinv.p, scalars.p);
+    bt_invert_kernel<<<1, kInvThreads, kBB * 8, stream>>>(bt_idx.p + bt_last_inv_off, bt_D.p, bt_Dinv.p, scalars.p);
     launches++;
   }
   bool owns_object(int o) const {
@@ -327,7 +355,7 @@ struct Solver {
     a.ptr = D.ptr.p; a.pos = D.pos.p; a.f = D.f.p; a.slot = D.slot.p; a.pair_ptr = D.pair_ptr.p; a.nslots = D.nslots.p;
     a.pair_blk = D.pair_blk.p; a.cst = D.cst.p; a.J = Jp; a.escale = D.escale.p; a.einv = D.einv.p; a.eg = D.eg.p;
     a.prior_H = D.has_prior ? D.prior_H.p : nullptr; a.prior_g = D.has_prior ? D.prior_g.p : nullptr;
-    a.overflow = D.overflow.p; a.overflow_off = D.overflow_off.p; a.ne = D.ne;
+    a.overflow = D.overflow.p; a.overflow_off = D.overflow_off.p; a.ne = D.ne; a.elist = nullptr;
     return a;
   }
   void zero_scalars(int first, int count) { CUDA_OK(cudaMemsetAsync(scalars.p + first, 0, count * sizeof(double), stream)); }
@@ -337,7 +365,11 @@ struct Solver {
     const Structure& S = st;
     zero_scalars(SC_COST, 3);
     if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p); launches++; }
-    if (S.n_obs) { reproj_jac_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, points[cur].p, apply_loss, J.p, scalars.p); launches++; }
+    if (S.n_obs) {
+      if (use_tma_jac) reproj_jac_tma_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, kJacSmemBytes, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, points[cur].p, apply_loss, jac_tile.p, J.p, scalars.p);
+      else reproj_jac_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, points[cur].p, apply_loss, J.p, scalars.p);
+      launches++;
+    }
     if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, stream>>>(bbox.p, S.n_bbox, pcam.p, S.C, objects[cur].p, 0, apply_loss, Jb.p, scalars.p); launches++; }
     if (S.n_unary) { launch_unary(0, apply_loss, cur); }
     if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, stream>>>(rel.p, S.n_rel, 0, apply_loss, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
@@ -364,7 +396,17 @@ struct Solver {
     if (S.n_obs && S.nf) { pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag); launches++; }
     if (S.n_unary) launch_unary(1, 1, cur);
     if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, stream>>>(rel.p, S.n_rel, 1, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
-    if (S.P) { schur_eblock_kernel<3, 2, 32, 16, false><<<S.P, 32, 0, stream>>>(eargs(pts, J.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
+    if (n_batches) {
+      BatchArgs B; B.first = pb_first.p; B.count = pb_count.p; B.win_f = pb_win_f.p; B.nwin = pb_nwin.p; B.mask = pb_mask.p;
+      B.pair_ptr = pb_pair_ptr.p; B.pair_info = pb_pair_info.p; B.pair_blk = pb_pair_blk.p;
+      schur_points_batched_kernel<<<n_batches, kBatchThreads, kSubPts * kPtStride * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
+      launches++;
+    }
+    if (n_fallback) {
+      EArgs a = eargs(pts, J.p); a.elist = pb_fallback.p;
+      schur_eblock_kernel<3, 2, 32, 16, false><<<n_fallback, 32, 0, stream>>>(a, lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p);
+      launches++;
+    }
     if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, stream>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
     if (world > 1) allreduce_sum(redbuf.p, redbuf.n);
     if (S.nf) {
@@ -406,7 +448,7 @@ struct Solver {
     const int cand = 1 - cur;
     zero_scalars(SC_MODEL, 2);
     if (S.nf) { pose_step_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(S.nf, pose_of_f.p, pscale.p, y.p, poses[cur].p, poses[cand].p, dpose.p, rank == 0, scalars.p); launches++; }
-    if (S.P) { backsub_eblock_kernel<3, 2, 32><<<S.P, 32, 0, stream>>>(eargs(pts, J.p), dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p); launches++; }
+    if (S.P) { backsub_points_kernel<<<nblk(S.P, 4), 128, 0, stream>>>(eargs(pts, J.p), dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p); launches++; }
     if (S.O) { backsub_eblock_kernel<7, 4, 128><<<S.O, 128, 0, stream>>>(eargs(objs, Jb.p), dpose.p, objects[cur].p, objects[cand].p, objs.delta.p, scalars.p); launches++; }
     if (S.n_unary) launch_unary(2, 1, cur);
     if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, stream>>>(rel.p, S.n_rel, 2, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
