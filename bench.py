@@ -1,0 +1,233 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/s of the global bundle adjustment (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (through the C ABI)
+  python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the Ceres-semantics restatement (oracle/)
+
+A "step" is one Levenberg-Marquardt iteration (one linear solve + one candidate-cost evaluation, plus one
+Jacobian evaluation when the step is accepted) on the synthetic graph S(2000, 200000, 500, seed 0) with the full
+residual set (BASELINE.json configs[2]); W warm-up iterations, then EXACTLY K timed iterations from the same
+initial point with all tolerances disabled.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LM iterations/sec (global BA, 2k KF / 200k pts / 500 obj)"
+UNIT = "LM it/s"
+WORKLOAD = dict(workload="C3: 2000 keyframes / 200k points / 500 objects, full residual set (reproj + bbox + shape-prior + rel-pose)",
+                generator="obvi-slam_b200/synth.py make_config('C3', seed=0)",
+                solver="LM (Ceres semantics), radius 100 / max 1e4, non-monotonic, Huber 1.0/0.5/10/1.0, tolerances disabled for timing",
+                l2="working set per iteration (0.09 GB observations + 0.44 GB Jacobian chunks) exceeds the 126 MB L2: no flush needed")
+
+
+def solver_opts(iters):
+    return dict(max_num_iterations=iters, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
+                initial_trust_region_radius=100.0, max_trust_region_radius=1e4, use_nonmonotonic_steps=1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.t0, self.t1 = [], None, None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.05] or [r for _, r in self.rows]
+        sm, smax, reasons = [], [], set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peak_gbs():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_leg(g, iters, threads=0):
+    """The Ceres-semantics CPU restatement (oracle/ba_oracle.cpp) on the same graph; returns (it/s, info)."""
+    from oracle import oracle_lib
+    gc = g.copy()
+    r = oracle_lib.solve(gc, max_num_iterations=iters, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
+                         initial_radius=100.0, max_radius=1e4, use_nonmonotonic_steps=True, num_threads=threads)
+    loop = r["jacobian_time"] + r["linear_solver_time"] + r["residual_time"]
+    return r["lm_steps"] / loop, r, loop
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import obvi_b200 as ob
+    g = ob.synth.make_config(args.config, seed=args.seed)
+    if args.warmup > 0:
+        cpu_leg(g, min(args.warmup, 1))
+    t0 = time.time()
+    v, r, loop = cpu_leg(g, args.steps)
+    cores = r["num_threads"]
+    line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=r["lm_steps"], warmup=args.warmup,
+                ms_per_step=1e3 * loop / r["lm_steps"], higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                data="synthetic", config=WORKLOAD,
+                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{r['lm_steps']} LM iterations of the full C3 graph, Ceres-semantics restatement "
+                                         f"(dual-number autodiff, Schur, sparse Cholesky), OpenMP {cores} threads; "
+                                         f"jac {r['jacobian_time']:.2f}s lin {r['linear_solver_time']:.2f}s res {r['residual_time']:.2f}s"),
+                e2e=dict(value=r["lm_steps"] / (time.time() - t0), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="Ceres + SuiteSparse are not installable here (SURVEY.md 8c): this arm is the CPU restatement, not a Ceres binary")
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import obvi_b200 as ob
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    g = ob.synth.make_config(args.config, seed=args.seed)
+    p = ob.problem_from_graph(g, device=local_rank)
+    if world > 1:
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(ob.Problem.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        p.comm_init(bytes(uid.cpu().tolist()), rank, world)
+    x0 = (g.poses.copy(), g.points.copy(), g.objects.copy())
+
+    def reset():
+        g.poses[:], g.points[:], g.objects[:] = x0
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # warm-up: W untimed iterations (also builds + uploads the structure, like the first Solve on a ceres::Problem)
+    s_first = p.solve(**solver_opts(max(args.warmup, 1)))
+    reset()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.2)
+    barrier()
+    t0 = time.time()
+    s = p.solve(**solver_opts(args.steps))  # the call synchronises the device before returning
+    t1 = time.time()
+    barrier()
+    dev_t, wall_t = s.minimizer_device_time_in_seconds, t1 - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_t, wall_t], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_t, wall_t = t.tolist()
+    clocks = None
+    if sampler:
+        time.sleep(0.1)
+        sampler.stop()
+        clocks = sampler.summary(t0, t1)
+    steps = s.num_lm_steps
+    gpu_cost = s.iterations[-1]["cost"] if s.iterations else float("nan")
+    roof = cpu = parity = None
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        if world == 1:
+            reset()
+            sec, nbytes, nobs = p.profile_jacobian(reps=30)
+            roof = dict(bound="hbm", kernel="reproj_jac_tma_kernel (reprojection residual + Jacobian evaluation)",
+                        achieved=nbytes / sec / 1e9, peak=peak, unit="GB/s", frac=nbytes / sec / 1e9 / peak, traffic=None,
+                        peak_source=peak_src, algorithmic_bytes_per_launch=nbytes, observations=nobs, us_per_launch=sec * 1e6)
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", "r01_jacobian_traffic.json")))
+                roof["traffic"] = prof.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+            # CPU baseline on a bounded sample of the same workload + cost parity at the same iteration count
+            n_cpu = args.cpu_iters
+            v, r, loop = cpu_leg(g, n_cpu)
+            cpu = dict(value=v, unit=UNIT, cores=r["num_threads"], kind="port",
+                       sample=f"{r['lm_steps']} LM iterations of the full C3 graph (Ceres-semantics restatement, oracle/ba_oracle.cpp), "
+                              f"{loop:.1f} s of CPU work")
+            reset()
+            sp = p.solve(**solver_opts(n_cpu))
+            parity = dict(iterations=n_cpu, gpu_cost=sp.iterations[-1]["cost"], cpu_cost=r["iterations"][-1]["cost"],
+                          rel_diff=abs(sp.iterations[-1]["cost"] - r["iterations"][-1]["cost"]) / r["iterations"][-1]["cost"])
+        nparam = (g.poses.size + g.points.size + g.objects.size) * 8
+        line = dict(metric=METRIC, value=steps / dev_t, unit=UNIT, n_gpus=world, steps=steps, warmup=args.warmup,
+                    ms_per_step=1e3 * dev_t / steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                    data="synthetic", config=dict(WORKLOAD, parallelism=f"e-blocks sharded over {world} rank(s), reduced system all-reduced" if world > 1 else "single GPU",
+                                                  counts=g.counts(), seed=args.seed),
+                    clocks=clocks,
+                    e2e=dict(value=steps / wall_t, unit=UNIT, h2d_bytes_per_step=nparam / steps, d2h_bytes_per_step=nparam / steps,
+                             note="obvi_solve through the C ABI with host parameter blocks: gather + H2D, K iterations, D2H + scatter; "
+                                  "factor records are device-resident from the first solve, as in a persistent ceres::Problem",
+                             first_call_preprocess_s=s_first.preprocessor_time_in_seconds),
+                    gpu_launches=int(s.kernel_launches), roofline=roof, cpu_baseline=cpu, parity=parity,
+                    final_cost=gpu_cost, pcg_iterations=int(s.pcg_iterations_total),
+                    phases_ms_per_step=dict(jacobian=1e3 * s.jacobian_evaluation_time_in_seconds / steps,
+                                            linear=1e3 * s.linear_solver_time_in_seconds / steps,
+                                            residual=1e3 * s.residual_evaluation_time_in_seconds / steps))
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-iters", type=int, default=6, help="LM iterations of the bounded CPU-baseline sample")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,7 +49,9 @@ enum obvi_factor_type {
   OBVI_FACTOR_PARAM_PRIOR = 6
 };
 
-/* ---- problem lifetime (ceres::Problem problem; offline_problem_runner.h:113) -------------------- */
+/* ---- problem lifetime (ceres::Problem problem; offline_problem_runner.h:113) --------------------
+ * cuda_device = -1 creates a host-only handle: the problem can be assembled and inspected
+ * (obvi_debug_partition), every compute call on it fails with OBVI_ERR_CUDA. */
 int obvi_problem_create(int cuda_device, obvi_problem** out);
 void obvi_problem_destroy(obvi_problem* p);
 /* Last error text of this handle (or of creation when p == NULL). Never NULL. */
@@ -205,6 +207,17 @@ int obvi_topk_outliers(obvi_problem* p, int factor_type, double fraction, obvi_f
  *      produced by obvi_comm_unique_id on rank 0 and distributed by the caller. */
 int obvi_comm_unique_id(void* unique_id_128_bytes);
 int obvi_comm_init(obvi_problem* p, const void* unique_id_128_bytes, int rank, int world_size);
+
+/* ---- measurement hook (bench.py): times `reps` back-to-back launches of the reprojection Jacobian-evaluation
+ *      kernel at the current host values with CUDA events on the solver's stream (after 3 warm-up launches) and
+ *      reports the average seconds per launch and the algorithmic bytes one launch moves (SURVEY.md section 8d:
+ *      192 B per observation + the unique parameter blocks it reads). */
+int obvi_profile_jacobian(obvi_problem* p, int reps, double* seconds_per_launch, int64_t* algorithmic_bytes,
+                          int64_t* num_observations);
+
+/* Host-only inspection of how the structure build shards the graph for (rank, world_size); stats has 12 entries
+ * (see solver.cu).  Used by the CPU-side multi-process tests. */
+int obvi_debug_partition(obvi_problem* p, int rank, int world_size, int64_t* stats);
 
 /* Library / build information, e.g. "obvi_ba 0.1 sm_100a". */
 const char* obvi_version(void);

@@ -120,6 +120,8 @@ def lib():
         "obvi_evaluate": ([vp, C.c_int, _d, _d, i64, C.POINTER(i64)], C.c_int),
         "obvi_evaluate_factor_type": ([vp, C.c_int, C.c_int, _d, _d, _d], C.c_int),
         "obvi_topk_outliers": ([vp, C.c_int, dbl, u64p, i64, C.POINTER(i64)], C.c_int),
+        "obvi_profile_jacobian": ([vp, C.c_int, _d, C.POINTER(i64), C.POINTER(i64)], C.c_int),
+        "obvi_debug_partition": ([vp, C.c_int, C.c_int, C.POINTER(i64)], C.c_int),
         "obvi_comm_unique_id": ([vp], C.c_int),
         "obvi_comm_init": ([vp, vp, C.c_int, C.c_int], C.c_int),
     }
@@ -137,7 +139,8 @@ EXPORTED_SYMBOLS = [
     "obvi_factor_add_reproj", "obvi_factor_add_reproj_batch", "obvi_factor_add_bbox", "obvi_factor_add_bbox_batch",
     "obvi_factor_add_shape_prior", "obvi_factor_add_ltm_prior", "obvi_factor_add_rel_pose", "obvi_factor_add_param_prior",
     "obvi_factor_remove", "obvi_num_factors", "obvi_residual_blocks", "obvi_solver_options_init", "obvi_solve",
-    "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_comm_unique_id", "obvi_comm_init",
+    "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_profile_jacobian", "obvi_debug_partition", "obvi_comm_unique_id",
+    "obvi_comm_init",
 ]
 
 
@@ -325,6 +328,20 @@ class Problem:
         ids = np.zeros(max(cap, 1), np.uint64)
         self._ck(self._lib.obvi_topk_outliers(self._h, ftype, float(fraction), ids.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n)))
         return ids[:n.value]
+
+    def profile_jacobian(self, reps=20):
+        """(seconds per launch, algorithmic bytes per launch, observations) of the Jacobian-evaluation kernel."""
+        sec = C.c_double(0); nb = C.c_int64(0); no = C.c_int64(0)
+        self._ck(self._lib.obvi_profile_jacobian(self._h, int(reps), C.byref(sec), C.byref(nb), C.byref(no)))
+        return sec.value, nb.value, no.value
+
+    def debug_partition(self, rank, world):
+        """Host-only: how the structure build shards the graph for (rank, world); see obvi_debug_partition."""
+        st = (C.c_int64 * 12)()
+        self._ck(self._lib.obvi_debug_partition(self._h, rank, world, st))
+        keys = ["n_obs", "n_bbox", "n_unary", "n_rel", "nf", "n_upper", "points_here", "objects_here", "point_batches",
+                "structure_checksum", "num_parameters_reduced", "num_residual_blocks_reduced"]
+        return dict(zip(keys, list(st)))
 
     # ---- multi-GPU
     @staticmethod

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kJacThreads) reproj_jac_kernel(const ObsRec* _
     const double s = r[0] * r[0] + r[1] * r[1];
     double sc = 1.0, c = 0.5 * s;
     if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
-    if (id.w == 3u) fixed = c; else cost = c;
+    if ((id.w & 3u) == 3u) fixed = c; else cost = c;
     double2* out = reinterpret_cast<double2*>(J + (size_t)i * kChunk);
 #pragma unroll
     for (int a = 0; a < 6; a++) out[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
@@ -164,45 +164,49 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 //   * each thread writes its 160-byte chunk into a shared-memory image of the output tile, and one elected thread
 //     stores the whole contiguous 40 KB tile with a single TMA bulk store: full-line HBM writes, no LSU store traffic.
 constexpr int kJacMaxPc = 6;                       // staged pose/camera entries per tile
+constexpr int kJacMaxCls = 16;                     // calibration classes staged in shared memory
 constexpr int kJacTileBytes = kJacThreads * kChunk * 8;
 constexpr int kJacSmemBytes = kJacTileBytes + kJacMaxPc * (int)sizeof(PoseCam) + 16;
 
-__global__ void __launch_bounds__(kJacThreads, 3) reproj_jac_tma_kernel(const ObsRec* __restrict__ obs, int64_t n,
+__global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const ObsRec* __restrict__ obs, int64_t n,
                                                                          const PoseCam* __restrict__ pcam, int C,
-                                                                         const CalibClass* __restrict__ cls,
+                                                                         const CalibClass* __restrict__ cls, int ncls,
                                                                          const double* __restrict__ points, int apply_loss,
                                                                          const uint2* __restrict__ tile_pc,
                                                                          double* __restrict__ J, double* __restrict__ scalars) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[33];
+  __shared__ CalibClass cls_s[kJacMaxCls];
   double* out_tile = reinterpret_cast<double*>(smem);
   PoseCam* pc_s = reinterpret_cast<PoseCam*>(smem + kJacTileBytes);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kJacTileBytes + kJacMaxPc * sizeof(PoseCam));
   const int64_t i0 = (int64_t)blockIdx.x * kJacThreads;
   const int nt = (int)min((int64_t)kJacThreads, n - i0);
   const uint2 tp = tile_pc[blockIdx.x];  // first pose/camera entry of the tile, number of entries staged
+  const int64_t i = i0 + threadIdx.x;
+  const bool active = (int)threadIdx.x < nt;
+  double2 uv = make_double2(0.0, 0.0);
+  uint4 id = make_uint4(0, 0, 0, 0);
+  if (active) {  // issue the record loads first: they head the longest dependency chain (record -> point)
+    uv = reinterpret_cast<const double2*>(obs)[2 * i];
+    id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];
+  }
   if (threadIdx.x == 0) mbar_init(bar, 1);
+  if ((int)threadIdx.x < ncls * 4) reinterpret_cast<double*>(cls_s)[threadIdx.x] = reinterpret_cast<const double*>(cls)[threadIdx.x];
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, tp.y * (uint32_t)sizeof(PoseCam));
     tma_load_1d(pc_s, pcam + tp.x, tp.y * (uint32_t)sizeof(PoseCam), bar);
   }
-  const int64_t i = i0 + threadIdx.x;
   double cost = 0.0, fixed = 0.0;
-  double2 uv = make_double2(0.0, 0.0);
-  uint4 id = make_uint4(0, 0, 0, 0);
-  CalibClass cc;
   double X[3] = {0.0, 0.0, 0.0};
-  const bool active = (int)threadIdx.x < nt;
   if (active) {
-    uv = reinterpret_cast<const double2*>(obs)[2 * i];
-    id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];
-    cc = cls[id.z];
     X[0] = points[3 * (size_t)id.y]; X[1] = points[3 * (size_t)id.y + 1]; X[2] = points[3 * (size_t)id.y + 2];
   }
+  const CalibClass cc = cls_s[id.z];
   mbar_wait(bar, 0);
   if (active) {
-    const uint32_t pci = id.x * (uint32_t)C + (uint32_t)cc.cam;
+    const uint32_t pci = id.x * (uint32_t)C + ((id.w >> 8) & 0xffu);
     const uint32_t rel = pci - tp.x;
     const PoseCam& pc = rel < tp.y ? pc_s[rel] : pcam[pci];
     double r[2], Jp[12], Jl[6];
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(kJacThreads, 3) reproj_jac_tma_kernel(const Ob
     const double s = r[0] * r[0] + r[1] * r[1];
     double sc = 1.0, c = 0.5 * s;
     if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
-    if (id.w == 3u) fixed = c; else cost = c;
+    if ((id.w & 3u) == 3u) fixed = c; else cost = c;
     double2* out = reinterpret_cast<double2*>(out_tile + (size_t)threadIdx.x * kChunk);
 #pragma unroll
     for (int a = 0; a < 6; a++) out[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(kJacThreads) reproj_cost_kernel(const ObsRec* 
     const double s = r[0] * r[0] + r[1] * r[1];
     double sc, c = 0.5 * s;
     if (cc.huber > 0.0) c = huber(cc.huber, s, &sc);
-    if (id.w == 3u) fixed = c; else cost = c;
+    if ((id.w & 3u) == 3u) fixed = c; else cost = c;
   }
   cost = block_sum_all<kJacThreads>(cost, red);
   fixed = block_sum_all<kJacThreads>(fixed, red);

@@ -46,7 +46,7 @@ struct ObsRec {       // 32 B, one per reprojection observation, pose-major orde
   uint32_t pose;      // pose index
   uint32_t point;     // internal point index
   uint32_t cls;       // calibration class (camera, sigma, huber)
-  uint32_t flags;     // bit0: pose constant, bit1: point constant
+  uint32_t flags;     // bit0: pose constant, bit1: point constant, bits 8-15: camera index
 };
 struct CalibClass { double mx, my, huber; int32_t cam; int32_t pad; };  // 32 B
 struct BBoxRec {      // one per bbox observation, object-major order
@@ -253,7 +253,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
       ObsRec& o = S.obs[cur[k]];
       o.ur = (f.px - c.intr[2]) / c.intr[0]; o.vr = (f.py - c.intr[3]) / c.intr[1];
       o.pose = k; o.point = pt; o.cls = last_cls;
-      o.flags = (S.f_of_pose[k] < 0 ? 1u : 0u) | (S.point_const[pt] ? 2u : 0u);
+      o.flags = (S.f_of_pose[k] < 0 ? 1u : 0u) | (S.point_const[pt] ? 2u : 0u) | ((uint32_t)f.cam << 8);
       S.obs_user[cur[k]] = (uint32_t)n;
       cur[k]++;
     }

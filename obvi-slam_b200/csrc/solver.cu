@@ -322,10 +322,13 @@ struct Solver {
     for (int k = 0; k < S.K; k++) std::memcpy(&h_poses[6 * (size_t)k], pb.blocks[S.pose_block[k]].host, 48);
     for (int i = 0; i < S.P; i++) std::memcpy(&h_points[3 * (size_t)i], pb.blocks[S.point_block[i]].host, 24);
     for (int i = 0; i < S.O; i++) std::memcpy(&h_objects[7 * (size_t)i], pb.blocks[S.obj_block[i]].host, 56);
-    for (int b = 0; b < 3; b++) {
-      if (S.K) CUDA_OK(cudaMemcpyAsync(poses[b].p, h_poses.data(), h_poses.size() * 8, cudaMemcpyHostToDevice, stream));
-      if (S.P) CUDA_OK(cudaMemcpyAsync(points[b].p, h_points.data(), h_points.size() * 8, cudaMemcpyHostToDevice, stream));
-      if (S.O) CUDA_OK(cudaMemcpyAsync(objects[b].p, h_objects.data(), h_objects.size() * 8, cudaMemcpyHostToDevice, stream));
+    if (S.K) CUDA_OK(cudaMemcpyAsync(poses[0].p, h_poses.data(), h_poses.size() * 8, cudaMemcpyHostToDevice, stream));
+    if (S.P) CUDA_OK(cudaMemcpyAsync(points[0].p, h_points.data(), h_points.size() * 8, cudaMemcpyHostToDevice, stream));
+    if (S.O) CUDA_OK(cudaMemcpyAsync(objects[0].p, h_objects.data(), h_objects.size() * 8, cudaMemcpyHostToDevice, stream));
+    for (int b = 1; b < 3; b++) {  // candidate / best buffers start as copies (constant blocks are never rewritten)
+      if (S.K) CUDA_OK(cudaMemcpyAsync(poses[b].p, poses[0].p, h_poses.size() * 8, cudaMemcpyDeviceToDevice, stream));
+      if (S.P) CUDA_OK(cudaMemcpyAsync(points[b].p, points[0].p, h_points.size() * 8, cudaMemcpyDeviceToDevice, stream));
+      if (S.O) CUDA_OK(cudaMemcpyAsync(objects[b].p, objects[0].p, h_objects.size() * 8, cudaMemcpyDeviceToDevice, stream));
     }
     cur = 0;
   }
@@ -366,7 +369,7 @@ struct Solver {
     zero_scalars(SC_COST, 3);
     if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p); launches++; }
     if (S.n_obs) {
-      if (use_tma_jac) reproj_jac_tma_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, kJacSmemBytes, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, points[cur].p, apply_loss, jac_tile.p, J.p, scalars.p);
+      if (use_tma_jac && (int)S.classes.size() <= kJacMaxCls && S.C <= 256) reproj_jac_tma_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, kJacSmemBytes, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, (int)S.classes.size(), points[cur].p, apply_loss, jac_tile.p, J.p, scalars.p);
       else reproj_jac_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, points[cur].p, apply_loss, J.p, scalars.p);
       launches++;
     }
@@ -489,6 +492,7 @@ struct Solver {
   }
 
   void ensure_structure(double* preprocess_seconds) {
+    if (!stream) throw std::runtime_error("host-only problem handle (cuda_device = -1): no CUDA device attached, and this backend has no CPU fallback");
     const auto t0 = std::chrono::steady_clock::now();
     if (pb.dirty || !uploaded) {
       std::string err;
@@ -702,6 +706,12 @@ int obvi_problem_create(int device, obvi_problem** out) {
   *out = nullptr;
   obvi_problem* p = nullptr;
   try {
+    if (device == -1) {  // host-only handle: problem assembly / structure inspection, every compute call fails
+      p = new obvi_problem();
+      p->s.pb.device = -1;
+      *out = p;
+      return OBVI_OK;
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) { g_create_error = std::string("no usable CUDA device: ") + cudaGetErrorString(e) + " (this backend has no CPU fallback)"; return OBVI_ERR_CUDA; }
@@ -717,7 +727,7 @@ int obvi_problem_create(int device, obvi_problem** out) {
     return OBVI_ERR_CUDA;
   }
 }
-void obvi_problem_destroy(obvi_problem* p) { if (p) { cudaSetDevice(p->s.pb.device); delete p; } }
+void obvi_problem_destroy(obvi_problem* p) { if (p) { if (p->s.pb.device >= 0) cudaSetDevice(p->s.pb.device); delete p; } }
 const char* obvi_last_error(const obvi_problem* p) { return p ? p->s.pb.error.c_str() : g_create_error.c_str(); }
 
 int obvi_param_add(obvi_problem* p, double* host, int size) {
@@ -927,6 +937,7 @@ void obvi_solver_options_init(obvi_solver_options* o) {
 int obvi_solve(obvi_problem* p, const obvi_solver_options* o, obvi_summary* sum, obvi_iteration_summary* its, int32_t cap) {
   if (!p || !o || !sum) return OBVI_ERR_INVALID_ARGUMENT;
   API_BEGIN
+  if (p->s.pb.device < 0) return fail(p, OBVI_ERR_CUDA, "host-only problem handle: no CUDA device attached (no CPU fallback exists)");
   CUDA_OK(cudaSetDevice(p->s.pb.device));
   return p->s.solve(*o, sum, its, cap);
   API_END(p)
@@ -944,6 +955,7 @@ int obvi_evaluate_factor_type(obvi_problem* p, int type, int apply_loss, double*
   if (!p) return OBVI_ERR_INVALID_ARGUMENT;
   API_BEGIN
   Solver& s = p->s;
+  if (s.pb.device < 0) return fail(p, OBVI_ERR_CUDA, "host-only problem handle: no CUDA device attached (no CPU fallback exists)");
   CUDA_OK(cudaSetDevice(s.pb.device));
   if (s.world > 1) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "obvi_evaluate_factor_type is single-rank only");
   evaluate_all(s, apply_loss);
@@ -1017,6 +1029,7 @@ int obvi_evaluate(obvi_problem* p, int apply_loss, double* cost, double* residua
   if (!p) return OBVI_ERR_INVALID_ARGUMENT;
   API_BEGIN
   Solver& s = p->s;
+  if (s.pb.device < 0) return fail(p, OBVI_ERR_CUDA, "host-only problem handle: no CUDA device attached (no CPU fallback exists)");
   CUDA_OK(cudaSetDevice(s.pb.device));
   evaluate_all(s, apply_loss);
   if (cost) *cost = s.h_scalars[SC_COST] + s.h_scalars[SC_FIXED];
@@ -1062,6 +1075,7 @@ int obvi_topk_outliers(obvi_problem* p, int type, double fraction, obvi_factor_i
   if (!p || !n) return OBVI_ERR_INVALID_ARGUMENT;
   API_BEGIN
   Solver& s = p->s;
+  if (s.pb.device < 0) return fail(p, OBVI_ERR_CUDA, "host-only problem handle: no CUDA device attached (no CPU fallback exists)");
   CUDA_OK(cudaSetDevice(s.pb.device));
   int64_t nres = 0;
   int rc = obvi_evaluate(p, 0, nullptr, nullptr, 0, &nres);
@@ -1089,6 +1103,64 @@ int obvi_topk_outliers(obvi_problem* p, int type, double fraction, obvi_factor_i
   API_END(p)
 }
 
+int obvi_profile_jacobian(obvi_problem* p, int reps, double* sec, int64_t* bytes, int64_t* nobs) {
+  if (!p || reps < 1 || !sec) return OBVI_ERR_INVALID_ARGUMENT;
+  API_BEGIN
+  Solver& s = p->s;
+  if (s.pb.device < 0) return fail(p, OBVI_ERR_CUDA, "host-only problem handle: no CUDA device attached (no CPU fallback exists)");
+  CUDA_OK(cudaSetDevice(s.pb.device));
+  s.ensure_structure(nullptr);
+  s.gather_params();
+  const Structure& S = s.st;
+  if (!S.n_obs) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "no reprojection observations");
+  pose_cam_kernel<<<Solver::nblk((int64_t)S.K * S.C, 128), 128, 0, s.stream>>>(s.poses[0].p, S.K, s.cams.p, S.C, 1, s.pcam.p);
+  auto launch = [&]() {
+    if (s.use_tma_jac && (int)S.classes.size() <= kJacMaxCls && S.C <= 256) reproj_jac_tma_kernel<<<Solver::nblk(S.n_obs, kJacThreads), kJacThreads, kJacSmemBytes, s.stream>>>(s.obs.p, S.n_obs, s.pcam.p, S.C, s.classes.p, (int)S.classes.size(), s.points[0].p, 1, s.jac_tile.p, s.J.p, s.scalars.p);
+    else reproj_jac_kernel<<<Solver::nblk(S.n_obs, kJacThreads), kJacThreads, 0, s.stream>>>(s.obs.p, S.n_obs, s.pcam.p, S.C, s.classes.p, s.points[0].p, 1, s.J.p, s.scalars.p);
+  };
+  for (int i = 0; i < 3; i++) launch();
+  CUDA_OK(cudaEventRecord(s.ev[0], s.stream));
+  for (int i = 0; i < reps; i++) launch();
+  CUDA_OK(cudaEventRecord(s.ev[1], s.stream));
+  CUDA_OK(cudaStreamSynchronize(s.stream));
+  CUDA_OK(cudaGetLastError());
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]));
+  *sec = ms * 1e-3 / reps;
+  // unique parameter blocks read by one launch
+  int64_t npts = 0;
+  for (int i = 0; i < S.P; i++) npts += S.pts.ptr[i + 1] > S.pts.ptr[i];
+  if (bytes) *bytes = S.n_obs * 192 + (int64_t)S.K * 48 + npts * 24;
+  if (nobs) *nobs = S.n_obs;
+  return OBVI_OK;
+  API_END(p)
+}
+
+// Host-only inspection of the structure build for a given (rank, world): how the graph is sharded.
+// stats: [0] observations on this rank, [1] bbox observations, [2] unary factors, [3] rel-pose factors,
+// [4] variable poses, [5] upper blocks of the reduced matrix, [6] points with observations on this rank,
+// [7] objects with observations on this rank, [8] point batches, [9] sum of sf_col (structure checksum),
+// [10] reduced parameters, [11] reduced residual blocks.
+int obvi_debug_partition(obvi_problem* p, int rank, int world, int64_t* stats) {
+  if (!p || !stats || world < 1 || rank < 0 || rank >= world) return OBVI_ERR_INVALID_ARGUMENT;
+  try {
+    Structure S;
+    std::string err;
+    if (!build_structure(p->s.pb, S, rank, world, err)) return fail(p, OBVI_ERR_INVALID_ARGUMENT, err.c_str());
+    int64_t np = 0, no = 0, ck = 0;
+    for (int i = 0; i < S.P; i++) np += S.pts.ptr[i + 1] > S.pts.ptr[i];
+    for (int i = 0; i < S.O; i++) no += S.objs.ptr[i + 1] > S.objs.ptr[i];
+    for (uint32_t c : S.sf_col) ck += c;
+    const int64_t v[12] = {S.n_obs, S.n_bbox, S.n_unary, S.n_rel, S.nf, S.n_upper, np, no, (int64_t)S.pbatch.first.size(), ck,
+                           S.num_params_reduced, S.num_residual_blocks_reduced};
+    std::memcpy(stats, v, sizeof(v));
+    return OBVI_OK;
+  } catch (const std::exception& e) {
+    p->s.pb.error = e.what();
+    return OBVI_ERR_INVALID_ARGUMENT;
+  }
+}
+
 int obvi_comm_unique_id(void* out) {
   if (!out) return OBVI_ERR_INVALID_ARGUMENT;
   std::string err;
@@ -1103,6 +1175,7 @@ int obvi_comm_init(obvi_problem* p, const void* uid, int rank, int world) {
   if (!p || !uid || world < 1 || rank < 0 || rank >= world) return OBVI_ERR_INVALID_ARGUMENT;
   API_BEGIN
   Solver& s = p->s;
+  if (s.pb.device < 0) return fail(p, OBVI_ERR_CUDA, "host-only problem handle: no CUDA device attached (no CPU fallback exists)");
   CUDA_OK(cudaSetDevice(s.pb.device));
   std::string err;
   if (!g_nccl.load(err)) return fail(p, OBVI_ERR_COMM, err.c_str());

@@ -1,0 +1,78 @@
+"""CPU: the C-ABI library loads, exports every symbol include/obvi_ba.h declares, and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "obvi_ba.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(obvi_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(ob):
+    lib = ob.lib()
+    names = declared_symbols()
+    assert len(names) >= 28
+    for n in names:
+        assert hasattr(lib, n), f"libobvi_ba.so does not export {n}"
+    assert set(ob.EXPORTED_SYMBOLS) <= set(names)
+    assert b"sm_100a" in lib.obvi_version()
+
+
+def test_no_cpu_fallback(ob):
+    """Without a CUDA device the product refuses to compute (it never routes through the oracle)."""
+    import shutil
+    if shutil.which("nvidia-smi") and os.system("nvidia-smi -L > /dev/null 2>&1") == 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(ob.ObviError):
+        ob.Problem(0)
+    p = ob.Problem(-1)  # host-only handle: assembly works, compute fails loudly
+    poses = np.zeros((2, 6)); pts = np.ones((1, 3))
+    p.add_parameter_array(poses); p.add_parameter_array(pts)
+    cam = p.add_camera((400, 400, 320, 240), np.eye(3), np.zeros(3))
+    p.add_reprojection(poses[0], pts[0], cam, (300.0, 200.0), 1.5, 1.0)
+    assert p.num_residual_blocks() == 1
+    with pytest.raises(ob.ObviError, match="no CUDA device|no CPU fallback"):
+        p.solve(max_num_iterations=1)
+    with pytest.raises(ob.ObviError):
+        p.evaluate()
+
+
+def test_problem_bookkeeping_host_only(ob):
+    """Add / remove / constant bookkeeping mirrors ceres::Problem (no compute involved)."""
+    p = ob.Problem(-1)
+    poses = np.zeros((3, 6)); pts = np.ones((4, 3)); objs = np.ones((1, 7))
+    for a in (poses, pts, objs):
+        p.add_parameter_array(a)
+    cam = p.add_camera((400, 400, 320, 240), np.eye(3), np.zeros(3))
+    assert p.add_camera((400, 400, 320, 240), np.eye(3), np.zeros(3)) == cam  # deduplicated
+    ids = [p.add_reprojection(poses[i % 3], pts[i % 4], cam, (10.0 * i, 5.0), 1.5, 1.0) for i in range(6)]
+    b = p.add_bounding_box(objs[0], poses[1], cam, (1, 2, 3, 4), np.eye(4) * 900, 1000.0, 0.5)
+    s = p.add_shape_prior(objs[0], (1, 1, 1), np.eye(3), 10.0)
+    r = p.add_relative_pose(poses[0], poses[1], np.zeros(3), np.eye(3), np.eye(6), 1.0)
+    pr = p.add_parameter_prior(objs[0], 3, 0.1, 0.5)
+    assert p.num_residual_blocks() == 10
+    got, types, sizes = p.residual_blocks()
+    assert list(got) == ids + [b, s, r, pr] and list(sizes) == [2] * 6 + [4, 3, 6, 1]
+    assert list(types) == [0] * 6 + [2, 3, 5, 6]
+    p.remove_residual_block(ids[2])
+    with pytest.raises(ob.ObviError):
+        p.remove_residual_block(ids[2])
+    assert p.num_residual_blocks() == 9 and ids[2] not in p.residual_blocks()[0]
+    assert not p.is_parameter_block_constant(poses[0])
+    p.set_parameter_block_constant(poses[0])
+    assert p.is_parameter_block_constant(poses[0])
+    p.set_parameter_block_variable(poses[0])
+    assert not p.is_parameter_block_constant(poses[0])
+    p.remove_parameter_block(pts[0])      # removes the residual blocks that use it, like Ceres
+    assert p.num_residual_blocks() == 7
+    with pytest.raises(ob.ObviError):
+        p.add_relative_pose(poses[0], poses[1], np.zeros(3), np.eye(3), np.full((6, 6), np.nan), 1.0)
+    st = p.debug_partition(0, 1)
+    assert st["nf"] == 3 and st["n_obs"] == 3 and st["n_bbox"] == 1 and st["n_rel"] == 1 and st["n_unary"] == 2
