@@ -557,13 +557,13 @@ struct BatchArgs {
   const uint32_t* first; const uint32_t* count; const int32_t* win_f; const uint32_t* nwin; const uint64_t* mask;
   const uint32_t* pair_ptr; const uint32_t* pair_info; const uint32_t* pair_blk;
 };
-constexpr int kBatchThreads = 512;
+constexpr int kBatchThreads = 256;
 constexpr int kSubPts = kBatchThreads / 32;   // 16 points per pass
 constexpr int kStageSlots = 16;
 constexpr int kSlotStride = 37;               // 36 doubles (Z 6x3, W 6x3) + 1 pad: conflict-free across slots
 constexpr int kPtStride = kStageSlots * kSlotStride;
 
-__global__ void __launch_bounds__(kBatchThreads) schur_points_batched_kernel(EArgs A, BatchArgs B, LMParams lm,
+__global__ void __launch_bounds__(kBatchThreads, 2) schur_points_batched_kernel(EArgs A, BatchArgs B, LMParams lm,
                                                                               double* __restrict__ S_upper,
                                                                               double* __restrict__ b_schur,
                                                                               double* __restrict__ scalars) {
@@ -588,7 +588,9 @@ __global__ void __launch_bounds__(kBatchThreads) schur_points_batched_kernel(EAr
   double bacc = 0.0, gmax = 0.0;
 
   for (uint32_t s0 = 0; s0 < np; s0 += kSubPts) {
-    // ---------------- phase 1: warp `wib` handles point p_first + s0 + wib
+    // ---------------- phase 1: warp `wib` handles point p_first + s0 + wib, lane = observation (<= 32 per point).
+    // All global loads are issued up front (index entries, then the whole 160-byte chunk of the lane's observation);
+    // observations of the same keyframe (stereo) are merged with warp shuffles, so there is no dependent reload.
     {
       const uint32_t pi = s0 + wib;
       unsigned long long mk = 0ull;
@@ -597,17 +599,34 @@ __global__ void __launch_bounds__(kBatchThreads) schur_points_batched_kernel(EAr
         const int e = (int)(p_first + pi);
         const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
         if (!A.cst[e] && b1 > b0) {
-          double H[6] = {0, 0, 0, 0, 0, 0};
-          for (uint32_t q = b0 + lane; q < b1; q += 32) {
+          const uint32_t q = b0 + lane;
+          const bool have = q < b1;
+          uint16_t sl = 0xFFFF;
+          double jp[12], jl[6], r0 = 0.0, r1 = 0.0;
+#pragma unroll
+          for (int a = 0; a < 12; a++) jp[a] = 0.0;
+#pragma unroll
+          for (int a = 0; a < 6; a++) jl[a] = 0.0;
+          if (have) {
+            sl = A.slot[q];
             const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)A.pos[q] * kChunk);
-            const double2 l0 = ch[6], l1 = ch[7], l2 = ch[8], rr = ch[9];  // Jl rows (3+3), r
-            const double je0[3] = {l0.x, l0.y, l1.x}, je1[3] = {l1.y, l2.x, l2.y};
+#pragma unroll
+            for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
+#pragma unroll
+            for (int a = 0; a < 3; a++) { const double2 v = ch[6 + a]; jl[2 * a] = v.x; jl[2 * a + 1] = v.y; }
+            const double2 rv = ch[9]; r0 = rv.x; r1 = rv.y;
+          }
+          const unsigned long long my_mask = B.mask[e];
+          double s[3];
+          if (!lm.compute_scale) { s[0] = A.escale[(size_t)e * 3]; s[1] = A.escale[(size_t)e * 3 + 1]; s[2] = A.escale[(size_t)e * 3 + 2]; }
+          double H[6];
+          {
             int t = 0;
 #pragma unroll
             for (int a = 0; a < 3; a++) {
-              g[a] += je0[a] * rr.x + je1[a] * rr.y;
+              g[a] = jl[a] * r0 + jl[3 + a] * r1;
 #pragma unroll
-              for (int b = a; b < 3; b++) H[t++] += je0[a] * je0[b] + je1[a] * je1[b];
+              for (int b = a; b < 3; b++) H[t++] = jl[a] * jl[b] + jl[3 + a] * jl[3 + b];
             }
           }
 #pragma unroll
@@ -621,10 +640,9 @@ __global__ void __launch_bounds__(kBatchThreads) schur_points_batched_kernel(EAr
             for (int a = 0; a < 3; a++) g[a] += A.prior_g[(size_t)e * 3 + a];
           }
           const double hd[3] = {H[0], H[3], H[5]};
-          double s[3];
 #pragma unroll
           for (int a = 0; a < 3; a++) {
-            s[a] = lm.compute_scale ? 1.0 / (1.0 + sqrt(hd[a])) : A.escale[(size_t)e * 3 + a];
+            if (lm.compute_scale) s[a] = 1.0 / (1.0 + sqrt(hd[a]));
             gmax = fmax(gmax, fabs(g[a]));
           }
           double Hs[9], hinv[9];
@@ -633,6 +651,25 @@ __global__ void __launch_bounds__(kBatchThreads) schur_points_batched_kernel(EAr
 #pragma unroll
           for (int a = 0; a < 3; a++) Hs[4 * a] += fmin(fmax(Hs[4 * a], lm.min_diag), lm.max_diag) / lm.radius;
           const bool ok = spd_inverse<3>(Hs, hinv);
+          // W = Jp^T Jl of the lane's observation, then merge runs of equal slot (same keyframe, several cameras)
+          double Wm[18];
+#pragma unroll
+          for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) Wm[3 * a + c] = jp[a] * jl[c] + jp[6 + a] * jl[3 + c];
+          const uint32_t sl_prev = __shfl_up_sync(0xffffffffu, (uint32_t)sl, 1);
+          const bool head = have && sl != 0xFFFF && (lane == 0 || sl_prev != (uint32_t)sl);
+          // run length is bounded by the number of cameras; loop until no lane has a longer run
+          for (int d = 1; d < 32; d++) {
+            const uint32_t sl_d = __shfl_down_sync(0xffffffffu, (uint32_t)sl, d);
+            const bool take = head && (lane + d < 32) && sl_d == (uint32_t)sl;
+            if (!__any_sync(0xffffffffu, take)) break;
+#pragma unroll
+            for (int a = 0; a < 18; a++) {
+              const double v = __shfl_down_sync(0xffffffffu, Wm[a], d);
+              if (take) Wm[a] += v;
+            }
+          }
           if (!ok) {
             if (lane == 0) atomicAdd(&scalars[SC_FAIL], 1.0);
           } else {
@@ -647,28 +684,9 @@ __global__ void __launch_bounds__(kBatchThreads) schur_points_batched_kernel(EAr
 #pragma unroll
               for (int a = 0; a < 3; a++) A.eg[(size_t)e * 3 + a] = g[a];
             }
-            mk = B.mask[e];
-            double* st_pt = stage + (size_t)wib * kPtStride;
-            for (uint32_t q = b0 + lane; q < b1; q += 32) {
-              const uint16_t sl = A.slot[q];
-              if (sl == 0xFFFF) continue;
-              if (q > b0 && A.slot[q - 1] == sl) continue;  // not the head of its run
-              double Wm[18];
-#pragma unroll
-              for (int a = 0; a < 18; a++) Wm[a] = 0.0;
-              for (uint32_t q2 = q; q2 < b1 && A.slot[q2] == sl; q2++) {
-                const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)A.pos[q2] * kChunk);
-                double jp[12];
-#pragma unroll
-                for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
-                const double2 l0 = ch[6], l1 = ch[7], l2 = ch[8];
-                const double je0[3] = {l0.x, l0.y, l1.x}, je1[3] = {l1.y, l2.x, l2.y};
-#pragma unroll
-                for (int a = 0; a < 6; a++)
-#pragma unroll
-                  for (int c = 0; c < 3; c++) Wm[3 * a + c] += jp[a] * je0[c] + jp[6 + a] * je1[c];
-              }
-              double* st = st_pt + (size_t)sl * kSlotStride;
+            mk = my_mask;
+            if (head) {
+              double* st = stage + (size_t)wib * kPtStride + (size_t)sl * kSlotStride;
 #pragma unroll
               for (int a = 0; a < 6; a++)
 #pragma unroll

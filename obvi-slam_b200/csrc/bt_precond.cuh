@@ -45,43 +45,69 @@ __global__ void bt_assemble_kernel(int nf, int nsb, const uint32_t* __restrict__
   }
 }
 
-// In-place Gauss-Jordan inverse (no pivoting: the blocks are SPD) of 96 x 96 matrices in shared memory.
-// One CTA of 1024 threads per matrix; thread (ty, tx) owns rows ty + 32 m and columns tx + 32 n (m, n < 3), so a
-// warp touches 32 consecutive columns of one row: conflict-free shared-memory traffic, 2 barriers per pivot.
+// Gauss-Jordan inverse (no pivoting: the blocks are SPD) of 96 x 96 matrices.  One CTA of 1024 threads per matrix;
+// thread (ty, tx) keeps its 3 x 3 elements (rows ty + 32 m, columns tx + 32 n) in REGISTERS for the whole
+// elimination.  Per pivot only the pivot row and column travel through shared memory (double-buffered), so there
+// is a single block barrier per pivot.
 constexpr int kInvThreads = 1024;
 __global__ void __launch_bounds__(kInvThreads) bt_invert_kernel(const int* __restrict__ idx, const double* __restrict__ D,
                                                                  double* __restrict__ Dinv, double* __restrict__ scalars) {
-  extern __shared__ double sm[];
+  __shared__ double prow[2][kB], pcol[2][kB];
   const int blk = idx[blockIdx.x];
   const double* src = D + (size_t)blk * kBB;
   double* dst = Dinv + (size_t)blk * kBB;
-  for (int t = threadIdx.x; t < kBB; t += kInvThreads) sm[t] = src[t];
-  __syncthreads();
   const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+  double v[3][3];
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+#pragma unroll
+    for (int n = 0; n < 3; n++) v[m][n] = src[(size_t)(ty + 32 * m) * kB + tx + 32 * n];
   bool bad = false;
+  // publish pivot row / column 0
+  if (ty == 0) {
+#pragma unroll
+    for (int n = 0; n < 3; n++) prow[0][tx + 32 * n] = v[0][n];
+  }
+  if (tx == 0) {
+#pragma unroll
+    for (int m = 0; m < 3; m++) pcol[0][ty + 32 * m] = v[m][0];
+  }
+  __syncthreads();
   for (int p = 0; p < kB; p++) {
-    const double piv = sm[p * kB + p];
+    const int buf = p & 1;
+    const double piv = prow[buf][p];
     if (!(piv > 0.0)) bad = true;
     const double d = 1.0 / piv;
-    double f[3], g[3], v[3][3];
+    double f[3], g[3];
 #pragma unroll
-    for (int m = 0; m < 3; m++) { f[m] = sm[(ty + 32 * m) * kB + p]; g[m] = sm[p * kB + tx + 32 * m] * d; }
+    for (int m = 0; m < 3; m++) { f[m] = pcol[buf][ty + 32 * m]; g[m] = prow[buf][tx + 32 * m] * d; }
 #pragma unroll
     for (int m = 0; m < 3; m++)
 #pragma unroll
       for (int n = 0; n < 3; n++) {
         const int i = ty + 32 * m, j = tx + 32 * n;
-        const double cur = sm[i * kB + j];
-        v[m][n] = (i == p) ? ((j == p) ? d : g[n]) : ((j == p) ? -f[m] * d : cur - f[m] * g[n]);
+        v[m][n] = (i == p) ? ((j == p) ? d : g[n]) : ((j == p) ? -f[m] * d : v[m][n] - f[m] * g[n]);
       }
-    __syncthreads();
+    // publish the next pivot row / column from the updated registers
+    const int q = p + 1;
+    if (q < kB) {
+      const int nb = q & 1;
+      const int qb = q >> 5;  // which of the thread's 3 rows / columns (selected without dynamic register indexing)
+      if ((q & 31) == ty) {
 #pragma unroll
-    for (int m = 0; m < 3; m++)
+        for (int n = 0; n < 3; n++) prow[nb][tx + 32 * n] = qb == 0 ? v[0][n] : (qb == 1 ? v[1][n] : v[2][n]);
+      }
+      if ((q & 31) == tx) {
 #pragma unroll
-      for (int n = 0; n < 3; n++) sm[(ty + 32 * m) * kB + tx + 32 * n] = v[m][n];
+        for (int m = 0; m < 3; m++) pcol[nb][ty + 32 * m] = qb == 0 ? v[m][0] : (qb == 1 ? v[m][1] : v[m][2]);
+      }
+    }
     __syncthreads();
   }
-  for (int t = threadIdx.x; t < kBB; t += kInvThreads) dst[t] = sm[t];
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+#pragma unroll
+    for (int n = 0; n < 3; n++) dst[(size_t)(ty + 32 * m) * kB + tx + 32 * n] = v[m][n];
   if (bad && threadIdx.x == 0) atomicAdd(&scalars[SC_BT_FAIL], 1.0);
 }
 
@@ -185,34 +211,72 @@ __device__ __forceinline__ void bt_forward_block(const BtApply& P, int a, int i,
     P.w[(size_t)a * kB + r0 + lane] -= v;
   }
 }
-__device__ __forceinline__ void bt_backward_block(const BtApply& P, int i, int a, int c) {
-  // z_i = Dinv_i w_i - GaT[i]^T z_a - GcT[i]^T z_c   (thread j < 96 owns output j; coalesced over j)
-  const int j = threadIdx.x;
-  if (j >= kB) return;
+// z_i = Dinv_i w_i - GaT[i]^T z_a - GcT[i]^T z_c.  All 16 warps of the CTA take part: warp w handles the 6 rows
+// k = 6w .. 6w+5 of the three matrices for all 96 outputs (lane owns outputs lane, lane+32, lane+64; loads are
+// coalesced over the outputs and all independent), the 16 partial sums are combined through shared memory.
+// Also accumulates r . z over the block's rows into *rz (when r != nullptr).
+__device__ __forceinline__ void bt_backward_block(const BtApply& P, int i, int a, int c, double (*part)[kB],
+                                                  const double* r, int n, double* rz) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const double* Di = P.Dinv + (size_t)i * kBB;
   const double* wi = P.w + (size_t)i * kB;
-  double acc = 0.0;
-#pragma unroll 8
-  for (int k = 0; k < kB; k++) acc += Di[(size_t)k * kB + j] * wi[k];
+  double acc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int kk = 0; kk < 6; kk++) {
+    const int k = 6 * w + kk;
+    const double wk = wi[k];
+#pragma unroll
+    for (int m = 0; m < 3; m++) acc[m] += Di[(size_t)k * kB + lane + 32 * m] * wk;
+  }
   if (a >= 0) {
     const double* M = P.GaT + (size_t)i * kBB;
     const double* za = P.z + (size_t)a * kB;
-#pragma unroll 8
-    for (int k = 0; k < kB; k++) acc -= M[(size_t)k * kB + j] * za[k];
+#pragma unroll
+    for (int kk = 0; kk < 6; kk++) {
+      const int k = 6 * w + kk;
+      const double zk = za[k];
+#pragma unroll
+      for (int m = 0; m < 3; m++) acc[m] -= M[(size_t)k * kB + lane + 32 * m] * zk;
+    }
   }
   if (c >= 0) {
     const double* M = P.GcT + (size_t)i * kBB;
     const double* zc = P.z + (size_t)c * kB;
-#pragma unroll 8
-    for (int k = 0; k < kB; k++) acc -= M[(size_t)k * kB + j] * zc[k];
+#pragma unroll
+    for (int kk = 0; kk < 6; kk++) {
+      const int k = 6 * w + kk;
+      const double zk = zc[k];
+#pragma unroll
+      for (int m = 0; m < 3; m++) acc[m] -= M[(size_t)k * kB + lane + 32 * m] * zk;
+    }
   }
-  P.z[(size_t)i * kB + j] = acc;
+  __syncthreads();  // `part` may still be read by the previous call
+#pragma unroll
+  for (int m = 0; m < 3; m++) part[w][lane + 32 * m] = acc[m];
+  __syncthreads();
+  if (threadIdx.x < kB) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < kPcgThreads / 32; q++) s += part[q][threadIdx.x];
+    const int row = i * kB + threadIdx.x;
+    P.z[row] = s;
+    if (r != nullptr) {
+      double d = row < n ? r[row] * s : 0.0;
+      d = warp_sum(d);
+      if (lane == 0 && d != 0.0) atomicAdd(rz, d);
+    }
+  }
 }
 
-// z = T^-1 w (w is overwritten).  Called by every thread of the grid; contains 2 nlev + 1 grid barriers.
-__device__ void bt_apply(cg::grid_group& grid, const BtApply& P) {
+// z = T^-1 w (w is overwritten).  Called by every thread of the grid.  Levels that still have more than kNarrow
+// active super-blocks are spread over the grid (one grid barrier each); the narrow top of the reduction tree is
+// done by CTA 0 alone with block barriers, which removes most of the grid-wide barriers from the PCG iteration.
+constexpr int kNarrow = 4;
+__device__ void bt_apply(cg::grid_group& grid, const BtApply& P, double (*part)[kB], const double* r, int n, double* rz) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  for (int l = 0; l < P.nlev; l++) {
+  int lsplit = 0;  // first level handled by CTA 0 alone
+  while (lsplit < P.nlev && (P.nsb + (1 << lsplit) - 1) / (1 << lsplit) > kNarrow) lsplit++;
+  for (int l = 0; l < lsplit; l++) {
     const int s = 1 << l, nl = (P.nsb + s - 1) / s;
     const int nsurv = (nl + 1) / 2;
     for (int t = blockIdx.x; t < nsurv; t += gridDim.x) {
@@ -221,14 +285,32 @@ __device__ void bt_apply(cg::grid_group& grid, const BtApply& P) {
     }
     grid.sync();
   }
-  if (blockIdx.x == 0) bt_backward_block(P, 0, -1, -1);
+  if (blockIdx.x == 0) {
+    for (int l = lsplit; l < P.nlev; l++) {
+      const int s = 1 << l, nl = (P.nsb + s - 1) / s;
+      for (int k = 0; k < nl; k += 2) bt_forward_block(P, k * s, (k + 1 < nl) ? (k + 1) * s : -1, (k >= 1) ? (k - 1) * s : -1, lane, wib);
+      __threadfence_block();
+      __syncthreads();
+    }
+    bt_backward_block(P, 0, -1, -1, part, r, n, rz);
+    __threadfence_block();
+    __syncthreads();
+    for (int l = P.nlev - 1; l >= lsplit; l--) {
+      const int s = 1 << l, nl = (P.nsb + s - 1) / s;
+      for (int k = 1; k < nl; k += 2) {
+        bt_backward_block(P, k * s, (k - 1) * s, (k + 1 < nl) ? (k + 1) * s : -1, part, r, n, rz);
+      }
+      __threadfence_block();
+      __syncthreads();
+    }
+  }
   grid.sync();
-  for (int l = P.nlev - 1; l >= 0; l--) {
+  for (int l = lsplit - 1; l >= 0; l--) {
     const int s = 1 << l, nl = (P.nsb + s - 1) / s;
     const int nel = nl / 2;
     for (int t = blockIdx.x; t < nel; t += gridDim.x) {
       const int k = 2 * t + 1;
-      bt_backward_block(P, k * s, (k - 1) * s, (k + 1 < nl) ? (k + 1) * s : -1);
+      bt_backward_block(P, k * s, (k - 1) * s, (k + 1 < nl) ? (k + 1) * s : -1, part, r, n, rz);
     }
     grid.sync();
   }
@@ -242,6 +324,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_bt_kernel(int nf, const uint3
                                                              double* __restrict__ scalars) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double red[3][kPcgThreads / 32];
+  __shared__ double part[kPcgThreads / 32][kB];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gw = (blockIdx.x * kPcgThreads + threadIdx.x) >> 5;
   const int GW = (gridDim.x * kPcgThreads) >> 5;
@@ -275,12 +358,8 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_bt_kernel(int nf, const uint3
     block_acc(0.0, bb, 0.0, acc);
   }
   grid.sync();
-  bt_apply(grid, P);
-  {
-    double rz = 0.0;
-    for (int i = gt; i < n; i += GT) { const double zv = z[i]; p[i] = zv; rz += r[i] * zv; }
-    block_acc(rz, 0.0, 0.0, acc);
-  }
+  bt_apply(grid, P, part, r, n, &acc[0]);   // acc[0] += r . z (fused into the back-substitution)
+  for (int i = gt; i < n; i += GT) p[i] = z[i];
   grid.sync();
   double rho = ((volatile double*)acc)[0];
   const double bb = ((volatile double*)acc)[1];
@@ -298,11 +377,24 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_bt_kernel(int nf, const uint3
         const uint32_t len = nb * 6;
         const double* row = Sf + (size_t)p0 * 36;
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
-        for (uint32_t e = lane; e < len; e += 32) {
-          const uint32_t k = e / 6, c = e - 6 * k;
-          const double xv = p[6 * sf_col[p0 + k] + c];
-          a0 += row[e] * xv; a1 += row[len + e] * xv; a2 += row[2 * len + e] * xv;
-          a3 += row[3 * len + e] * xv; a4 += row[4 * len + e] * xv; a5 += row[5 * len + e] * xv;
+        for (uint32_t e0 = lane; e0 < len; e0 += 128) {
+          // 4 entries per lane per trip, every load issued before the first use
+          uint32_t ee[4]; double xv[4], sv[4][6];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            ee[u] = e0 + 32 * u;
+            const bool in = ee[u] < len;
+            const uint32_t e = in ? ee[u] : 0u;
+            const uint32_t k = e / 6, c = e - 6 * k;
+            xv[u] = in ? p[6 * sf_col[p0 + k] + c] : 0.0;
+#pragma unroll
+            for (int a = 0; a < 6; a++) sv[u][a] = in ? row[a * len + e] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            a0 += sv[u][0] * xv[u]; a1 += sv[u][1] * xv[u]; a2 += sv[u][2] * xv[u];
+            a3 += sv[u][3] * xv[u]; a4 += sv[u][4] * xv[u]; a5 += sv[u][5] * xv[u];
+          }
         }
         a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4); a5 = warp_sum(a5);
         if (lane < 6) {
@@ -328,11 +420,7 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_bt_kernel(int nf, const uint3
       rr = ((volatile double*)A)[2];
       it++;
       if (rr <= tol * tol * bb) break;
-      bt_apply(grid, P);
-      double rz = 0.0;
-      for (int i = gt; i < n; i += GT) rz += r[i] * z[i];
-      block_acc(0.0, rz, 0.0, A);
-      grid.sync();
+      bt_apply(grid, P, part, r, n, &A[1]);   // A[1] += r . z
       const double rho_new = ((volatile double*)A)[1];
       const double beta = rho_new / rho;
       rho = rho_new;

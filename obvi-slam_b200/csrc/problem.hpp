@@ -421,7 +421,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
   }
   // ---- point batches: consecutive points (first-observing-keyframe order) whose poses fit a 64-wide window
   {
-    constexpr int kMaxPts = 128, kMaxWin = 64, kMaxPairs = 512, kMaxSlots = 16;
+    constexpr int kMaxPts = 128, kMaxWin = 64, kMaxPairs = 256, kMaxSlots = 16;  // kMaxPairs = threads of the batched kernel
     Structure::PointBatches& B = S.pbatch;
     B.mask.assign(S.P, 0); B.pair_ptr.push_back(0);
     std::vector<int32_t> win; std::vector<uint32_t> members;
@@ -450,7 +450,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     for (int e = 0; e < S.P; e++) {
       if (S.point_const[e] || S.pts.ptr[e] == S.pts.ptr[e + 1]) { continue; }
       const int ns = S.pts.nslots[e];
-      if (ns > kMaxSlots) { close_batch(); cur_pairs = 0; B.fallback.push_back((uint32_t)e); continue; }
+      if (ns > kMaxSlots || S.pts.ptr[e + 1] - S.pts.ptr[e] > 32) { close_batch(); cur_pairs = 0; B.fallback.push_back((uint32_t)e); continue; }
       const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]];
       int add = 0;
       for (int a = 0; a < ns; a++) if (std::find(win.begin(), win.end(), sf[a]) == win.end()) add++;

@@ -142,6 +142,13 @@ struct Solver {
   std::vector<BtLevel> bt_levels;
   int bt_last_inv_off = 0;
   bool use_bt = true;
+  // The factorisation is reused across LM iterations while it still preconditions well: it is redone when the
+  // trust-region radius moved by more than 2x since it was computed or the last PCG needed more than
+  // kRefactorPcgIters iterations.  (A stale preconditioner changes the PCG iteration count, never its answer.)
+  double bt_radius = -1.0;
+  int last_pcg_iters = 0;
+  static constexpr int kRefactorPcgIters = 8;
+  int64_t bt_factorizations = 0;
   double* h_scalars = nullptr;  // pinned
   std::vector<double> h_poses, h_points, h_objects;
   int64_t launches = 0;
@@ -165,7 +172,6 @@ struct Solver {
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_blocks_per_sm, pcg_kernel, kPcgThreads, 0));
     if (pcg_blocks_per_sm < 1) throw std::runtime_error("pcg_kernel cannot be made resident");
     CUDA_OK(cudaFuncSetAttribute(schur_points_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubPts * kPtStride * 8));
-    CUDA_OK(cudaFuncSetAttribute(bt_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBB * 8));
     CUDA_OK(cudaFuncSetAttribute(bt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBB * 8));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_bt_blocks_per_sm, pcg_bt_kernel, kPcgThreads, 0));
     if (pcg_bt_blocks_per_sm < 1) throw std::runtime_error("pcg_bt_kernel cannot be made resident");
@@ -300,11 +306,11 @@ struct Solver {
     bt_assemble_kernel<<<nblk((int64_t)nsb * kSbPoses * 32, 256), 256, 0, stream>>>(S.nf, nsb, sf_ptr.p, sf_col.p, Sf.p, bt_D.p, bt_C.p);
     launches++;
     for (const BtLevel& L : bt_levels) {
-      if (L.inv_n) { bt_invert_kernel<<<L.inv_n, kInvThreads, kBB * 8, stream>>>(bt_idx.p + L.inv_off, bt_D.p, bt_Dinv.p, scalars.p); launches++; }
+      if (L.inv_n) { bt_invert_kernel<<<L.inv_n, kInvThreads, 0, stream>>>(bt_idx.p + L.inv_off, bt_D.p, bt_Dinv.p, scalars.p); launches++; }
       if (L.g_n) { bt_gemm_kernel<<<L.g_n, 256, 2 * kBB * 8, stream>>>(bt_tasks.p + L.g_off); launches++; }
       if (L.u_n) { bt_gemm_kernel<<<L.u_n, 256, 2 * kBB * 8, stream>>>(bt_tasks.p + L.u_off); launches++; }
     }
-    bt_invert_kernel<<<1, kInvThreads, kBB * 8, stream>>>(bt_idx.p + bt_last_inv_off, bt_D.p, bt_Dinv.p, scalars.p);
+    bt_invert_kernel<<<1, kInvThreads, 0, stream>>>(bt_idx.p + bt_last_inv_off, bt_D.p, bt_Dinv.p, scalars.p);
     launches++;
   }
   bool owns_object(int o) const {
@@ -416,7 +422,8 @@ struct Solver {
       if (lm.compute_scale) { pose_scale_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(hpp_diag, S.nf * 6, pscale.p); launches++; }
       finish_kernel<<<nblk((int64_t)S.nf * 32, 256), 256, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, sf_src.p, S_upper, pscale.p, hpp_diag, gp, b_schur, lm, Sf.p, rhs.p, Minv.p, scalars.p);
       launches++;
-      factor_bt();
+      const bool stale = bt_radius <= 0.0 || lm.radius > 2.0 * bt_radius || lm.radius < 0.5 * bt_radius || last_pcg_iters > kRefactorPcgIters;
+      if (stale) { factor_bt(); bt_radius = lm.radius; bt_factorizations++; }
     }
   }
   void solve_reduced(const obvi_solver_options& o, bool force_jacobi = false) {
@@ -532,6 +539,7 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
   sum->num_residual_blocks_reduced = (int32_t)S.num_residual_blocks_reduced;
   sum->num_residuals_reduced = (int32_t)S.num_residuals_reduced;
   gather_params();
+  bt_radius = -1.0; last_pcg_iters = 0;
 
   int n_log = 0;
   auto push = [&](int iter, bool valid, bool ok, int lin_it, double cost, double cc, double gmax, double sn, double rd, double radius) {
@@ -599,6 +607,7 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
     }
     const int pcg_it = (int)h_scalars[SC_PCG_IT];
     pcg_total += pcg_it;
+    last_pcg_iters = pcg_it;
     const double model_change = -h_scalars[SC_MODEL];
     bool valid = !build_failed && h_scalars[SC_FAIL] == 0.0 && h_scalars[SC_PCG_BREAK] == 0.0 && std::isfinite(model_change) &&
                  std::isfinite(h_scalars[SC_STEP2]) && model_change > 0.0;
