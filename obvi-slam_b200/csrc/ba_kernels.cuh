@@ -33,7 +33,7 @@ enum : int {
   SC_PCG_BREAK = 12, SC_BT_FAIL = 13, SC_COUNT = 16
 };
 
-struct LMParams { double radius, min_diag, max_diag; int compute_scale; };
+struct LMParams { double radius, min_diag, max_diag; int compute_scale; double inv_radius; };
 
 // ------------------------------------------------------------------------------------------ reductions
 __device__ __forceinline__ double warp_sum(double v) {
@@ -563,14 +563,28 @@ constexpr int kStageSlots = 16;
 constexpr int kSlotStride = 37;               // 36 doubles (Z 6x3, W 6x3) + 1 pad: conflict-free across slots
 constexpr int kPtStride = kStageSlots * kSlotStride;
 
+// USE_MMA = true: phase 2 runs on the fp64 tensor-core path (mma.sync m8n8k4, SASS DMMA): warp w owns the block rows
+// wa = w (mod 8) of the window; for every staged point that observes wa it walks the point's later slots and issues
+// one DMMA per block pair, A = Z_a (6x3 in an 8x4 fragment), B = W_b^T, C = the pair's 6x6 accumulator kept in shared
+// memory (the warp is the only writer of its rows, so plain load / store, no atomics).  ~12 instructions per
+// (point, pair) instead of ~170 on the scalar path.
+constexpr int kMmaMaxWin = 20;
+constexpr int kMmaMaxPairs = kMmaMaxWin * (kMmaMaxWin + 1) / 2;
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <bool USE_MMA>
 __global__ void __launch_bounds__(kBatchThreads, 2) schur_points_batched_kernel(EArgs A, BatchArgs B, LMParams lm,
                                                                               double* __restrict__ S_upper,
                                                                               double* __restrict__ b_schur,
                                                                               double* __restrict__ scalars) {
-  extern __shared__ double stage[];          // [kSubPts][kStageSlots][kSlotStride]
+  extern __shared__ double stage[];          // [kSubPts][kStageSlots][kSlotStride] (+ [kMmaMaxPairs][36] accumulators)
+  double* accs = stage + kSubPts * kPtStride;
   __shared__ unsigned long long s_mask[kSubPts];
   __shared__ double s_g[kSubPts][3];
   __shared__ double s_gmax[kSubPts];
+  __shared__ unsigned char s_wb[kSubPts][kStageSlots];   // window index of each staged slot
   const int batch = blockIdx.x;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t p_first = B.first[batch], np = B.count[batch];
@@ -582,10 +596,14 @@ __global__ void __launch_bounds__(kBatchThreads, 2) schur_points_batched_kernel(
   if (own_pair) { const uint32_t info = B.pair_info[pr0 + threadIdx.x]; wa = info & 0xff; wb = (info >> 8) & 0xff; }
   const bool own_b = (int)threadIdx.x < nwin * 6;
   const int bw = threadIdx.x / 6, brow = threadIdx.x - 6 * bw;
-  double acc[36];
+  double acc[USE_MMA ? 1 : 36];
 #pragma unroll
-  for (int a = 0; a < 36; a++) acc[a] = 0.0;
+  for (int a = 0; a < (USE_MMA ? 1 : 36); a++) acc[a] = 0.0;
   double bacc = 0.0, gmax = 0.0;
+  if (USE_MMA) {
+    for (int t = threadIdx.x; t < kMmaMaxPairs * 36; t += kBatchThreads) accs[t] = 0.0;
+    // (the first __syncthreads of the pass loop orders this before any accumulation)
+  }
 
   for (uint32_t s0 = 0; s0 < np; s0 += kSubPts) {
     // ---------------- phase 1: warp `wib` handles point p_first + s0 + wib, lane = observation (<= 32 per point).
@@ -649,8 +667,8 @@ __global__ void __launch_bounds__(kBatchThreads, 2) schur_points_batched_kernel(
           Hs[0] = s[0] * H[0] * s[0]; Hs[1] = Hs[3] = s[0] * H[1] * s[1]; Hs[2] = Hs[6] = s[0] * H[2] * s[2];
           Hs[4] = s[1] * H[3] * s[1]; Hs[5] = Hs[7] = s[1] * H[4] * s[2]; Hs[8] = s[2] * H[5] * s[2];
 #pragma unroll
-          for (int a = 0; a < 3; a++) Hs[4 * a] += fmin(fmax(Hs[4 * a], lm.min_diag), lm.max_diag) / lm.radius;
-          const bool ok = spd_inverse<3>(Hs, hinv);
+          for (int a = 0; a < 3; a++) Hs[4 * a] += fmin(fmax(Hs[4 * a], lm.min_diag), lm.max_diag) * lm.inv_radius;
+          const bool ok = spd_inverse3_cofactor(Hs, hinv);
           // W = Jp^T Jl of the lane's observation, then merge runs of equal slot (same keyframe, several cameras)
           double Wm[18];
 #pragma unroll
@@ -686,6 +704,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) schur_points_batched_kernel(
             }
             mk = my_mask;
             if (head) {
+              if (USE_MMA) s_wb[wib][sl] = (unsigned char)__fns((unsigned int)my_mask, 0, (int)sl + 1);
               double* st = stage + (size_t)wib * kPtStride + (size_t)sl * kSlotStride;
 #pragma unroll
               for (int a = 0; a < 6; a++)
@@ -702,7 +721,37 @@ __global__ void __launch_bounds__(kBatchThreads, 2) schur_points_batched_kernel(
     }
     __syncthreads();
     // ---------------- phase 2: owner-computes accumulation over the staged points
-    if (own_pair) {
+    if (USE_MMA) {
+      const int frag = 3 * (lane >> 2) + (lane & 3);                // element of a 6x3 matrix held by this lane (A and B alike)
+      const bool fvalid = (lane >> 2) < 6 && (lane & 3) < 3;
+      const int coff = 6 * (lane >> 2) + 2 * (lane & 3);            // first of the lane's two accumulator elements
+      const bool cvalid = fvalid;
+      for (int pt = 0; pt < kSubPts; pt++) {
+        const unsigned int m = (unsigned int)s_mask[pt];
+        // rows of this warp that the point observes
+        unsigned int rows = m & (0x01010101u << wib);
+        if (rows == 0u) continue;
+        const int ns = __popc(m);
+        const double* st_pt = stage + (size_t)pt * kPtStride + frag;
+        const unsigned char* wbt = s_wb[pt];
+        while (rows) {
+          const int wa_ = __ffs(rows) - 1;
+          rows &= rows - 1;
+          const int sa = __popc(m & ((1u << wa_) - 1u));
+          const double a = fvalid ? st_pt[(size_t)sa * kSlotStride] : 0.0;
+          double* Crow = accs + (size_t)(wa_ * nwin - (wa_ * (wa_ - 1)) / 2 - wa_) * 36 + coff;  // pair (wa, wb) at Crow + 36 wb
+          const double* bp = st_pt + (size_t)sa * kSlotStride + 18;
+#pragma unroll 2
+          for (int sb = sa; sb < ns; sb++, bp += kSlotStride) {
+            const double b = fvalid ? *bp : 0.0;
+            double* C = Crow + 36 * (int)wbt[sb];
+            double2 c = cvalid ? *reinterpret_cast<double2*>(C) : make_double2(0.0, 0.0);
+            dmma_m8n8k4(c.x, c.y, a, b);
+            if (cvalid) *reinterpret_cast<double2*>(C) = c;
+          }
+        }
+      }
+    } else if (own_pair) {
 #pragma unroll 1
       for (int pt = 0; pt < kSubPts; pt++) {
         const unsigned long long m = s_mask[pt];
@@ -734,7 +783,17 @@ __global__ void __launch_bounds__(kBatchThreads, 2) schur_points_batched_kernel(
     __syncthreads();
   }
   // ---------------- flush: one set of atomics per batch
-  if (own_pair) {
+  if (USE_MMA) {
+    __syncwarp();
+    // (the last pass ended with __syncthreads: every warp's accumulators are visible)
+    for (int t = threadIdx.x; t < npairs * 36; t += kBatchThreads) {
+      const int pr = t / 36, el = t - 36 * pr;
+      const uint32_t info = B.pair_info[pr0 + pr];
+      const int a_ = info & 0xff, b_ = (info >> 8) & 0xff;
+      const double v = accs[(size_t)(a_ * nwin - (a_ * (a_ - 1)) / 2 + (b_ - a_)) * 36 + el];
+      if (v != 0.0) atomicAdd(&S_upper[(size_t)B.pair_blk[pr0 + pr] * 36 + el], -v);
+    }
+  } else if (own_pair) {
     double* Sb = S_upper + (size_t)B.pair_blk[pr0 + threadIdx.x] * 36;
 #pragma unroll
     for (int a = 0; a < 36; a++) atomicAdd(&Sb[a], -acc[a]);

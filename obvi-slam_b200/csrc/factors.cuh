@@ -378,4 +378,18 @@ OBVI_HD bool spd_inverse(const double* A, double* inv) {
   return true;
 }
 
+// 3x3 SPD inverse by cofactors: one division instead of the ~24 of the Cholesky route (fp64 division costs ~35
+// instructions on the GPU and this sits in the per-point path).  SPD is checked through the leading minors.
+OBVI_HD bool spd_inverse3_cofactor(const double* A, double* inv) {
+  const double c00 = A[4] * A[8] - A[5] * A[5], c01 = A[2] * A[5] - A[1] * A[8], c02 = A[1] * A[5] - A[2] * A[4];
+  const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+  const double m2 = A[0] * A[4] - A[1] * A[1];
+  if (!(A[0] > 0.0) || !(m2 > 0.0) || !(det > 0.0)) return false;
+  const double id = 1.0 / det;
+  inv[0] = c00 * id; inv[1] = inv[3] = c01 * id; inv[2] = inv[6] = c02 * id;
+  inv[4] = (A[0] * A[8] - A[2] * A[2]) * id; inv[5] = inv[7] = (A[1] * A[2] - A[0] * A[5]) * id;
+  inv[8] = m2 * id;
+  return true;
+}
+
 }  // namespace obvi

@@ -421,7 +421,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
   }
   // ---- point batches: consecutive points (first-observing-keyframe order) whose poses fit a 64-wide window
   {
-    constexpr int kMaxPts = 128, kMaxWin = 64, kMaxPairs = 256, kMaxSlots = 16;  // kMaxPairs = threads of the batched kernel
+    constexpr int kMaxPts = 128, kMaxWin = 20, kMaxPairs = 256, kMaxSlots = 16;  // kMaxWin: window of the tensor-core path (u32 masks, 210 pair accumulators)
     Structure::PointBatches& B = S.pbatch;
     B.mask.assign(S.P, 0); B.pair_ptr.push_back(0);
     std::vector<int32_t> win; std::vector<uint32_t> members;
@@ -439,7 +439,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
       }
       B.first.push_back(members.front()); B.count.push_back((uint32_t)(members.back() - members.front() + 1));
       B.nwin.push_back((uint32_t)win.size());
-      for (int a = 0; a < kMaxWin; a++) B.win_f.push_back(a < (int)win.size() ? win[a] : -1);
+      for (int a = 0; a < 64; a++) B.win_f.push_back(a < (int)win.size() ? win[a] : -1);  // fixed stride of 64 per batch
       for (int a = 0; a < (int)win.size(); a++) for (int b = a; b < (int)win.size(); b++) if ((pm[a] >> b) & 1) {
         B.pair_info.push_back((uint32_t)a | ((uint32_t)b << 8)); B.pair_blk.push_back(blk_of(win[a], win[b]));
       }

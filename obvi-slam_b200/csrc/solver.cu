@@ -98,6 +98,8 @@ struct Solver {
   Problem pb;
   Structure st;
   cudaStream_t stream = nullptr;
+  cudaStream_t s2 = nullptr;       // side stream: the small kernels (objects, priors, rel-pose) overlap the big point kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev[8] = {};
   bool uploaded = false;
   int num_sms = 0;
@@ -123,6 +125,7 @@ struct Solver {
   DBuf<int32_t> pb_win_f;
   DBuf<uint64_t> pb_mask;
   int n_batches = 0, n_fallback = 0;
+  bool use_mma_schur = true;
   // state
   DBuf<double> poses[3], points[3], objects[3];  // cur, cand, best
   int cur = 0;
@@ -157,6 +160,9 @@ struct Solver {
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     if (h_scalars) cudaFreeHost(h_scalars);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (s2) cudaStreamDestroy(s2);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -167,11 +173,16 @@ struct Solver {
     if (prop.major < 10) throw std::runtime_error(std::string("obvi_ba is built for sm_100a (B200); found ") + prop.name);
     num_sms = prop.multiProcessorCount;
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
     CUDA_OK(cudaMallocHost((void**)&h_scalars, SC_COUNT * sizeof(double)));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_blocks_per_sm, pcg_kernel, kPcgThreads, 0));
     if (pcg_blocks_per_sm < 1) throw std::runtime_error("pcg_kernel cannot be made resident");
-    CUDA_OK(cudaFuncSetAttribute(schur_points_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubPts * kPtStride * 8));
+    CUDA_OK(cudaFuncSetAttribute(schur_points_batched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubPts * kPtStride * 8));
+    CUDA_OK(cudaFuncSetAttribute(schur_points_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kSubPts * kPtStride + kMmaMaxPairs * 36) * 8));
+    if (const char* e = getenv("OBVI_SCHUR")) use_mma_schur = std::string(e) != "scalar";
     CUDA_OK(cudaFuncSetAttribute(bt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBB * 8));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_bt_blocks_per_sm, pcg_bt_kernel, kPcgThreads, 0));
     if (pcg_bt_blocks_per_sm < 1) throw std::runtime_error("pcg_bt_kernel cannot be made resident");
@@ -367,6 +378,8 @@ struct Solver {
     a.overflow = D.overflow.p; a.overflow_off = D.overflow_off.p; a.ne = D.ne; a.elist = nullptr;
     return a;
   }
+  void fork() { CUDA_OK(cudaEventRecord(ev_fork, stream)); CUDA_OK(cudaStreamWaitEvent(s2, ev_fork, 0)); }
+  void join() { CUDA_OK(cudaEventRecord(ev_join, s2)); CUDA_OK(cudaStreamWaitEvent(stream, ev_join, 0)); }
   void zero_scalars(int first, int count) { CUDA_OK(cudaMemsetAsync(scalars.p + first, 0, count * sizeof(double), stream)); }
 
   // residuals + Jacobians at the current point
@@ -374,41 +387,46 @@ struct Solver {
     const Structure& S = st;
     zero_scalars(SC_COST, 3);
     if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p); launches++; }
+    fork();
     if (S.n_obs) {
       if (use_tma_jac && (int)S.classes.size() <= kJacMaxCls && S.C <= 256) reproj_jac_tma_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, kJacSmemBytes, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, (int)S.classes.size(), points[cur].p, apply_loss, jac_tile.p, J.p, scalars.p);
       else reproj_jac_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, points[cur].p, apply_loss, J.p, scalars.p);
       launches++;
     }
-    if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, stream>>>(bbox.p, S.n_bbox, pcam.p, S.C, objects[cur].p, 0, apply_loss, Jb.p, scalars.p); launches++; }
-    if (S.n_unary) { launch_unary(0, apply_loss, cur); }
-    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, stream>>>(rel.p, S.n_rel, 0, apply_loss, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
-    if (S.K) { xnorm_kernel<<<nblk((int64_t)S.K * 6, 256), 256, 0, stream>>>(poses[cur].p, pose_skip.p, S.K, 6, scalars.p); launches++; }
-    if (S.P) { xnorm_kernel<<<nblk((int64_t)S.P * 3, 256), 256, 0, stream>>>(points[cur].p, point_skip.p, S.P, 3, scalars.p); launches++; }
-    if (S.O) { xnorm_kernel<<<nblk((int64_t)S.O * 7, 256), 256, 0, stream>>>(objects[cur].p, obj_skip.p, S.O, 7, scalars.p); launches++; }
+    if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, s2>>>(bbox.p, S.n_bbox, pcam.p, S.C, objects[cur].p, 0, apply_loss, Jb.p, scalars.p); launches++; }
+    if (S.n_unary) { launch_unary(0, apply_loss, cur, s2); }
+    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 0, apply_loss, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    if (S.K) { xnorm_kernel<<<nblk((int64_t)S.K * 6, 256), 256, 0, s2>>>(poses[cur].p, pose_skip.p, S.K, 6, scalars.p); launches++; }
+    if (S.P) { xnorm_kernel<<<nblk((int64_t)S.P * 3, 256), 256, 0, s2>>>(points[cur].p, point_skip.p, S.P, 3, scalars.p); launches++; }
+    if (S.O) { xnorm_kernel<<<nblk((int64_t)S.O * 7, 256), 256, 0, s2>>>(objects[cur].p, obj_skip.p, S.O, 7, scalars.p); launches++; }
+    join();
   }
-  void launch_unary(int mode, int apply_loss, int buf) {
+  void launch_unary(int mode, int apply_loss, int buf, cudaStream_t strm) {
     const Structure& S = st;
-    unary_kernel<<<nblk(S.n_unary, 64), 64, 0, stream>>>(unary.p, S.n_unary, mode, apply_loss, poses[buf].p, points[buf].p, objects[buf].p,
+    unary_kernel<<<nblk(S.n_unary, 64), 64, 0, strm>>>(unary.p, S.n_unary, mode, apply_loss, poses[buf].p, points[buf].p, objects[buf].p,
                                                          unary_out.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag, pts.prior_H.p,
                                                          pts.prior_g.p, objs.prior_H.p, objs.prior_g.p, dpose.p, pts.delta.p,
                                                          objs.delta.p, scalars.p);
     launches++;
   }
   // Schur complement + rhs for the given radius (J fixed)
-  void build_reduced(const LMParams& lm) {
+  void build_reduced(LMParams& lm) {
     const Structure& S = st;
+    lm.inv_radius = 1.0 / lm.radius;
     redbuf.zero(stream);
     zero_scalars(SC_GMAX, 2);  // gmax + fail
     zero_scalars(SC_BT_FAIL, 1);
     if (pts.has_prior) { pts.prior_H.zero(stream); pts.prior_g.zero(stream); }
     if (objs.has_prior) { objs.prior_H.zero(stream); objs.prior_g.zero(stream); }
+    // unary factors on points feed the point elimination: keep them on the main stream in that case
+    if (S.n_unary && pts.has_prior) launch_unary(1, 1, cur, stream);
+    fork();
     if (S.n_obs && S.nf) { pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag); launches++; }
-    if (S.n_unary) launch_unary(1, 1, cur);
-    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, stream>>>(rel.p, S.n_rel, 1, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
     if (n_batches) {
       BatchArgs B; B.first = pb_first.p; B.count = pb_count.p; B.win_f = pb_win_f.p; B.nwin = pb_nwin.p; B.mask = pb_mask.p;
       B.pair_ptr = pb_pair_ptr.p; B.pair_info = pb_pair_info.p; B.pair_blk = pb_pair_blk.p;
-      schur_points_batched_kernel<<<n_batches, kBatchThreads, kSubPts * kPtStride * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
+      if (use_mma_schur) schur_points_batched_kernel<true><<<n_batches, kBatchThreads, (kSubPts * kPtStride + kMmaMaxPairs * 36) * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
+      else schur_points_batched_kernel<false><<<n_batches, kBatchThreads, kSubPts * kPtStride * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
       launches++;
     }
     if (n_fallback) {
@@ -416,7 +434,11 @@ struct Solver {
       schur_eblock_kernel<3, 2, 32, 16, false><<<n_fallback, 32, 0, stream>>>(a, lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p);
       launches++;
     }
-    if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, stream>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
+    // side stream: priors, rel-pose and the object elimination (all accumulate with atomics)
+    if (S.n_unary && !pts.has_prior) launch_unary(1, 1, cur, s2);
+    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 1, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
+    join();
     if (world > 1) allreduce_sum(redbuf.p, redbuf.n);
     if (S.nf) {
       if (lm.compute_scale) { pose_scale_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(hpp_diag, S.nf * 6, pscale.p); launches++; }
@@ -458,22 +480,25 @@ struct Solver {
     const int cand = 1 - cur;
     zero_scalars(SC_MODEL, 2);
     if (S.nf) { pose_step_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(S.nf, pose_of_f.p, pscale.p, y.p, poses[cur].p, poses[cand].p, dpose.p, rank == 0, scalars.p); launches++; }
+    fork();
     if (S.P) { backsub_points_kernel<<<nblk(S.P, 4), 128, 0, stream>>>(eargs(pts, J.p), dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p); launches++; }
-    if (S.O) { backsub_eblock_kernel<7, 4, 128><<<S.O, 128, 0, stream>>>(eargs(objs, Jb.p), dpose.p, objects[cur].p, objects[cand].p, objs.delta.p, scalars.p); launches++; }
-    if (S.n_unary) launch_unary(2, 1, cur);
-    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, stream>>>(rel.p, S.n_rel, 2, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    if (S.O) { backsub_eblock_kernel<7, 4, 128><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), dpose.p, objects[cur].p, objects[cand].p, objs.delta.p, scalars.p); launches++; }
+    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 2, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    join();
+    if (S.n_unary) launch_unary(2, 1, cur, stream);
   }
   void candidate_cost() {
     const Structure& S = st;
     const int cand = 1 - cur;
     zero_scalars(SC_CAND, 2);
     if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cand].p, S.K, cams.p, S.C, 0, pcam_cand.p); launches++; }
+    fork();
     if (S.n_obs) { reproj_cost_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam_cand.p, S.C, classes.p, points[cand].p, scalars.p); launches++; }
-    if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, stream>>>(bbox.p, S.n_bbox, pcam_cand.p, S.C, objects[cand].p, 1, 1, Jb.p, scalars.p); launches++; }
-    if (S.n_unary) launch_unary(3, 1, cand);
-    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, stream>>>(rel.p, S.n_rel, 3, 1, poses[cand].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, s2>>>(bbox.p, S.n_bbox, pcam_cand.p, S.C, objects[cand].p, 1, 1, Jb.p, scalars.p); launches++; }
+    if (S.n_unary) launch_unary(3, 1, cand, s2);
+    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 3, 1, poses[cand].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    join();
   }
-  // scalars -> host (with the cross-rank reduction when sharded)
   // stage 0: after linearize () + build_reduced (); stage 1: after take_step () + candidate_cost ()
   void fetch_scalars(int stage) {
     if (world > 1) {
@@ -554,6 +579,7 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
   double t_jac = 0, t_lin = 0, t_res = 0;
   LMParams lm;
   lm.radius = o.initial_trust_region_radius; lm.min_diag = o.min_lm_diagonal; lm.max_diag = o.max_lm_diagonal; lm.compute_scale = 1;
+  lm.inv_radius = 1.0 / lm.radius;
 
   CUDA_OK(cudaEventRecord(ev[6], stream));
   // ---- iteration 0
