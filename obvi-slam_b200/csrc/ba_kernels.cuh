@@ -812,6 +812,237 @@ __global__ void __launch_bounds__(kBatchThreads, 2) schur_points_batched_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------ points: pipelined tensor-core elimination
+// Second-generation point elimination (replaces schur_points_batched_kernel<true> on the fast path).  Same
+// owner-computes idea -- a CTA takes a batch of consecutive points, warp w owns the block rows wa = w (mod 8) of the
+// batch's pose window and accumulates Z_a W_b^T with DMMA into shared-memory 6x6 accumulators -- restructured as a
+// software pipeline so that the three latencies no longer add up:
+//   * only W (6x3 per merged slot) and the point's Hinv / Hinv g are staged (Z = W Hinv is rebuilt in the A fragment),
+//     which halves the staging footprint and pays for DOUBLE BUFFERING: one block barrier per pass instead of two;
+//   * the global loads of the NEXT pass (index entries two passes ahead, the 160-byte chunk one pass ahead) are issued
+//     before the tensor-core phase of the current pass and consumed after it.
+constexpr int kPipeThreads = 256;
+constexpr int kPipePts = kPipeThreads / 32;        // points per pass (one warp each)
+constexpr int kWStride = 19;                       // 18 doubles of W + 1 pad: conflict-free across slots
+constexpr int kWPt = kStageSlots * kWStride;       // doubles per staged point
+constexpr int kPipeSmemDoubles = 2 * kPipePts * kWPt + kMmaMaxPairs * 36;
+
+struct PipePoint {   // per-lane registers of a point whose loads are in flight (lane = observation)
+  int e; uint32_t b0, b1; bool act, have; uint32_t sl; uint32_t pos;
+  double jp[12], jl[6], r0, r1;
+};
+
+__global__ void __launch_bounds__(kPipeThreads, 2) schur_points_mma_kernel(EArgs A, BatchArgs B, LMParams lm,
+                                                                            double* __restrict__ S_upper,
+                                                                            double* __restrict__ b_schur,
+                                                                            double* __restrict__ scalars) {
+  extern __shared__ double smem_d[];
+  double* stW = smem_d;                                   // [2][kPipePts][kStageSlots][kWStride]
+  double* accs = smem_d + 2 * kPipePts * kWPt;            // [kMmaMaxPairs][36]
+  __shared__ unsigned int s_mask[2][kPipePts];
+  __shared__ double s_hinv[2][kPipePts][9];
+  __shared__ double s_hg[2][kPipePts][3];
+  __shared__ unsigned char s_wb[2][kPipePts][kStageSlots];
+  __shared__ double s_b[kMmaMaxWin][6];
+  __shared__ double s_gmax[kPipePts];
+  const int batch = blockIdx.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t p_first = B.first[batch], np = B.count[batch];
+  const uint32_t pr0 = B.pair_ptr[batch];
+  const int npairs = (int)(B.pair_ptr[batch + 1] - pr0);
+  const int nwin = (int)B.nwin[batch];
+  const int npass = (int)((np + kPipePts - 1) / kPipePts);
+  double gmax = 0.0;
+  for (int t = threadIdx.x; t < kMmaMaxPairs * 36; t += kPipeThreads) accs[t] = 0.0;
+  if (threadIdx.x < kMmaMaxWin * 6) (&s_b[0][0])[threadIdx.x] = 0.0;
+
+  // index entries of the point this warp handles in pass `ps` (ptr -> slot / pos)
+  auto load_index = [&](int ps, PipePoint& P) {
+    const uint32_t pi = (uint32_t)ps * kPipePts + wib;
+    P.act = false; P.have = false; P.sl = 0xFFFFu; P.pos = 0; P.e = 0; P.b0 = P.b1 = 0;
+    if (ps < npass && pi < np) {
+      P.e = (int)(p_first + pi);
+      P.b0 = A.ptr[P.e]; P.b1 = A.ptr[P.e + 1];
+      P.act = !A.cst[P.e] && P.b1 > P.b0;
+      const uint32_t q = P.b0 + lane;
+      P.have = P.act && q < P.b1;
+      if (P.have) { P.sl = A.slot[q]; P.pos = A.pos[q]; }
+    }
+  };
+  auto load_chunk = [&](PipePoint& P) {
+#pragma unroll
+    for (int a = 0; a < 12; a++) P.jp[a] = 0.0;
+#pragma unroll
+    for (int a = 0; a < 6; a++) P.jl[a] = 0.0;
+    P.r0 = P.r1 = 0.0;
+    if (P.have) {
+      const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)P.pos * kChunk);
+#pragma unroll
+      for (int a = 0; a < 6; a++) { const double2 v = ch[a]; P.jp[2 * a] = v.x; P.jp[2 * a + 1] = v.y; }
+#pragma unroll
+      for (int a = 0; a < 3; a++) { const double2 v = ch[6 + a]; P.jl[2 * a] = v.x; P.jl[2 * a + 1] = v.y; }
+      const double2 rv = ch[9]; P.r0 = rv.x; P.r1 = rv.y;
+    }
+  };
+  // reductions, damping, inverse, merged W per slot -> staging buffer `buf`
+  auto finish_point = [&](const PipePoint& P, int buf) {
+    unsigned int mk = 0u;
+    if (P.act) {
+      const int e = P.e;
+      const unsigned int my_mask = (unsigned int)B.mask[e];
+      double s[3];
+      if (!lm.compute_scale) { s[0] = A.escale[(size_t)e * 3]; s[1] = A.escale[(size_t)e * 3 + 1]; s[2] = A.escale[(size_t)e * 3 + 2]; }
+      double H[6], g[3];
+      {
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          g[a] = P.jl[a] * P.r0 + P.jl[3 + a] * P.r1;
+#pragma unroll
+          for (int b = a; b < 3; b++) H[t++] = P.jl[a] * P.jl[b] + P.jl[3 + a] * P.jl[3 + b];
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 6; a++) H[a] = warp_sum(H[a]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) g[a] = warp_sum(g[a]);
+      if (A.prior_H) {
+        const double* ph = A.prior_H + (size_t)e * 9;
+        H[0] += ph[0]; H[1] += ph[1]; H[2] += ph[2]; H[3] += ph[4]; H[4] += ph[5]; H[5] += ph[8];
+#pragma unroll
+        for (int a = 0; a < 3; a++) g[a] += A.prior_g[(size_t)e * 3 + a];
+      }
+      const double hd[3] = {H[0], H[3], H[5]};
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        if (lm.compute_scale) s[a] = 1.0 / (1.0 + sqrt(hd[a]));
+        gmax = fmax(gmax, fabs(g[a]));
+      }
+      double Hs[9], hinv[9];
+      Hs[0] = s[0] * H[0] * s[0]; Hs[1] = Hs[3] = s[0] * H[1] * s[1]; Hs[2] = Hs[6] = s[0] * H[2] * s[2];
+      Hs[4] = s[1] * H[3] * s[1]; Hs[5] = Hs[7] = s[1] * H[4] * s[2]; Hs[8] = s[2] * H[5] * s[2];
+#pragma unroll
+      for (int a = 0; a < 3; a++) Hs[4 * a] += fmin(fmax(Hs[4 * a], lm.min_diag), lm.max_diag) * lm.inv_radius;
+      const bool ok = spd_inverse3_cofactor(Hs, hinv);
+      double Wm[18];
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) Wm[3 * a + c] = P.jp[a] * P.jl[c] + P.jp[6 + a] * P.jl[3 + c];
+      const uint32_t sl = P.sl;
+      const uint32_t sl_prev = __shfl_up_sync(0xffffffffu, sl, 1);
+      const bool head = P.have && sl != 0xFFFFu && (lane == 0 || sl_prev != sl);
+      for (int d = 1; d < 32; d++) {   // merge the observations of one keyframe (stereo: one trip)
+        const uint32_t sl_d = __shfl_down_sync(0xffffffffu, sl, d);
+        const bool take = head && (lane + d < 32) && sl_d == sl;
+        if (!__any_sync(0xffffffffu, take)) break;
+#pragma unroll
+        for (int a = 0; a < 18; a++) {
+          const double v = __shfl_down_sync(0xffffffffu, Wm[a], d);
+          if (take) Wm[a] += v;
+        }
+      }
+      if (!ok) {
+        if (lane == 0) atomicAdd(&scalars[SC_FAIL], 1.0);
+      } else {
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) hinv[3 * a + b] *= s[a] * s[b];
+        if (lane == 0) {
+          if (lm.compute_scale) { A.escale[(size_t)e * 3] = s[0]; A.escale[(size_t)e * 3 + 1] = s[1]; A.escale[(size_t)e * 3 + 2] = s[2]; }
+#pragma unroll
+          for (int a = 0; a < 9; a++) { A.einv[(size_t)e * 9 + a] = hinv[a]; s_hinv[buf][wib][a] = hinv[a]; }
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            A.eg[(size_t)e * 3 + a] = g[a];
+            s_hg[buf][wib][a] = hinv[3 * a] * g[0] + hinv[3 * a + 1] * g[1] + hinv[3 * a + 2] * g[2];
+          }
+        }
+        mk = my_mask;
+        if (head) {
+          s_wb[buf][wib][sl] = (unsigned char)__fns(my_mask, 0, (int)sl + 1);
+          double* st = stW + ((size_t)(buf * kPipePts + wib) * kStageSlots + sl) * kWStride;
+#pragma unroll
+          for (int a = 0; a < 18; a++) st[a] = Wm[a];
+        }
+      }
+    }
+    if (lane == 0) s_mask[buf][wib] = mk;
+  };
+  // tensor-core accumulation over the points staged in `buf`
+  const int frow = lane >> 2, fk = lane & 3;
+  const bool fvalid = frow < 6 && fk < 3;
+  const int coff = 6 * frow + 2 * fk;
+  auto accumulate = [&](int buf) {
+    for (int pt = 0; pt < kPipePts; pt++) {
+      const unsigned int m = s_mask[buf][pt];
+      unsigned int rows = m & (0x01010101u << wib);
+      if (rows == 0u) continue;
+      const int ns = __popc(m);
+      const double* Wp = stW + (size_t)(buf * kPipePts + pt) * kWPt;
+      const unsigned char* wbt = s_wb[buf][pt];
+      // column fk of Hinv (for the A fragment) and Hinv g
+      const double h0 = fvalid ? s_hinv[buf][pt][fk] : 0.0, h1 = fvalid ? s_hinv[buf][pt][3 + fk] : 0.0, h2 = fvalid ? s_hinv[buf][pt][6 + fk] : 0.0;
+      const double hg0 = s_hg[buf][pt][0], hg1 = s_hg[buf][pt][1], hg2 = s_hg[buf][pt][2];
+      while (rows) {
+        const int wa_ = __ffs(rows) - 1;
+        rows &= rows - 1;
+        const int sa = __popc(m & ((1u << wa_) - 1u));
+        const double* Wa = Wp + (size_t)sa * kWStride;
+        double a = 0.0;
+        if (fvalid) a = Wa[3 * frow] * h0 + Wa[3 * frow + 1] * h1 + Wa[3 * frow + 2] * h2;   // (W_a Hinv)[frow][fk]
+        if (lane < 6) s_b[wa_][lane] += Wa[3 * lane] * hg0 + Wa[3 * lane + 1] * hg1 + Wa[3 * lane + 2] * hg2;
+        double* Crow = accs + (size_t)(wa_ * nwin - (wa_ * (wa_ - 1)) / 2 - wa_) * 36 + coff;
+        const double* bp = Wa + 3 * frow + fk;
+#pragma unroll 2
+        for (int sb = sa; sb < ns; sb++, bp += kWStride) {
+          const double b = fvalid ? *bp : 0.0;
+          double* C = Crow + 36 * (int)wbt[sb];
+          double2 c = fvalid ? *reinterpret_cast<double2*>(C) : make_double2(0.0, 0.0);
+          dmma_m8n8k4(c.x, c.y, a, b);
+          if (fvalid) *reinterpret_cast<double2*>(C) = c;
+        }
+      }
+    }
+  };
+
+  PipePoint cur, nxt;
+  load_index(0, cur);
+  load_chunk(cur);
+  load_index(1, nxt);
+  finish_point(cur, 0);
+  __syncthreads();
+  for (int ps = 0; ps < npass; ps++) {
+    cur = nxt;
+    load_chunk(cur);            // chunk of pass ps + 1: in flight during the tensor-core phase
+    load_index(ps + 2, nxt);    // index entries of pass ps + 2
+    accumulate(ps & 1);
+    if (ps + 1 < npass) finish_point(cur, (ps + 1) & 1);
+    __syncthreads();
+  }
+  // ---------------- flush: one set of atomics per batch
+  for (int t = threadIdx.x; t < npairs * 36; t += kPipeThreads) {
+    const int pr = t / 36, el = t - 36 * pr;
+    const uint32_t info = B.pair_info[pr0 + pr];
+    const int a_ = info & 0xff, b_ = (info >> 8) & 0xff;
+    const double v = accs[(size_t)(a_ * nwin - (a_ * (a_ - 1)) / 2 + (b_ - a_)) * 36 + el];
+    if (v != 0.0) atomicAdd(&S_upper[(size_t)B.pair_blk[pr0 + pr] * 36 + el], -v);
+  }
+  if ((int)threadIdx.x < nwin * 6) {
+    const int bw = threadIdx.x / 6, brow = threadIdx.x - 6 * bw;
+    const double v = s_b[bw][brow];
+    if (v != 0.0) atomicAdd(&b_schur[6 * B.win_f[(size_t)batch * 64 + bw] + brow], -v);
+  }
+  if (lane == 0) s_gmax[wib] = gmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mx = 0.0;
+    for (int i = 0; i < kPipePts; i++) mx = fmax(mx, s_gmax[i]);
+    atomic_max_nonneg(&scalars[SC_GMAX], mx);
+  }
+}
+
 // Back-substitution for one e-block + its share of the model cost change and of the candidate point:
 //   delta_e = -Hinv (g_e + sum_obs Je^T (Jp delta_p)),  model += sum m (r + m/2), m = Jp delta_p + Je delta_e
 template <int NE, int KR, int T>

@@ -126,6 +126,7 @@ struct Solver {
   DBuf<uint64_t> pb_mask;
   int n_batches = 0, n_fallback = 0;
   bool use_mma_schur = true;
+  int schur_mode = 2;  // 2: pipelined tensor-core kernel, 1: two-barrier tensor-core kernel, 0: scalar
   // state
   DBuf<double> poses[3], points[3], objects[3];  // cur, cand, best
   int cur = 0;
@@ -182,7 +183,8 @@ struct Solver {
     if (pcg_blocks_per_sm < 1) throw std::runtime_error("pcg_kernel cannot be made resident");
     CUDA_OK(cudaFuncSetAttribute(schur_points_batched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubPts * kPtStride * 8));
     CUDA_OK(cudaFuncSetAttribute(schur_points_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kSubPts * kPtStride + kMmaMaxPairs * 36) * 8));
-    if (const char* e = getenv("OBVI_SCHUR")) use_mma_schur = std::string(e) != "scalar";
+    if (const char* e = getenv("OBVI_SCHUR")) { use_mma_schur = std::string(e) != "scalar"; schur_mode = std::string(e) == "scalar" ? 0 : (std::string(e) == "mma1" ? 1 : 2); }
+    CUDA_OK(cudaFuncSetAttribute(schur_points_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemDoubles * 8));
     CUDA_OK(cudaFuncSetAttribute(bt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBB * 8));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_bt_blocks_per_sm, pcg_bt_kernel, kPcgThreads, 0));
     if (pcg_bt_blocks_per_sm < 1) throw std::runtime_error("pcg_bt_kernel cannot be made resident");
@@ -425,7 +427,8 @@ struct Solver {
     if (n_batches) {
       BatchArgs B; B.first = pb_first.p; B.count = pb_count.p; B.win_f = pb_win_f.p; B.nwin = pb_nwin.p; B.mask = pb_mask.p;
       B.pair_ptr = pb_pair_ptr.p; B.pair_info = pb_pair_info.p; B.pair_blk = pb_pair_blk.p;
-      if (use_mma_schur) schur_points_batched_kernel<true><<<n_batches, kBatchThreads, (kSubPts * kPtStride + kMmaMaxPairs * 36) * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
+      if (schur_mode == 2) schur_points_mma_kernel<<<n_batches, kPipeThreads, kPipeSmemDoubles * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
+      else if (use_mma_schur) schur_points_batched_kernel<true><<<n_batches, kBatchThreads, (kSubPts * kPtStride + kMmaMaxPairs * 36) * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
       else schur_points_batched_kernel<false><<<n_batches, kBatchThreads, kSubPts * kPtStride * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
       launches++;
     }
