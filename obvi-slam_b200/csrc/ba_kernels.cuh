@@ -63,7 +63,7 @@ __device__ __forceinline__ void atomic_max_nonneg(double* slot, double v) {
 // One thread per (pose, camera): R_cw, t_cw and the rotation-derivative matrices shared by every
 // observation of that pose (the reference recomputes them per observation on 9-wide Jets).
 __global__ void pose_cam_kernel(const double* __restrict__ poses, int K, const Camera* __restrict__ cams, int C, int jac,
-                                PoseCam* __restrict__ out) {
+                                PoseCam* __restrict__ out, PoseCamR* __restrict__ out_r = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K * C) return;
   const int k = i / C, c = i % C;
@@ -72,8 +72,10 @@ __global__ void pose_cam_kernel(const double* __restrict__ poses, int K, const C
   for (int a = 0; a < 6; a++) p[a] = poses[6 * k + a];
   PoseCam pc;
   make_pose_cam(p, cams[c].Rinv, cams[c].tinv, jac != 0, &pc);
-  if (jac) { out[i] = pc; }
-  else {
+  if (jac) {
+    out[i] = pc;
+    if (out_r) compact_pose_cam(pc, p, &out_r[i]);
+  } else {
 #pragma unroll
     for (int a = 0; a < 9; a++) out[i].Rcw[a] = pc.Rcw[a];
 #pragma unroll
@@ -230,6 +232,125 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const Ob
     if (cost != 0.0) atomicAdd(&scalars[SC_COST], cost);
     if (fixed != 0.0) atomicAdd(&scalars[SC_FIXED], fixed);
     tma_store_wait_read();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ reprojection Jacobians, persistent + pipelined
+// Third revision of the Jacobian-evaluation kernel.  The per-tile arithmetic is the one of reproj_jac_tma_kernel;
+// the difference is that a CTA is PERSISTENT (2 per SM, grid-stride over the 256-observation tiles) and the tile loop is
+// software-pipelined so that the DRAM latencies of consecutive tiles overlap instead of adding up:
+//   iteration t:  [records of tile t+2 -> registers]  [points of tile t+1 -> registers]  [PoseCam range of tile t+1 by TMA]
+//                 compute tile t from registers / shared memory -> shared-memory image of the output tile (double-buffered)
+//                 one elected thread issues the TMA bulk store; its completion is only awaited two tiles later.
+// The cost is reduced once per CTA at the end (one atomic per CTA) instead of once per tile.
+constexpr int kJacPersistSmem = 2 * kJacTileBytes + 2 * kJacMaxPc * (int)sizeof(PoseCamR) + 32;
+constexpr int kJacMaxCam = 16;
+
+template <bool ROT>
+__global__ void __launch_bounds__(kJacThreads, 2) reproj_jac_persistent_kernel(const ObsRec* __restrict__ obs, int64_t n,
+                                                                               const PoseCamR* __restrict__ pcam, const Camera* __restrict__ cams, int C,
+                                                                               const CalibClass* __restrict__ cls, int ncls,
+                                                                               const double* __restrict__ points, int apply_loss,
+                                                                               const uint2* __restrict__ tile_pc, int ntiles,
+                                                                               double* __restrict__ J, double* __restrict__ scalars) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ double red[33];
+  __shared__ CalibClass cls_s[kJacMaxCls];
+  auto out_tile = [&](int b) { return reinterpret_cast<double*>(smem + (size_t)b * kJacTileBytes); };
+  auto pc_stage = [&](int b) { return reinterpret_cast<PoseCamR*>(smem + 2 * kJacTileBytes + (size_t)b * kJacMaxPc * sizeof(PoseCamR)); };
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * kJacTileBytes + 2 * kJacMaxPc * sizeof(PoseCamR));  // bar[0], bar[1]
+  __shared__ double cam_tinv[kJacMaxCam][3];
+  const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  if (tid < ncls * 4) reinterpret_cast<double*>(cls_s)[tid] = reinterpret_cast<const double*>(cls)[tid];
+  if (tid < C * 3) cam_tinv[tid / 3][tid % 3] = cams[tid / 3].tinv[tid % 3];
+  __syncthreads();
+
+  auto rec_load = [&](int t, double2& uv, uint4& id) {
+    uv = make_double2(0.0, 0.0); id = make_uint4(0u, 0u, 0u, 0xffffffffu);   // flags = ~0 marks "no observation"
+    const int64_t i = (int64_t)t * kJacThreads + tid;
+    if (t < ntiles && i < n) { uv = reinterpret_cast<const double2*>(obs)[2 * i]; id = reinterpret_cast<const uint4*>(obs)[2 * i + 1]; }
+  };
+  auto pt_load = [&](const uint4& id, double* X) {
+    X[0] = X[1] = X[2] = 0.0;
+    if (id.w != 0xffffffffu) { X[0] = points[3 * (size_t)id.y]; X[1] = points[3 * (size_t)id.y + 1]; X[2] = points[3 * (size_t)id.y + 2]; }
+  };
+  auto pc_issue = [&](int t, int buf) {   // thread 0 only
+    if (t < ntiles) {
+      const uint2 tp = tile_pc[t];
+      mbar_expect_tx(&bar[buf], tp.y * (uint32_t)sizeof(PoseCamR));
+      tma_load_1d(pc_stage(buf), pcam + tp.x, tp.y * (uint32_t)sizeof(PoseCamR), &bar[buf]);
+    }
+  };
+
+  const int t0 = blockIdx.x, stride = gridDim.x;
+  double2 uv0, uv1, uv2; uint4 id0, id1, id2; double X0[3], X1[3];
+  rec_load(t0, uv0, id0);
+  rec_load(t0 + stride, uv1, id1);
+  if (tid == 0) pc_issue(t0, 0);
+  pt_load(id0, X0);
+  double cost = 0.0, fixed = 0.0;
+  uint32_t phase_bits = 0u;   // bit b = parity to wait for on bar[b]
+  int it = 0;
+  for (int t = t0; t < ntiles; t += stride, it++) {
+    const int buf = it & 1;
+    // ---- prefetch for the next two tiles
+    rec_load(t + 2 * stride, uv2, id2);
+    pt_load(id1, X1);
+    if (tid == 0) pc_issue(t + stride, buf ^ 1);
+    // ---- the output buffer was handed to a TMA store two tiles ago: make sure it has been read
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
+    const uint2 tp = tile_pc[t];
+    mbar_wait(&bar[buf], (phase_bits >> buf) & 1u);
+    phase_bits ^= 1u << buf;
+    const int64_t i0 = (int64_t)t * kJacThreads;
+    const int nt = (int)min((int64_t)kJacThreads, n - i0);
+    if (id0.w != 0xffffffffu) {
+      const CalibClass cc = cls_s[id0.z];
+      const uint32_t camidx = (id0.w >> 8) & 0xffu;
+      const uint32_t pci = id0.x * (uint32_t)C + camidx;
+      const uint32_t rel = pci - tp.x;
+      const double2* q2 = reinterpret_cast<const double2*>(rel < tp.y ? &pc_stage(buf)[rel] : &pcam[pci]);
+      double q[40];
+#pragma unroll
+      for (int a = 0; a < 20; a++) { const double2 v = q2[a]; q[2 * a] = v.x; q[2 * a + 1] = v.y; }   // 16-byte loads
+      double r[2], Jp[12], Jl[6];
+      reproj_residual_jacobian_compact(q, cam_tinv[camidx], X0, uv0.x, uv0.y, cc.mx, cc.my, r, Jp, Jl);
+      const double s = r[0] * r[0] + r[1] * r[1];
+      double sc = 1.0, c = 0.5 * s;
+      if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
+      if ((id0.w & 3u) == 3u) fixed += c; else cost += c;
+      double2* out = reinterpret_cast<double2*>(out_tile(buf) + (size_t)tid * kChunk);
+      double2 pc10[10];
+#pragma unroll
+      for (int a = 0; a < 6; a++) pc10[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) pc10[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
+      pc10[9] = make_double2(sc * r[0], sc * r[1]);
+      // A thread's chunk is 160 B = 40 banks: the 8 lanes of one store phase would collide pairwise.  Lanes with an odd
+      // (lane >> 2) therefore write their ten 16-byte pieces rotated by one, which makes every phase conflict-free.
+      if (ROT && ((tid >> 2) & 1)) {
+#pragma unroll
+        for (int a = 0; a < 10; a++) out[(a + 1) % 10] = pc10[(a + 1) % 10];
+      } else {
+#pragma unroll
+        for (int a = 0; a < 10; a++) out[a] = pc10[a];
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) tma_store_1d(J + (size_t)i0 * kChunk, out_tile(buf), (uint32_t)nt * kChunk * 8);
+    // ---- rotate the pipeline registers
+    uv0 = uv1; id0 = id1; X0[0] = X1[0]; X0[1] = X1[1]; X0[2] = X1[2];
+    uv1 = uv2; id1 = id2;
+  }
+  if (tid == 0) tma_store_wait_read();
+  cost = block_sum_all<kJacThreads>(cost, red);
+  fixed = block_sum_all<kJacThreads>(fixed, red);
+  if (tid == 0) {
+    if (cost != 0.0) atomicAdd(&scalars[SC_COST], cost);
+    if (fixed != 0.0) atomicAdd(&scalars[SC_FIXED], fixed);
   }
 }
 

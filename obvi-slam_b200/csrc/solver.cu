@@ -116,6 +116,8 @@ struct Solver {
   DBuf<uint8_t> pose_skip, point_skip, obj_skip;
   DBuf<uint2> jac_tile;  // per 256-observation tile: first pose/camera entry, entries staged by TMA
   bool use_tma_jac = true;
+  bool jac_rot = false;
+  int jac_mode = 1;  // 0 plain, 1 TMA per tile (default), 2 persistent + pipelined + compact entries (measured slower: 170 vs 128 us at C3)
   DBuf<BBoxRec> bbox;
   DBuf<UnaryRec> unary;
   DBuf<RelRec> rel;
@@ -131,6 +133,7 @@ struct Solver {
   DBuf<double> poses[3], points[3], objects[3];  // cur, cand, best
   int cur = 0;
   DBuf<PoseCam> pcam, pcam_cand;
+  DBuf<PoseCamR> pcam_r;  // compact entries for the persistent Jacobian kernel
   DBuf<double> J, Jb;
   DBuf<UnaryOut> unary_out;
   DBuf<RelOut> rel_out;
@@ -189,7 +192,10 @@ struct Solver {
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_bt_blocks_per_sm, pcg_bt_kernel, kPcgThreads, 0));
     if (pcg_bt_blocks_per_sm < 1) throw std::runtime_error("pcg_bt_kernel cannot be made resident");
     if (const char* e = getenv("OBVI_PRECOND")) use_bt = std::string(e) != "jacobi";
-    if (const char* e = getenv("OBVI_JAC")) use_tma_jac = std::string(e) != "plain";
+    if (const char* e = getenv("OBVI_JAC")) { const std::string v(e); jac_mode = v == "plain" ? 0 : (v == "persistent" ? 2 : 1); use_tma_jac = jac_mode > 0; }
+    CUDA_OK(cudaFuncSetAttribute(reproj_jac_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacPersistSmem));
+    CUDA_OK(cudaFuncSetAttribute(reproj_jac_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacPersistSmem));
+    if (const char* e = getenv("OBVI_JAC_ROT")) jac_rot = std::string(e) == "1";
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes));
   }
 
@@ -246,7 +252,7 @@ struct Solver {
     for (int i = 0; i < S.O; i++) ob[i] = S.obj_const[i] || !owns_object(i);
     pose_skip.upload(ps, stream); point_skip.upload(pt, stream); obj_skip.upload(ob, stream);
     for (int b = 0; b < 3; b++) { poses[b].alloc((size_t)S.K * 6); points[b].alloc((size_t)S.P * 3); objects[b].alloc((size_t)S.O * 7); }
-    pcam.alloc((size_t)S.K * std::max(S.C, 1)); pcam_cand.alloc((size_t)S.K * std::max(S.C, 1));
+    pcam.alloc((size_t)S.K * std::max(S.C, 1)); pcam_cand.alloc((size_t)S.K * std::max(S.C, 1)); pcam_r.alloc((size_t)S.K * std::max(S.C, 1));
     J.alloc((size_t)S.n_obs * kChunk); Jb.alloc((size_t)S.n_bbox * kBBoxChunk);
     unary_out.alloc(S.n_unary); rel_out.alloc(S.n_rel);
     const size_t nf6 = (size_t)S.nf * 6;
@@ -388,13 +394,9 @@ struct Solver {
   void linearize(int apply_loss) {
     const Structure& S = st;
     zero_scalars(SC_COST, 3);
-    if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p); launches++; }
+    if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p, pcam_r.p); launches++; }
     fork();
-    if (S.n_obs) {
-      if (use_tma_jac && (int)S.classes.size() <= kJacMaxCls && S.C <= 256) reproj_jac_tma_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, kJacSmemBytes, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, (int)S.classes.size(), points[cur].p, apply_loss, jac_tile.p, J.p, scalars.p);
-      else reproj_jac_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, points[cur].p, apply_loss, J.p, scalars.p);
-      launches++;
-    }
+    if (S.n_obs) launch_jacobian(apply_loss, points[cur].p);
     if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, s2>>>(bbox.p, S.n_bbox, pcam.p, S.C, objects[cur].p, 0, apply_loss, Jb.p, scalars.p); launches++; }
     if (S.n_unary) { launch_unary(0, apply_loss, cur, s2); }
     if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 0, apply_loss, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
@@ -402,6 +404,22 @@ struct Solver {
     if (S.P) { xnorm_kernel<<<nblk((int64_t)S.P * 3, 256), 256, 0, s2>>>(points[cur].p, point_skip.p, S.P, 3, scalars.p); launches++; }
     if (S.O) { xnorm_kernel<<<nblk((int64_t)S.O * 7, 256), 256, 0, s2>>>(objects[cur].p, obj_skip.p, S.O, 7, scalars.p); launches++; }
     join();
+  }
+  // the reprojection Jacobian-evaluation kernel (three revisions, selectable with OBVI_JAC = plain | tma | persistent)
+  void launch_jacobian(int apply_loss, const double* pts_dev) {
+    const Structure& S = st;
+    const bool tma_ok = (int)S.classes.size() <= kJacMaxCls && S.C <= 256;
+    const int ntiles = nblk(S.n_obs, kJacThreads);
+    if (jac_mode == 2 && tma_ok && S.C <= kJacMaxCam) {
+      const int grid = std::min(ntiles, 2 * num_sms);
+      if (jac_rot) reproj_jac_persistent_kernel<true><<<grid, kJacThreads, kJacPersistSmem, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, ntiles, J.p, scalars.p);
+      else reproj_jac_persistent_kernel<false><<<grid, kJacThreads, kJacPersistSmem, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, ntiles, J.p, scalars.p);
+    } else if (jac_mode >= 1 && tma_ok) {
+      reproj_jac_tma_kernel<<<ntiles, kJacThreads, kJacSmemBytes, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
+    } else {
+      reproj_jac_kernel<<<ntiles, kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, pts_dev, apply_loss, J.p, scalars.p);
+    }
+    launches++;
   }
   void launch_unary(int mode, int apply_loss, int buf, cudaStream_t strm) {
     const Structure& S = st;
@@ -1151,11 +1169,8 @@ int obvi_profile_jacobian(obvi_problem* p, int reps, double* sec, int64_t* bytes
   s.gather_params();
   const Structure& S = s.st;
   if (!S.n_obs) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "no reprojection observations");
-  pose_cam_kernel<<<Solver::nblk((int64_t)S.K * S.C, 128), 128, 0, s.stream>>>(s.poses[0].p, S.K, s.cams.p, S.C, 1, s.pcam.p);
-  auto launch = [&]() {
-    if (s.use_tma_jac && (int)S.classes.size() <= kJacMaxCls && S.C <= 256) reproj_jac_tma_kernel<<<Solver::nblk(S.n_obs, kJacThreads), kJacThreads, kJacSmemBytes, s.stream>>>(s.obs.p, S.n_obs, s.pcam.p, S.C, s.classes.p, (int)S.classes.size(), s.points[0].p, 1, s.jac_tile.p, s.J.p, s.scalars.p);
-    else reproj_jac_kernel<<<Solver::nblk(S.n_obs, kJacThreads), kJacThreads, 0, s.stream>>>(s.obs.p, S.n_obs, s.pcam.p, S.C, s.classes.p, s.points[0].p, 1, s.J.p, s.scalars.p);
-  };
+  pose_cam_kernel<<<Solver::nblk((int64_t)S.K * S.C, 128), 128, 0, s.stream>>>(s.poses[0].p, S.K, s.cams.p, S.C, 1, s.pcam.p, s.pcam_r.p);
+  auto launch = [&]() { s.launch_jacobian(1, s.points[0].p); };
   for (int i = 0; i < 3; i++) launch();
   CUDA_OK(cudaEventRecord(s.ev[0], s.stream));
   for (int i = 0; i < reps; i++) launch();
