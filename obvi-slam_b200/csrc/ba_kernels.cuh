@@ -235,6 +235,96 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const Ob
   }
 }
 
+// Variant of reproj_jac_tma_kernel on the compact pose/camera entries (16-byte shared-memory loads) with optional
+// conflict-free staging of the output tile.
+template <bool ROT, int STORE = 0>
+__global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma2_kernel(const ObsRec* __restrict__ obs, int64_t n,
+                                                                         const PoseCamR* __restrict__ pcam, const Camera* __restrict__ cams, int C,
+                                                                         const CalibClass* __restrict__ cls, int ncls,
+                                                                         const double* __restrict__ points, int apply_loss,
+                                                                         const uint2* __restrict__ tile_pc,
+                                                                         double* __restrict__ J, double* __restrict__ scalars) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ double red[33];
+  __shared__ CalibClass cls_s[kJacMaxCls];
+  double* out_tile = reinterpret_cast<double*>(smem);
+  PoseCamR* pc_s = reinterpret_cast<PoseCamR*>(smem + kJacTileBytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kJacTileBytes + kJacMaxPc * sizeof(PoseCamR));
+  __shared__ double cam_tinv[16][3];
+  const int64_t i0 = (int64_t)blockIdx.x * kJacThreads;
+  const int nt = (int)min((int64_t)kJacThreads, n - i0);
+  const uint2 tp = tile_pc[blockIdx.x];  // first pose/camera entry of the tile, number of entries staged
+  const int64_t i = i0 + threadIdx.x;
+  const bool active = (int)threadIdx.x < nt;
+  double2 uv = make_double2(0.0, 0.0);
+  uint4 id = make_uint4(0, 0, 0, 0);
+  if (active) {  // issue the record loads first: they head the longest dependency chain (record -> point)
+    uv = reinterpret_cast<const double2*>(obs)[2 * i];
+    id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];
+  }
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  if ((int)threadIdx.x < ncls * 4) reinterpret_cast<double*>(cls_s)[threadIdx.x] = reinterpret_cast<const double*>(cls)[threadIdx.x];
+  if ((int)threadIdx.x < C * 3) cam_tinv[threadIdx.x / 3][threadIdx.x % 3] = cams[threadIdx.x / 3].tinv[threadIdx.x % 3];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, tp.y * (uint32_t)sizeof(PoseCamR));
+    tma_load_1d(pc_s, pcam + tp.x, tp.y * (uint32_t)sizeof(PoseCamR), bar);
+  }
+  double cost = 0.0, fixed = 0.0;
+  double X[3] = {0.0, 0.0, 0.0};
+  if (active) {
+    X[0] = points[3 * (size_t)id.y]; X[1] = points[3 * (size_t)id.y + 1]; X[2] = points[3 * (size_t)id.y + 2];
+  }
+  const CalibClass cc = cls_s[id.z];
+  mbar_wait(bar, 0);
+  if (active) {
+    const uint32_t camidx = (id.w >> 8) & 0xffu;
+    const uint32_t pci = id.x * (uint32_t)C + camidx;
+    const uint32_t rel = pci - tp.x;
+    const PoseCamR* pcr = rel < tp.y ? &pc_s[rel] : &pcam[pci];
+    double r[2], Jp[12], Jl[6];
+    reproj_residual_jacobian_compact(pcr, cam_tinv[camidx], X, uv.x, uv.y, cc.mx, cc.my, r, Jp, Jl);
+    const double s = r[0] * r[0] + r[1] * r[1];
+    double sc = 1.0, c = 0.5 * s;
+    if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
+    if ((id.w & 3u) == 3u) fixed = c; else cost = c;
+    double2* out = reinterpret_cast<double2*>(out_tile + (size_t)threadIdx.x * kChunk);
+    double2 pc10[10];
+#pragma unroll
+    for (int a = 0; a < 6; a++) pc10[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) pc10[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
+    pc10[9] = make_double2(sc * r[0], sc * r[1]);
+    // 160 B per thread = 40 banks: the 8 lanes of one store phase would collide pairwise; lanes with an odd (lane >> 2)
+    // write their ten 16-byte pieces rotated by one, which makes every phase conflict-free
+    if (ROT && ((threadIdx.x >> 2) & 1)) {
+#pragma unroll
+      for (int a = 0; a < 10; a++) out[(a + 1) % 10] = pc10[(a + 1) % 10];
+    } else {
+#pragma unroll
+      for (int a = 0; a < 10; a++) out[a] = pc10[a];
+    }
+  }
+  fence_proxy_async_smem();
+  cost = block_sum_all<kJacThreads>(cost, red);     // contains __syncthreads: the tile image is complete after it
+  fixed = block_sum_all<kJacThreads>(fixed, red);
+  if (STORE == 1) {
+    // cooperative copy-out: consecutive threads store consecutive 16-byte pieces (512 B per warp instruction)
+    const double2* src = reinterpret_cast<const double2*>(out_tile);
+    double2* dst = reinterpret_cast<double2*>(J + (size_t)i0 * kChunk);
+    for (int p = threadIdx.x; p < nt * 10; p += kJacThreads) dst[p] = src[p];
+    if (threadIdx.x == 0) {
+      if (cost != 0.0) atomicAdd(&scalars[SC_COST], cost);
+      if (fixed != 0.0) atomicAdd(&scalars[SC_FIXED], fixed);
+    }
+  } else if (threadIdx.x == 0) {
+    tma_store_1d(J + (size_t)i0 * kChunk, out_tile, (uint32_t)nt * kChunk * 8);
+    if (cost != 0.0) atomicAdd(&scalars[SC_COST], cost);
+    if (fixed != 0.0) atomicAdd(&scalars[SC_FIXED], fixed);
+    tma_store_wait_read();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ reprojection Jacobians, persistent + pipelined
 // Third revision of the Jacobian-evaluation kernel.  The per-tile arithmetic is the one of reproj_jac_tma_kernel;
 // the difference is that a CTA is PERSISTENT (2 per SM, grid-stride over the 256-observation tiles) and the tile loop is
@@ -244,6 +334,7 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const Ob
 //                 one elected thread issues the TMA bulk store; its completion is only awaited two tiles later.
 // The cost is reduced once per CTA at the end (one atomic per CTA) instead of once per tile.
 constexpr int kJacPersistSmem = 2 * kJacTileBytes + 2 * kJacMaxPc * (int)sizeof(PoseCamR) + 32;
+constexpr int kJacSmemBytes2 = kJacTileBytes + kJacMaxPc * (int)sizeof(PoseCamR) + 16;
 constexpr int kJacMaxCam = 16;
 
 template <bool ROT>
@@ -311,12 +402,9 @@ __global__ void __launch_bounds__(kJacThreads, 2) reproj_jac_persistent_kernel(c
       const uint32_t camidx = (id0.w >> 8) & 0xffu;
       const uint32_t pci = id0.x * (uint32_t)C + camidx;
       const uint32_t rel = pci - tp.x;
-      const double2* q2 = reinterpret_cast<const double2*>(rel < tp.y ? &pc_stage(buf)[rel] : &pcam[pci]);
-      double q[40];
-#pragma unroll
-      for (int a = 0; a < 20; a++) { const double2 v = q2[a]; q[2 * a] = v.x; q[2 * a + 1] = v.y; }   // 16-byte loads
+      const PoseCamR* pcr = rel < tp.y ? &pc_stage(buf)[rel] : &pcam[pci];
       double r[2], Jp[12], Jl[6];
-      reproj_residual_jacobian_compact(q, cam_tinv[camidx], X0, uv0.x, uv0.y, cc.mx, cc.my, r, Jp, Jl);
+      reproj_residual_jacobian_compact(pcr, cam_tinv[camidx], X0, uv0.x, uv0.y, cc.mx, cc.my, r, Jp, Jl);
       const double s = r[0] * r[0] + r[1] * r[1];
       double sc = 1.0, c = 0.5 * s;
       if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);

@@ -192,10 +192,13 @@ struct Solver {
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_bt_blocks_per_sm, pcg_bt_kernel, kPcgThreads, 0));
     if (pcg_bt_blocks_per_sm < 1) throw std::runtime_error("pcg_bt_kernel cannot be made resident");
     if (const char* e = getenv("OBVI_PRECOND")) use_bt = std::string(e) != "jacobi";
-    if (const char* e = getenv("OBVI_JAC")) { const std::string v(e); jac_mode = v == "plain" ? 0 : (v == "persistent" ? 2 : 1); use_tma_jac = jac_mode > 0; }
+    if (const char* e = getenv("OBVI_JAC")) { const std::string v(e); jac_mode = v == "plain" ? 0 : (v == "persistent" ? 2 : (v == "tma2" ? 3 : (v == "tma2rot" ? 4 : (v == "tma2stg" ? 5 : 1)))); use_tma_jac = jac_mode > 0; }
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacPersistSmem));
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacPersistSmem));
     if (const char* e = getenv("OBVI_JAC_ROT")) jac_rot = std::string(e) == "1";
+    CUDA_OK(cudaFuncSetAttribute(reproj_jac_tma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes2));
+    CUDA_OK(cudaFuncSetAttribute(reproj_jac_tma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes2));
+    CUDA_OK((cudaFuncSetAttribute(reproj_jac_tma2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes2)));
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes));
   }
 
@@ -414,6 +417,10 @@ struct Solver {
       const int grid = std::min(ntiles, 2 * num_sms);
       if (jac_rot) reproj_jac_persistent_kernel<true><<<grid, kJacThreads, kJacPersistSmem, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, ntiles, J.p, scalars.p);
       else reproj_jac_persistent_kernel<false><<<grid, kJacThreads, kJacPersistSmem, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, ntiles, J.p, scalars.p);
+    } else if (jac_mode >= 3 && tma_ok && S.C <= 16) {
+      if (jac_mode == 5) reproj_jac_tma2_kernel<false, 1><<<ntiles, kJacThreads, kJacSmemBytes2, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
+      else if (jac_mode == 4) reproj_jac_tma2_kernel<true><<<ntiles, kJacThreads, kJacSmemBytes2, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
+      else reproj_jac_tma2_kernel<false><<<ntiles, kJacThreads, kJacSmemBytes2, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
     } else if (jac_mode >= 1 && tma_ok) {
       reproj_jac_tma_kernel<<<ntiles, kJacThreads, kJacSmemBytes, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
     } else {

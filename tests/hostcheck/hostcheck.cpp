@@ -27,10 +27,10 @@ void hc_reproj_compact(const double* pose, const double* point, const double* px
   invert_extrinsics(Re, te, Ri, ti);
   PoseCam pc;
   make_pose_cam(pose, Ri, ti, true, &pc);
-  PoseCamR pr;
+  alignas(16) PoseCamR pr;
   compact_pose_cam(pc, pose, &pr);
   const double ur = (px[0] - intr[2]) / intr[0], vr = (px[1] - intr[3]) / intr[1];
-  reproj_residual_jacobian_compact(reinterpret_cast<const double*>(&pr), ti, point, ur, vr, intr[0] / sigma, intr[1] / sigma, r, Jp, Jl);
+  reproj_residual_jacobian_compact(&pr, ti, point, ur, vr, intr[0] / sigma, intr[1] / sigma, r, Jp, Jl);
 }
 
 void hc_bbox(const double* ell, const double* pose, const double* corners, const double* cov4, const double* intr,
