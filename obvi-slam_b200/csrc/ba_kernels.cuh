@@ -210,9 +210,11 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const Ob
   if (active) {
     const uint32_t pci = id.x * (uint32_t)C + ((id.w >> 8) & 0xffu);
     const uint32_t rel = pci - tp.x;
-    const PoseCam& pc = rel < tp.y ? pc_s[rel] : pcam[pci];
     double r[2], Jp[12], Jl[6];
-    reproj_residual_jacobian(pc, X, uv.x, uv.y, cc.mx, cc.my, r, Jp, Jl);
+    // two explicit paths so that the staged entries are read with shared-memory loads (a `cond ? smem : global`
+    // reference would compile to generic loads, tracked by the long scoreboard)
+    if (rel < tp.y) reproj_residual_jacobian(pc_s[rel], X, uv.x, uv.y, cc.mx, cc.my, r, Jp, Jl);
+    else reproj_residual_jacobian(pcam[pci], X, uv.x, uv.y, cc.mx, cc.my, r, Jp, Jl);
     const double s = r[0] * r[0] + r[1] * r[1];
     double sc = 1.0, c = 0.5 * s;
     if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);

@@ -9,5 +9,5 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     c, _ = p.evaluate(apply_loss_function=True, residuals=False)
     print(json.dumps(dict(mode=os.environ.get("OBVI_JAC", "persistent"), us=sec * 1e6, gbs=nb / sec / 1e9, frac=nb / sec / 1e9 / 6556.2, cost=c)))
 else:
-    for m, rot in (("tma", "0"), ("tma2", "0"), ("tma2stg", "0")):
+    for m, rot in (("tma", "0"), ("tma2", "0")):
         print(rot, subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, OBVI_JAC=m, OBVI_JAC_ROT=rot), capture_output=True, text=True).stdout.strip())
