@@ -167,3 +167,41 @@ def test_topk_outliers_semantics(ob):
     ids = p.factor_ids["reproj"]
     worst = set(ids[np.argsort(-sq)[:k]].tolist())
     assert set(got.tolist()) == worst
+
+
+def test_pgo_with_objects(ob, oracle):
+    """The "global" step of the reference (pose_graph_plus_objects_optimizer.h:24-353): no visual factors, a relative-pose
+    factor on every consecutive pair (Huber 5.0 there), bbox + shape factors; after eliminating the objects the reduced
+    system is the whole pose graph."""
+    g = ob.synth.make_graph(K=60, P=0, O=8, seed=5, objects_on=True, relpose="all", n_const_poses=1, min_obj_obs=4)
+    g.relpose["huber"] = 5.0
+    assert g.counts()["reproj"] == 0 and g.counts()["bbox"] > 50
+    check_solve(ob, oracle, g, OPTS)
+
+
+def test_tracking_solve_mostly_constant_poses(ob, oracle):
+    """Pre-PGO tracking (offline_problem_runner.h:438-496): only the newest poses are variable."""
+    g = ob.synth.make_graph(K=30, P=600, O=4, seed=12, objects_on=True, relpose="starved", n_const_poses=27, min_obj_obs=4)
+    check_solve(ob, oracle, g, OPTS)
+
+
+def test_remove_factors_and_resolve(ob, oracle):
+    """Problem edits between solves (RemoveResidualBlock + SetParameterBlockConstant, object_pose_graph_optimizer.h:412-613):
+    the structure is rebuilt and the next solve matches an oracle run on the edited graph."""
+    g = small_graph(ob, seed=13)
+    p = ob.problem_from_graph(g)
+    p.solve(**dict(OPTS, max_num_iterations=3))
+    drop = np.arange(0, len(g.reproj["pose"]), 7)
+    for fid in p.factor_ids["reproj"][drop]:
+        p.remove_residual_block(fid)
+    p.set_parameter_block_constant(g.poses[2])
+    keep = np.ones(len(g.reproj["pose"]), bool); keep[drop] = False
+    g_ref = g.copy()
+    for k in ("pose", "point", "cam", "px", "sigma"):
+        g_ref.reproj[k] = g_ref.reproj[k][keep]
+    g_ref.const_pose[2] = True
+    s = p.solve(**OPTS)
+    ref = oracle.solve(g_ref, **oracle_opts(OPTS))
+    assert s.num_iterations == len(ref["iterations"]) and s.termination == ref["termination"]
+    assert abs(s.final_cost - ref["final_cost"]) <= 1e-5 * ref["final_cost"]
+    assert np.abs(g.poses[:, :3] - g_ref.poses[:, :3]).max() < 1e-4
