@@ -1799,6 +1799,25 @@ __global__ void pose_step_kernel(int nf, const int32_t* __restrict__ pose_of_f, 
   if (threadIdx.x == 0 && s2 != 0.0 && contribute) atomicAdd(&scalars[SC_STEP2], s2);
 }
 
+// Per-block squared norm of the residual stored in a Jacobian chunk, written at the block's rank in order of
+// addition (two-phase outlier rejection, offline_problem_runner.h:689-749: sum over the block's residual entries,
+// accumulated left to right without fused multiply-add so that the keys equal the host arithmetic bit for bit).
+__global__ void block_sqnorm_kernel(const double* __restrict__ chunks, int64_t n, int chunk, int roff, int k,
+                                    const uint32_t* __restrict__ rank, double* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* r = chunks + (size_t)i * chunk + roff;
+  double e = 0.0;
+  for (int a = 0; a < k; a++) e = __dadd_rn(e, __dmul_rn(r[a], r[a]));
+  keys[rank[i]] = e;
+  vals[rank[i]] = rank[i];
+}
+// flag the last element of every run of equal keys in the (stably) sorted sequence
+__global__ void run_end_flags_kernel(const double* __restrict__ keys, int64_t n, uint8_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (i == n - 1) || (keys[i] != keys[i + 1]);
+}
+
 // |x|^2 over the variable blocks: `mask` (per block, nonzero = skip), block size bs
 __global__ void xnorm_kernel(const double* __restrict__ x, const uint8_t* __restrict__ skip, int64_t nblocks, int bs,
                              double* __restrict__ scalars) {

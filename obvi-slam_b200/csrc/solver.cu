@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 #include "ba_kernels.cuh"
 #include "bt_precond.cuh"
 
@@ -1140,6 +1142,50 @@ int obvi_topk_outliers(obvi_problem* p, int type, double fraction, obvi_factor_i
   Solver& s = p->s;
   if (s.pb.device < 0) return fail(p, OBVI_ERR_CUDA, "host-only problem handle: no CUDA device attached (no CPU fallback exists)");
   CUDA_OK(cudaSetDevice(s.pb.device));
+  if ((type == OBVI_FACTOR_REPROJECTION || type == OBVI_FACTOR_BBOX) && s.world == 1) {
+    // ---- device path: raw residuals -> per-block keys -> stable radix sort (descending) -> last of every run of equal
+    //      keys (std::map semantics: equal keys overwrite, the last inserted block survives) -> first floor(n_u * fraction)
+    evaluate_all(s, 0);
+    const Structure& S = s.st;
+    const bool rp = type == OBVI_FACTOR_REPROJECTION;
+    const int64_t nb = rp ? S.n_obs : S.n_bbox;
+    if (nb == 0) { *n = 0; return OBVI_OK; }
+    // rank of every internal block among the live blocks of its type, in order of addition (= std::map insertion order)
+    std::vector<uint32_t> rank(nb);
+    std::vector<obvi_factor_id> id_of_rank(nb);
+    {
+      const size_t total = rp ? s.pb.reproj.size() : s.pb.bbox.size();
+      std::vector<int64_t> live_rank(total, -1);
+      int64_t c = 0;
+      for (size_t i = 0; i < total; i++) if (rp ? s.pb.reproj[i].alive : s.pb.bbox[i].alive) { live_rank[i] = c; id_of_rank[c] = make_id(type, i); c++; }
+      for (int64_t q = 0; q < nb; q++) rank[q] = (uint32_t)live_rank[rp ? S.obs_user[q] : S.bbox_user[q]];
+    }
+    DBuf<uint32_t> d_rank, d_vals, d_vals_sorted, d_sel;
+    DBuf<double> d_keys, d_keys_sorted;
+    DBuf<uint8_t> d_flags, d_tmp;
+    DBuf<int64_t> d_count;
+    d_rank.upload(rank, s.stream);
+    d_vals.alloc(nb); d_vals_sorted.alloc(nb); d_sel.alloc(nb); d_keys.alloc(nb); d_keys_sorted.alloc(nb); d_flags.alloc(nb); d_count.alloc(1);
+    if (rp) block_sqnorm_kernel<<<Solver::nblk(nb, 256), 256, 0, s.stream>>>(s.J.p, nb, kChunk, 18, 2, d_rank.p, d_keys.p, d_vals.p);
+    else block_sqnorm_kernel<<<Solver::nblk(nb, 256), 256, 0, s.stream>>>(s.Jb.p, nb, kBBoxChunk, 52, 4, d_rank.p, d_keys.p, d_vals.p);
+    size_t tmp1 = 0, tmp2 = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp1, d_keys.p, d_keys_sorted.p, d_vals.p, d_vals_sorted.p, (int)nb, 0, 64, s.stream);
+    cub::DeviceSelect::Flagged(nullptr, tmp2, d_vals_sorted.p, d_flags.p, d_sel.p, d_count.p, (int)nb, s.stream);
+    d_tmp.alloc(std::max(tmp1, tmp2));
+    cub::DeviceRadixSort::SortPairsDescending(d_tmp.p, tmp1, d_keys.p, d_keys_sorted.p, d_vals.p, d_vals_sorted.p, (int)nb, 0, 64, s.stream);
+    run_end_flags_kernel<<<Solver::nblk(nb, 256), 256, 0, s.stream>>>(d_keys_sorted.p, nb, d_flags.p);
+    cub::DeviceSelect::Flagged(d_tmp.p, tmp2, d_vals_sorted.p, d_flags.p, d_sel.p, d_count.p, (int)nb, s.stream);
+    int64_t n_unique = 0;
+    CUDA_OK(cudaMemcpyAsync(&n_unique, d_count.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_OK(cudaStreamSynchronize(s.stream));
+    const size_t k = (size_t)(n_unique * fraction);
+    std::vector<uint32_t> sel(k);
+    if (k) CUDA_OK(cudaMemcpy(sel.data(), d_sel.p, k * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t c = 0; c < k && (int64_t)c < cap; c++) if (ids) ids[c] = id_of_rank[sel[c]];
+    *n = (int64_t)k;
+    return OBVI_OK;
+  }
+  // ---- other factor types (a handful of blocks): host ranking with the reference's std::map
   int64_t nres = 0;
   int rc = obvi_evaluate(p, 0, nullptr, nullptr, 0, &nres);
   if (rc != OBVI_OK) return rc;

@@ -156,17 +156,34 @@ def test_topk_outliers_semantics(ob):
     """offline_problem_runner.h:752-801: blocks ranked by raw squared norm in a std::map (equal keys collapse),
     the first (size_t)(n * fraction) are excluded."""
     g = small_graph(ob, seed=8)
+    # duplicate the 300 worst-looking observations at the end: exact ties, of which only the LAST inserted block may survive
+    rp = g.reproj
+    dup = np.arange(0, 300)
+    for key in ("pose", "point", "cam", "px", "sigma"):
+        rp[key] = np.concatenate([rp[key], rp[key][dup]])
     p = ob.problem_from_graph(g)
     _, r = p.evaluate(apply_loss_function=False)
     n = g.counts()["reproj"]
-    sq = (r[:2 * n].reshape(n, 2) ** 2).sum(axis=1)
-    uniq = np.unique(sq)
-    k = int(len(uniq) * 0.1)
-    got = p.topk_outliers(ob.FACTOR_REPROJECTION, 0.1)
-    assert len(got) == k
-    ids = p.factor_ids["reproj"]
-    worst = set(ids[np.argsort(-sq)[:k]].tolist())
-    assert set(got.tolist()) == worst
+    rr = r[:2 * n].reshape(n, 2)
+    sq = rr[:, 0] * rr[:, 0] + rr[:, 1] * rr[:, 1]
+    by_err = {}
+    for i, e in enumerate(sq):          # std::map<double, id, greater>: equal keys overwrite
+        by_err[e] = i
+    order = sorted(by_err, reverse=True)
+    assert len(order) <= n - 300
+    for frac, ftype in ((0.1, ob.FACTOR_REPROJECTION), (0.37, ob.FACTOR_REPROJECTION)):
+        k = int(len(order) * frac)
+        got = p.topk_outliers(ftype, frac)
+        assert len(got) == k
+        ids = p.factor_ids["reproj"]
+        assert got.tolist() == [int(ids[by_err[e]]) for e in order[:k]]
+    nb = g.counts()["bbox"]
+    rb = r[2 * n:2 * n + 4 * nb].reshape(nb, 4)
+    sqb = ((rb[:, 0] * rb[:, 0] + rb[:, 1] * rb[:, 1]) + rb[:, 2] * rb[:, 2]) + rb[:, 3] * rb[:, 3]
+    kb = int(len(np.unique(sqb)) * 0.2)
+    gotb = p.topk_outliers(ob.FACTOR_BBOX, 0.2)
+    assert gotb.tolist() == [int(p.factor_ids["bbox"][i]) for i in np.argsort(-sqb, kind="stable")[:kb]]
+    assert len(p.topk_outliers(ob.FACTOR_SHAPE_PRIOR, 0.5)) == int(g.counts()["shape"] * 0.5)
 
 
 def test_pgo_with_objects(ob, oracle):
