@@ -1254,6 +1254,214 @@ __global__ void __launch_bounds__(kPipeThreads, 2) schur_points_mma_kernel(EArgs
   }
 }
 
+// ------------------------------------------------------------------------------------------ points: row-owner elimination
+// Two kernels replace the batched kernels above (kept selectable for A/B measurements):
+//   point_prep_kernel  - 8 lanes per point, a lane per pose group (the stereo pair of one keyframe): H_ll, g_l by three
+//                        xor-shuffle steps, damping, 3x3 inverse, and per (point, pose) slot the record
+//                        [W = sum Jp^T Jl (6x3) | Z = W Hinv (6x3) | Z g_l (6)] written to `WZ` (42 doubles per slot);
+//   schur_rows_kernel  - a warp per work item = (row a of the reduced matrix, 5 consecutive column offsets, <= 128 slots of
+//                        pose a): for every slot, A = Z_a, B = W_b^T of the point's slots at a + d, one DMMA per block pair,
+//                        the 6x6 accumulators live in REGISTERS for the whole item and are flushed once.
+// Compared with the batched kernel: no shared-memory accumulators (one LDG + one DMMA per block pair instead of
+// LDS.128 + DMMA + STS.128), no block barriers, lanes are never idle in the per-point phase.
+constexpr int kWZ = 42;
+struct RowGroupD { uint32_t pos0, pos1, gs, cnt; };
+struct RowItemD { uint32_t row, dlo, off, cnt; };
+
+__global__ void __launch_bounds__(256) point_prep_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr,
+                                                          const uint4* __restrict__ grp, const uint8_t* __restrict__ regular,
+                                                          LMParams lm, double* __restrict__ WZ, double* __restrict__ scalars) {
+  __shared__ double s_gmax[8];
+  const int e = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int sub = threadIdx.x & 7;
+  const bool act = e < A.ne && regular[e];
+  uint32_t g0 = 0, g1 = 0;
+  if (act) { g0 = grp_ptr[e]; g1 = grp_ptr[e + 1]; }
+  double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+  for (uint32_t gi = g0 + sub; gi < g1; gi += 8) {
+    const uint4 G = grp[gi];
+    double W[18];
+#pragma unroll
+    for (int a = 0; a < 18; a++) W[a] = 0.0;
+    for (uint32_t k = 0; k < G.w; k++) {
+      const uint32_t pos = k == 0 ? G.x : (G.w <= 2 ? G.y : A.pos[G.y + k]);
+      const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)pos * kChunk);
+      double jp[12], jl[6];
+#pragma unroll
+      for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
+#pragma unroll
+      for (int a = 0; a < 3; a++) { const double2 v = ch[6 + a]; jl[2 * a] = v.x; jl[2 * a + 1] = v.y; }
+      const double2 rv = ch[9];
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        g[a] += jl[a] * rv.x + jl[3 + a] * rv.y;
+#pragma unroll
+        for (int b = a; b < 3; b++) H[t++] += jl[a] * jl[b] + jl[3 + a] * jl[3 + b];
+      }
+      if (G.z != 0xFFFFFFFFu) {
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) W[3 * a + c] += jp[a] * jl[c] + jp[6 + a] * jl[3 + c];
+      }
+    }
+    if (G.z != 0xFFFFFFFFu) {
+      double2* out = reinterpret_cast<double2*>(WZ + (size_t)G.z * kWZ);
+#pragma unroll
+      for (int a = 0; a < 9; a++) out[a] = make_double2(W[2 * a], W[2 * a + 1]);
+    }
+  }
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) {
+#pragma unroll
+    for (int a = 0; a < 6; a++) H[a] += __shfl_xor_sync(0xffffffffu, H[a], d);
+#pragma unroll
+    for (int a = 0; a < 3; a++) g[a] += __shfl_xor_sync(0xffffffffu, g[a], d);
+  }
+  double gmax = 0.0;
+  if (act) {
+    if (A.prior_H) {
+      const double* ph = A.prior_H + (size_t)e * 9;
+      H[0] += ph[0]; H[1] += ph[1]; H[2] += ph[2]; H[3] += ph[4]; H[4] += ph[5]; H[5] += ph[8];
+#pragma unroll
+      for (int a = 0; a < 3; a++) g[a] += A.prior_g[(size_t)e * 3 + a];
+    }
+    double s[3];
+    const double hd[3] = {H[0], H[3], H[5]};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      s[a] = lm.compute_scale ? 1.0 / (1.0 + sqrt(hd[a])) : A.escale[(size_t)e * 3 + a];
+      gmax = fmax(gmax, fabs(g[a]));
+    }
+    double Hs[9], hinv[9];
+    Hs[0] = s[0] * H[0] * s[0]; Hs[1] = Hs[3] = s[0] * H[1] * s[1]; Hs[2] = Hs[6] = s[0] * H[2] * s[2];
+    Hs[4] = s[1] * H[3] * s[1]; Hs[5] = Hs[7] = s[1] * H[4] * s[2]; Hs[8] = s[2] * H[5] * s[2];
+#pragma unroll
+    for (int a = 0; a < 3; a++) Hs[4 * a] += fmin(fmax(Hs[4 * a], lm.min_diag), lm.max_diag) * lm.inv_radius;
+    const bool ok = spd_inverse3_cofactor(Hs, hinv);
+    if (!ok) {
+      if (sub == 0) atomicAdd(&scalars[SC_FAIL], 1.0);
+#pragma unroll
+      for (int a = 0; a < 9; a++) hinv[a] = 0.0;
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) hinv[3 * a + b] *= s[a] * s[b];
+      if (sub == 0) {
+        if (lm.compute_scale) { A.escale[(size_t)e * 3] = s[0]; A.escale[(size_t)e * 3 + 1] = s[1]; A.escale[(size_t)e * 3 + 2] = s[2]; }
+#pragma unroll
+        for (int a = 0; a < 9; a++) A.einv[(size_t)e * 9 + a] = hinv[a];
+#pragma unroll
+        for (int a = 0; a < 3; a++) A.eg[(size_t)e * 3 + a] = g[a];
+      }
+    }
+    for (uint32_t gi = g0 + sub; gi < g1; gi += 8) {
+      const uint32_t gs = grp[gi].z;
+      if (gs == 0xFFFFFFFFu) continue;
+      double2* rec = reinterpret_cast<double2*>(WZ + (size_t)gs * kWZ);
+      double W[18], Z[18], zg[6];
+#pragma unroll
+      for (int a = 0; a < 9; a++) { const double2 v = rec[a]; W[2 * a] = v.x; W[2 * a + 1] = v.y; }
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) Z[3 * a + c] = W[3 * a] * hinv[c] + W[3 * a + 1] * hinv[3 + c] + W[3 * a + 2] * hinv[6 + c];
+        zg[a] = Z[3 * a] * g[0] + Z[3 * a + 1] * g[1] + Z[3 * a + 2] * g[2];
+      }
+#pragma unroll
+      for (int a = 0; a < 9; a++) rec[9 + a] = make_double2(Z[2 * a], Z[2 * a + 1]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) rec[18 + a] = make_double2(zg[2 * a], zg[2 * a + 1]);
+    }
+  }
+  gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 8));
+  gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 16));
+  if ((threadIdx.x & 31) == 0) s_gmax[threadIdx.x >> 5] = gmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) mx = fmax(mx, s_gmax[i]);
+    if (mx > 0.0) atomic_max_nonneg(&scalars[SC_GMAX], mx);
+  }
+}
+
+constexpr int kRowWarps = 4;
+__global__ void __launch_bounds__(32 * kRowWarps) schur_rows_kernel(const uint4* __restrict__ items, int n_items,
+                                                                     const uint32_t* __restrict__ ent, const double* __restrict__ WZ,
+                                                                     const uint32_t* __restrict__ rowblk, int row_span,
+                                                                     double* __restrict__ S_upper, double* __restrict__ b_schur) {
+  const int item = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (item >= n_items) return;
+  const int lane = threadIdx.x & 31;
+  const uint4 it = items[item];
+  const int frow = lane >> 2, fk = lane & 3;
+  const bool fvalid = frow < 6 && fk < 3;
+  const int off = 3 * frow + fk;
+  double2 acc[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) acc[j] = make_double2(0.0, 0.0);
+  double accb = 0.0;
+  const uint32_t* ep = ent + it.z;
+  const bool first_range = it.y == 0;
+  // Software pipeline: the operands of entry i + 1 are in flight while the tensor-core products of entry i issue (two
+  // register sets, loop unrolled by two); entry descriptors are fetched 32 at a time (one per lane) and broadcast with
+  // a shuffle.  Only the k = 3 column of the A fragment has to be zero: rows / columns 6-7 of C are never flushed, so
+  // the B fragment is loaded without a validity predicate from a clamped (always finite) element.  Slots are dense, so
+  // column j of the range is the record (dlo + j) slots after the row's own.
+  struct Ops { double a, b[5], zb; uint32_t n; };
+  const int offb = 3 * (frow < 6 ? frow : 5) + (fk < 3 ? fk : 2);
+  const double* WZb = WZ + (size_t)it.y * kWZ + offb;
+  auto load_ops = [&](uint32_t e, Ops& o) {
+    const uint32_t gs = e & 0x7ffffffu;
+    o.n = e >> 27;
+    const double* za = WZ + (size_t)gs * kWZ;
+    const double* zb = WZb + (size_t)gs * kWZ;
+    o.a = fvalid ? za[18 + off] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 5; j++)
+      if ((uint32_t)j < o.n) o.b[j] = zb[j * kWZ];
+    if (first_range) o.zb = lane < 6 ? za[36 + lane] : 0.0;
+  };
+  auto consume = [&](const Ops& o) {
+    if (first_range) accb += o.zb;
+#pragma unroll
+    for (int j = 0; j < 5; j++)
+      if ((uint32_t)j < o.n) dmma_m8n8k4(acc[j].x, acc[j].y, o.a, o.b[j]);
+  };
+  Ops o0, o1;
+  uint32_t mine = 0u;
+  auto fetch = [&](uint32_t i, Ops& o) {   // i < it.w
+    if ((i & 31u) == 0u) { mine = 0u; if (i + lane < it.w) mine = ep[i + lane]; }
+    load_ops(__shfl_sync(0xffffffffu, mine, (int)(i & 31u)), o);
+  };
+  fetch(0, o0);
+  uint32_t i = 0;
+  for (; i + 2 <= it.w; i += 2) {
+    fetch(i + 1, o1);
+    consume(o0);
+    if (i + 2 < it.w) fetch(i + 2, o0);
+    consume(o1);
+  }
+  if (i < it.w) consume(o0);
+  if (fvalid) {
+    const uint32_t* rb = rowblk + (size_t)it.x * row_span + it.y;
+    const int coff = 6 * frow + 2 * fk;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      if ((int)it.y + j >= row_span) break;
+      const uint32_t blk = rb[j];
+      if (blk == 0xFFFFFFFFu) continue;
+      double* C = S_upper + (size_t)blk * 36 + coff;
+      if (acc[j].x != 0.0) atomicAdd(C, -acc[j].x);
+      if (acc[j].y != 0.0) atomicAdd(C + 1, -acc[j].y);
+    }
+  }
+  if (first_range && lane < 6 && accb != 0.0) atomicAdd(&b_schur[6 * it.x + lane], -accb);
+}
+
 // Back-substitution for one e-block + its share of the model cost change and of the candidate point:
 //   delta_e = -Hinv (g_e + sum_obs Je^T (Jp delta_p)),  model += sum m (r + m/2), m = Jp delta_p + Je delta_e
 template <int NE, int KR, int T>

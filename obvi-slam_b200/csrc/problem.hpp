@@ -58,6 +58,9 @@ struct BBoxRec {      // one per bbox observation, object-major order
 struct UnaryRec { double A[49]; double mean[7]; double huber; int32_t kind /*0 pose 1 point 2 obj*/, idx, k, off; uint32_t flags, pad; };
 struct RelRec { double tm[3]; double Rm_inv[9]; double A6[36]; double huber; int32_t p1, p2, f1, f2; int32_t blk11, blk12, blk22, swap12; };
 
+constexpr int kRowSpan = 20;        // widest pose span (in f indices) of a point handled by the row-owner kernels
+constexpr int kRowItemEnts = 128;   // entries per warp work item
+
 // Flat structure produced by the build (host copies; the solver uploads them).
 struct Structure {
   int K = 0, P = 0, O = 0, C = 0;   // poses, points, objects (referenced by live factors), cameras
@@ -97,6 +100,23 @@ struct Structure {
     std::vector<uint32_t> pair_blk;         // S_upper block of the pair
     std::vector<uint32_t> fallback;         // points handled by the generic per-e-block kernel instead
   } pbatch;
+  // Row-owner point elimination (point_prep_kernel + schur_rows_kernel).  A point is "regular" when its variable poses
+  // span fewer than kRowSpan consecutive f indices; every other point goes to the generic per-e-block kernel.
+  //   groups : per point, one record per run of observations taken from the same pose (stereo pair = one group)
+  //   entries: per (reduced-matrix row a, column range [a + 5r, a + 5r + 5)): the (point, pose a) slots that contribute
+  //   items  : <= kRowItemEnts consecutive entries of one (row, range) list = the work of one warp
+  struct RowGroup { uint32_t pos0, pos1, gs, cnt; };   // cnt <= 2: chunk positions; cnt > 2: pos1 = first list entry
+  struct RowItem { uint32_t row, dlo, off, cnt; };
+  struct PointRows {
+    std::vector<uint32_t> grp_ptr;      // P + 1
+    std::vector<RowGroup> grp;
+    std::vector<uint8_t> regular;       // P
+    std::vector<uint32_t> ent;          // slot | columns in this range (1..5) << 27
+    std::vector<RowItem> items;
+    std::vector<uint32_t> rowblk;       // nf * kRowSpan: S_upper block of (a, a + d) or 0xFFFFFFFF
+    std::vector<uint32_t> fallback;
+    int64_t n_slots = 0;
+  } prow;
   std::vector<BBoxRec> bbox;
   std::vector<uint32_t> bbox_user;
   std::vector<UnaryRec> unary;
@@ -464,6 +484,61 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     }
     close_batch();
     (void)cur_pairs;
+  }
+  // ---- row-owner structure.  Slots are DENSE per point: one record for every f index between the point's first and
+  // last variable pose (gap poses keep an all-zero record), so the column at offset d of slot gs is simply slot gs + d.
+  {
+    Structure::PointRows& R = S.prow;
+    R.regular.assign(S.P, 0); R.grp_ptr.assign(S.P + 1, 0);
+    constexpr int kRanges = (kRowSpan + 4) / 5;
+    std::vector<uint32_t> cnt((size_t)nf * kRanges + 1, 0);
+    std::vector<uint32_t> dptr(S.P + 1, 0);
+    for (int e = 0; e < S.P; e++) {
+      R.grp_ptr[e + 1] = R.grp_ptr[e]; dptr[e + 1] = dptr[e];
+      if (S.point_const[e] || S.pts.ptr[e] == S.pts.ptr[e + 1]) continue;
+      const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]]; const int ns = S.pts.nslots[e];
+      if (ns > 0 && sf[ns - 1] - sf[0] >= kRowSpan) { R.fallback.push_back((uint32_t)e); continue; }
+      R.regular[e] = 1;
+      const int span = ns ? sf[ns - 1] - sf[0] + 1 : 0;
+      dptr[e + 1] = dptr[e] + (uint32_t)span;
+      int ngs = 0;
+      for (uint32_t d = S.pts.ptr[e]; d < S.pts.ptr[e + 1];) {
+        uint32_t d2 = d + 1;
+        // a run of entries from the same pose (constant poses: one group per entry is fine, they carry no slot)
+        while (d2 < S.pts.ptr[e + 1] && S.pts.slot[d] != 0xFFFF && S.pts.slot[d2] == S.pts.slot[d]) d2++;
+        Structure::RowGroup G;
+        G.cnt = d2 - d; G.pos0 = S.pts.pos[d]; G.pos1 = G.cnt == 2 ? S.pts.pos[d + 1] : (G.cnt > 2 ? d : 0u);
+        G.gs = S.pts.slot[d] == 0xFFFF ? 0xFFFFFFFFu : dptr[e] + (uint32_t)(S.pts.f[d] - sf[0]);
+        R.grp.push_back(G); ngs++;
+        d = d2;
+      }
+      R.grp_ptr[e + 1] = R.grp_ptr[e] + (uint32_t)ngs;
+      for (int a = 0; a < ns; a++) {
+        const int ncol = sf[ns - 1] - sf[a] + 1;
+        for (int r = 0; 5 * r < ncol; r++) cnt[(size_t)sf[a] * kRanges + r + 1]++;
+      }
+    }
+    R.n_slots = dptr[S.P];
+    if (R.n_slots >= (1ll << 27)) { err = "too many point slots for the row-owner elimination"; return false; }
+    for (size_t i = 0; i + 1 < cnt.size(); i++) cnt[i + 1] += cnt[i];
+    R.ent.resize(cnt.back());
+    std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
+    for (int e = 0; e < S.P; e++) {
+      if (!R.regular[e]) continue;
+      const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]]; const int ns = S.pts.nslots[e];
+      for (int a = 0; a < ns; a++) {
+        const int ncol = sf[ns - 1] - sf[a] + 1;
+        const uint32_t gs = dptr[e] + (uint32_t)(sf[a] - sf[0]);
+        for (int r = 0; 5 * r < ncol; r++) R.ent[cur[(size_t)sf[a] * kRanges + r]++] = gs | ((uint32_t)std::min(5, ncol - 5 * r) << 27);
+      }
+    }
+    for (int a = 0; a < nf; a++) for (int r = 0; r < kRanges; r++) {
+      const uint32_t b0 = cnt[(size_t)a * kRanges + r], b1 = cnt[(size_t)a * kRanges + r + 1];
+      for (uint32_t o = b0; o < b1; o += kRowItemEnts) R.items.push_back({(uint32_t)a, (uint32_t)(5 * r), o, std::min<uint32_t>(kRowItemEnts, b1 - o)});
+    }
+    R.rowblk.assign((size_t)nf * kRowSpan, 0xFFFFFFFFu);
+    for (int a = 0; a < nf; a++) for (int d = 0; d < kRowSpan && a + d < nf; d++)
+      if ((bits[(size_t)a * W + ((a + d) >> 6)] >> ((a + d) & 63)) & 1) R.rowblk[(size_t)a * kRowSpan + d] = blk_of(a, a + d);
   }
   for (RelRec& r : S.rel) {
     r.blk11 = r.f1 >= 0 ? (int32_t)blk_of(r.f1, r.f1) : -1;

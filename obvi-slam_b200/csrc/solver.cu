@@ -130,7 +130,15 @@ struct Solver {
   DBuf<uint64_t> pb_mask;
   int n_batches = 0, n_fallback = 0;
   bool use_mma_schur = true;
-  int schur_mode = 2;  // 2: pipelined tensor-core kernel, 1: two-barrier tensor-core kernel, 0: scalar
+  int schur_mode = 3;  // 3: row-owner kernels (default), 2: pipelined batched tensor-core kernel, 1: two-barrier one, 0: scalar
+  // row-owner point elimination (point_prep_kernel + schur_rows_kernel)
+  DBuf<uint32_t> pr_grp_ptr, pr_rowblk, pr_fallback;
+  DBuf<Structure::RowGroup> pr_grp;
+  DBuf<uint32_t> pr_ent;
+  DBuf<Structure::RowItem> pr_items;
+  DBuf<uint8_t> pr_regular;
+  DBuf<double> WZ;
+  int n_row_items = 0, n_row_fallback = 0;
   // state
   DBuf<double> poses[3], points[3], objects[3];  // cur, cand, best
   int cur = 0;
@@ -188,7 +196,7 @@ struct Solver {
     if (pcg_blocks_per_sm < 1) throw std::runtime_error("pcg_kernel cannot be made resident");
     CUDA_OK(cudaFuncSetAttribute(schur_points_batched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubPts * kPtStride * 8));
     CUDA_OK(cudaFuncSetAttribute(schur_points_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kSubPts * kPtStride + kMmaMaxPairs * 36) * 8));
-    if (const char* e = getenv("OBVI_SCHUR")) { use_mma_schur = std::string(e) != "scalar"; schur_mode = std::string(e) == "scalar" ? 0 : (std::string(e) == "mma1" ? 1 : 2); }
+    if (const char* e = getenv("OBVI_SCHUR")) { const std::string v(e); use_mma_schur = v != "scalar"; schur_mode = v == "scalar" ? 0 : (v == "mma1" ? 1 : (v == "mma" ? 2 : 3)); }
     CUDA_OK(cudaFuncSetAttribute(schur_points_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemDoubles * 8));
     CUDA_OK(cudaFuncSetAttribute(bt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBB * 8));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_bt_blocks_per_sm, pcg_bt_kernel, kPcgThreads, 0));
@@ -245,6 +253,13 @@ struct Solver {
       pb_first.upload(B.first, stream); pb_count.upload(B.count, stream); pb_nwin.upload(B.nwin, stream); pb_win_f.upload(B.win_f, stream);
       pb_mask.upload(B.mask, stream); pb_pair_ptr.upload(B.pair_ptr, stream); pb_pair_info.upload(B.pair_info, stream);
       pb_pair_blk.upload(B.pair_blk, stream); pb_fallback.upload(B.fallback, stream);
+    }
+    {
+      const Structure::PointRows& R = S.prow;
+      n_row_items = (int)R.items.size(); n_row_fallback = (int)R.fallback.size();
+      pr_grp_ptr.upload(R.grp_ptr, stream); pr_grp.upload(R.grp, stream); pr_regular.upload(R.regular, stream);
+      pr_ent.upload(R.ent, stream); pr_items.upload(R.items, stream); pr_rowblk.upload(R.rowblk, stream); pr_fallback.upload(R.fallback, stream);
+      if (schur_mode == 3) { WZ.alloc((size_t)std::max<int64_t>(R.n_slots, 1) * kWZ); WZ.zero(stream); }  // gap slots stay zero
     }
     pts.has_prior = objs.has_prior = false;
     for (const UnaryRec& u : S.unary) { if (u.kind == 1) pts.has_prior = true; if (u.kind == 2) objs.has_prior = true; }
@@ -451,7 +466,15 @@ struct Solver {
     if (S.n_unary && pts.has_prior) launch_unary(1, 1, cur, stream);
     fork();
     if (S.n_obs && S.nf) { pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag); launches++; }
-    if (n_batches) {
+    if (schur_mode == 3) {
+      if (S.P) { point_prep_kernel<<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
+      if (n_row_items) { schur_rows_kernel<<<nblk(n_row_items, kRowWarps), 32 * kRowWarps, 0, stream>>>(reinterpret_cast<const uint4*>(pr_items.p), n_row_items, pr_ent.p, WZ.p, pr_rowblk.p, kRowSpan, S_upper, b_schur); launches++; }
+      if (n_row_fallback) {
+        EArgs a = eargs(pts, J.p); a.elist = pr_fallback.p;
+        schur_eblock_kernel<3, 2, 32, 16, false><<<n_row_fallback, 32, 0, stream>>>(a, lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p);
+        launches++;
+      }
+    } else if (n_batches) {
       BatchArgs B; B.first = pb_first.p; B.count = pb_count.p; B.win_f = pb_win_f.p; B.nwin = pb_nwin.p; B.mask = pb_mask.p;
       B.pair_ptr = pb_pair_ptr.p; B.pair_info = pb_pair_info.p; B.pair_blk = pb_pair_blk.p;
       if (schur_mode == 2) schur_points_mma_kernel<<<n_batches, kPipeThreads, kPipeSmemDoubles * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
@@ -459,7 +482,7 @@ struct Solver {
       else schur_points_batched_kernel<false><<<n_batches, kBatchThreads, kSubPts * kPtStride * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
       launches++;
     }
-    if (n_fallback) {
+    if (schur_mode != 3 && n_fallback) {
       EArgs a = eargs(pts, J.p); a.elist = pb_fallback.p;
       schur_eblock_kernel<3, 2, 32, 16, false><<<n_fallback, 32, 0, stream>>>(a, lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p);
       launches++;
