@@ -1268,7 +1268,7 @@ constexpr int kWZ = 42;
 struct RowGroupD { uint32_t pos0, pos1, gs, cnt; };
 struct RowItemD { uint32_t row, dlo, off, cnt; };
 
-__global__ void __launch_bounds__(256) point_prep_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr,
+__global__ void __launch_bounds__(256, 2) point_prep_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr,
                                                           const uint4* __restrict__ grp, const uint8_t* __restrict__ regular,
                                                           LMParams lm, double* __restrict__ WZ, double* __restrict__ scalars) {
   __shared__ double s_gmax[8];
@@ -1278,11 +1278,13 @@ __global__ void __launch_bounds__(256) point_prep_kernel(EArgs A, const uint32_t
   uint32_t g0 = 0, g1 = 0;
   if (act) { g0 = grp_ptr[e]; g1 = grp_ptr[e + 1]; }
   double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-  for (uint32_t gi = g0 + sub; gi < g1; gi += 8) {
-    const uint4 G = grp[gi];
-    double W[18];
+  // the lane's FIRST group keeps its W in registers across the reduction (the common case: <= 8 groups per point, so
+  // every lane has at most one); further groups (gi + 8, ...) park W in the record and reload it for the Z pass
+  double W0[18];
+  uint32_t gs0 = 0xFFFFFFFFu;
 #pragma unroll
-    for (int a = 0; a < 18; a++) W[a] = 0.0;
+  for (int a = 0; a < 18; a++) W0[a] = 0.0;
+  auto sweep = [&](const uint4 G, double* W) {
     for (uint32_t k = 0; k < G.w; k++) {
       const uint32_t pos = k == 0 ? G.x : (G.w <= 2 ? G.y : A.pos[G.y + k]);
       const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)pos * kChunk);
@@ -1306,6 +1308,18 @@ __global__ void __launch_bounds__(256) point_prep_kernel(EArgs A, const uint32_t
           for (int c = 0; c < 3; c++) W[3 * a + c] += jp[a] * jl[c] + jp[6 + a] * jl[3 + c];
       }
     }
+  };
+  if (g0 + sub < g1) {
+    const uint4 G = grp[g0 + sub];
+    gs0 = G.z;
+    sweep(G, W0);
+  }
+  for (uint32_t gi = g0 + sub + 8; gi < g1; gi += 8) {
+    const uint4 G = grp[gi];
+    double W[18];
+#pragma unroll
+    for (int a = 0; a < 18; a++) W[a] = 0.0;
+    sweep(G, W);
     if (G.z != 0xFFFFFFFFu) {
       double2* out = reinterpret_cast<double2*>(WZ + (size_t)G.z * kWZ);
 #pragma unroll
@@ -1357,23 +1371,33 @@ __global__ void __launch_bounds__(256) point_prep_kernel(EArgs A, const uint32_t
         for (int a = 0; a < 3; a++) A.eg[(size_t)e * 3 + a] = g[a];
       }
     }
-    for (uint32_t gi = g0 + sub; gi < g1; gi += 8) {
-      const uint32_t gs = grp[gi].z;
-      if (gs == 0xFFFFFFFFu) continue;
+    auto emit = [&](uint32_t gs, const double* W, bool store_w) {
       double2* rec = reinterpret_cast<double2*>(WZ + (size_t)gs * kWZ);
-      double W[18], Z[18], zg[6];
-#pragma unroll
-      for (int a = 0; a < 9; a++) { const double2 v = rec[a]; W[2 * a] = v.x; W[2 * a + 1] = v.y; }
+      double Z[18], zg[6];
 #pragma unroll
       for (int a = 0; a < 6; a++) {
 #pragma unroll
         for (int c = 0; c < 3; c++) Z[3 * a + c] = W[3 * a] * hinv[c] + W[3 * a + 1] * hinv[3 + c] + W[3 * a + 2] * hinv[6 + c];
         zg[a] = Z[3 * a] * g[0] + Z[3 * a + 1] * g[1] + Z[3 * a + 2] * g[2];
       }
+      if (store_w) {
+#pragma unroll
+        for (int a = 0; a < 9; a++) rec[a] = make_double2(W[2 * a], W[2 * a + 1]);
+      }
 #pragma unroll
       for (int a = 0; a < 9; a++) rec[9 + a] = make_double2(Z[2 * a], Z[2 * a + 1]);
 #pragma unroll
       for (int a = 0; a < 3; a++) rec[18 + a] = make_double2(zg[2 * a], zg[2 * a + 1]);
+    };
+    if (gs0 != 0xFFFFFFFFu) emit(gs0, W0, true);
+    for (uint32_t gi = g0 + sub + 8; gi < g1; gi += 8) {
+      const uint32_t gs = grp[gi].z;
+      if (gs == 0xFFFFFFFFu) continue;
+      const double2* rec = reinterpret_cast<const double2*>(WZ + (size_t)gs * kWZ);
+      double W[18];
+#pragma unroll
+      for (int a = 0; a < 9; a++) { const double2 v = rec[a]; W[2 * a] = v.x; W[2 * a + 1] = v.y; }
+      emit(gs, W, false);
     }
   }
   gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 8));
@@ -1542,14 +1566,15 @@ __global__ void __launch_bounds__(T) backsub_eblock_kernel(EArgs A, const double
 
 // Back-substitution for points, one warp per point, lane = observation, the 160-byte chunk held in registers
 // between the two passes (10 x 16-byte loads per observation).
-__global__ void __launch_bounds__(128) backsub_points_kernel(EArgs A, const double* __restrict__ dpose,
+__global__ void __launch_bounds__(128) backsub_points_kernel(EArgs A, int n_e, const double* __restrict__ dpose,
                                                              const double* __restrict__ x, double* __restrict__ x_cand,
                                                              double* __restrict__ delta_e, double* __restrict__ scalars) {
   __shared__ double s_mc[4], s_s2[4];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int e = blockIdx.x * 4 + wib;
+  const int ei = blockIdx.x * 4 + wib;
+  const int e = ei < n_e ? (A.elist ? (int)A.elist[ei] : ei) : 0;
   double mc = 0.0, s2 = 0.0;
-  if (e < A.ne) {
+  if (ei < n_e) {
     const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
     const bool cst = A.cst[e] != 0;
     if (b1 > b0 || (!cst && A.prior_H != nullptr)) {
@@ -1630,6 +1655,89 @@ __global__ void __launch_bounds__(128) backsub_points_kernel(EArgs A, const doub
   __syncthreads();
   if (threadIdx.x == 0) {
     const double m = s_mc[0] + s_mc[1] + s_mc[2] + s_mc[3], s = s_s2[0] + s_s2[1] + s_s2[2] + s_s2[3];
+    if (m != 0.0) atomicAdd(&scalars[SC_MODEL], m);
+    if (s != 0.0) atomicAdd(&scalars[SC_STEP2], s);
+  }
+}
+
+// Single-pass back-substitution for the points the row-owner path handles (8 lanes per point, a lane per pose group).
+// With a = Jp delta_p per observation, the point's share of the model cost change expands to
+//   sum m (r + m/2),  m = a + Jl delta_e   =   sum a.(r + a/2)  +  delta_e.(g_l + t)  +  delta_e^T H_ll delta_e / 2
+// with t = sum Jl^T a, g_l = sum Jl^T r, H_ll = sum Jl^T Jl, so one sweep over the Jacobian chunks is enough (the generic
+// kernel above sweeps twice: once for t, once for m after delta_e is known).
+__global__ void __launch_bounds__(256) backsub_rows_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr, const uint4* __restrict__ grp,
+                                                            const int32_t* __restrict__ grp_f, const uint8_t* __restrict__ regular,
+                                                            const double* __restrict__ dpose, const double* __restrict__ x,
+                                                            double* __restrict__ x_cand, double* __restrict__ delta_e,
+                                                            double* __restrict__ scalars) {
+  __shared__ double s_mc[8], s_s2[8];
+  const int e = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int sub = threadIdx.x & 7;
+  const bool act = e < A.ne && regular[e];
+  uint32_t g0 = 0, g1 = 0;
+  if (act) { g0 = grp_ptr[e]; g1 = grp_ptr[e + 1]; }
+  double H[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0}, t[3] = {0, 0, 0}, sa = 0.0;
+  for (uint32_t gi = g0 + sub; gi < g1; gi += 8) {
+    const uint4 G = grp[gi];
+    const int fi = grp_f[gi];
+    double dp[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) dp[a] = fi >= 0 ? dpose[6 * fi + a] : 0.0;
+    for (uint32_t k = 0; k < G.w; k++) {
+      const uint32_t pos = k == 0 ? G.x : (G.w <= 2 ? G.y : A.pos[G.y + k]);
+      const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)pos * kChunk);
+      double jp[12], jl[6];
+#pragma unroll
+      for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
+#pragma unroll
+      for (int a = 0; a < 3; a++) { const double2 v = ch[6 + a]; jl[2 * a] = v.x; jl[2 * a + 1] = v.y; }
+      const double2 rv = ch[9];
+      const double a0 = jp[0] * dp[0] + jp[1] * dp[1] + jp[2] * dp[2] + jp[3] * dp[3] + jp[4] * dp[4] + jp[5] * dp[5];
+      const double a1 = jp[6] * dp[0] + jp[7] * dp[1] + jp[8] * dp[2] + jp[9] * dp[3] + jp[10] * dp[4] + jp[11] * dp[5];
+      sa += a0 * (rv.x + 0.5 * a0) + a1 * (rv.y + 0.5 * a1);
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        t[a] += jl[a] * a0 + jl[3 + a] * a1;
+        gl[a] += jl[a] * rv.x + jl[3 + a] * rv.y;
+#pragma unroll
+        for (int b = a; b < 3; b++) H[q++] += jl[a] * jl[b] + jl[3 + a] * jl[3 + b];
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) {
+#pragma unroll
+    for (int a = 0; a < 6; a++) H[a] += __shfl_xor_sync(0xffffffffu, H[a], d);
+#pragma unroll
+    for (int a = 0; a < 3; a++) { gl[a] += __shfl_xor_sync(0xffffffffu, gl[a], d); t[a] += __shfl_xor_sync(0xffffffffu, t[a], d); }
+    sa += __shfl_xor_sync(0xffffffffu, sa, d);
+  }
+  double mc = 0.0, s2 = 0.0;
+  if (act && sub == 0) {
+    const double* hinv = A.einv + (size_t)e * 9;
+    double u[3], de[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) u[a] = t[a] + A.eg[(size_t)e * 3 + a];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      de[a] = -(hinv[3 * a] * u[0] + hinv[3 * a + 1] * u[1] + hinv[3 * a + 2] * u[2]);
+      delta_e[(size_t)e * 3 + a] = de[a];
+      x_cand[(size_t)e * 3 + a] = x[(size_t)e * 3 + a] + de[a];
+      s2 += de[a] * de[a];
+    }
+    const double hd0 = H[0] * de[0] + H[1] * de[1] + H[2] * de[2];
+    const double hd1 = H[1] * de[0] + H[3] * de[1] + H[4] * de[2];
+    const double hd2 = H[2] * de[0] + H[4] * de[1] + H[5] * de[2];
+    mc = sa + de[0] * (gl[0] + t[0] + 0.5 * hd0) + de[1] * (gl[1] + t[1] + 0.5 * hd1) + de[2] * (gl[2] + t[2] + 0.5 * hd2);
+  }
+  mc = warp_sum(mc); s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { s_mc[threadIdx.x >> 5] = mc; s_s2[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0, s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { m += s_mc[i]; s += s_s2[i]; }
     if (m != 0.0) atomicAdd(&scalars[SC_MODEL], m);
     if (s != 0.0) atomicAdd(&scalars[SC_STEP2], s);
   }

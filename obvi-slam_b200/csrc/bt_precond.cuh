@@ -173,6 +173,196 @@ __global__ void __launch_bounds__(256) bt_gemm_kernel(const GemmTask* __restrict
     }
 }
 
+// ---- second-generation factorisation kernels (default; the two above are kept selectable with OBVI_BT=v1) ----
+//
+// bt_invert8_kernel: BLOCKED Gauss-Jordan (block size 8, no pivoting) of a 96 x 96 SPD matrix, one CTA of 1024 threads,
+// thread (ty, tx) keeps its 3 x 3 elements in registers.  Per block pivot: (1) the 8 pivot rows and 8 pivot columns go
+// to shared memory, (2) warp 0 inverts the 8 x 8 pivot block with shuffles (two elements per lane), (3) everybody scales
+// the row panel by the inverse, (4) one rank-8 update of the registers.  12 block pivots x 3 barriers instead of 96
+// scalar pivots each with its own barrier and per-element select logic.
+__global__ void __launch_bounds__(kInvThreads) bt_invert8_kernel(const int* __restrict__ idx, const double* __restrict__ D,
+                                                                  double* __restrict__ Dinv, double* __restrict__ scalars) {
+  constexpr int b = 8;
+  __shared__ double rowp[b][kB];    // raw pivot rows A[P, :]
+  __shared__ double rowq[b][kB];    // scaled pivot rows  Pinv A[P, :]  (columns in P: Pinv itself)
+  __shared__ double colp[2][kB][b + 1];  // raw pivot columns A[:, P] (double-buffered: read in step 4, rewritten in the next step 1)
+  __shared__ double pinv[b][b];
+  __shared__ int s_bad;
+  const int blk = idx[blockIdx.x];
+  const double* src = D + (size_t)blk * kBB;
+  double* dst = Dinv + (size_t)blk * kBB;
+  const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+  double v[3][3];
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+#pragma unroll
+    for (int n = 0; n < 3; n++) v[m][n] = src[(size_t)(ty + 32 * m) * kB + tx + 32 * n];
+  if (threadIdx.x == 0) s_bad = 0;
+  for (int pb = 0; pb < kB; pb += b) {
+    const int pm = pb >> 5, po = pb & 31;   // the pivot rows are the thread rows ty + 32 pm with ty in [po, po + 8)
+    // (1) publish the panels
+    if (ty >= po && ty < po + b) {
+#pragma unroll
+      for (int n = 0; n < 3; n++) rowp[ty - po][tx + 32 * n] = pm == 0 ? v[0][n] : (pm == 1 ? v[1][n] : v[2][n]);
+    }
+    if (tx >= po && tx < po + b) {
+#pragma unroll
+      for (int m = 0; m < 3; m++) colp[(pb >> 3) & 1][ty + 32 * m][tx - po] = pm == 0 ? v[m][0] : (pm == 1 ? v[m][1] : v[m][2]);
+    }
+    __syncthreads();
+    // (2) warp 0: Gauss-Jordan on the 8 x 8 pivot block, lane (r = lane / 4, c0 = 2 (lane % 4)) holds [r][c0], [r][c0 + 1]
+    if (ty == 0) {
+      const int r = tx >> 2, c0 = 2 * (tx & 3);
+      double e0 = rowp[r][pb + c0], e1 = rowp[r][pb + c0 + 1];
+      bool bad = false;
+#pragma unroll
+      for (int p = 0; p < b; p++) {
+        const int src_p = (p << 2) | (p >> 1);          // lane holding [p][p]
+        const double pv0 = __shfl_sync(0xffffffffu, e0, src_p), pv1 = __shfl_sync(0xffffffffu, e1, src_p);
+        const double piv = (p & 1) ? pv1 : pv0;
+        if (!(piv > 0.0)) bad = true;
+        const double d = __drcp_rn(piv);
+        // pivot row entries for my two columns, pivot column entry for my row
+        const int src_r = (p << 2) | (tx & 3);
+        const double g0 = __shfl_sync(0xffffffffu, e0, src_r) * d, g1 = __shfl_sync(0xffffffffu, e1, src_r) * d;
+        const int src_c = (r << 2) | (p >> 1);
+        const double f0 = __shfl_sync(0xffffffffu, e0, src_c), f1 = __shfl_sync(0xffffffffu, e1, src_c);
+        const double f = (p & 1) ? f1 : f0;
+        if (r == p) {
+          e0 = (c0 == p) ? d : g0;
+          e1 = (c0 + 1 == p) ? d : g1;
+        } else {
+          e0 = (c0 == p) ? -f * d : e0 - f * g0;
+          e1 = (c0 + 1 == p) ? -f * d : e1 - f * g1;
+        }
+      }
+      pinv[r][c0] = e0; pinv[r][c0 + 1] = e1;
+      if (bad) s_bad = 1;
+    }
+    __syncthreads();
+    // (3) scaled row panel: rowq[k][j] = sum_m pinv[k][m] rowp[m][j]  (j outside P), pinv[k][j - pb] inside
+    if (threadIdx.x < b * kB) {
+      const int k = threadIdx.x / kB, j = threadIdx.x - k * kB;
+      double s;
+      if (j >= pb && j < pb + b) s = pinv[k][j - pb];
+      else {
+        s = 0.0;
+#pragma unroll
+        for (int m = 0; m < b; m++) s += pinv[k][m] * rowp[m][j];
+      }
+      rowq[k][j] = s;
+    }
+    __syncthreads();
+    // (4) rank-8 update of the registers
+    double s[3][3];
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+      for (int n = 0; n < 3; n++) s[m][n] = 0.0;
+#pragma unroll
+    for (int k = 0; k < b; k++) {
+      double c[3], q[3];
+#pragma unroll
+      for (int m = 0; m < 3; m++) { c[m] = colp[(pb >> 3) & 1][ty + 32 * m][k]; q[m] = rowq[k][tx + 32 * m]; }
+#pragma unroll
+      for (int m = 0; m < 3; m++)
+#pragma unroll
+        for (int n = 0; n < 3; n++) s[m][n] += c[m] * q[n];
+    }
+    // i in P: the scaled pivot row;  j in P (i outside): -A[i, P] Pinv = -s;  otherwise A[i][j] - A[i, P] Pinv A[P, j]
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const int i = ty + 32 * m;
+      const bool irow = i >= pb && i < pb + b;
+#pragma unroll
+      for (int n = 0; n < 3; n++) {
+        const int j = tx + 32 * n;
+        const bool jcol = j >= pb && j < pb + b;
+        v[m][n] = irow ? rowq[irow ? i - pb : 0][j] : (jcol ? -s[m][n] : v[m][n] - s[m][n]);
+      }
+    }
+    // hazards: rowp is rewritten after barrier (3), rowq / pinv after the next barriers (1)-(2); colp is double-buffered
+  }
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+#pragma unroll
+    for (int n = 0; n < 3; n++) dst[(size_t)(ty + 32 * m) * kB + tx + 32 * n] = v[m][n];
+  __syncthreads();
+  if (threadIdx.x == 0 && s_bad) atomicAdd(&scalars[SC_BT_FAIL], 1.0);
+}
+
+// bt_gemm_mma_kernel: same task list as bt_gemm_kernel, on the fp64 tensor-core path (mma.sync m8n8k4, SASS DMMA).
+// The two 96 x 96 operands of a term are staged in shared memory by TMA, one 768-byte bulk copy per matrix row into a
+// row stride of 100 doubles: with that stride both the plain and the transposed fragment reads (8 x 4 / 4 x 8 doubles per
+// warp) are bank-conflict free, so a transposed operand needs no transposing copy.  16 warps in a 4 x 4 grid, each owns a
+// 24 x 24 output tile (3 x 3 fragments): 6 LDS + 9 DMMA per k-step of 4.
+constexpr int kGemmLd = 100;
+constexpr int kGemmSmem = 2 * kB * kGemmLd * 8;
+__global__ void __launch_bounds__(512) bt_gemm_mma_kernel(const GemmTask* __restrict__ tasks) {
+  extern __shared__ __align__(16) double gsm[];
+  __shared__ uint64_t bar;
+  double* As = gsm;
+  double* Bs = gsm + kB * kGemmLd;
+  const GemmTask T = tasks[blockIdx.x];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int m0 = 24 * (w >> 2), n0 = 24 * (w & 3);
+  const int fr = lane >> 2, fk = lane & 3;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  double2 acc[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) acc[i][j] = make_double2(0.0, 0.0);
+  for (int term = 0; term < 2; term++) {
+    const double* A = term ? T.A2 : T.A1;
+    const double* Bm = term ? T.B2 : T.B1;
+    if (!A) break;
+    const int tA = term ? T.tA2 : T.tA1, tB = term ? T.tB2 : T.tB1;
+    const double alpha = term ? T.alpha2 : T.alpha1;
+    if (term) { __syncthreads(); fence_proxy_async_smem(); }   // everybody is done reading the previous operands
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, 2 * kBB * 8);
+    __syncthreads();
+    if (threadIdx.x < kB) tma_load_1d(As + threadIdx.x * kGemmLd, A + (size_t)threadIdx.x * kB, kB * 8, &bar);
+    else if (threadIdx.x < 2 * kB) tma_load_1d(Bs + (threadIdx.x - kB) * kGemmLd, Bm + (size_t)(threadIdx.x - kB) * kB, kB * 8, &bar);
+    mbar_wait(&bar, (uint32_t)term);
+    // element strides in shared memory: op(A)[m][k] = As[m sAm + k sAk],  op(B)[k][n] = Bs[k sBk + n sBn]
+    const int sAm = tA ? 1 : kGemmLd, sAk = tA ? kGemmLd : 1, sBk = tB ? 1 : kGemmLd, sBn = tB ? kGemmLd : 1;
+    const double* ap = As + (m0 + fr) * sAm + fk * sAk;
+    const double* bp = Bs + fk * sBk + (n0 + fr) * sBn;
+    double2 part[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) part[i][j] = make_double2(0.0, 0.0);
+#pragma unroll 4
+    for (int k0 = 0; k0 < kB; k0 += 4) {
+      double a[3], b[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) a[i] = ap[8 * i * sAm + k0 * sAk];
+#pragma unroll
+      for (int j = 0; j < 3; j++) b[j] = bp[k0 * sBk + 8 * j * sBn];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) dmma_m8n8k4(part[i][j].x, part[i][j].y, a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) { acc[i][j].x += alpha * part[i][j].x; acc[i][j].y += alpha * part[i][j].y; }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double2* c = reinterpret_cast<double2*>(T.C + (size_t)(m0 + 8 * i + fr) * kB + n0 + 8 * j + 2 * fk);
+      double2 o = acc[i][j];
+      if (T.beta != 0.0) { const double2 old = *c; o.x += T.beta * old.x; o.y += T.beta * old.y; }
+      *c = o;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // PCG on S~ y = b~ with the block-tridiagonal preconditioner.  Persistent cooperative kernel, 16 warps per CTA.
 // Vectors are padded to nsb * 96 entries (zeros beyond 6 nf).

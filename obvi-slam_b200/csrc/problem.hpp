@@ -110,6 +110,7 @@ struct Structure {
   struct PointRows {
     std::vector<uint32_t> grp_ptr;      // P + 1
     std::vector<RowGroup> grp;
+    std::vector<int32_t> grp_f;         // f index of the group's pose (-1 constant)
     std::vector<uint8_t> regular;       // P
     std::vector<uint32_t> ent;          // slot | columns in this range (1..5) << 27
     std::vector<RowItem> items;
@@ -493,9 +494,13 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     constexpr int kRanges = (kRowSpan + 4) / 5;
     std::vector<uint32_t> cnt((size_t)nf * kRanges + 1, 0);
     std::vector<uint32_t> dptr(S.P + 1, 0);
+    std::vector<uint8_t> pt_has_prior(S.P, 0);
+    for (const UnaryRec& u : S.unary) if (u.kind == 1) pt_has_prior[u.idx] = 1;
     for (int e = 0; e < S.P; e++) {
       R.grp_ptr[e + 1] = R.grp_ptr[e]; dptr[e + 1] = dptr[e];
-      if (S.point_const[e] || S.pts.ptr[e] == S.pts.ptr[e + 1]) continue;
+      // constant points with observations (they still carry model-cost terms) and prior-only points keep the generic kernels
+      if (S.pts.ptr[e] == S.pts.ptr[e + 1]) { if (!S.point_const[e] && pt_has_prior[e]) R.fallback.push_back((uint32_t)e); continue; }
+      if (S.point_const[e]) { R.fallback.push_back((uint32_t)e); continue; }
       const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]]; const int ns = S.pts.nslots[e];
       if (ns > 0 && sf[ns - 1] - sf[0] >= kRowSpan) { R.fallback.push_back((uint32_t)e); continue; }
       R.regular[e] = 1;
@@ -509,7 +514,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
         Structure::RowGroup G;
         G.cnt = d2 - d; G.pos0 = S.pts.pos[d]; G.pos1 = G.cnt == 2 ? S.pts.pos[d + 1] : (G.cnt > 2 ? d : 0u);
         G.gs = S.pts.slot[d] == 0xFFFF ? 0xFFFFFFFFu : dptr[e] + (uint32_t)(S.pts.f[d] - sf[0]);
-        R.grp.push_back(G); ngs++;
+        R.grp.push_back(G); R.grp_f.push_back(S.pts.f[d]); ngs++;
         d = d2;
       }
       R.grp_ptr[e + 1] = R.grp_ptr[e] + (uint32_t)ngs;

@@ -96,8 +96,38 @@ struct EListDev {
   bool has_prior = false;
 };
 
+// In-situ phase timer (OBVI_PROFILE=1): CUDA events recorded on the main stream around named phases, resolved when the
+// solve ends.  Timing in place sees warm caches and real overlap, unlike a serialised ncu launch list.
+struct PhaseProfiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  struct Span { int tag; size_t e0, e1; };
+  std::vector<Span> spans;
+  std::vector<const char*> names;
+  size_t used = 0;
+  size_t ev(cudaStream_t s) {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    cudaEventRecord(pool[used], s);
+    return used++;
+  }
+  int tag(const char* n) { for (size_t i = 0; i < names.size(); i++) if (names[i] == n) return (int)i; names.push_back(n); return (int)names.size() - 1; }
+  size_t begin(cudaStream_t s) { return on ? ev(s) : 0; }
+  void end(const char* n, size_t e0, cudaStream_t s) { if (on) spans.push_back({tag(n), e0, ev(s)}); }
+  void report(int steps) {
+    if (!on) return;
+    std::vector<double> tot(names.size(), 0.0); std::vector<int> cnt(names.size(), 0);
+    for (const Span& sp : spans) { float ms = 0; cudaEventElapsedTime(&ms, pool[sp.e0], pool[sp.e1]); tot[sp.tag] += ms; cnt[sp.tag]++; }
+    double all = 0; for (double t : tot) all += t;
+    fprintf(stderr, "[obvi profile] %d LM steps, %.3f ms in timed phases (%.3f ms / step)\n", steps, all, all / std::max(steps, 1));
+    for (size_t i = 0; i < names.size(); i++) fprintf(stderr, "[obvi profile]   %-22s n=%4d  mean %8.1f us  total %8.3f ms  %5.1f%%\n", names[i], cnt[i], 1e3 * tot[i] / std::max(cnt[i], 1), tot[i], 100.0 * tot[i] / all);
+    spans.clear(); used = 0;
+  }
+  ~PhaseProfiler() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
+};
+
 struct Solver {
   Problem pb;
+  PhaseProfiler prof;
   Structure st;
   cudaStream_t stream = nullptr;
   cudaStream_t s2 = nullptr;       // side stream: the small kernels (objects, priors, rel-pose) overlap the big point kernels
@@ -137,6 +167,7 @@ struct Solver {
   DBuf<uint32_t> pr_ent;
   DBuf<Structure::RowItem> pr_items;
   DBuf<uint8_t> pr_regular;
+  DBuf<int32_t> pr_grp_f;
   DBuf<double> WZ;
   int n_row_items = 0, n_row_fallback = 0;
   // state
@@ -159,6 +190,7 @@ struct Solver {
   std::vector<BtLevel> bt_levels;
   int bt_last_inv_off = 0;
   bool use_bt = true;
+  bool bt_v1 = false;   // OBVI_BT=v1: first-generation factorisation kernels (scalar-pivot Gauss-Jordan, FMA GEMM)
   // The factorisation is reused across LM iterations while it still preconditions well: it is redone when the
   // trust-region radius moved by more than 2x since it was computed or the last PCG needed more than
   // kRefactorPcgIters iterations.  (A stale preconditioner changes the PCG iteration count, never its answer.)
@@ -199,9 +231,12 @@ struct Solver {
     if (const char* e = getenv("OBVI_SCHUR")) { const std::string v(e); use_mma_schur = v != "scalar"; schur_mode = v == "scalar" ? 0 : (v == "mma1" ? 1 : (v == "mma" ? 2 : 3)); }
     CUDA_OK(cudaFuncSetAttribute(schur_points_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemDoubles * 8));
     CUDA_OK(cudaFuncSetAttribute(bt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBB * 8));
+    CUDA_OK(cudaFuncSetAttribute(bt_gemm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_bt_blocks_per_sm, pcg_bt_kernel, kPcgThreads, 0));
     if (pcg_bt_blocks_per_sm < 1) throw std::runtime_error("pcg_bt_kernel cannot be made resident");
     if (const char* e = getenv("OBVI_PRECOND")) use_bt = std::string(e) != "jacobi";
+    if (const char* e = getenv("OBVI_BT")) bt_v1 = std::string(e) == "v1";
+    if (const char* e = getenv("OBVI_PROFILE")) prof.on = std::string(e) == "1";
     if (const char* e = getenv("OBVI_JAC")) { const std::string v(e); jac_mode = v == "plain" ? 0 : (v == "persistent" ? 2 : (v == "tma2" ? 3 : (v == "tma2rot" ? 4 : (v == "tma2stg" ? 5 : 1)))); use_tma_jac = jac_mode > 0; }
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacPersistSmem));
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacPersistSmem));
@@ -257,7 +292,7 @@ struct Solver {
     {
       const Structure::PointRows& R = S.prow;
       n_row_items = (int)R.items.size(); n_row_fallback = (int)R.fallback.size();
-      pr_grp_ptr.upload(R.grp_ptr, stream); pr_grp.upload(R.grp, stream); pr_regular.upload(R.regular, stream);
+      pr_grp_ptr.upload(R.grp_ptr, stream); pr_grp.upload(R.grp, stream); pr_grp_f.upload(R.grp_f, stream); pr_regular.upload(R.regular, stream);
       pr_ent.upload(R.ent, stream); pr_items.upload(R.items, stream); pr_rowblk.upload(R.rowblk, stream); pr_fallback.upload(R.fallback, stream);
       if (schur_mode == 3) { WZ.alloc((size_t)std::max<int64_t>(R.n_slots, 1) * kWZ); WZ.zero(stream); }  // gap slots stay zero
     }
@@ -345,11 +380,18 @@ struct Solver {
     bt_assemble_kernel<<<nblk((int64_t)nsb * kSbPoses * 32, 256), 256, 0, stream>>>(S.nf, nsb, sf_ptr.p, sf_col.p, Sf.p, bt_D.p, bt_C.p);
     launches++;
     for (const BtLevel& L : bt_levels) {
-      if (L.inv_n) { bt_invert_kernel<<<L.inv_n, kInvThreads, 0, stream>>>(bt_idx.p + L.inv_off, bt_D.p, bt_Dinv.p, scalars.p); launches++; }
-      if (L.g_n) { bt_gemm_kernel<<<L.g_n, 256, 2 * kBB * 8, stream>>>(bt_tasks.p + L.g_off); launches++; }
-      if (L.u_n) { bt_gemm_kernel<<<L.u_n, 256, 2 * kBB * 8, stream>>>(bt_tasks.p + L.u_off); launches++; }
+      if (bt_v1) {
+        if (L.inv_n) { bt_invert_kernel<<<L.inv_n, kInvThreads, 0, stream>>>(bt_idx.p + L.inv_off, bt_D.p, bt_Dinv.p, scalars.p); launches++; }
+        if (L.g_n) { bt_gemm_kernel<<<L.g_n, 256, 2 * kBB * 8, stream>>>(bt_tasks.p + L.g_off); launches++; }
+        if (L.u_n) { bt_gemm_kernel<<<L.u_n, 256, 2 * kBB * 8, stream>>>(bt_tasks.p + L.u_off); launches++; }
+      } else {
+        if (L.inv_n) { bt_invert8_kernel<<<L.inv_n, kInvThreads, 0, stream>>>(bt_idx.p + L.inv_off, bt_D.p, bt_Dinv.p, scalars.p); launches++; }
+        if (L.g_n) { bt_gemm_mma_kernel<<<L.g_n, 512, kGemmSmem, stream>>>(bt_tasks.p + L.g_off); launches++; }
+        if (L.u_n) { bt_gemm_mma_kernel<<<L.u_n, 512, kGemmSmem, stream>>>(bt_tasks.p + L.u_off); launches++; }
+      }
     }
-    bt_invert_kernel<<<1, kInvThreads, 0, stream>>>(bt_idx.p + bt_last_inv_off, bt_D.p, bt_Dinv.p, scalars.p);
+    if (bt_v1) bt_invert_kernel<<<1, kInvThreads, 0, stream>>>(bt_idx.p + bt_last_inv_off, bt_D.p, bt_Dinv.p, scalars.p);
+    else bt_invert8_kernel<<<1, kInvThreads, 0, stream>>>(bt_idx.p + bt_last_inv_off, bt_D.p, bt_Dinv.p, scalars.p);
     launches++;
   }
   bool owns_object(int o) const {
@@ -413,6 +455,7 @@ struct Solver {
   // residuals + Jacobians at the current point
   void linearize(int apply_loss) {
     const Structure& S = st;
+    const size_t pt0 = prof.begin(stream);
     zero_scalars(SC_COST, 3);
     if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p, pcam_r.p); launches++; }
     fork();
@@ -424,6 +467,7 @@ struct Solver {
     if (S.P) { xnorm_kernel<<<nblk((int64_t)S.P * 3, 256), 256, 0, s2>>>(points[cur].p, point_skip.p, S.P, 3, scalars.p); launches++; }
     if (S.O) { xnorm_kernel<<<nblk((int64_t)S.O * 7, 256), 256, 0, s2>>>(objects[cur].p, obj_skip.p, S.O, 7, scalars.p); launches++; }
     join();
+    prof.end("linearize", pt0, stream);
   }
   // the reprojection Jacobian-evaluation kernel (three revisions, selectable with OBVI_JAC = plain | tma | persistent)
   void launch_jacobian(int apply_loss, const double* pts_dev) {
@@ -457,6 +501,7 @@ struct Solver {
   void build_reduced(LMParams& lm) {
     const Structure& S = st;
     lm.inv_radius = 1.0 / lm.radius;
+    size_t pt0 = prof.begin(stream);
     redbuf.zero(stream);
     zero_scalars(SC_GMAX, 2);  // gmax + fail
     zero_scalars(SC_BT_FAIL, 1);
@@ -466,8 +511,10 @@ struct Solver {
     if (S.n_unary && pts.has_prior) launch_unary(1, 1, cur, stream);
     fork();
     if (S.n_obs && S.nf) { pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag); launches++; }
+    prof.end("zero+pose_accum", pt0, stream); pt0 = prof.begin(stream);
     if (schur_mode == 3) {
       if (S.P) { point_prep_kernel<<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
+      prof.end("point_prep", pt0, stream); pt0 = prof.begin(stream);
       if (n_row_items) { schur_rows_kernel<<<nblk(n_row_items, kRowWarps), 32 * kRowWarps, 0, stream>>>(reinterpret_cast<const uint4*>(pr_items.p), n_row_items, pr_ent.p, WZ.p, pr_rowblk.p, kRowSpan, S_upper, b_schur); launches++; }
       if (n_row_fallback) {
         EArgs a = eargs(pts, J.p); a.elist = pr_fallback.p;
@@ -491,14 +538,17 @@ struct Solver {
     if (S.n_unary && !pts.has_prior) launch_unary(1, 1, cur, s2);
     if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 1, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
     if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
+    prof.end("schur_points", pt0, stream); pt0 = prof.begin(stream);
     join();
-    if (world > 1) allreduce_sum(redbuf.p, redbuf.n);
+    prof.end("join(objects,rel)", pt0, stream); pt0 = prof.begin(stream);
+    if (world > 1) { allreduce_sum(redbuf.p, redbuf.n); prof.end("allreduce S", pt0, stream); pt0 = prof.begin(stream); }
     if (S.nf) {
       if (lm.compute_scale) { pose_scale_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(hpp_diag, S.nf * 6, pscale.p); launches++; }
       finish_kernel<<<nblk((int64_t)S.nf * 32, 256), 256, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, sf_src.p, S_upper, pscale.p, hpp_diag, gp, b_schur, lm, Sf.p, rhs.p, Minv.p, scalars.p);
       launches++;
+      prof.end("finish", pt0, stream); pt0 = prof.begin(stream);
       const bool stale = bt_radius <= 0.0 || lm.radius > 2.0 * bt_radius || lm.radius < 0.5 * bt_radius || last_pcg_iters > kRefactorPcgIters;
-      if (stale) { factor_bt(); bt_radius = lm.radius; bt_factorizations++; }
+      if (stale) { factor_bt(); bt_radius = lm.radius; bt_factorizations++; prof.end("factor_bt", pt0, stream); }
     }
   }
   void solve_reduced(const obvi_solver_options& o, bool force_jacobi = false) {
@@ -534,7 +584,15 @@ struct Solver {
     zero_scalars(SC_MODEL, 2);
     if (S.nf) { pose_step_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(S.nf, pose_of_f.p, pscale.p, y.p, poses[cur].p, poses[cand].p, dpose.p, rank == 0, scalars.p); launches++; }
     fork();
-    if (S.P) { backsub_points_kernel<<<nblk(S.P, 4), 128, 0, stream>>>(eargs(pts, J.p), dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p); launches++; }
+    if (S.P && schur_mode == 3) {
+      backsub_rows_kernel<<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_grp_f.p, pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
+      launches++;
+      if (n_row_fallback) {   // points outside the row-owner path: generic kernel on the fallback list
+        EArgs a = eargs(pts, J.p); a.elist = pr_fallback.p;
+        backsub_points_kernel<<<nblk(n_row_fallback, 4), 128, 0, stream>>>(a, n_row_fallback, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
+        launches++;
+      }
+    } else if (S.P) { backsub_points_kernel<<<nblk(S.P, 4), 128, 0, stream>>>(eargs(pts, J.p), S.P, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p); launches++; }
     if (S.O) { backsub_eblock_kernel<7, 4, 128><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), dpose.p, objects[cur].p, objects[cand].p, objs.delta.p, scalars.p); launches++; }
     if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 2, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
     join();
@@ -669,10 +727,14 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
     iter++; lm_steps++;
     CUDA_OK(cudaEventRecord(ev[2], stream));
     if (need_build) { build_reduced(lm); need_build = false; }
+    size_t pt0 = prof.begin(stream);
     solve_reduced(o);
+    prof.end("pcg", pt0, stream); pt0 = prof.begin(stream);
     take_step();
+    prof.end("step+backsub", pt0, stream); pt0 = prof.begin(stream);
     CUDA_OK(cudaEventRecord(ev[3], stream));
     candidate_cost();
+    prof.end("candidate_cost", pt0, stream);
     CUDA_OK(cudaEventRecord(ev[4], stream));
     fetch_scalars(1);
     CUDA_OK(cudaEventElapsedTime(&ms, ev[2], ev[3])); t_lin += ms * 1e-3;
@@ -756,6 +818,7 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
   CUDA_OK(cudaStreamSynchronize(stream));
   CUDA_OK(cudaEventElapsedTime(&ms, ev[6], ev[7]));
   sum->minimizer_device_time_in_seconds = ms * 1e-3;
+  prof.report(lm_steps);
   // write the minimum-cost iterate back to the caller's blocks (on FAILURE the initial values stay)
   if (termination != OBVI_FAILURE) scatter_params(best);
   sum->termination_type = termination;
