@@ -626,4 +626,254 @@ __global__ void __launch_bounds__(kPcgThreads) pcg_bt_kernel(int nf, const uint3
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// pcg_bt_resident_kernel: the same PCG, organised around the B200's shared memory.  One CTA per super-block, all
+// co-resident (cooperative launch, nsb <= #SMs).  CTA i keeps the three factor matrices of ITS super-block
+// (Dinv_i, GaT_i, GcT_i: 3 x 96 x 96 doubles = 221 KB, row stride 97 -> conflict-free in both orientations) in shared
+// memory for the whole solve: 148 SMs x 227 KB hold the entire 27 MB factorisation on chip, so applying the
+// preconditioner touches only 96-double vectors in L2.  The cyclic-reduction sweeps run as a DATAFLOW instead of one grid
+// barrier per level: an eliminated block pushes its two updates to its neighbours with red.add and bumps their arrival
+// counters; a block starts as soon as its own counter reaches the expected value (forward) or its two neighbours have
+// published z (backward).  Only the CG scalars (p.q, |r|^2, r.z) and the p exchange are grid-wide synchronisations.
+constexpr int kLdR = 97;
+constexpr int kResidentSmem = (3 * kB * kLdR + 5 * kB + 4 * kB) * 8;
+struct ResidentSync {
+  double* red_val;          // [4][4] rotating reduction slots
+  unsigned int* red_cnt;    // [4]
+  double* u;                // [nsb][96] forward contributions pushed by neighbours (zero between applies)
+  unsigned int* cnt_w;      // [nsb] arrivals into u
+  unsigned int* ready_z;    // [nsb] epoch of the published z block
+};
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_inc(unsigned int* p) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kPcgThreads, 1) pcg_bt_resident_kernel(int nf, const uint32_t* __restrict__ sf_ptr,
+                                                                          const uint32_t* __restrict__ sf_col,
+                                                                          const double* __restrict__ Sf, const double* __restrict__ rhs,
+                                                                          BtApply P, ResidentSync Y, double* __restrict__ y, double* r,
+                                                                          double* p, int max_iter, double tol,
+                                                                          double* __restrict__ scalars) {
+  extern __shared__ __align__(16) double rsm[];
+  double* sD = rsm;                       // Dinv_i
+  double* sA = rsm + kB * kLdR;           // GaT_i
+  double* sC = rsm + 2 * kB * kLdR;       // GcT_i
+  double* part = rsm + 3 * kB * kLdR;     // [5][96] partial sums
+  double* sw = part + 5 * kB;             // w_i
+  double* sz = sw + kB;                   // z_i
+  double* sv1 = sz + kB;                  // z_a  (or scratch)
+  double* sv2 = sv1 + kB;                 // z_c
+  __shared__ double red[kPcgThreads / 32];
+  __shared__ double s_bcast;
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  const int I = blockIdx.x, nsb = P.nsb, nCTA = gridDim.x;
+  const int n = 6 * nf;
+  const int row0 = I * kB;
+  const int my = row0 + tid;              // this thread's vector entry (tid < 96)
+  const bool own = tid < kB && my < n;
+
+  // ---- tree position of this block
+  int lev = 0;                            // elimination level (root: nlev)
+  if (I == 0) lev = P.nlev; else while (((I >> lev) & 1) == 0) lev++;
+  const int sstep = 1 << lev;
+  const int na = I == 0 ? -1 : I - sstep;
+  int nc = -1;
+  if (I != 0) { const int k = I >> lev, nl = (nsb + sstep - 1) >> lev; if (k + 1 < nl) nc = I + sstep; }
+  int expected = 0;                       // contributions pushed into u_I before I is eliminated
+  for (int l = 0; l < lev; l++) {
+    const int s = 1 << l, k = I >> l, nl = (nsb + s - 1) >> l;
+    if (k >= 1) expected++;
+    if (k + 1 < nl) expected++;
+  }
+
+  // ---- factors -> shared memory (once per solve)
+  for (int t = tid; t < kBB; t += kPcgThreads) {
+    const int rr_ = t / kB, cc = t - rr_ * kB;
+    sD[rr_ * kLdR + cc] = P.Dinv[(size_t)I * kBB + t];
+    sA[rr_ * kLdR + cc] = P.GaT[(size_t)I * kBB + t];
+    sC[rr_ * kLdR + cc] = P.GcT[(size_t)I * kBB + t];
+  }
+
+  unsigned int seq = 0;                   // grid-wide reduction / barrier sequence number (same in every CTA)
+  // sum `v` (meaningful in thread 0 of each CTA after the block reduction) over the grid; everybody gets the total
+  auto grid_sum = [&](double v) -> double {
+    v = warp_sum(v);
+    if (lane == 0) red[wib] = v;
+    __syncthreads();
+    const unsigned int slot = seq & 3u;
+    if (tid == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < kPcgThreads / 32; i++) s += red[i];
+      if (I == 0) Y.red_val[4 * ((seq + 2u) & 3u)] = 0.0;   // nobody touches slot seq + 2 before CTA 0 arrives at seq + 1
+      if (s != 0.0) atomicAdd(&Y.red_val[4 * slot], s);
+      __threadfence();
+      red_release_inc(&Y.red_cnt[slot]);
+      const unsigned int target = (unsigned int)nCTA * (seq / 4u + 1u);
+      while (ld_acquire_u32(&Y.red_cnt[slot]) < target) {}
+      s_bcast = __ldcg(&Y.red_val[4 * slot]);
+    }
+    __syncthreads();
+    seq++;
+    return s_bcast;
+  };
+
+  unsigned int epoch = 0;
+  // z_I = (T^-1 r)_I for every block, dataflow over the elimination tree.  Returns this CTA's share of r . z.
+  auto apply = [&]() -> double {
+    epoch++;
+    // forward: wait for the neighbours' pushes, w_I = r_I - u_I
+    if (tid == 0 && expected) { const unsigned int target = (unsigned int)expected * epoch; while (ld_acquire_u32(&Y.cnt_w[I]) < target) {} }
+    __syncthreads();
+    if (tid < kB) {
+      const double rv = my < n ? r[my] : 0.0;
+      double uv = 0.0;
+      if (expected) { uv = __ldcg(&Y.u[(size_t)I * kB + tid]); Y.u[(size_t)I * kB + tid] = 0.0; }
+      sw[tid] = rv - uv;
+    }
+    __syncthreads();
+    if (I != 0) {
+      // push GaT_I w_I to the left survivor, GcT_I w_I to the right one: thread (row, part) sums 20 columns
+      if (tid < 5 * kB) {
+        const int row = tid % kB, pt = tid / kB;
+        const int c0 = pt * 20, c1 = min(c0 + 20, kB);
+        double a = 0.0, c = 0.0;
+        for (int cc = c0; cc < c1; cc++) { const double wv = sw[cc]; a += sA[row * kLdR + cc] * wv; c += sC[row * kLdR + cc] * wv; }
+        // 5 partial sums per row go straight to the neighbours' accumulators
+        if (na >= 0 && a != 0.0) atomicAdd(&Y.u[(size_t)na * kB + row], a);
+        if (nc >= 0 && c != 0.0) atomicAdd(&Y.u[(size_t)nc * kB + row], c);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        if (na >= 0) red_release_inc(&Y.cnt_w[na]);
+        if (nc >= 0) red_release_inc(&Y.cnt_w[nc]);
+      }
+      // backward: wait for z of the two survivors
+      if (tid == 0) {
+        if (na >= 0) while (ld_acquire_u32(&Y.ready_z[na]) < epoch) {}
+        if (nc >= 0) while (ld_acquire_u32(&Y.ready_z[nc]) < epoch) {}
+      }
+      __syncthreads();
+      if (tid < kB) {
+        sv1[tid] = na >= 0 ? __ldcg(&P.z[(size_t)na * kB + tid]) : 0.0;
+        sv2[tid] = nc >= 0 ? __ldcg(&P.z[(size_t)nc * kB + tid]) : 0.0;
+      }
+      __syncthreads();
+    }
+    // z_I[c] = sum_r Dinv[r][c] w[r] - GaT[r][c] za[r] - GcT[r][c] zc[r]   (thread (c, part) sums 20 rows)
+    if (tid < 5 * kB) {
+      const int col = tid % kB, pt = tid / kB;
+      const int r0 = pt * 20, r1 = min(r0 + 20, kB);
+      double a = 0.0;
+      if (I != 0) {
+        for (int rr_ = r0; rr_ < r1; rr_++) a += sD[rr_ * kLdR + col] * sw[rr_] - sA[rr_ * kLdR + col] * sv1[rr_] - sC[rr_ * kLdR + col] * sv2[rr_];
+      } else {
+        for (int rr_ = r0; rr_ < r1; rr_++) a += sD[rr_ * kLdR + col] * sw[rr_];
+      }
+      part[pt * kB + col] = a;
+    }
+    __syncthreads();
+    double rz = 0.0;
+    if (tid < kB) {
+      const double zv = part[tid] + part[kB + tid] + part[2 * kB + tid] + part[3 * kB + tid] + part[4 * kB + tid];
+      sz[tid] = zv;
+      P.z[(size_t)row0 + tid] = zv;
+      if (my < n) rz = r[my] * zv;
+    }
+    __syncthreads();
+    if (tid == 0) { __threadfence(); st_release_u32(&Y.ready_z[I], epoch); }
+    return rz;
+  };
+
+  // ---- initial residual
+  double bbp = 0.0;
+  if (tid < kB) {
+    const double rv = my < n ? rhs[my] : 0.0;
+    if (my < n) { y[my] = 0.0; r[my] = rv; }
+    bbp = rv * rv;
+  }
+  __syncthreads();
+  const double bb = grid_sum(bbp);
+  int it = 0, brk = 0;
+  double rr = bb;
+  if (((volatile double*)scalars)[SC_BT_FAIL] != 0.0) brk = 2;  // factorisation failed: the host falls back to block-Jacobi
+  if (bb > 0.0 && brk == 0) {
+    double rho = grid_sum(apply());
+    if (own) p[my] = sz[tid];
+    (void)grid_sum(0.0);                  // p exchange
+    while (it < max_iter) {
+      // q_I = (S p)_I: one warp per pose row of this super-block
+      double pq = 0.0, qv = 0.0;          // lanes 0..5 of warp w hold q for pose 16 I + w
+      {
+        const int i = I * kSbPoses + wib;
+        if (i < nf) {
+          const uint32_t p0 = sf_ptr[i], nb = sf_ptr[i + 1] - p0;
+          const uint32_t len = nb * 6;
+          const double* row = Sf + (size_t)p0 * 36;
+          double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+          for (uint32_t e0 = lane; e0 < len; e0 += 128) {
+            uint32_t ee[4]; double xv[4], sv[4][6];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              ee[u] = e0 + 32 * u;
+              const bool in = ee[u] < len;
+              const uint32_t e = in ? ee[u] : 0u;
+              const uint32_t k = e / 6, c = e - 6 * k;
+              xv[u] = in ? __ldcg(&p[6 * sf_col[p0 + k] + c]) : 0.0;   // other CTAs' entries: L2, never a stale L1 line
+#pragma unroll
+              for (int a = 0; a < 6; a++) sv[u][a] = in ? row[a * len + e] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              a0 += sv[u][0] * xv[u]; a1 += sv[u][1] * xv[u]; a2 += sv[u][2] * xv[u];
+              a3 += sv[u][3] * xv[u]; a4 += sv[u][4] * xv[u]; a5 += sv[u][5] * xv[u];
+            }
+          }
+          a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4); a5 = warp_sum(a5);
+          if (lane < 6) {
+            qv = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : lane == 3 ? a3 : lane == 4 ? a4 : a5;
+            pq = qv * p[6 * i + lane];
+          }
+        }
+      }
+      // q travels through shared memory to the owner threads (tid < 96)
+      if (lane < 6) sv1[6 * wib + lane] = qv;
+      const double pqs = grid_sum(pq);    // (contains the block barriers that publish sv1)
+      if (!(pqs > 0.0)) { brk = 1; break; }
+      const double alpha = rho / pqs;
+      double r2 = 0.0;
+      if (own) {
+        y[my] += alpha * p[my];
+        const double rv = r[my] - alpha * sv1[tid];
+        r[my] = rv;
+        r2 = rv * rv;
+      }
+      __syncthreads();
+      rr = grid_sum(r2);
+      it++;
+      if (rr <= tol * tol * bb) break;
+      const double rho_new = grid_sum(apply());
+      const double beta = rho_new / rho;
+      rho = rho_new;
+      if (own) p[my] = sz[tid] + beta * p[my];
+      (void)grid_sum(0.0);                // p exchange
+    }
+  }
+  if (I == 0 && tid == 0) {
+    scalars[SC_PCG_IT] = (double)it;
+    scalars[SC_PCG_RES] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+    scalars[SC_PCG_BB] = bb;
+    scalars[SC_PCG_BREAK] = (double)brk;
+  }
+}
+
 }  // namespace obvi

@@ -190,6 +190,10 @@ struct Solver {
   std::vector<BtLevel> bt_levels;
   int bt_last_inv_off = 0;
   bool use_bt = true;
+  bool pcg_resident = true;  // OBVI_PCG=grid: the grid-barrier PCG kernel instead of the shared-memory-resident dataflow one
+  bool resident_ok = false;
+  DBuf<double> rs_dbl;        // [16 reduction slots | nsb * 96 forward accumulators]
+  DBuf<unsigned int> rs_u32;  // [4 reduction counters | nsb arrival counters | nsb z epochs]
   bool bt_v1 = false;   // OBVI_BT=v1: first-generation factorisation kernels (scalar-pivot Gauss-Jordan, FMA GEMM)
   // The factorisation is reused across LM iterations while it still preconditions well: it is redone when the
   // trust-region radius moved by more than 2x since it was computed or the last PCG needed more than
@@ -236,6 +240,8 @@ struct Solver {
     if (pcg_bt_blocks_per_sm < 1) throw std::runtime_error("pcg_bt_kernel cannot be made resident");
     if (const char* e = getenv("OBVI_PRECOND")) use_bt = std::string(e) != "jacobi";
     if (const char* e = getenv("OBVI_BT")) bt_v1 = std::string(e) == "v1";
+    if (const char* e = getenv("OBVI_PCG")) pcg_resident = std::string(e) != "grid";
+    CUDA_OK(cudaFuncSetAttribute(pcg_bt_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentSmem));
     if (const char* e = getenv("OBVI_PROFILE")) prof.on = std::string(e) == "1";
     if (const char* e = getenv("OBVI_JAC")) { const std::string v(e); jac_mode = v == "plain" ? 0 : (v == "persistent" ? 2 : (v == "tma2" ? 3 : (v == "tma2rot" ? 4 : (v == "tma2stg" ? 5 : 1)))); use_tma_jac = jac_mode > 0; }
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacPersistSmem));
@@ -327,6 +333,12 @@ struct Solver {
     while ((1 << nlev) < nsb) nlev++;
     bt_levels.clear();
     if (nsb == 0) return;
+    {
+      int per_sm = 0;
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_bt_resident_kernel, kPcgThreads, kResidentSmem));
+      resident_ok = pcg_resident && per_sm >= 1 && nsb <= num_sms * per_sm;
+      rs_dbl.alloc(16 + (size_t)nsb * kB); rs_u32.alloc(4 + 2 * (size_t)nsb);
+    }
     bt_D.alloc((size_t)nsb * kBB); bt_Dinv.alloc((size_t)nsb * kBB); bt_GaT.alloc((size_t)nsb * kBB); bt_GcT.alloc((size_t)nsb * kBB);
     bt_w.alloc((size_t)nsb * kB); bt_z.alloc((size_t)nsb * kB);
     // couplings: level l holds n_l - 1 blocks
@@ -556,6 +568,19 @@ struct Solver {
     if (!S.nf) return;
     int nf = S.nf, max_iter = o.pcg_max_iterations;
     double tol = o.pcg_relative_tolerance;
+    if (use_bt && !force_jacobi && resident_ok) {
+      BtApply P; P.nsb = nsb; P.nlev = nlev; P.Dinv = bt_Dinv.p; P.GaT = bt_GaT.p; P.GcT = bt_GcT.p; P.w = bt_w.p; P.z = bt_z.p;
+      ResidentSync Y; Y.red_val = rs_dbl.p; Y.u = rs_dbl.p + 16; Y.red_cnt = rs_u32.p; Y.cnt_w = rs_u32.p + 4; Y.ready_z = rs_u32.p + 4 + nsb;
+      rs_dbl.zero(stream); rs_u32.zero(stream);
+      const uint32_t *a1 = sf_ptr.p, *a2 = sf_col.p;
+      const double *a3 = Sf.p, *a4 = rhs.p;
+      double *a6 = y.p, *a7 = cg_r.p, *a9 = cg_p.p, *a14 = scalars.p;
+      void* args[] = {&nf, &a1, &a2, &a3, &a4, &P, &Y, &a6, &a7, &a9, &max_iter, &tol, &a14};
+      CUDA_OK(cudaLaunchCooperativeKernel((void*)pcg_bt_resident_kernel, dim3(nsb), dim3(kPcgThreads), args, kResidentSmem, stream));
+      launches++;
+      if (world > 1) broadcast0(y.p, (size_t)nf * 6);
+      return;
+    }
     if (use_bt && !force_jacobi) {
       BtApply P; P.nsb = nsb; P.nlev = nlev; P.Dinv = bt_Dinv.p; P.GaT = bt_GaT.p; P.GcT = bt_GcT.p; P.w = bt_w.p; P.z = bt_z.p;
       int grid = std::min(num_sms * pcg_bt_blocks_per_sm, std::max(1, nblk(nf, kPcgThreads / 32)));
