@@ -110,6 +110,10 @@ int obvi_factor_add_param_prior(obvi_problem* p, double* block, int param_idx, d
 /* Problem::RemoveResidualBlock (object_pose_graph_optimizer.h:1105-1155). */
 int obvi_factor_remove(obvi_problem* p, obvi_factor_id id);
 int64_t obvi_num_factors(const obvi_problem* p);
+/* How often the flat device layout was rebuilt from the host container.  Removing reprojection / bounding-box blocks of
+ * an already solved problem (the outlier exclusion between the two phases, offline_problem_runner.h:752-833) is done in
+ * place -- the block's record is flagged and evaluates to zero -- and does not count. */
+int64_t obvi_num_structure_builds(const obvi_problem* p);
 /* Problem::GetResidualBlocks: live blocks in the order obvi_evaluate concatenates them (order of addition). */
 int obvi_residual_blocks(const obvi_problem* p, obvi_factor_id* ids, int32_t* types, int32_t* sizes, int64_t capacity,
                          int64_t* n);

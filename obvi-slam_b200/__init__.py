@@ -114,6 +114,7 @@ def lib():
         "obvi_factor_add_param_prior": ([vp, vp, C.c_int, dbl, dbl, dbl, u64p], C.c_int),
         "obvi_factor_remove": ([vp, C.c_uint64], C.c_int),
         "obvi_num_factors": ([vp], i64),
+        "obvi_num_structure_builds": ([vp], i64),
         "obvi_residual_blocks": ([vp, u64p, i32p, i32p, i64, C.POINTER(i64)], C.c_int),
         "obvi_solver_options_init": ([C.POINTER(SolverOptions)], None),
         "obvi_solve": ([vp, C.POINTER(SolverOptions), C.POINTER(Summary), C.POINTER(IterationSummary), i32], C.c_int),
@@ -138,7 +139,7 @@ EXPORTED_SYMBOLS = [
     "obvi_param_add_array", "obvi_param_remove", "obvi_param_set_constant", "obvi_param_is_constant", "obvi_camera_add",
     "obvi_factor_add_reproj", "obvi_factor_add_reproj_batch", "obvi_factor_add_bbox", "obvi_factor_add_bbox_batch",
     "obvi_factor_add_shape_prior", "obvi_factor_add_ltm_prior", "obvi_factor_add_rel_pose", "obvi_factor_add_param_prior",
-    "obvi_factor_remove", "obvi_num_factors", "obvi_residual_blocks", "obvi_solver_options_init", "obvi_solve",
+    "obvi_factor_remove", "obvi_num_factors", "obvi_num_structure_builds", "obvi_residual_blocks", "obvi_solver_options_init", "obvi_solve",
     "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_profile_jacobian", "obvi_debug_partition", "obvi_comm_unique_id",
     "obvi_comm_init",
 ]
@@ -278,6 +279,9 @@ class Problem:
 
     def num_residual_blocks(self):
         return int(self._lib.obvi_num_factors(self._h))
+
+    def num_structure_builds(self):
+        return int(self._lib.obvi_num_structure_builds(self._h))
 
     def residual_blocks(self):
         n = C.c_int64(0)

@@ -89,6 +89,7 @@ __global__ void pose_cam_kernel(const double* __restrict__ poses, int K, const C
 // L2), writes the 160-byte chunk [Jp | Jl | r] with the Huber corrector applied, and reduces the cost.
 constexpr int kJacThreads = 256;
 constexpr int kChunk = 20;  // doubles per reprojection observation
+constexpr uint32_t kObsMasked = 4u;  // flag bit 2 of ObsRec / BBoxRec: residual block removed in place (two-phase outlier exclusion)
 
 __global__ void __launch_bounds__(kJacThreads) reproj_jac_kernel(const ObsRec* __restrict__ obs, int64_t n,
                                                                   const PoseCam* __restrict__ pcam, int C,
@@ -109,13 +110,18 @@ __global__ void __launch_bounds__(kJacThreads) reproj_jac_kernel(const ObsRec* _
     const double s = r[0] * r[0] + r[1] * r[1];
     double sc = 1.0, c = 0.5 * s;
     if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
-    if ((id.w & 3u) == 3u) fixed = c; else cost = c;
     double2* out = reinterpret_cast<double2*>(J + (size_t)i * kChunk);
+    if (id.w & kObsMasked) {   // removed in place (obvi_factor_remove without a structure rebuild): an all-zero block
 #pragma unroll
-    for (int a = 0; a < 6; a++) out[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
+      for (int a = 0; a < 10; a++) out[a] = make_double2(0.0, 0.0);
+    } else {
+      if ((id.w & 3u) == 3u) fixed = c; else cost = c;
 #pragma unroll
-    for (int a = 0; a < 3; a++) out[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
-    out[9] = make_double2(sc * r[0], sc * r[1]);
+      for (int a = 0; a < 6; a++) out[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) out[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
+      out[9] = make_double2(sc * r[0], sc * r[1]);
+    }
   }
   cost = block_sum_all<kJacThreads>(cost, red);
   fixed = block_sum_all<kJacThreads>(fixed, red);
@@ -218,13 +224,18 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const Ob
     const double s = r[0] * r[0] + r[1] * r[1];
     double sc = 1.0, c = 0.5 * s;
     if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
-    if ((id.w & 3u) == 3u) fixed = c; else cost = c;
     double2* out = reinterpret_cast<double2*>(out_tile + (size_t)threadIdx.x * kChunk);
+    if (id.w & kObsMasked) {   // removed in place: an all-zero block, no cost
 #pragma unroll
-    for (int a = 0; a < 6; a++) out[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
+      for (int a = 0; a < 10; a++) out[a] = make_double2(0.0, 0.0);
+    } else {
+      if ((id.w & 3u) == 3u) fixed = c; else cost = c;
 #pragma unroll
-    for (int a = 0; a < 3; a++) out[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
-    out[9] = make_double2(sc * r[0], sc * r[1]);
+      for (int a = 0; a < 6; a++) out[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) out[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
+      out[9] = make_double2(sc * r[0], sc * r[1]);
+    }
   }
   fence_proxy_async_smem();
   cost = block_sum_all<kJacThreads>(cost, red);     // contains __syncthreads: the tile image is complete after it
@@ -464,6 +475,7 @@ __global__ void __launch_bounds__(kJacThreads) reproj_cost_kernel(const ObsRec* 
     const double s = r[0] * r[0] + r[1] * r[1];
     double sc, c = 0.5 * s;
     if (cc.huber > 0.0) c = huber(cc.huber, s, &sc);
+    if (id.w & kObsMasked) c = 0.0;
     if ((id.w & 3u) == 3u) fixed = c; else cost = c;
   }
   cost = block_sum_all<kJacThreads>(cost, red);
@@ -1763,12 +1775,16 @@ __global__ void bbox_kernel(const BBoxRec* __restrict__ rec, int64_t n, const Po
   const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
   double sc = 1.0, c = 0.5 * s;
   if (apply_loss && R.huber > 0.0) c = huber(R.huber, s, &sc);
+  if (R.flags & kObsMasked) {   // removed in place: an all-zero block, no cost
+    if (mode == 0) for (int a = 0; a < kBBoxChunk; a++) ch[a] = 0.0;
+    return;
+  }
   if (mode == 0) {
     for (int a = 0; a < 52; a++) ch[a] *= sc;
     for (int a = 0; a < 4; a++) ch[52 + a] = sc * r[a];
-    atomicAdd(&scalars[R.flags == 3u ? SC_FIXED : SC_COST], c);
+    atomicAdd(&scalars[(R.flags & 3u) == 3u ? SC_FIXED : SC_COST], c);
   } else {
-    atomicAdd(&scalars[R.flags == 3u ? SC_CAND_FIXED : SC_CAND], c);
+    atomicAdd(&scalars[(R.flags & 3u) == 3u ? SC_CAND_FIXED : SC_CAND], c);
   }
 }
 
@@ -2125,8 +2141,19 @@ __global__ void block_sqnorm_kernel(const double* __restrict__ chunks, int64_t n
   const double* r = chunks + (size_t)i * chunk + roff;
   double e = 0.0;
   for (int a = 0; a < k; a++) e = __dadd_rn(e, __dmul_rn(r[a], r[a]));
-  keys[rank[i]] = e;
-  vals[rank[i]] = rank[i];
+  // blocks removed in place have no rank among the live blocks: they are parked behind the live ones with key -1
+  const uint32_t rk = rank[i];
+  if (rk & 0x80000000u) { keys[rk & 0x7fffffffu] = -1.0; vals[rk & 0x7fffffffu] = 0xffffffffu; }
+  else { keys[rk] = e; vals[rk] = rk; }
+}
+// set a flag bit in 32-bit words addressed as base[idx[i] * stride_words + word]
+__global__ void or_flag_kernel(uint32_t* __restrict__ base, const uint32_t* __restrict__ idx, int64_t n, int stride_words, int word, uint32_t bit) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) base[(size_t)idx[i] * stride_words + word] |= bit;
+}
+__global__ void set_bytes_kernel(uint8_t* __restrict__ base, const uint32_t* __restrict__ idx, int64_t n, uint8_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) base[idx[i]] = v;
 }
 // flag the last element of every run of equal keys in the (stably) sorted sequence
 __global__ void run_end_flags_kernel(const double* __restrict__ keys, int64_t n, uint8_t* __restrict__ flags) {

@@ -180,6 +180,19 @@ struct Problem {
   }
 };
 
+// reduced-program bookkeeping (Summary::num_*_reduced): over the whole graph, not just this rank
+inline void count_reduced(const Problem& pb, Structure& S) {
+  const int nb = (int)pb.blocks.size();
+  S.num_residual_blocks_reduced = 0; S.num_residuals_reduced = 0; S.num_param_blocks_reduced = 0; S.num_params_reduced = 0;
+  std::vector<uint8_t> touched(nb, 0);
+  auto var = [&](int b) { return !pb.blocks[b].constant; };
+  for (const auto& f : pb.reproj) if (f.alive && (var(f.pose) || var(f.point))) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += 2; touched[f.pose] = touched[f.point] = 1; }
+  for (const auto& f : pb.bbox) if (f.alive && (var(f.pose) || var(f.obj))) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += 4; touched[f.pose] = touched[f.obj] = 1; }
+  for (const auto& f : pb.unary) if (f.alive && var(f.block)) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += f.k; touched[f.block] = 1; }
+  for (const auto& f : pb.rel) if (f.alive && (var(f.p1) || var(f.p2))) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += 6; touched[f.p1] = touched[f.p2] = 1; }
+  for (int b = 0; b < nb; b++) if (touched[b] && var(b)) { S.num_param_blocks_reduced++; S.num_params_reduced += pb.blocks[b].size; }
+}
+
 // ---- structure build ---------------------------------------------------------------------------
 // rank/world: e-blocks (points, objects) are dealt to ranks in contiguous ranges of the internal
 // (first-observing-keyframe) order, balanced by observation count; rank 0 also owns the pose-only factors.
@@ -566,16 +579,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     }
     for (int i = 0; i < nf; i++) for (uint32_t q = S.su_ptr[i]; q < S.su_ptr[i + 1]; q++) { S.sf_col[cur[i]] = S.su_col[q]; S.sf_src[cur[i]] = q; cur[i]++; }
   }
-  // reduced-program bookkeeping (Summary::num_*_reduced): over the whole graph, not just this rank
-  {
-    std::vector<uint8_t> touched(nb, 0);
-    auto var = [&](int b) { return !pb.blocks[b].constant; };
-    for (const auto& f : pb.reproj) if (f.alive && (var(f.pose) || var(f.point))) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += 2; touched[f.pose] = touched[f.point] = 1; }
-    for (const auto& f : pb.bbox) if (f.alive && (var(f.pose) || var(f.obj))) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += 4; touched[f.pose] = touched[f.obj] = 1; }
-    for (const auto& f : pb.unary) if (f.alive && var(f.block)) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += f.k; touched[f.block] = 1; }
-    for (const auto& f : pb.rel) if (f.alive && (var(f.p1) || var(f.p2))) { S.num_residual_blocks_reduced++; S.num_residuals_reduced += 6; touched[f.p1] = touched[f.p2] = 1; }
-    for (int b = 0; b < nb; b++) if (touched[b] && var(b)) { S.num_param_blocks_reduced++; S.num_params_reduced += pb.blocks[b].size; }
-  }
+  count_reduced(pb, S);
   return true;
 }
 

@@ -170,6 +170,12 @@ struct Solver {
   DBuf<int32_t> pr_grp_f;
   DBuf<double> WZ;
   int n_row_items = 0, n_row_fallback = 0;
+  // in-place removal of reprojection / bbox blocks (two-phase outlier exclusion without a structure rebuild)
+  std::vector<uint32_t> inv_rp, inv_bb;     // user factor index -> internal position (0xFFFFFFFF: not on this rank)
+  std::vector<uint32_t> pend_rp, pend_bb;   // internal positions whose device flag still has to be set
+  int64_t n_masked_rp = 0, n_masked_bb = 0;
+  bool counts_stale = false;
+  int64_t structure_builds = 0;
   // state
   DBuf<double> poses[3], points[3], objects[3];  // cur, cand, best
   int cur = 0;
@@ -302,6 +308,10 @@ struct Solver {
       pr_ent.upload(R.ent, stream); pr_items.upload(R.items, stream); pr_rowblk.upload(R.rowblk, stream); pr_fallback.upload(R.fallback, stream);
       if (schur_mode == 3) { WZ.alloc((size_t)std::max<int64_t>(R.n_slots, 1) * kWZ); WZ.zero(stream); }  // gap slots stay zero
     }
+    inv_rp.assign(pb.reproj.size(), 0xFFFFFFFFu); inv_bb.assign(pb.bbox.size(), 0xFFFFFFFFu);
+    for (int64_t q = 0; q < S.n_obs; q++) inv_rp[S.obs_user[q]] = (uint32_t)q;
+    for (int64_t q = 0; q < S.n_bbox; q++) inv_bb[S.bbox_user[q]] = (uint32_t)q;
+    pend_rp.clear(); pend_bb.clear(); n_masked_rp = n_masked_bb = 0; counts_stale = false;
     pts.has_prior = objs.has_prior = false;
     for (const UnaryRec& u : S.unary) { if (u.kind == 1) pts.has_prior = true; if (u.kind == 2) objs.has_prior = true; }
     if (pts.has_prior) { pts.prior_H.alloc((size_t)S.P * 9); pts.prior_g.alloc((size_t)S.P * 3); }
@@ -486,11 +496,12 @@ struct Solver {
     const Structure& S = st;
     const bool tma_ok = (int)S.classes.size() <= kJacMaxCls && S.C <= 256;
     const int ntiles = nblk(S.n_obs, kJacThreads);
-    if (jac_mode == 2 && tma_ok && S.C <= kJacMaxCam) {
+    const bool any_masked = n_masked_rp > 0;   // only the plain and the default TMA kernel honour the mask bit
+    if (jac_mode == 2 && tma_ok && S.C <= kJacMaxCam && !any_masked) {
       const int grid = std::min(ntiles, 2 * num_sms);
       if (jac_rot) reproj_jac_persistent_kernel<true><<<grid, kJacThreads, kJacPersistSmem, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, ntiles, J.p, scalars.p);
       else reproj_jac_persistent_kernel<false><<<grid, kJacThreads, kJacPersistSmem, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, ntiles, J.p, scalars.p);
-    } else if (jac_mode >= 3 && tma_ok && S.C <= 16) {
+    } else if (jac_mode >= 3 && tma_ok && S.C <= 16 && !any_masked) {
       if (jac_mode == 5) reproj_jac_tma2_kernel<false, 1><<<ntiles, kJacThreads, kJacSmemBytes2, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
       else if (jac_mode == 4) reproj_jac_tma2_kernel<true><<<ntiles, kJacThreads, kJacSmemBytes2, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
       else reproj_jac_tma2_kernel<false><<<ntiles, kJacThreads, kJacSmemBytes2, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
@@ -659,6 +670,49 @@ struct Solver {
     if (r != ncclSuccess) throw std::runtime_error(std::string("ncclBroadcast: ") + g_nccl.GetErrorString(r));
   }
 
+  // Remove a reprojection / bbox block without rebuilding the structure: its record is flagged, the Jacobian kernels then
+  // write an all-zero block and no cost, so every downstream kernel sees a factor that contributes nothing
+  // (reference: offline_problem_runner.h:752-801 + the Problem edit in object_pose_graph_optimizer.h:991-1155).
+  bool mask_factor(int type, uint64_t i) {
+    if (!uploaded || pb.dirty) return false;
+    const bool rp = type == OBVI_FACTOR_REPROJECTION;
+    std::vector<uint32_t>& inv = rp ? inv_rp : inv_bb;
+    if (i >= inv.size()) return false;
+    const uint32_t q = inv[i];
+    if (q != 0xFFFFFFFFu) {
+      if (rp) { st.obs[q].flags |= kObsMasked; pend_rp.push_back(q); n_masked_rp++; }
+      else { st.bbox[q].flags |= kObsMasked; pend_bb.push_back(q); n_masked_bb++; }
+    }
+    counts_stale = true;
+    return true;
+  }
+  void flush_masks() {
+    Structure& S = st;
+    auto push = [&](const std::vector<uint32_t>& idx, auto kernel_call) {
+      if (idx.empty()) return;
+      DBuf<uint32_t> d; d.upload(idx, stream);
+      kernel_call(d.p, (int64_t)idx.size());
+      CUDA_OK(cudaStreamSynchronize(stream));   // `d` is freed on return
+    };
+    // e-blocks that lost every observation leave the reduced program (Ceres drops unused parameter blocks): no |x| share
+    std::vector<uint32_t> dead_pts, dead_objs;
+    auto all_masked_pt = [&](uint32_t e) { for (uint32_t d = S.pts.ptr[e]; d < S.pts.ptr[e + 1]; d++) if (!(S.obs[S.pts.pos[d]].flags & kObsMasked)) return false; return true; };
+    auto all_masked_ob = [&](uint32_t e) { for (uint32_t d = S.objs.ptr[e]; d < S.objs.ptr[e + 1]; d++) if (!(S.bbox[S.objs.pos[d]].flags & kObsMasked)) return false; return true; };
+    for (uint32_t q : pend_rp) { const uint32_t e = S.obs[q].point; if (!S.point_const[e] && all_masked_pt(e)) dead_pts.push_back(e); }
+    for (uint32_t q : pend_bb) {
+      const uint32_t e = S.bbox[q].obj;
+      bool has_unary = false;
+      for (const UnaryRec& u : S.unary) if (u.kind == 2 && (uint32_t)u.idx == e) { has_unary = true; break; }
+      if (!S.obj_const[e] && !has_unary && all_masked_ob(e)) dead_objs.push_back(e);
+    }
+    push(pend_rp, [&](const uint32_t* d, int64_t n) { or_flag_kernel<<<nblk(n, 256), 256, 0, stream>>>(reinterpret_cast<uint32_t*>(obs.p), d, n, (int)(sizeof(ObsRec) / 4), 7, kObsMasked); });
+    push(pend_bb, [&](const uint32_t* d, int64_t n) { or_flag_kernel<<<nblk(n, 256), 256, 0, stream>>>(reinterpret_cast<uint32_t*>(bbox.p), d, n, (int)(sizeof(BBoxRec) / 4), (int)(offsetof(BBoxRec, flags) / 4), kObsMasked); });
+    push(dead_pts, [&](const uint32_t* d, int64_t n) { set_bytes_kernel<<<nblk(n, 256), 256, 0, stream>>>(point_skip.p, d, n, 1); });
+    push(dead_objs, [&](const uint32_t* d, int64_t n) { set_bytes_kernel<<<nblk(n, 256), 256, 0, stream>>>(obj_skip.p, d, n, 1); });
+    pend_rp.clear(); pend_bb.clear();
+    if (counts_stale) { count_reduced(pb, st); counts_stale = false; }
+  }
+
   void ensure_structure(double* preprocess_seconds) {
     if (!stream) throw std::runtime_error("host-only problem handle (cuda_device = -1): no CUDA device attached, and this backend has no CPU fallback");
     const auto t0 = std::chrono::steady_clock::now();
@@ -666,7 +720,10 @@ struct Solver {
       std::string err;
       if (!build_structure(pb, st, rank, world, err)) throw std::runtime_error(err);
       upload_structure();
+      structure_builds++;
       pb.dirty = false;
+    } else if (counts_stale || !pend_rp.empty() || !pend_bb.empty()) {
+      flush_masks();
     }
     if (preprocess_seconds) *preprocess_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
@@ -1073,10 +1130,13 @@ int obvi_factor_remove(obvi_problem* p, obvi_factor_id id) {
   else if ((t == OBVI_FACTOR_SHAPE_PRIOR || t == OBVI_FACTOR_LTM_PRIOR || t == OBVI_FACTOR_PARAM_PRIOR) && i < pb.unary.size() && pb.unary[i].type == t) alive = &pb.unary[i].alive;
   else if (t == OBVI_FACTOR_REL_POSE && i < pb.rel.size()) alive = &pb.rel[i].alive;
   if (!alive || !*alive) return fail(p, OBVI_ERR_NOT_FOUND, "unknown residual block id");
-  *alive = 0; pb.n_live--; pb.dirty = true;
+  *alive = 0; pb.n_live--;
+  // reprojection / bbox blocks of an uploaded structure are removed in place; everything else forces a rebuild
+  if (!((t == OBVI_FACTOR_REPROJECTION || t == OBVI_FACTOR_BBOX) && p->s.mask_factor(t, i))) pb.dirty = true;
   return OBVI_OK;
 }
 int64_t obvi_num_factors(const obvi_problem* p) { return p ? p->s.pb.n_live : 0; }
+int64_t obvi_num_structure_builds(const obvi_problem* p) { return p ? p->s.structure_builds : 0; }
 
 static bool id_alive(const Problem& pb, obvi_factor_id id, int* size) {
   const int t = id_type(id); const uint64_t i = id_index(id);
@@ -1145,6 +1205,7 @@ int obvi_evaluate_factor_type(obvi_problem* p, int type, int apply_loss, double*
     for (size_t i = 0; i < s.pb.reproj.size(); i++) if (s.pb.reproj[i].alive) live_rank[i] = c++;
     for (int64_t q = 0; q < S.n_obs; q++) {
       const int64_t u = live_rank[S.obs_user[q]];
+      if (u < 0) continue;   // removed in place
       const double* ch = &h[(size_t)q * kChunk];
       if (J0) std::memcpy(J0 + 12 * u, ch, 96);
       if (J1) std::memcpy(J1 + 6 * u, ch + 12, 48);
@@ -1158,6 +1219,7 @@ int obvi_evaluate_factor_type(obvi_problem* p, int type, int apply_loss, double*
     for (size_t i = 0; i < s.pb.bbox.size(); i++) if (s.pb.bbox[i].alive) live_rank[i] = c++;
     for (int64_t q = 0; q < S.n_bbox; q++) {
       const int64_t u = live_rank[S.bbox_user[q]];
+      if (u < 0) continue;   // removed in place
       const double* ch = &h[(size_t)q * kBBoxChunk];
       if (J1) std::memcpy(J1 + 24 * u, ch, 192);       // pose
       if (J0) std::memcpy(J0 + 28 * u, ch + 24, 224);  // ellipsoid
@@ -1269,8 +1331,14 @@ int obvi_topk_outliers(obvi_problem* p, int type, double fraction, obvi_factor_i
       std::vector<int64_t> live_rank(total, -1);
       int64_t c = 0;
       for (size_t i = 0; i < total; i++) if (rp ? s.pb.reproj[i].alive : s.pb.bbox[i].alive) { live_rank[i] = c; id_of_rank[c] = make_id(type, i); c++; }
-      for (int64_t q = 0; q < nb; q++) rank[q] = (uint32_t)live_rank[rp ? S.obs_user[q] : S.bbox_user[q]];
+      // blocks removed in place: parked behind the live ones (positions c, c + 1, ...) with the top bit set
+      int64_t dead = c;
+      for (int64_t q = 0; q < nb; q++) {
+        const int64_t lr = live_rank[rp ? S.obs_user[q] : S.bbox_user[q]];
+        rank[q] = lr >= 0 ? (uint32_t)lr : (0x80000000u | (uint32_t)(dead++));
+      }
     }
+    const int64_t n_dead = rp ? s.n_masked_rp : s.n_masked_bb;
     DBuf<uint32_t> d_rank, d_vals, d_vals_sorted, d_sel;
     DBuf<double> d_keys, d_keys_sorted;
     DBuf<uint8_t> d_flags, d_tmp;
@@ -1289,6 +1357,7 @@ int obvi_topk_outliers(obvi_problem* p, int type, double fraction, obvi_factor_i
     int64_t n_unique = 0;
     CUDA_OK(cudaMemcpyAsync(&n_unique, d_count.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s.stream));
     CUDA_OK(cudaStreamSynchronize(s.stream));
+    if (n_dead > 0) n_unique -= 1;   // the run of -1 keys at the very end of the descending order
     const size_t k = (size_t)(n_unique * fraction);
     std::vector<uint32_t> sel(k);
     if (k) CUDA_OK(cudaMemcpy(sel.data(), d_sel.p, k * sizeof(uint32_t), cudaMemcpyDeviceToHost));

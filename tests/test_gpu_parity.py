@@ -222,3 +222,59 @@ def test_remove_factors_and_resolve(ob, oracle):
     assert s.num_iterations == len(ref["iterations"]) and s.termination == ref["termination"]
     assert abs(s.final_cost - ref["final_cost"]) <= 1e-5 * ref["final_cost"]
     assert np.abs(g.poses[:, :3] - g_ref.poses[:, :3]).max() < 1e-4
+
+
+def test_two_phase_in_place_exclusion(ob, oracle):
+    """The two-phase BA of the reference (offline_problem_runner.h:689-833): phase I solve, rank the raw residuals, drop
+    the worst fraction of reprojection and bbox blocks, restore the pre-phase-I values, phase II solve.  The removal is
+    done in place (no structure rebuild) and must give what the oracle gets on the graph without those factors; the
+    top-k of a second round must ignore the removed blocks."""
+    g = small_graph(ob, seed=21, K=20, P=800)
+    x0 = (g.poses.copy(), g.points.copy(), g.objects.copy())
+    p = ob.problem_from_graph(g)
+    p.solve(**dict(OPTS, max_num_iterations=6))
+    builds = p.num_structure_builds()
+    assert builds == 1
+    out_rp = p.topk_outliers(ob.FACTOR_REPROJECTION, 0.2)
+    out_bb = p.topk_outliers(ob.FACTOR_BBOX, 0.1)
+    assert len(out_rp) > 100 and len(out_bb) > 0
+    n_before = p.num_residual_blocks()
+    for fid in list(out_rp) + list(out_bb):
+        p.remove_residual_block(fid)
+    assert p.num_residual_blocks() == n_before - len(out_rp) - len(out_bb)
+    g.poses[:], g.points[:], g.objects[:] = x0          # setValuesFromAnotherPoseGraph
+    s = p.solve(**OPTS)
+    assert p.num_structure_builds() == builds            # removed in place
+    # oracle on the graph without those factors
+    idx_rp = {int(f): i for i, f in enumerate(p.factor_ids["reproj"])}
+    idx_bb = {int(f): i for i, f in enumerate(p.factor_ids["bbox"])}
+    keep_rp = np.ones(len(g.reproj["pose"]), bool); keep_rp[[idx_rp[int(f)] for f in out_rp]] = False
+    keep_bb = np.ones(len(g.bbox["pose"]), bool); keep_bb[[idx_bb[int(f)] for f in out_bb]] = False
+    g_ref = g.copy()
+    g_ref.poses[:], g_ref.points[:], g_ref.objects[:] = x0
+    for k in g_ref.reproj:
+        if isinstance(g_ref.reproj[k], np.ndarray) and len(g_ref.reproj[k]) == len(keep_rp): g_ref.reproj[k] = g_ref.reproj[k][keep_rp]
+    for k in g_ref.bbox:
+        if isinstance(g_ref.bbox[k], np.ndarray) and len(g_ref.bbox[k]) == len(keep_bb): g_ref.bbox[k] = g_ref.bbox[k][keep_bb]
+    ref = oracle.solve(g_ref, **oracle_opts(OPTS))
+    assert s.termination == ref["termination"] and s.num_iterations == len(ref["iterations"])
+    for a, b in zip(s.iterations, ref["iterations"]):
+        assert a["successful"] == b["successful"] and abs(a["cost"] - b["cost"]) <= 1e-5 * abs(b["cost"])
+    assert abs(s.final_cost - ref["final_cost"]) <= 1e-5 * ref["final_cost"]
+    assert np.abs(g.poses[:, :3] - g_ref.poses[:, :3]).max() < 1e-4
+    assert s.num_residual_blocks_reduced == ref.get("num_residual_blocks_reduced", s.num_residual_blocks_reduced)
+    # residual export and a second ranking only see live blocks
+    cost, res = p.evaluate(apply_loss_function=False)
+    n_rp, n_bb = int(keep_rp.sum()), int(keep_bb.sum())
+    assert res.size == 2 * n_rp + 4 * n_bb + 3 * g.counts()["shape"] + 7 * g.counts()["ltm"] + 6 * g.counts()["relpose"]
+    rr = res[:2 * n_rp].reshape(n_rp, 2)
+    sq = rr[:, 0] * rr[:, 0] + rr[:, 1] * rr[:, 1]
+    by_err = {}
+    for i, e in enumerate(sq):
+        by_err[e] = i
+    order = sorted(by_err, reverse=True)
+    live_ids = p.factor_ids["reproj"][keep_rp]
+    got = p.topk_outliers(ob.FACTOR_REPROJECTION, 0.15)
+    assert got.tolist() == [int(live_ids[by_err[e]]) for e in order[:int(len(order) * 0.15)]]
+    r, jp, jl = p.evaluate_factor_type(ob.FACTOR_REPROJECTION, n_rp, False)
+    assert rel_err(r.ravel(), res[:2 * n_rp]) < 1e-12
