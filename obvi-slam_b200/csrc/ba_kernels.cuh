@@ -1947,8 +1947,7 @@ __global__ void finish_kernel(int nf, const uint32_t* __restrict__ sf_ptr, const
                               const uint32_t* __restrict__ sf_src, const double* __restrict__ S_upper,
                               const double* __restrict__ pscale, const double* __restrict__ hpp_diag,
                               const double* __restrict__ gp, const double* __restrict__ b_schur, LMParams lm,
-                              double* __restrict__ Sf, double* __restrict__ rhs, double* __restrict__ Minv,
-                              double* __restrict__ scalars) {
+                              double* __restrict__ Sf, double* __restrict__ rhs, double* __restrict__ scalars) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= nf) return;
@@ -1975,19 +1974,26 @@ __global__ void finish_kernel(int nf, const uint32_t* __restrict__ sf_ptr, const
     rhs[6 * i + lane] = pscale[6 * i + lane] * (g + b_schur[6 * i + lane]);
     atomic_max_nonneg(&scalars[SC_GMAX], fabs(g));
   }
-  if (lane == 0) {
-    // locate the diagonal block in this row
-    uint32_t kd = 0;
-    for (uint32_t k = 0; k < nb; k++) if (sf_col[p0 + k] == (uint32_t)i) { kd = k; break; }
-    double D[36], inv[36];
-    for (int a = 0; a < 6; a++)
-      for (int c = 0; c < 6; c++) D[a * 6 + c] = row[a * nb * 6 + kd * 6 + c];
-    if (!spd_inverse<6>(D, inv)) {
-      atomicAdd(&scalars[SC_FAIL], 1.0);
-      for (int a = 0; a < 36; a++) inv[a] = (a % 7 == 0) ? 1.0 / D[a] : 0.0;
-    }
-    for (int a = 0; a < 36; a++) Minv[(size_t)i * 36 + a] = inv[a];
+}
+
+// Inverse of the diagonal 6x6 blocks of the finished matrix (block-Jacobi preconditioner): only needed when the
+// block-tridiagonal factorisation is switched off or hit a non-positive pivot, so it is not part of finish_kernel.
+__global__ void minv_kernel(int nf, const uint32_t* __restrict__ sf_ptr, const uint32_t* __restrict__ sf_col,
+                            const double* __restrict__ Sf, double* __restrict__ Minv, double* __restrict__ scalars) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nf) return;
+  const uint32_t p0 = sf_ptr[i], nb = sf_ptr[i + 1] - p0;
+  const double* row = Sf + (size_t)p0 * 36;
+  uint32_t kd = 0;
+  for (uint32_t k = 0; k < nb; k++) if (sf_col[p0 + k] == (uint32_t)i) { kd = k; break; }
+  double D[36], inv[36];
+  for (int a = 0; a < 6; a++)
+    for (int c = 0; c < 6; c++) D[a * 6 + c] = row[a * nb * 6 + kd * 6 + c];
+  if (!spd_inverse<6>(D, inv)) {
+    atomicAdd(&scalars[SC_FAIL], 1.0);
+    for (int a = 0; a < 36; a++) inv[a] = (a % 7 == 0) ? 1.0 / D[a] : 0.0;
   }
+  for (int a = 0; a < 36; a++) Minv[(size_t)i * 36 + a] = inv[a];
 }
 
 // ------------------------------------------------------------------------------------------ reduced system: PCG

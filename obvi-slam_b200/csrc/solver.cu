@@ -130,6 +130,8 @@ struct Solver {
   PhaseProfiler prof;
   Structure st;
   cudaStream_t stream = nullptr;
+  cudaStream_t s3 = nullptr;       // second side stream (candidate cost: bbox on s2, priors + rel-pose on s3)
+  cudaEvent_t ev_join3 = nullptr;
   cudaStream_t s2 = nullptr;       // side stream: the small kernels (objects, priors, rel-pose) overlap the big point kernels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev[8] = {};
@@ -219,6 +221,8 @@ struct Solver {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (s2) cudaStreamDestroy(s2);
+    if (s3) cudaStreamDestroy(s3);
+    if (ev_join3) cudaEventDestroy(ev_join3);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -230,6 +234,8 @@ struct Solver {
     num_sms = prop.multiProcessorCount;
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_join3, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
@@ -567,8 +573,9 @@ struct Solver {
     if (world > 1) { allreduce_sum(redbuf.p, redbuf.n); prof.end("allreduce S", pt0, stream); pt0 = prof.begin(stream); }
     if (S.nf) {
       if (lm.compute_scale) { pose_scale_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(hpp_diag, S.nf * 6, pscale.p); launches++; }
-      finish_kernel<<<nblk((int64_t)S.nf * 32, 256), 256, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, sf_src.p, S_upper, pscale.p, hpp_diag, gp, b_schur, lm, Sf.p, rhs.p, Minv.p, scalars.p);
+      finish_kernel<<<nblk((int64_t)S.nf * 32, 256), 256, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, sf_src.p, S_upper, pscale.p, hpp_diag, gp, b_schur, lm, Sf.p, rhs.p, scalars.p);
       launches++;
+      if (!use_bt) { minv_kernel<<<nblk(S.nf, 64), 64, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, Sf.p, Minv.p, scalars.p); launches++; }
       prof.end("finish", pt0, stream); pt0 = prof.begin(stream);
       const bool stale = bt_radius <= 0.0 || lm.radius > 2.0 * bt_radius || lm.radius < 0.5 * bt_radius || last_pcg_iters > kRefactorPcgIters;
       if (stale) { factor_bt(); bt_radius = lm.radius; bt_factorizations++; prof.end("factor_bt", pt0, stream); }
@@ -641,9 +648,11 @@ struct Solver {
     if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cand].p, S.K, cams.p, S.C, 0, pcam_cand.p); launches++; }
     fork();
     if (S.n_obs) { reproj_cost_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam_cand.p, S.C, classes.p, points[cand].p, scalars.p); launches++; }
+    CUDA_OK(cudaStreamWaitEvent(s3, ev_fork, 0));
     if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, s2>>>(bbox.p, S.n_bbox, pcam_cand.p, S.C, objects[cand].p, 1, 1, Jb.p, scalars.p); launches++; }
-    if (S.n_unary) launch_unary(3, 1, cand, s2);
-    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 3, 1, poses[cand].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    if (S.n_unary) launch_unary(3, 1, cand, s3);
+    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s3>>>(rel.p, S.n_rel, 3, 1, poses[cand].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    CUDA_OK(cudaEventRecord(ev_join3, s3)); CUDA_OK(cudaStreamWaitEvent(stream, ev_join3, 0));
     join();
   }
   // stage 0: after linearize () + build_reduced (); stage 1: after take_step () + candidate_cost ()
@@ -823,6 +832,7 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
     CUDA_OK(cudaEventElapsedTime(&ms, ev[3], ev[4])); t_res += ms * 1e-3;
     if (h_scalars[SC_PCG_BREAK] == 2.0) {
       // the block-tridiagonal factorisation hit a non-positive pivot: redo this step with block-Jacobi PCG
+      minv_kernel<<<nblk(S.nf, 64), 64, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, Sf.p, Minv.p, scalars.p); launches++;
       solve_reduced(o, true);
       take_step();
       candidate_cost();
