@@ -206,6 +206,14 @@ int obvi_evaluate_factor_type(obvi_problem* p, int factor_type, int apply_loss_f
 int obvi_topk_outliers(obvi_problem* p, int factor_type, double fraction, obvi_factor_id* ids, int64_t capacity,
                        int64_t* n);
 
+/* ---- marginal covariances of ellipsoid blocks: ceres::Covariance::Compute + GetCovarianceBlock as the long-term-map
+ *      extraction uses them (src/refactoring/long_term_map/long_term_object_map_extraction.cpp:362-440; block lists in
+ *      include/refactoring/long_term_map/long_term_object_map_extraction.h:269-284 (pairs) and :459-467 (diagonal)).
+ *      out[i] = 7x7 row-major block [obj_a[i], obj_b[i]] of (J^T J)^-1 at the current values, loss functions applied,
+ *      constant blocks left out (their blocks are zero).  Computed from the same Schur elimination as the solve, without
+ *      damping; OBVI_ERR_NUMERIC when J is rank deficient (no gauge fix), as Ceres' SPARSE_QR path reports failure. */
+int obvi_object_covariances(obvi_problem* p, int64_t n_pairs, double* const* obj_a, double* const* obj_b, double* out);
+
 /* ---- multi-GPU: one process per GPU; e-blocks (points / objects) are sharded over ranks, the reduced
  *      camera system is all-reduced over NCCL each LM iteration.  unique_id is a 128-byte ncclUniqueId
  *      produced by obvi_comm_unique_id on rank 0 and distributed by the caller. */

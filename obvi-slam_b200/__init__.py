@@ -121,6 +121,7 @@ def lib():
         "obvi_evaluate": ([vp, C.c_int, _d, _d, i64, C.POINTER(i64)], C.c_int),
         "obvi_evaluate_factor_type": ([vp, C.c_int, C.c_int, _d, _d, _d], C.c_int),
         "obvi_topk_outliers": ([vp, C.c_int, dbl, u64p, i64, C.POINTER(i64)], C.c_int),
+        "obvi_object_covariances": ([vp, i64, C.POINTER(vp), C.POINTER(vp), _d], C.c_int),
         "obvi_profile_jacobian": ([vp, C.c_int, _d, C.POINTER(i64), C.POINTER(i64)], C.c_int),
         "obvi_debug_partition": ([vp, C.c_int, C.c_int, C.POINTER(i64)], C.c_int),
         "obvi_comm_unique_id": ([vp], C.c_int),
@@ -140,7 +141,7 @@ EXPORTED_SYMBOLS = [
     "obvi_factor_add_reproj", "obvi_factor_add_reproj_batch", "obvi_factor_add_bbox", "obvi_factor_add_bbox_batch",
     "obvi_factor_add_shape_prior", "obvi_factor_add_ltm_prior", "obvi_factor_add_rel_pose", "obvi_factor_add_param_prior",
     "obvi_factor_remove", "obvi_num_factors", "obvi_num_structure_builds", "obvi_residual_blocks", "obvi_solver_options_init", "obvi_solve",
-    "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_profile_jacobian", "obvi_debug_partition", "obvi_comm_unique_id",
+    "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_object_covariances", "obvi_profile_jacobian", "obvi_debug_partition", "obvi_comm_unique_id",
     "obvi_comm_init",
 ]
 
@@ -332,6 +333,14 @@ class Problem:
         ids = np.zeros(max(cap, 1), np.uint64)
         self._ck(self._lib.obvi_topk_outliers(self._h, ftype, float(fraction), ids.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n)))
         return ids[:n.value]
+
+    def object_covariances(self, blocks_a, blocks_b):
+        """7x7 blocks [a_i, b_i] of (J^T J)^-1 (ceres::Covariance on ellipsoid blocks); blocks are the registered arrays."""
+        n = len(blocks_a)
+        pa = (C.c_void_p * n)(*[b.ctypes.data for b in blocks_a]); pb = (C.c_void_p * n)(*[b.ctypes.data for b in blocks_b])
+        out = np.zeros((n, 7, 7))
+        self._ck(self._lib.obvi_object_covariances(self._h, n, pa, pb, out.ctypes.data_as(_d)))
+        return out
 
     def profile_jacobian(self, reps=20):
         """(seconds per launch, algorithmic bytes per launch, observations) of the Jacobian-evaluation kernel."""

@@ -2167,6 +2167,60 @@ __global__ void run_end_flags_kernel(const double* __restrict__ keys, int64_t n,
   if (i < n) flags[i] = (i == n - 1) || (keys[i] != keys[i + 1]);
 }
 
+// ------------------------------------------------------------------------------------------ marginal covariances of objects
+// (J^T J)^-1 restricted to ellipsoid blocks, from the same elimination as the solve (no damping):
+//   Sigma_ab = [a == b] H_a^-1 + Z_a^T S^-1 Z_b,   Z_o = E_po H_o^-1  (one 6x7 block per pose slot of the object),
+// where S is the reduced camera matrix (reference: ceres::Covariance on the LTM-extraction problem,
+// src/refactoring/long_term_map/long_term_object_map_extraction.cpp:362-440).
+// One thread per (object, pose slot): W = sum Jp^T Jo over the slot's bbox observations, Z = W Hinv.
+__global__ void obj_z_kernel(int64_t n_slots, const uint32_t* __restrict__ slot_obj, const uint32_t* __restrict__ slot_d0,
+                             const uint32_t* __restrict__ slot_cnt, const uint32_t* __restrict__ pos, const double* __restrict__ Jb,
+                             const double* __restrict__ einv, double* __restrict__ Zo) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_slots) return;
+  double W[42];
+  for (int a = 0; a < 42; a++) W[a] = 0.0;
+  for (uint32_t k = 0; k < slot_cnt[g]; k++) {
+    const double* ch = Jb + (size_t)pos[slot_d0[g] + k] * 56;   // [Jp 4x6 | Jo 4x7 | r 4]
+    for (int q = 0; q < 4; q++)
+      for (int a = 0; a < 6; a++)
+        for (int c = 0; c < 7; c++) W[a * 7 + c] += ch[q * 6 + a] * ch[24 + q * 7 + c];
+  }
+  const double* hinv = einv + (size_t)slot_obj[g] * 49;
+  for (int a = 0; a < 6; a++)
+    for (int c = 0; c < 7; c++) {
+      double z = 0.0;
+      for (int d = 0; d < 7; d++) z += W[a * 7 + d] * hinv[d * 7 + c];
+      Zo[(size_t)g * 42 + a * 7 + c] = z;
+    }
+}
+// rhs (scaled system) = P Z_o[:, col] scattered to the object's pose rows; rhs must be zero before
+__global__ void cov_rhs_kernel(uint32_t s0, uint32_t ns, int col, const int32_t* __restrict__ slot_f, const double* __restrict__ Zo,
+                               const double* __restrict__ pscale, double* __restrict__ rhs) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ns * 6) return;
+  const uint32_t s = t / 6, a = t - 6 * s;
+  const int f = slot_f[s0 + s];
+  rhs[6 * f + a] = pscale[6 * f + a] * Zo[(size_t)(s0 + s) * 42 + a * 7 + col];
+}
+// out[pair][r][c] = [a == b] Hinv_a[r][c] + sum_slots sum_x Z_a[slot][x][r] pscale[6 f + x] Y[c][6 f + x]
+struct CovPair { uint32_t s0, ns, obj_a, same; uint64_t out; };
+__global__ void cov_dot_kernel(const CovPair* __restrict__ pairs, int n_pairs, const int32_t* __restrict__ slot_f,
+                               const double* __restrict__ Zo, const double* __restrict__ pscale, const double* __restrict__ Y,
+                               size_t ystride, const double* __restrict__ einv, double* __restrict__ out) {
+  const int pi = blockIdx.x;
+  if (pi >= n_pairs) return;
+  const CovPair P = pairs[pi];
+  const int r = threadIdx.x / 7, c = threadIdx.x - 7 * r;
+  if (r >= 7) return;
+  double acc = P.same ? einv[(size_t)P.obj_a * 49 + r * 7 + c] : 0.0;
+  for (uint32_t s = 0; s < P.ns; s++) {
+    const int f = slot_f[P.s0 + s];
+    for (int x = 0; x < 6; x++) acc += Zo[(size_t)(P.s0 + s) * 42 + x * 7 + r] * pscale[6 * f + x] * Y[(size_t)c * ystride + 6 * f + x];
+  }
+  out[P.out + r * 7 + c] = acc;
+}
+
 // |x|^2 over the variable blocks: `mask` (per block, nonzero = skip), block size bs
 __global__ void xnorm_kernel(const double* __restrict__ x, const uint8_t* __restrict__ skip, int64_t nblocks, int bs,
                              double* __restrict__ scalars) {

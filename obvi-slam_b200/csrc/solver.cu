@@ -738,6 +738,7 @@ struct Solver {
   }
 
   int solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteration_summary* its, int cap);
+  int object_covariances(int64_t n_pairs, double* const* obj_a, double* const* obj_b, double* out, std::string& err);
 };
 
 __global__ void mask_blocks_kernel(double* x, const uint8_t* skip, int64_t n, int bs) {
@@ -749,6 +750,85 @@ void Solver::merge_sharded(double* x, const uint8_t* skip, int nblocks, int bs) 
   // constant blocks are skipped by every rank: they are never written back, so zeros are harmless
   mask_blocks_kernel<<<nblk((int64_t)nblocks * bs, 256), 256, 0, stream>>>(x, skip, nblocks, bs);
   allreduce_sum(x, (size_t)nblocks * bs);
+}
+
+// Marginal covariance blocks of ellipsoids (ceres::Covariance::Compute + GetCovarianceBlock on the LTM-extraction problem,
+// long_term_object_map_extraction.cpp:362-440).  See obj_z_kernel for the algebra.
+int Solver::object_covariances(int64_t n_pairs, double* const* obj_a, double* const* obj_b, double* out, std::string& err) {
+  if (world > 1) { err = "obvi_object_covariances is single-rank only"; return OBVI_ERR_INVALID_ARGUMENT; }
+  ensure_structure(nullptr);
+  const Structure& S = st;
+  std::unordered_map<int32_t, int> obj_of_block;
+  for (int o = 0; o < S.O; o++) obj_of_block[S.obj_block[o]] = o;
+  std::vector<int> ia(n_pairs), ib(n_pairs);
+  for (int64_t i = 0; i < n_pairs; i++) {
+    const int32_t ba = pb.find_block(obj_a[i]), bb = pb.find_block(obj_b[i]);
+    auto fa = obj_of_block.find(ba), fb = obj_of_block.find(bb);
+    if (ba < 0 || bb < 0 || fa == obj_of_block.end() || fb == obj_of_block.end()) { err = "covariance requested for a block that is not an ellipsoid of this problem"; return OBVI_ERR_NOT_FOUND; }
+    ia[i] = fa->second; ib[i] = fb->second;
+  }
+  gather_params();
+  LMParams lm;
+  lm.radius = std::numeric_limits<double>::infinity(); lm.inv_radius = 0.0; lm.min_diag = 1e-6; lm.max_diag = 1e32; lm.compute_scale = 1;
+  bt_radius = -1.0; last_pcg_iters = 0;
+  linearize(1);
+  build_reduced(lm);
+  fetch_scalars(0);
+  if (h_scalars[SC_FAIL] != 0.0) { err = "covariance: a point / object block of J^T J is singular (rank-deficient Jacobian)"; return OBVI_ERR_NUMERIC; }
+  // per (object, slot) tables
+  const int64_t n_os = S.objs.slot_ptr[S.O];
+  std::vector<uint32_t> so(n_os), sd0(n_os), scnt(n_os, 0);
+  for (int o = 0; o < S.O; o++) {
+    for (uint32_t d = S.objs.ptr[o]; d < S.objs.ptr[o + 1]; d++) {
+      if (S.objs.slot[d] == 0xFFFF) continue;
+      const uint32_t g = S.objs.slot_ptr[o] + S.objs.slot[d];
+      if (scnt[g] == 0) { sd0[g] = d; so[g] = (uint32_t)o; }
+      scnt[g]++;
+    }
+  }
+  DBuf<uint32_t> d_so, d_sd0, d_scnt;
+  DBuf<int32_t> d_sf;
+  DBuf<double> Zo, Y, d_out;
+  d_so.upload(so, stream); d_sd0.upload(sd0, stream); d_scnt.upload(scnt, stream); d_sf.upload(S.objs.slot_f, stream);
+  Zo.alloc((size_t)std::max<int64_t>(n_os, 1) * 42);
+  if (n_os) { obj_z_kernel<<<nblk(n_os, 64), 64, 0, stream>>>(n_os, d_so.p, d_sd0.p, d_scnt.p, objs.pos.p, Jb.p, objs.einv.p, Zo.p); launches++; }
+  const size_t nf6 = (size_t)S.nf * 6;
+  Y.alloc(7 * std::max<size_t>(nf6, 1));
+  d_out.alloc((size_t)n_pairs * 49); d_out.zero(stream);
+  obvi_solver_options so_opts; obvi_solver_options_init(&so_opts);
+  // group the requested pairs by their second object: 7 reduced solves per distinct one
+  std::map<int, std::vector<int64_t>> by_b;
+  for (int64_t i = 0; i < n_pairs; i++) if (!S.obj_const[ia[i]] && !S.obj_const[ib[i]]) by_b[ib[i]].push_back(i);
+  int rc = OBVI_OK;
+  for (auto& kv : by_b) {
+    const int o = kv.first;
+    const uint32_t s0 = S.objs.slot_ptr[o], ns = S.objs.slot_ptr[o + 1] - s0;
+    Y.zero(stream);
+    if (S.nf && ns) {
+      for (int c = 0; c < 7 && rc == OBVI_OK; c++) {
+        rhs.zero(stream);
+        cov_rhs_kernel<<<nblk(ns * 6, 64), 64, 0, stream>>>(s0, ns, c, d_sf.p, Zo.p, pscale.p, rhs.p); launches++;
+        solve_reduced(so_opts);
+        CUDA_OK(cudaMemcpyAsync(Y.p + (size_t)c * nf6, y.p, nf6 * 8, cudaMemcpyDeviceToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(h_scalars, scalars.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        // an all-zero column (bb == 0) is solved trivially; otherwise PCG must have converged on an SPD system
+        if (h_scalars[SC_PCG_BREAK] != 0.0 || !(h_scalars[SC_PCG_RES] <= 1e-6)) { err = "covariance: the reduced camera system is not positive definite (rank-deficient Jacobian, e.g. no gauge fix)"; rc = OBVI_ERR_NUMERIC; }
+      }
+    }
+    if (rc != OBVI_OK) break;
+    std::vector<CovPair> cp;
+    for (int64_t i : kv.second) {
+      const int a = ia[i];
+      CovPair P; P.s0 = S.objs.slot_ptr[a]; P.ns = S.nf ? S.objs.slot_ptr[a + 1] - P.s0 : 0u; P.obj_a = (uint32_t)a; P.same = a == o; P.out = (uint64_t)i * 49;
+      cp.push_back(P);
+    }
+    DBuf<CovPair> d_cp; d_cp.upload(cp, stream);
+    cov_dot_kernel<<<(int)cp.size(), 64, 0, stream>>>(d_cp.p, (int)cp.size(), d_sf.p, Zo.p, pscale.p, Y.p, std::max<size_t>(nf6, 1), objs.einv.p, d_out.p); launches++;
+    CUDA_OK(cudaStreamSynchronize(stream));
+  }
+  if (rc == OBVI_OK && n_pairs) CUDA_OK(cudaMemcpy(out, d_out.p, (size_t)n_pairs * 49 * 8, cudaMemcpyDeviceToHost));
+  return rc;
 }
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -1398,6 +1478,19 @@ int obvi_topk_outliers(obvi_problem* p, int type, double fraction, obvi_factor_i
   int64_t c = 0;
   for (auto it = by_err.begin(); it != by_err.end() && (size_t)c < k; ++it, ++c) if (ids && c < cap) ids[c] = it->second;
   *n = (int64_t)k;
+  return OBVI_OK;
+  API_END(p)
+}
+
+int obvi_object_covariances(obvi_problem* p, int64_t n_pairs, double* const* obj_a, double* const* obj_b, double* out) {
+  if (!p || n_pairs < 0 || (n_pairs && (!obj_a || !obj_b || !out))) return OBVI_ERR_INVALID_ARGUMENT;
+  API_BEGIN
+  Solver& s = p->s;
+  if (s.pb.device < 0) return fail(p, OBVI_ERR_CUDA, "host-only problem handle: no CUDA device attached (no CPU fallback exists)");
+  CUDA_OK(cudaSetDevice(s.pb.device));
+  std::string err;
+  const int rc = s.object_covariances(n_pairs, obj_a, obj_b, out, err);
+  if (rc != OBVI_OK) return fail(p, rc, err.c_str());
   return OBVI_OK;
   API_END(p)
 }

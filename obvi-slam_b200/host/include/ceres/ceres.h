@@ -6,7 +6,8 @@
 //             SetParameterBlockVariable, IsParameterBlockConstant, GetResidualBlocks, GetParameterBlocksForResidualBlock,
 //             NumResidualBlocks, NumParameterBlocks, Evaluate}
 //   Solver::Options (the fields object_pose_graph_optimizer.h:651-672 sets), Solver::Summary, IterationSummary, Solve,
-//   CostFunction, AutoDiffCostFunction, SizedCostFunction, LossFunction, HuberLoss, IterationCallback, ResidualBlockId.
+//   CostFunction, AutoDiffCostFunction, SizedCostFunction, LossFunction, HuberLoss, IterationCallback, ResidualBlockId,
+//   Covariance::{Options, Compute, GetCovarianceBlock} on ellipsoid blocks (long-term-map extraction).
 // so that include/refactoring/optimization/{residual_creator.h, object_pose_graph_optimizer.h},
 // include/refactoring/offline/offline_problem_runner.h and include/run_optimization_utils/* compile against it unchanged
 // once the factor headers next to this file (refactoring/factors/*.h) replace the reference's.
@@ -341,6 +342,49 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
   for (IterationCallback* cb : options.callbacks)
     for (const IterationSummary& it : summary->iterations) (*cb)(it);
 }
+
+// ---------------------------------------------------------------------------------------------- covariance
+// ceres::Covariance as the long-term-map extraction uses it (long_term_object_map_extraction.cpp:412-440,
+// long_term_object_map_extraction.h:269-345,459-520): Compute() on a list of (ellipsoid, ellipsoid) block pairs, then
+// GetCovarianceBlock() per pair (7x7 row-major).  Only ellipsoid blocks are supported.
+enum CovarianceAlgorithmType { DENSE_SVD, SPARSE_QR };
+enum SparseLinearAlgebraLibraryType { SUITE_SPARSE, EIGEN_SPARSE, NO_SPARSE };
+class Covariance {
+ public:
+  struct Options {
+    int num_threads = 1;
+    CovarianceAlgorithmType algorithm_type = SPARSE_QR;
+    SparseLinearAlgebraLibraryType sparse_linear_algebra_library_type = SUITE_SPARSE;
+    bool apply_loss_function = true;
+  };
+  explicit Covariance(const Options& o) : options_(o) {}
+  bool Compute(const std::vector<std::pair<const double*, const double*>>& blocks, Problem* problem) {
+    blocks_.clear(); values_.clear();
+    if (!options_.apply_loss_function) return false;   // the backend evaluates the loss-corrected Jacobian (Ceres' default)
+    std::vector<double*> a, b;
+    for (auto& pr : blocks) {
+      if (problem->ParameterBlockSize(pr.first) != 7 || problem->ParameterBlockSize(pr.second) != 7) return false;
+      a.push_back(const_cast<double*>(pr.first)); b.push_back(const_cast<double*>(pr.second));
+    }
+    values_.assign(blocks.size() * 49, 0.0);
+    if (obvi_object_covariances(problem->obvi_handle(), (int64_t)blocks.size(), a.data(), b.data(), values_.data()) != OBVI_OK) { values_.clear(); return false; }
+    for (size_t i = 0; i < blocks.size(); i++) blocks_[blocks[i]] = i;
+    return true;
+  }
+  bool GetCovarianceBlock(const double* p1, const double* p2, double* out) const {
+    auto it = blocks_.find(std::make_pair(p1, p2));
+    if (it != blocks_.end()) { for (int i = 0; i < 49; i++) out[i] = values_[it->second * 49 + i]; return true; }
+    it = blocks_.find(std::make_pair(p2, p1));   // Ceres serves the transposed block as well
+    if (it == blocks_.end()) return false;
+    for (int r = 0; r < 7; r++) for (int c = 0; c < 7; c++) out[r * 7 + c] = values_[it->second * 49 + c * 7 + r];
+    return true;
+  }
+ private:
+  struct PairHash { size_t operator()(const std::pair<const double*, const double*>& p) const { return std::hash<const double*>()(p.first) * 1000003u ^ std::hash<const double*>()(p.second); } };
+  Options options_;
+  std::unordered_map<std::pair<const double*, const double*>, size_t, PairHash> blocks_;
+  std::vector<double> values_;
+};
 
 }  // namespace ceres
 #endif  // OBVI_CERES_SHIM_CERES_H_

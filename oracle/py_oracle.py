@@ -490,3 +490,20 @@ def solve_lm_dense(g, max_num_iterations=50, function_tolerance=1e-6, gradient_t
             b = _get(g, k, i)
             b[:] = x_min[o:o + len(b)]
     return out
+
+
+def covariance_blocks(g, pairs):
+    """ceres::Covariance on ellipsoid blocks (long_term_object_map_extraction.cpp:362-440): blocks [(a, b)] of (J^T J)^-1
+    with the loss-corrected Jacobian over the variable blocks; dense inverse (small graphs only)."""
+    off, n = _layout(g)
+    _, _, J = evaluate(g, apply_loss=True)
+    J = J[:, :n]
+    used = np.abs(J).sum(axis=0) > 0          # blocks without residuals are not part of the reduced program
+    cov = np.zeros((n, n))
+    cov[np.ix_(used, used)] = np.linalg.inv(J[:, used].T @ J[:, used])
+    out = np.zeros((len(pairs), 7, 7))
+    for i, (a, b) in enumerate(pairs):
+        if ("obj", a) in off and ("obj", b) in off:
+            oa, ob_ = off[("obj", a)], off[("obj", b)]
+            out[i] = cov[oa:oa + 7, ob_:ob_ + 7]
+    return out

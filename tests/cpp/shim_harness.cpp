@@ -136,6 +136,22 @@ int main(int argc, char** argv) {
   std::vector<double> out = {summary.initial_cost, summary.final_cost, (double)summary.iterations.size(), raw_cost, (double)residuals.size(),
                              (double)n_excl, summary2.initial_cost, summary2.final_cost, (double)summary2.iterations.size(),
                              (double)problem.NumResidualBlocks(), (double)summary.num_parameters_reduced};
+  // ---- long-term-map extraction pattern (long_term_object_map_extraction.h:459-520): diagonal covariance block of
+  //      every ellipsoid that has observations, in object order; 49 values each (zeros when Compute fails)
+  {
+    ceres::Covariance::Options cov_options;
+    cov_options.num_threads = 20; cov_options.algorithm_type = ceres::SPARSE_QR;
+    ceres::Covariance covariance(cov_options);
+    std::vector<std::pair<const double*, const double*>> cov_blocks;
+    for (int k = 0; k < O; k++) if (problem.HasParameterBlock(objs[k].get())) cov_blocks.emplace_back(objs[k].get(), objs[k].get());
+    const bool ok = covariance.Compute(cov_blocks, &problem);
+    out.push_back(ok ? (double)cov_blocks.size() : -1.0);
+    for (auto& pr : cov_blocks) {
+      double blk[49] = {0};
+      if (ok) covariance.GetCovarianceBlock(pr.first, pr.second, blk);
+      out.insert(out.end(), blk, blk + 49);
+    }
+  }
   for (int k = 0; k < K; k++) out.insert(out.end(), poses[k].get(), poses[k].get() + 6);
   for (int k = 0; k < P; k++) out.insert(out.end(), points[k].get(), points[k].get() + 3);
   for (int k = 0; k < O; k++) out.insert(out.end(), objs[k].get(), objs[k].get() + 7);

@@ -278,3 +278,52 @@ def test_two_phase_in_place_exclusion(ob, oracle):
     assert got.tolist() == [int(live_ids[by_err[e]]) for e in order[:int(len(order) * 0.15)]]
     r, jp, jl = p.evaluate_factor_type(ob.FACTOR_REPROJECTION, n_rp, False)
     assert rel_err(r.ravel(), res[:2 * n_rp]) < 1e-12
+
+
+def test_object_covariances_match_dense_inverse(ob):
+    """Long-term-map extraction (long_term_object_map_extraction.cpp:362-440; block lists .h:269-284 and :459-467): marginal
+    covariance blocks of the ellipsoids, diagonal (IndependentEllipsoids) and pairwise, against the dense inverse of
+    J^T J from the NumPy oracle."""
+    from oracle import py_oracle as po
+    g = small_graph(ob, seed=31, K=14, P=250, O=6)
+    p = ob.problem_from_graph(g)
+    p.solve(**dict(OPTS, max_num_iterations=15))           # covariances are taken at the optimum
+    O = len(g.objects)
+    seen = sorted(set(int(o) for o in g.bbox["obj"]))
+    assert len(seen) >= 3
+    pairs = [(a, a) for a in seen] + [(seen[0], seen[1]), (seen[1], seen[2]), (seen[2], seen[0])]
+    got = p.object_covariances([g.objects[a] for a, _ in pairs], [g.objects[b] for _, b in pairs])
+    ref = po.covariance_blocks(g, pairs)
+    for i, (a, b) in enumerate(pairs):
+        scale = np.sqrt(np.outer(np.abs(np.diag(ref[pairs.index((a, a))])), np.abs(np.diag(ref[pairs.index((b, b))])))) if (b, b) in pairs else 1.0
+        assert np.abs(got[i] - ref[i]).max() <= 1e-6 * np.max(scale) + 1e-12, (a, b, np.abs(got[i] - ref[i]).max())
+    # symmetric, positive definite diagonal blocks; cross blocks transpose into each other
+    for i, (a, b) in enumerate(pairs[:len(seen)]):
+        assert np.allclose(got[i], got[i].T, rtol=1e-8, atol=1e-14) and np.all(np.linalg.eigvalsh(0.5 * (got[i] + got[i].T)) > 0)
+    ab = p.object_covariances([g.objects[seen[0]]], [g.objects[seen[1]]])[0]
+    ba = p.object_covariances([g.objects[seen[1]]], [g.objects[seen[0]]])[0]
+    assert np.allclose(ab, ba.T, rtol=1e-7, atol=1e-14)
+    # the solve after a covariance query is unaffected (scaling / preconditioner state is rebuilt)
+    s2 = p.solve(**dict(OPTS, max_num_iterations=2))
+    assert s2.final_cost <= s2.initial_cost * (1 + 1e-12)
+
+
+def test_object_covariances_without_gauge_fix_fail(ob):
+    """No constant pose and no priors on poses: J is rank deficient, ceres::Covariance (SPARSE_QR) reports failure."""
+    g = ob.synth.make_graph(K=8, P=150, O=3, seed=32, objects_on=True, relpose="none", n_const_poses=0, min_obj_obs=4)
+    p = ob.problem_from_graph(g)
+    seen = sorted(set(int(o) for o in g.bbox["obj"]))
+    with pytest.raises(Exception):
+        p.object_covariances([g.objects[seen[0]]], [g.objects[seen[0]]])
+
+
+def test_pending_object_estimate_objects_only(ob, oracle):
+    """refineInitialEstimateForPendingObjects (pending_object_estimator.cpp:38-151): every pose constant, no visual
+    features; each pending ellipsoid is refined from its bounding boxes + shape prior -- a batch of independent 7-dof
+    problems handled by one solve (nothing is left in the reduced camera system)."""
+    g = ob.synth.make_graph(K=30, P=0, O=10, seed=33, objects_on=True, relpose="none", n_const_poses=30, min_obj_obs=4)
+    assert g.counts()["bbox"] > 40 and g.counts()["reproj"] == 0
+    # Ceres defaults there (monotonic steps, radius 1e4); a dozen iterations, before round-off decides accept / reject
+    o = dict(OPTS, max_num_iterations=12, use_nonmonotonic_steps=0, initial_trust_region_radius=1e4, max_trust_region_radius=1e16)
+    s, ref = check_solve(ob, oracle, g, o)
+    assert s.num_parameters_reduced == 7 * len(set(int(o) for o in g.bbox["obj"]) | set(int(o) for o in g.shape["obj"]))

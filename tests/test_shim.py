@@ -68,6 +68,15 @@ def test_shim_matches_c_abi_two_phase(ob, tmp_path):
     assert int(head[9]) == p.num_residual_blocks() and int(head[10]) == s1.num_parameters_reduced
     n = g.counts()
     K, P = n["poses"], n["points"]
+    # ceres::Covariance through the shim vs the binding (diagonal blocks of the ellipsoids registered with the problem)
+    ncov = int(res[11])
+    used = sorted(set(int(o) for o in g.bbox["obj"]) | set(int(o) for o in g.shape["obj"]) | set(int(o) for o in g.ltm["obj"]))
+    assert ncov == len(used) > 0
+    cov_shim = res[12:12 + 49 * ncov].reshape(ncov, 7, 7)
+    cov_py = p.object_covariances([g.objects[o] for o in used], [g.objects[o] for o in used])
+    for a, b in zip(cov_shim, cov_py):
+        assert np.abs(a - b).max() <= 1e-3 * np.abs(np.diag(b)).max()
+    res = np.concatenate([res[:11], res[12 + 49 * ncov:]])
     assert np.abs(res[11:11 + 6 * K].reshape(K, 6) - g.poses).max() < 1e-5
     assert np.abs(res[11 + 6 * K:11 + 6 * K + 3 * P].reshape(P, 3) - g.points).max() < 1e-3
     assert np.abs(res[11 + 6 * K + 3 * P:].reshape(-1, 7) - g.objects).max() < 1e-3
