@@ -10,5 +10,6 @@ if _ROOT not in sys.path:
 
 _pkg = importlib.import_module("obvi-slam_b200")
 synth = importlib.import_module("obvi-slam_b200.synth")
+schedule = importlib.import_module("obvi-slam_b200.schedule")
 
 globals().update({k: v for k, v in vars(_pkg).items() if not k.startswith("__")})
