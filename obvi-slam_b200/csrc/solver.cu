@@ -233,8 +233,12 @@ struct Solver {
     if (prop.major < 10) throw std::runtime_error(std::string("obvi_ba is built for sm_100a (B200); found ") + prop.name);
     num_sms = prop.multiProcessorCount;
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking));
+    // the side streams carry the small latency-bound kernels (objects, priors, rel-pose): highest priority, so that their
+    // few CTAs are placed as soon as a slot frees up instead of queueing behind the grid of a big point kernel
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_OK(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, prio_hi));
+    CUDA_OK(cudaStreamCreateWithPriority(&s3, cudaStreamNonBlocking, prio_hi));
     CUDA_OK(cudaEventCreateWithFlags(&ev_join3, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -487,15 +491,21 @@ struct Solver {
     zero_scalars(SC_COST, 3);
     if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p, pcam_r.p); launches++; }
     fork();
-    if (S.n_obs) launch_jacobian(apply_loss, points[cur].p);
+    prof.end("lin: pose_cam", pt0, stream);
+    CUDA_OK(cudaStreamWaitEvent(s3, ev_fork, 0));
     if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, s2>>>(bbox.p, S.n_bbox, pcam.p, S.C, objects[cur].p, 0, apply_loss, Jb.p, scalars.p); launches++; }
-    if (S.n_unary) { launch_unary(0, apply_loss, cur, s2); }
-    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 0, apply_loss, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
-    if (S.K) { xnorm_kernel<<<nblk((int64_t)S.K * 6, 256), 256, 0, s2>>>(poses[cur].p, pose_skip.p, S.K, 6, scalars.p); launches++; }
-    if (S.P) { xnorm_kernel<<<nblk((int64_t)S.P * 3, 256), 256, 0, s2>>>(points[cur].p, point_skip.p, S.P, 3, scalars.p); launches++; }
-    if (S.O) { xnorm_kernel<<<nblk((int64_t)S.O * 7, 256), 256, 0, s2>>>(objects[cur].p, obj_skip.p, S.O, 7, scalars.p); launches++; }
+    if (S.n_unary) { launch_unary(0, apply_loss, cur, s3); }
+    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s3>>>(rel.p, S.n_rel, 0, apply_loss, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    if (S.K) { xnorm_kernel<<<nblk((int64_t)S.K * 6, 256), 256, 0, s3>>>(poses[cur].p, pose_skip.p, S.K, 6, scalars.p); launches++; }
+    if (S.P) { xnorm_kernel<<<nblk((int64_t)S.P * 3, 256), 256, 0, s3>>>(points[cur].p, point_skip.p, S.P, 3, scalars.p); launches++; }
+    if (S.O) { xnorm_kernel<<<nblk((int64_t)S.O * 7, 256), 256, 0, s3>>>(objects[cur].p, obj_skip.p, S.O, 7, scalars.p); launches++; }
+    const size_t pt1 = prof.begin(stream);
+    if (S.n_obs) launch_jacobian(apply_loss, points[cur].p);
+    prof.end("lin: jacobian", pt1, stream);
+    const size_t pt2 = prof.begin(stream);
+    CUDA_OK(cudaEventRecord(ev_join3, s3)); CUDA_OK(cudaStreamWaitEvent(stream, ev_join3, 0));
     join();
-    prof.end("linearize", pt0, stream);
+    prof.end("lin: side join", pt2, stream);
   }
   // the reprojection Jacobian-evaluation kernel (three revisions, selectable with OBVI_JAC = plain | tma | persistent)
   void launch_jacobian(int apply_loss, const double* pts_dev) {
@@ -539,8 +549,13 @@ struct Solver {
     // unary factors on points feed the point elimination: keep them on the main stream in that case
     if (S.n_unary && pts.has_prior) launch_unary(1, 1, cur, stream);
     fork();
+    // side stream: priors, rel-pose and the object elimination (all accumulate with atomics); enqueued first, high priority
+    if (S.n_unary && !pts.has_prior) launch_unary(1, 1, cur, s2);
+    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 1, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
+    if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
+    prof.end("zero", pt0, stream); pt0 = prof.begin(stream);
     if (S.n_obs && S.nf) { pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag); launches++; }
-    prof.end("zero+pose_accum", pt0, stream); pt0 = prof.begin(stream);
+    prof.end("pose_accum", pt0, stream); pt0 = prof.begin(stream);
     if (schur_mode == 3) {
       if (S.P) { point_prep_kernel<<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
       prof.end("point_prep", pt0, stream); pt0 = prof.begin(stream);
@@ -563,10 +578,6 @@ struct Solver {
       schur_eblock_kernel<3, 2, 32, 16, false><<<n_fallback, 32, 0, stream>>>(a, lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p);
       launches++;
     }
-    // side stream: priors, rel-pose and the object elimination (all accumulate with atomics)
-    if (S.n_unary && !pts.has_prior) launch_unary(1, 1, cur, s2);
-    if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 1, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
-    if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
     prof.end("schur_points", pt0, stream); pt0 = prof.begin(stream);
     join();
     prof.end("join(objects,rel)", pt0, stream); pt0 = prof.begin(stream);
