@@ -90,6 +90,7 @@ struct Structure {
     int max_slots = 0;
   } pts, objs;
   // batches of consecutive points for the owner-computes Schur kernel (see schur_points_batched_kernel)
+  bool want_batches = false;
   struct PointBatches {
     std::vector<uint32_t> first, count;     // per batch: first point, number of points
     std::vector<int32_t> win_f;             // 64 per batch: f index of each window pose, ascending, -1 padded
@@ -197,7 +198,7 @@ inline void count_reduced(const Problem& pb, Structure& S) {
 // rank/world: e-blocks (points, objects) are dealt to ranks in contiguous ranges of the internal
 // (first-observing-keyframe) order, balanced by observation count; rank 0 also owns the pose-only factors.
 inline bool build_structure(const Problem& pb, Structure& S, int rank, int world, std::string& err) {
-  S = Structure();
+  { const bool wb = S.want_batches; S = Structure(); S.want_batches = wb; }
   const int nb = (int)pb.blocks.size();
   std::vector<int32_t> pose_of_block(nb, -1), point_of_block(nb, -1), obj_of_block(nb, -1);
   std::vector<uint8_t> used(nb, 0);
@@ -454,7 +455,8 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     }
   }
   // ---- point batches: consecutive points (first-observing-keyframe order) whose poses fit a 64-wide window
-  {
+  //      (only the batched kernels use them; the default row-owner path skips this pass)
+  if (S.want_batches) {
     constexpr int kMaxPts = 128, kMaxWin = 20, kMaxPairs = 256, kMaxSlots = 16;  // kMaxWin: window of the tensor-core path (u32 masks, 210 pair accumulators)
     Structure::PointBatches& B = S.pbatch;
     B.mask.assign(S.P, 0); B.pair_ptr.push_back(0);

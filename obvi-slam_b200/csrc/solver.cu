@@ -738,6 +738,7 @@ struct Solver {
     const auto t0 = std::chrono::steady_clock::now();
     if (pb.dirty || !uploaded) {
       std::string err;
+      st.want_batches = schur_mode != 3;
       if (!build_structure(pb, st, rank, world, err)) throw std::runtime_error(err);
       upload_structure();
       structure_builds++;
@@ -1545,6 +1546,7 @@ int obvi_debug_partition(obvi_problem* p, int rank, int world, int64_t* stats) {
   if (!p || !stats || world < 1 || rank < 0 || rank >= world) return OBVI_ERR_INVALID_ARGUMENT;
   try {
     Structure S;
+    S.want_batches = true;
     std::string err;
     if (!build_structure(p->s.pb, S, rank, world, err)) return fail(p, OBVI_ERR_INVALID_ARGUMENT, err.c_str());
     int64_t np = 0, no = 0, ck = 0;
