@@ -9,6 +9,7 @@
 #include <refactoring/factors/parameter_prior.h>
 #include <refactoring/factors/relative_pose_factor.h>
 #include <refactoring/factors/reprojection_cost_functor.h>
+#include <refactoring/factors/reprojection_cost_functor_analytic_jacobian.h>
 #include <refactoring/factors/shape_prior_factor.h>
 
 #include <algorithm>
@@ -54,8 +55,10 @@ int main(int argc, char** argv) {
   for (int n = 0; n < n_rp; n++) {
     const double* v = take(6);
     PixelCoord<double> px; px(0) = v[3]; px(1) = v[4];
-    ceres::ResidualBlockId id = problem.AddResidualBlock(ReprojectionCostFunctor::create(intr[(int)v[2]], extr[(int)v[2]], px, v[5]),
-                                                         new ceres::HuberLoss(hub_rp), poses[(int)v[0]].get(), points[(int)v[1]].get());
+    // every third block goes through the (reference-disabled) symforce class: same factor on the backend
+    ceres::CostFunction* cf = (n % 3 == 2) ? static_cast<ceres::CostFunction*>(new ReprojectionCostFunctorAnalyticJacobian(px, intr[(int)v[2]], extr[(int)v[2]], v[5]))
+                                           : static_cast<ceres::CostFunction*>(ReprojectionCostFunctor::create(intr[(int)v[2]], extr[(int)v[2]], px, v[5]));
+    ceres::ResidualBlockId id = problem.AddResidualBlock(cf, new ceres::HuberLoss(hub_rp), poses[(int)v[0]].get(), points[(int)v[1]].get());
     block_info[id] = {0, n};
   }
   for (int n = 0; n < n_bb; n++) {
