@@ -327,3 +327,69 @@ def test_pending_object_estimate_objects_only(ob, oracle):
     o = dict(OPTS, max_num_iterations=12, use_nonmonotonic_steps=0, initial_trust_region_radius=1e4, max_trust_region_radius=1e16)
     s, ref = check_solve(ob, oracle, g, o)
     assert s.num_parameters_reduced == 7 * len(set(int(o) for o in g.bbox["obj"]) | set(int(o) for o in g.shape["obj"]))
+
+
+def _add_observations(ob, g, pts, frames, cam, rng):
+    """Append reprojection observations of points `pts` from `frames` through camera `cam` (only where the point is in
+    front of the camera and inside the image), with pixel noise."""
+    syn = ob.synth
+    R = syn.rotvec_to_mat(g.poses_gt[frames, 3:6]); t = g.poses_gt[frames, 0:3]
+    c = g.cams[cam]
+    Xr = np.einsum("nji,nj->ni", R, g.points_gt[pts] - t)
+    Xc = (Xr - c["t"][None, :]) @ c["R"]
+    fx, fy, cx, cy = c["intr"]
+    u = fx * Xc[:, 0] / Xc[:, 2] + cx; v = fy * Xc[:, 1] / Xc[:, 2] + cy
+    ok = (Xc[:, 2] > 0.5) & (u > 5) & (u < 635) & (v > 5) & (v < 475)
+    n = int(ok.sum())
+    rp = g.reproj
+    rp["pose"] = np.concatenate([rp["pose"], frames[ok]]); rp["point"] = np.concatenate([rp["point"], pts[ok]])
+    rp["cam"] = np.concatenate([rp["cam"], np.full(n, cam, np.int64)])
+    rp["px"] = np.concatenate([rp["px"], np.stack([u[ok], v[ok]], -1) + rng.normal(0, 1.0, (n, 2))])
+    rp["sigma"] = np.concatenate([rp["sigma"], np.full(n, 1.5)])
+    return n
+
+
+def test_row_owner_edge_cases(ob, oracle):
+    """The default point-elimination path (point_prep / schur_rows / backsub_rows) on everything its structure build
+    special-cases: three cameras (pose groups of 3 observations take the list path), tracks spanning >= 20 keyframes
+    (generic per-e-block fallback), tracks with gap keyframes (all-zero dense slots), constant points with observations,
+    constant leading poses (groups without a slot)."""
+    rng = np.random.default_rng(7)
+    g = ob.synth.make_graph(K=40, P=1200, O=4, seed=51, objects_on=True, relpose="all", n_const_poses=3, min_obj_obs=4)
+    n0 = g.counts()["reproj"]
+    # a third camera, looking slightly to the side
+    th = 0.15
+    Rz = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
+    g.cams.append(dict(intr=g.cams[0]["intr"], R=g.cams[0]["R"] @ Rz, t=np.array([0.1, 0.0, 0.05])))
+    seen = np.unique(g.reproj["point"])
+    first = np.full(len(g.points), 10 ** 9, np.int64); np.minimum.at(first, g.reproj["point"], g.reproj["pose"])
+    last = np.full(len(g.points), -1, np.int64); np.maximum.at(last, g.reproj["point"], g.reproj["pose"])
+    # (1) camera 2 re-observes a third of the existing observations (same pose -> groups of 3)
+    sel = rng.choice(n0, n0 // 3, replace=False)
+    n3 = _add_observations(ob, g, g.reproj["point"][sel], g.reproj["pose"][sel], 2, rng)
+    # (2) long tracks: the early points get observations 22..30 keyframes after their first one
+    longp = seen[first[seen] < 12]
+    nl = _add_observations(ob, g, longp, np.minimum(first[longp] + rng.integers(22, 28, len(longp)), 39), 0, rng)
+    # (3) gaps: drop every observation of 150 points in one interior keyframe of their track
+    gapp = rng.choice(seen[(last[seen] - first[seen]) >= 4], 150, replace=False)
+    drop = np.zeros(len(g.reproj["pose"]), bool)
+    for pnt in gapp:
+        drop |= (g.reproj["point"] == pnt) & (g.reproj["pose"] == first[pnt] + 2)
+    for k in ("pose", "point", "cam", "px", "sigma"):
+        g.reproj[k] = g.reproj[k][~drop]
+    order = np.lexsort((g.reproj["point"], g.reproj["cam"], g.reproj["pose"]))
+    for k in ("pose", "point", "cam", "px", "sigma"):
+        g.reproj[k] = np.ascontiguousarray(g.reproj[k][order])
+    # (4) constant points that keep their observations
+    g.const_point[rng.choice(seen, 80, replace=False)] = True
+    assert n3 > 1000 and nl > 15 and drop.sum() > 100
+    s, ref = check_solve(ob, oracle, g, dict(OPTS, max_num_iterations=10))
+    assert s.fixed_cost > 0 and abs(s.fixed_cost - ref["fixed_cost"]) <= 1e-9 * ref["fixed_cost"]
+    # and the same through the two-phase in-place path
+    p = ob.problem_from_graph(g)
+    p.solve(**dict(OPTS, max_num_iterations=3))
+    out = p.topk_outliers(ob.FACTOR_REPROJECTION, 0.1)
+    for fid in out:
+        p.remove_residual_block(fid)
+    s2 = p.solve(**dict(OPTS, max_num_iterations=4))
+    assert p.num_structure_builds() == 1 and s2.final_cost < s2.initial_cost
