@@ -393,3 +393,31 @@ def test_row_owner_edge_cases(ob, oracle):
         p.remove_residual_block(fid)
     s2 = p.solve(**dict(OPTS, max_num_iterations=4))
     assert p.num_structure_builds() == 1 and s2.final_cost < s2.initial_cost
+
+
+@pytest.mark.parametrize("env", [dict(OBVI_PCG="grid"), dict(OBVI_SCHUR="mma", OBVI_BT="v1"), dict(OBVI_PRECOND="jacobi", OBVI_JAC="plain")])
+def test_alternate_kernel_paths_agree(ob, env, tmp_path):
+    """The kernels that are not on the default path must keep working: pcg_bt_kernel (grid-barrier PCG) is the fallback
+    for problems with more super-blocks than SMs (> 2368 keyframes), the batched point elimination and the first
+    factorisation kernels are kept for A/B measurements, block-Jacobi PCG is the fallback after a failed factorisation."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "alt.py"
+    script.write_text(f"""
+import sys, json
+sys.path.insert(0, {root!r})
+import obvi_b200 as ob
+g = ob.synth.make_graph(K=40, P=1500, O=6, seed=61, objects_on=True, relpose="all", n_const_poses=1, min_obj_obs=4)
+p = ob.problem_from_graph(g)
+s = p.solve(max_num_iterations=8, function_tolerance=1e-6, initial_trust_region_radius=100.0, max_trust_region_radius=1e4, use_nonmonotonic_steps=1)
+print("RESULT " + json.dumps(dict(costs=[it["cost"] for it in s.iterations], ok=[int(it["successful"]) for it in s.iterations], t=g.poses[:, :3].tolist())))
+""")
+    def run(extra):
+        out = subprocess.run([sys.executable, str(script)], env=dict(os.environ, **extra), capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+        return json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    a, b = run({}), run(env)
+    assert a["ok"] == b["ok"] and len(a["costs"]) == len(b["costs"])
+    for x, y in zip(a["costs"], b["costs"]):
+        assert abs(x - y) <= 1e-7 * abs(x)
+    assert np.abs(np.array(a["t"]) - np.array(b["t"])).max() < 1e-6
