@@ -91,3 +91,50 @@ def test_schedule_gpu_matches_oracle(ob, oracle):
     assert np.abs(g_gpu.objects - g_cpu.objects).max() < 1e-3
     # one structure build per window problem: the phase-II exclusion never rebuilt
     assert be.stats["excluded"] > 0 and be.stats["structure_builds"] == sum(1 for e in log_gpu)
+
+
+@pytest.mark.gpu
+def test_multi_session_ltm_chain_matches_oracle(ob, oracle):
+    """BASELINE config 5 shape at test size: sessions chained through the long-term map
+    (src/evaluation/ltm_trajectory_sequence_executor.py:44-83): solve session k, extract the ellipsoid estimates and their
+    marginal covariances (IndependentEllipsoids extractor, long_term_object_map_extraction.h:455-520), hand them to
+    session k + 1 as LTM prior factors (independent_object_map_factor.h:21-33).  GPU chain vs the same chain on the CPU
+    oracles (C++ LM + NumPy dense covariance)."""
+    from oracle import py_oracle as po
+    opts = dict(max_num_iterations=12, function_tolerance=1e-6, gradient_tolerance=1e-10, parameter_tolerance=1e-8,
+                initial_trust_region_radius=100.0, max_trust_region_radius=1e4, use_nonmonotonic_steps=0)
+    o_opts = ob.schedule.OracleBackend._o(opts)
+
+    def sessions():
+        return [ob.synth.make_graph(K=14, P=350, O=5, seed=71, objects_on=True, relpose="all", n_const_poses=1, min_obj_obs=4) for _ in range(3)]
+
+    def chain(gs, solve, covariances):
+        prior = None
+        finals = []
+        for g in gs:
+            if prior is not None:
+                objs, mean, cov = prior
+                g.ltm = dict(obj=objs.copy(), mean=mean.copy(), cov=cov.copy(), huber=1.0)
+                g.objects[objs] = mean          # the next session starts from the map
+            finals.append(solve(g))
+            objs = np.array(sorted(set(int(o) for o in g.bbox["obj"])), np.int64)
+            prior = (objs, g.objects[objs].copy(), covariances(g, objs))
+        return finals, prior
+
+    def gpu_solve(g):
+        p = ob.problem_from_graph(g)
+        gpu_solve.p = p
+        return p.solve(**opts).final_cost
+
+    def gpu_cov(g, objs):
+        return gpu_solve.p.object_covariances([g.objects[o] for o in objs], [g.objects[o] for o in objs])
+
+    fa, pa = chain(sessions(), gpu_solve, gpu_cov)
+    fb, pb = chain(sessions(), lambda g: oracle.solve(g, **o_opts)["final_cost"], lambda g, objs: po.covariance_blocks(g, [(int(o), int(o)) for o in objs]))
+    for x, y in zip(fa, fb):
+        assert abs(x - y) <= 1e-5 * abs(y)
+    assert np.array_equal(pa[0], pb[0])
+    assert np.abs(pa[1] - pb[1]).max() < 1e-4
+    assert np.abs(pa[2] - pb[2]).max() <= 1e-4 * np.abs(pb[2]).max()
+    # the map tightens from session to session
+    assert np.trace(pa[2][0]) > 0
