@@ -1948,13 +1948,14 @@ __global__ void finish_kernel(int nf, const uint32_t* __restrict__ sf_ptr, const
                               const double* __restrict__ pscale, const double* __restrict__ hpp_diag,
                               const double* __restrict__ gp, const double* __restrict__ b_schur, LMParams lm,
                               double* __restrict__ Sf, double* __restrict__ rhs, double* __restrict__ scalars) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  // one CTA per block row (a warp per row left most of the GPU idle: 2000 rows of ~1700 elements each)
+  const int i = blockIdx.x;
+  const int lane = threadIdx.x;
   if (i >= nf) return;
   const uint32_t p0 = sf_ptr[i], nb = sf_ptr[i + 1] - p0;
   double* row = Sf + (size_t)p0 * 36;
   const uint32_t total = nb * 36;
-  for (uint32_t t = lane; t < total; t += 32) {
+  for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
     // destination layout: [a][k][c] -> a * (nb*6) + k*6 + c
     const uint32_t a = t / (nb * 6), rem = t - a * nb * 6, k = rem / 6, c = rem - 6 * k;
     const uint32_t src = sf_src[p0 + k];
@@ -1968,7 +1969,6 @@ __global__ void finish_kernel(int nf, const uint32_t* __restrict__ sf_ptr, const
     }
     row[t] = v;
   }
-  __syncwarp();
   if (lane < 6) {
     const double g = gp[6 * i + lane];
     rhs[6 * i + lane] = pscale[6 * i + lane] * (g + b_schur[6 * i + lane]);

@@ -21,12 +21,12 @@ constexpr int kB = 6 * kSbPoses;      // 96
 constexpr int kBB = kB * kB;
 
 // Scatter the scaled + damped reduced matrix (full BSR, scalar rows contiguous) into the diagonal super-blocks D
-// and the sub-diagonal couplings C0[I] = T[I+1][I].  One warp per pose block row.  D / C0 must be zeroed before;
+// and the sub-diagonal couplings C0[I] = T[I+1][I].  One CTA per pose block row.  D / C0 must be zeroed before;
 // padding rows of the last super-block get a unit diagonal.
 __global__ void bt_assemble_kernel(int nf, int nsb, const uint32_t* __restrict__ sf_ptr, const uint32_t* __restrict__ sf_col,
                                    const double* __restrict__ Sf, double* __restrict__ D, double* __restrict__ C0) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x;        // one CTA per pose block row
+  const int lane = threadIdx.x;
   if (i >= nsb * kSbPoses) return;
   const int I = i / kSbPoses, li = i % kSbPoses;
   if (i >= nf) {  // padding pose: identity
@@ -36,7 +36,7 @@ __global__ void bt_assemble_kernel(int nf, int nsb, const uint32_t* __restrict__
   const uint32_t p0 = sf_ptr[i], nb = sf_ptr[i + 1] - p0;
   const double* row = Sf + (size_t)p0 * 36;
   const uint32_t total = nb * 36;
-  for (uint32_t t = lane; t < total; t += 32) {
+  for (uint32_t t = lane; t < total; t += blockDim.x) {
     const uint32_t a = t / (nb * 6), rem = t - a * nb * 6, k = rem / 6, c = rem - 6 * k;
     const int j = (int)sf_col[p0 + k];
     const int Jb = j / kSbPoses, lj = j % kSbPoses;

@@ -409,7 +409,7 @@ struct Solver {
     if (!use_bt || nsb == 0) return;
     bt_D.zero(stream);
     if (nsb > 1) CUDA_OK(cudaMemsetAsync(bt_C.p, 0, (size_t)(nsb - 1) * kBB * 8, stream));
-    bt_assemble_kernel<<<nblk((int64_t)nsb * kSbPoses * 32, 256), 256, 0, stream>>>(S.nf, nsb, sf_ptr.p, sf_col.p, Sf.p, bt_D.p, bt_C.p);
+    bt_assemble_kernel<<<nsb * kSbPoses, 128, 0, stream>>>(S.nf, nsb, sf_ptr.p, sf_col.p, Sf.p, bt_D.p, bt_C.p);
     launches++;
     for (const BtLevel& L : bt_levels) {
       if (bt_v1) {
@@ -584,7 +584,7 @@ struct Solver {
     if (world > 1) { allreduce_sum(redbuf.p, redbuf.n); prof.end("allreduce S", pt0, stream); pt0 = prof.begin(stream); }
     if (S.nf) {
       if (lm.compute_scale) { pose_scale_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(hpp_diag, S.nf * 6, pscale.p); launches++; }
-      finish_kernel<<<nblk((int64_t)S.nf * 32, 256), 256, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, sf_src.p, S_upper, pscale.p, hpp_diag, gp, b_schur, lm, Sf.p, rhs.p, scalars.p);
+      finish_kernel<<<S.nf, 128, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, sf_src.p, S_upper, pscale.p, hpp_diag, gp, b_schur, lm, Sf.p, rhs.p, scalars.p);
       launches++;
       if (!use_bt) { minv_kernel<<<nblk(S.nf, 64), 64, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, Sf.p, Minv.p, scalars.p); launches++; }
       prof.end("finish", pt0, stream); pt0 = prof.begin(stream);
