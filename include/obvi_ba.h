@@ -200,6 +200,15 @@ int obvi_evaluate(obvi_problem* p, int apply_loss_function, double* cost, double
 int obvi_evaluate_factor_type(obvi_problem* p, int factor_type, int apply_loss_function, double* residuals,
                               double* jacobian0, double* jacobian1);
 
+/* Problem::Evaluate with gradient / Jacobian output (long_term_object_map_extraction.cpp:251-252,591-598;
+ * EvaluateOptions{apply_loss_function, residual_blocks, parameter_blocks}).  Rows: the residual blocks `ids` in that order
+ * (NULL: all live blocks in order of addition); columns: the parameter blocks `blocks` in that order, constant ones left out, as
+ * Ceres does (NULL: every variable block -- poses, points, ellipsoids).  Call once with crs_* = NULL to size the arrays
+ * (crs_rows: num_rows + 1 entries, crs_cols / crs_values: nnz), then again to fill them.  gradient (optional, num_cols) = J^T r. */
+int obvi_evaluate_jacobian(obvi_problem* p, int apply_loss_function, const obvi_factor_id* ids, int64_t n_ids,
+                           double* const* blocks, int64_t n_blocks, int64_t* num_rows, int64_t* num_cols, int64_t* nnz,
+                           int32_t* crs_rows, int32_t* crs_cols, double* crs_values, double* gradient);
+
 /* ---- two-phase outlier rejection (offline_problem_runner.h:689-801): the ids of the
  *      floor(n_distinct * fraction) blocks of `factor_type` with the largest raw squared residual norm,
  *      ties collapsed as the reference's std::map<double, id, std::greater> does. */

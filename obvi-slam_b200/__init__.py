@@ -121,6 +121,7 @@ def lib():
         "obvi_evaluate": ([vp, C.c_int, _d, _d, i64, C.POINTER(i64)], C.c_int),
         "obvi_evaluate_factor_type": ([vp, C.c_int, C.c_int, _d, _d, _d], C.c_int),
         "obvi_topk_outliers": ([vp, C.c_int, dbl, u64p, i64, C.POINTER(i64)], C.c_int),
+        "obvi_evaluate_jacobian": ([vp, C.c_int, u64p, i64, C.POINTER(vp), i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i32p, i32p, _d, _d], C.c_int),
         "obvi_object_covariances": ([vp, i64, C.POINTER(vp), C.POINTER(vp), _d], C.c_int),
         "obvi_profile_jacobian": ([vp, C.c_int, _d, C.POINTER(i64), C.POINTER(i64)], C.c_int),
         "obvi_debug_partition": ([vp, C.c_int, C.c_int, C.POINTER(i64)], C.c_int),
@@ -141,7 +142,7 @@ EXPORTED_SYMBOLS = [
     "obvi_factor_add_reproj", "obvi_factor_add_reproj_batch", "obvi_factor_add_bbox", "obvi_factor_add_bbox_batch",
     "obvi_factor_add_shape_prior", "obvi_factor_add_ltm_prior", "obvi_factor_add_rel_pose", "obvi_factor_add_param_prior",
     "obvi_factor_remove", "obvi_num_factors", "obvi_num_structure_builds", "obvi_residual_blocks", "obvi_solver_options_init", "obvi_solve",
-    "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_object_covariances", "obvi_profile_jacobian", "obvi_debug_partition", "obvi_comm_unique_id",
+    "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_evaluate_jacobian", "obvi_object_covariances", "obvi_profile_jacobian", "obvi_debug_partition", "obvi_comm_unique_id",
     "obvi_comm_init",
 ]
 
@@ -333,6 +334,21 @@ class Problem:
         ids = np.zeros(max(cap, 1), np.uint64)
         self._ck(self._lib.obvi_topk_outliers(self._h, ftype, float(fraction), ids.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n)))
         return ids[:n.value]
+
+    def evaluate_jacobian(self, apply_loss_function=True, ids=None, blocks=None):
+        """(rows, cols, values, shape, gradient) of the CRS Jacobian (Problem::Evaluate with a CRSMatrix)."""
+        pid = None if ids is None else np.ascontiguousarray(ids, np.uint64)
+        nid = 0 if ids is None else len(pid)
+        pbl = None if blocks is None else (C.c_void_p * len(blocks))(*[b.ctypes.data for b in blocks])
+        nbl = 0 if blocks is None else len(blocks)
+        nr, nc, nz = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        idp = None if pid is None else pid.ctypes.data_as(C.POINTER(C.c_uint64))
+        self._ck(self._lib.obvi_evaluate_jacobian(self._h, int(apply_loss_function), idp, nid, pbl, nbl, C.byref(nr), C.byref(nc), C.byref(nz), None, None, None, None))
+        rows = np.zeros(nr.value + 1, np.int32); cols = np.zeros(max(nz.value, 1), np.int32); vals = np.zeros(max(nz.value, 1)); grad = np.zeros(max(nc.value, 1))
+        i32 = C.POINTER(C.c_int32)
+        self._ck(self._lib.obvi_evaluate_jacobian(self._h, int(apply_loss_function), idp, nid, pbl, nbl, C.byref(nr), C.byref(nc), C.byref(nz),
+                                                  rows.ctypes.data_as(i32), cols.ctypes.data_as(i32), vals.ctypes.data_as(_d), grad.ctypes.data_as(_d)))
+        return rows, cols[:nz.value], vals[:nz.value], (nr.value, nc.value), grad[:nc.value]
 
     def object_covariances(self, blocks_a, blocks_b):
         """7x7 blocks [a_i, b_i] of (J^T J)^-1 (ceres::Covariance on ellipsoid blocks); blocks are the registered arrays."""

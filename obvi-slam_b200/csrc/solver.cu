@@ -1408,6 +1408,98 @@ int obvi_evaluate(obvi_problem* p, int apply_loss, double* cost, double* residua
   API_END(p)
 }
 
+// Problem::Evaluate with gradient / Jacobian output (long_term_object_map_extraction.cpp:251-252,591-598): the Jacobian of the
+// listed residual blocks with respect to the listed parameter blocks as a CRS matrix.  Evaluated on the device, assembled here.
+int obvi_evaluate_jacobian(obvi_problem* p, int apply_loss, const obvi_factor_id* ids, int64_t n_ids, double* const* blocks,
+                           int64_t n_blocks, int64_t* num_rows, int64_t* num_cols, int64_t* nnz, int32_t* crs_rows,
+                           int32_t* crs_cols, double* crs_values, double* gradient) {
+  if (!p || !num_rows || !num_cols || !nnz) return OBVI_ERR_INVALID_ARGUMENT;
+  API_BEGIN
+  Solver& s = p->s;
+  if (s.pb.device < 0) return fail(p, OBVI_ERR_CUDA, "host-only problem handle: no CUDA device attached (no CPU fallback exists)");
+  CUDA_OK(cudaSetDevice(s.pb.device));
+  if (s.world > 1) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "Jacobian export is single-rank only");
+  evaluate_all(s, apply_loss);
+  const Structure& S = s.st;
+  const Problem& pb = s.pb;
+  // column offset of every variable parameter block (-1: constant / not listed)
+  std::vector<int64_t> col_of(pb.blocks.size(), -1);
+  int64_t ncol = 0;
+  if (blocks) {
+    for (int64_t i = 0; i < n_blocks; i++) {
+      const int32_t b = pb.find_block(blocks[i]);
+      if (b < 0) return fail(p, OBVI_ERR_NOT_FOUND, "Evaluate: unknown parameter block");
+      if (pb.blocks[b].constant || col_of[b] >= 0) continue;
+      col_of[b] = ncol; ncol += pb.blocks[b].size;
+    }
+  } else {   // every variable block of the built structure: poses, points, objects in internal order
+    for (int32_t b : S.pose_block) if (!pb.blocks[b].constant) { col_of[b] = ncol; ncol += 6; }
+    for (int32_t b : S.point_block) if (!pb.blocks[b].constant) { col_of[b] = ncol; ncol += 3; }
+    for (int32_t b : S.obj_block) if (!pb.blocks[b].constant) { col_of[b] = ncol; ncol += 7; }
+  }
+  std::vector<double> hJ((size_t)S.n_obs * kChunk), hB((size_t)S.n_bbox * kBBoxChunk);
+  std::vector<RelOut> hR(S.n_rel); std::vector<UnaryOut> hU(S.n_unary);
+  if (S.n_obs) CUDA_OK(cudaMemcpy(hJ.data(), s.J.p, hJ.size() * 8, cudaMemcpyDeviceToHost));
+  if (S.n_bbox) CUDA_OK(cudaMemcpy(hB.data(), s.Jb.p, hB.size() * 8, cudaMemcpyDeviceToHost));
+  if (S.n_rel) CUDA_OK(cudaMemcpy(hR.data(), s.rel_out.p, hR.size() * sizeof(RelOut), cudaMemcpyDeviceToHost));
+  if (S.n_unary) CUDA_OK(cudaMemcpy(hU.data(), s.unary_out.p, hU.size() * sizeof(UnaryOut), cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> inv_un(pb.unary.size(), 0), inv_rl(pb.rel.size(), 0);
+  for (int64_t q = 0; q < S.n_unary; q++) inv_un[S.unary_user[q]] = (uint32_t)q;
+  for (int64_t q = 0; q < S.n_rel; q++) inv_rl[S.rel_user[q]] = (uint32_t)q;
+  std::vector<obvi_factor_id> all;
+  if (!ids) { for (obvi_factor_id id : pb.order) { int sz; if (id_alive(pb, id, &sz)) all.push_back(id); } ids = all.data(); n_ids = (int64_t)all.size(); }
+  const bool fill = crs_rows && crs_cols && crs_values;
+  if (gradient) for (int64_t c = 0; c < ncol; c++) gradient[c] = 0.0;
+  int64_t row = 0, nz = 0;
+  if (fill) crs_rows[0] = 0;
+  for (int64_t n = 0; n < n_ids; n++) {
+    int sz;
+    if (!id_alive(pb, ids[n], &sz)) return fail(p, OBVI_ERR_NOT_FOUND, "Evaluate: unknown residual block id");
+    const uint64_t i = id_index(ids[n]);
+    // up to two parameter blocks per residual block: (block id, width, pointer to the k x width row-major Jacobian, leading dim)
+    struct Part { int32_t b; int w; const double* J; int ld; int off; double scale; };
+    Part parts[2]; int np = 0;
+    const double* r = nullptr;
+    double unaryJ[49];
+    switch (id_type(ids[n])) {
+      case OBVI_FACTOR_REPROJECTION: {
+        const double* ch = &hJ[(size_t)s.inv_rp[i] * kChunk];
+        parts[np++] = {pb.reproj[i].pose, 6, ch, 6, 0, 1.0}; parts[np++] = {pb.reproj[i].point, 3, ch + 12, 3, 0, 1.0}; r = ch + 18; break; }
+      case OBVI_FACTOR_BBOX: {
+        const double* ch = &hB[(size_t)s.inv_bb[i] * kBBoxChunk];
+        parts[np++] = {pb.bbox[i].obj, 7, ch + 24, 7, 0, 1.0}; parts[np++] = {pb.bbox[i].pose, 6, ch, 6, 0, 1.0}; r = ch + 52; break; }
+      case OBVI_FACTOR_REL_POSE: {
+        const RelOut& o = hR[inv_rl[i]];
+        parts[np++] = {pb.rel[i].p1, 6, o.J1, 6, 0, 1.0}; parts[np++] = {pb.rel[i].p2, 6, o.J2, 6, 0, 1.0}; r = o.r; break; }
+      default: {
+        const UnaryFactor& f = pb.unary[i];
+        const UnaryOut& o = hU[inv_un[i]];
+        for (int a = 0; a < f.k * f.k; a++) unaryJ[a] = o.sc * f.A[a];
+        parts[np++] = {f.block, f.k, unaryJ, f.k, f.off, 1.0}; r = o.r; break; }
+    }
+    // CRS rows list their columns in ascending order
+    if (np == 2 && col_of[parts[0].b] > col_of[parts[1].b]) std::swap(parts[0], parts[1]);
+    for (int a = 0; a < sz; a++) {
+      for (int q = 0; q < np; q++) {
+        const int64_t c0 = col_of[parts[q].b];
+        if (c0 < 0) continue;
+        if (np == 2 && q == 1 && parts[1].b == parts[0].b) continue;   // same block twice: not produced by the reference's factors
+        for (int c = 0; c < parts[q].w; c++) {
+          const double v = parts[q].J[a * parts[q].ld + c];
+          if (fill) { crs_cols[nz] = (int32_t)(c0 + parts[q].off + c); crs_values[nz] = v; }
+          if (gradient) gradient[c0 + parts[q].off + c] += v * r[a];
+          nz++;
+        }
+      }
+      row++;
+      if (fill) crs_rows[row] = (int32_t)nz;
+    }
+  }
+  *num_rows = row; *num_cols = ncol; *nnz = nz;
+  return OBVI_OK;
+  API_END(p)
+}
+
 // Two-phase outlier rejection support (offline_problem_runner.h:752-801): per block sum r^2 from the raw
 // residuals, inserted into std::map<double, id, std::greater<double>> (equal keys overwrite), then the first
 // (size_t)(map.size() * fraction) entries.

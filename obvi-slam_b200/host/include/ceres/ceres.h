@@ -182,20 +182,49 @@ class Problem {
   const CostFunction* GetCostFunctionForResidualBlock(const ResidualBlockId rb) const { return rb->cost; }
   const LossFunction* GetLossFunctionForResidualBlock(const ResidualBlockId rb) const { return rb->loss; }
 
-  // Problem::Evaluate as the reference calls it (object_pose_graph_optimizer.h:679-693): all residual blocks,
-  // apply_loss_function = false, cost and / or residuals.  Gradient / Jacobian export is not provided here.
+  // Problem::Evaluate as the reference calls it: all residual blocks with apply_loss_function = false for the raw
+  // residuals (object_pose_graph_optimizer.h:679-693), and with explicit residual / parameter block lists plus a CRS
+  // Jacobian for the long-term-map rank analysis (long_term_object_map_extraction.cpp:251-252,591-598).
   bool Evaluate(const EvaluateOptions& o, double* cost, std::vector<double>* residuals, std::vector<double>* gradient,
                 CRSMatrix* jacobian) {
-    if (gradient != nullptr || jacobian != nullptr) { last_error_ = "Evaluate: gradient / Jacobian export is not supported by this backend"; return false; }
-    if (!o.residual_blocks.empty() && (int)o.residual_blocks.size() != NumResidualBlocks()) { last_error_ = "Evaluate: residual-block subsets are not supported"; return false; }
-    int64_t n = 0;
-    double c = 0;
-    if (obvi_evaluate(handle_, o.apply_loss_function ? 1 : 0, &c, nullptr, 0, residuals ? &n : nullptr) != OBVI_OK) { last_error_ = obvi_last_error(handle_); return false; }
-    if (residuals) {
-      residuals->assign(n, 0.0);
-      if (obvi_evaluate(handle_, o.apply_loss_function ? 1 : 0, &c, residuals->data(), n, &n) != OBVI_OK) { last_error_ = obvi_last_error(handle_); return false; }
+    const int loss = o.apply_loss_function ? 1 : 0;
+    const bool subset = !o.residual_blocks.empty();
+    if ((cost || residuals) && subset && (int)o.residual_blocks.size() != NumResidualBlocks()) { last_error_ = "Evaluate: cost / residuals of a residual-block subset are not supported"; return false; }
+    if (cost || residuals) {
+      int64_t n = 0;
+      double c = 0;
+      if (obvi_evaluate(handle_, loss, &c, nullptr, 0, residuals ? &n : nullptr) != OBVI_OK) { last_error_ = obvi_last_error(handle_); return false; }
+      if (residuals) {
+        // obvi_evaluate concatenates in order of addition; reorder when the caller lists the blocks differently
+        std::vector<double> all(n, 0.0);
+        if (obvi_evaluate(handle_, loss, &c, all.data(), n, &n) != OBVI_OK) { last_error_ = obvi_last_error(handle_); return false; }
+        if (!subset) { *residuals = all; }
+        else {
+          std::vector<ResidualBlockId> order;
+          GetResidualBlocks(&order);
+          std::unordered_map<ResidualBlockId, std::pair<int64_t, int>> at;
+          int64_t w = 0;
+          for (ResidualBlockId rb : order) { at[rb] = {w, rb->cost->num_residuals()}; w += rb->cost->num_residuals(); }
+          residuals->clear();
+          for (ResidualBlockId rb : o.residual_blocks) { auto& e = at.at(rb); residuals->insert(residuals->end(), all.begin() + e.first, all.begin() + e.first + e.second); }
+        }
+      }
+      if (cost) *cost = c;
     }
-    if (cost) *cost = c;
+    if (gradient || jacobian) {
+      std::vector<obvi_factor_id> ids;
+      for (ResidualBlockId rb : o.residual_blocks) ids.push_back(rb->id);
+      std::vector<double*> pbs(o.parameter_blocks.begin(), o.parameter_blocks.end());
+      int64_t nr = 0, nc = 0, nz = 0;
+      const obvi_factor_id* idp = ids.empty() ? nullptr : ids.data();
+      double* const* pbp = pbs.empty() ? nullptr : pbs.data();
+      if (obvi_evaluate_jacobian(handle_, loss, idp, (int64_t)ids.size(), pbp, (int64_t)pbs.size(), &nr, &nc, &nz, nullptr, nullptr, nullptr, nullptr) != OBVI_OK) { last_error_ = obvi_last_error(handle_); return false; }
+      std::vector<int32_t> rows(nr + 1), cols(nz);
+      std::vector<double> vals(nz), grad(nc);
+      if (obvi_evaluate_jacobian(handle_, loss, idp, (int64_t)ids.size(), pbp, (int64_t)pbs.size(), &nr, &nc, &nz, rows.data(), cols.data(), vals.data(), grad.data()) != OBVI_OK) { last_error_ = obvi_last_error(handle_); return false; }
+      if (gradient) *gradient = grad;
+      if (jacobian) { jacobian->num_rows = (int)nr; jacobian->num_cols = (int)nc; jacobian->rows.assign(rows.begin(), rows.end()); jacobian->cols.assign(cols.begin(), cols.end()); jacobian->values = vals; }
+    }
     return true;
   }
 

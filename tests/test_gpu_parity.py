@@ -421,3 +421,38 @@ print("RESULT " + json.dumps(dict(costs=[it["cost"] for it in s.iterations], ok=
     for x, y in zip(a["costs"], b["costs"]):
         assert abs(x - y) <= 1e-7 * abs(x)
     assert np.abs(np.array(a["t"]) - np.array(b["t"])).max() < 1e-6
+
+
+def test_jacobian_crs_export_matches_dense_oracle(ob):
+    """Problem::Evaluate(options{residual_blocks, parameter_blocks, apply_loss_function}, ..., gradient, CRSMatrix)
+    (long_term_object_map_extraction.cpp:251-252,591-598) against the dense complex-step Jacobian of the NumPy oracle."""
+    from oracle import py_oracle as po
+    g = small_graph(ob, seed=81)
+    g.const_point[::9] = True
+    p = ob.problem_from_graph(g)
+    off, n = po._layout(g)
+    cost, r, J = po.evaluate(g, apply_loss=True)
+    blocks = [g.poses[i] for i in range(len(g.poses))] + [g.points[i] for i in range(len(g.points))] + [g.objects[i] for i in range(len(g.objects))]
+    rows, cols, vals, shape, grad = p.evaluate_jacobian(True, None, blocks)     # constant blocks are dropped, like Ceres
+    assert shape == (J.shape[0], n)
+    D = np.zeros(shape)
+    for i in range(shape[0]):
+        sl = slice(rows[i], rows[i + 1])
+        assert np.all(np.diff(cols[sl]) > 0)
+        D[i, cols[sl]] = vals[sl]
+    assert rel_err(D, J[:, :n]) < 1e-9
+    assert rel_err(grad, J[:, :n].T @ r) < 1e-9
+    # a residual-block subset in a different order, columns restricted to two ellipsoids
+    ids = np.concatenate([p.factor_ids["bbox"][::-1][:7], p.factor_ids["shape"][:2]])
+    objs = sorted(set(int(o) for o in g.bbox["obj"]))[:2]
+    rows2, cols2, vals2, shape2, _ = p.evaluate_jacobian(True, ids, [g.objects[o] for o in objs])
+    assert shape2 == (4 * 7 + 3 * 2, 14)
+    nb_rp = 2 * g.counts()["reproj"]
+    bb_rev = list(range(g.counts()["bbox"]))[::-1][:7]
+    for k, b in enumerate(bb_rev):
+        for a in range(4):
+            i = 4 * k + a
+            got = np.zeros(14); got[cols2[rows2[i]:rows2[i + 1]]] = vals2[rows2[i]:rows2[i + 1]]
+            ref_row = J[nb_rp + 4 * b + a]
+            want = np.concatenate([ref_row[off[("obj", o)]:off[("obj", o)] + 7] if ("obj", o) in off else np.zeros(7) for o in objs])
+            assert np.abs(got - want).max() <= 1e-9 * (1 + np.abs(want).max())
