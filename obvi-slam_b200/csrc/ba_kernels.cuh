@@ -1268,8 +1268,8 @@ __global__ void __launch_bounds__(kPipeThreads, 2) schur_points_mma_kernel(EArgs
 
 // ------------------------------------------------------------------------------------------ points: row-owner elimination
 // Two kernels replace the batched kernels above (kept selectable for A/B measurements):
-//   point_prep_kernel  - 8 lanes per point, a lane per pose group (the stereo pair of one keyframe): H_ll, g_l by three
-//                        xor-shuffle steps, damping, 3x3 inverse, and per (point, pose) slot the record
+//   point_prep_kernel  - LPP lanes per point (8 by default; 16 -- one sweep even for the longest tracks -- measured slower),
+//                        a lane per pose group (the stereo pair of one keyframe): H_ll, g_l by xor-shuffle steps, damping, 3x3 inverse, and per (point, pose) slot the record
 //                        [W = sum Jp^T Jl (6x3) | Z = W Hinv (6x3) | Z g_l (6)] written to `WZ` (42 doubles per slot);
 //   schur_rows_kernel  - a warp per work item = (row a of the reduced matrix, 5 consecutive column offsets, <= 128 slots of
 //                        pose a): for every slot, A = Z_a, B = W_b^T of the point's slots at a + d, one DMMA per block pair,
@@ -1280,12 +1280,13 @@ constexpr int kWZ = 42;
 struct RowGroupD { uint32_t pos0, pos1, gs, cnt; };
 struct RowItemD { uint32_t row, dlo, off, cnt; };
 
+template <int LPP>
 __global__ void __launch_bounds__(256, 2) point_prep_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr,
                                                           const uint4* __restrict__ grp, const uint8_t* __restrict__ regular,
                                                           LMParams lm, double* __restrict__ WZ, double* __restrict__ scalars) {
   __shared__ double s_gmax[8];
-  const int e = blockIdx.x * 32 + (threadIdx.x >> 3);
-  const int sub = threadIdx.x & 7;
+  const int e = blockIdx.x * (256 / LPP) + threadIdx.x / LPP;
+  const int sub = threadIdx.x % LPP;
   const bool act = e < A.ne && regular[e];
   uint32_t g0 = 0, g1 = 0;
   if (act) { g0 = grp_ptr[e]; g1 = grp_ptr[e + 1]; }
@@ -1326,7 +1327,7 @@ __global__ void __launch_bounds__(256, 2) point_prep_kernel(EArgs A, const uint3
     gs0 = G.z;
     sweep(G, W0);
   }
-  for (uint32_t gi = g0 + sub + 8; gi < g1; gi += 8) {
+  for (uint32_t gi = g0 + sub + LPP; gi < g1; gi += LPP) {
     const uint4 G = grp[gi];
     double W[18];
 #pragma unroll
@@ -1339,7 +1340,7 @@ __global__ void __launch_bounds__(256, 2) point_prep_kernel(EArgs A, const uint3
     }
   }
 #pragma unroll
-  for (int d = 1; d < 8; d <<= 1) {
+  for (int d = 1; d < LPP; d <<= 1) {
 #pragma unroll
     for (int a = 0; a < 6; a++) H[a] += __shfl_xor_sync(0xffffffffu, H[a], d);
 #pragma unroll
@@ -1402,7 +1403,7 @@ __global__ void __launch_bounds__(256, 2) point_prep_kernel(EArgs A, const uint3
       for (int a = 0; a < 3; a++) rec[18 + a] = make_double2(zg[2 * a], zg[2 * a + 1]);
     };
     if (gs0 != 0xFFFFFFFFu) emit(gs0, W0, true);
-    for (uint32_t gi = g0 + sub + 8; gi < g1; gi += 8) {
+    for (uint32_t gi = g0 + sub + LPP; gi < g1; gi += LPP) {
       const uint32_t gs = grp[gi].z;
       if (gs == 0xFFFFFFFFu) continue;
       const double2* rec = reinterpret_cast<const double2*>(WZ + (size_t)gs * kWZ);
@@ -1412,8 +1413,8 @@ __global__ void __launch_bounds__(256, 2) point_prep_kernel(EArgs A, const uint3
       emit(gs, W, false);
     }
   }
-  gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 8));
-  gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 16));
+#pragma unroll
+  for (int d = LPP; d < 32; d <<= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, d));
   if ((threadIdx.x & 31) == 0) s_gmax[threadIdx.x >> 5] = gmax;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1677,19 +1678,20 @@ __global__ void __launch_bounds__(128) backsub_points_kernel(EArgs A, int n_e, c
 //   sum m (r + m/2),  m = a + Jl delta_e   =   sum a.(r + a/2)  +  delta_e.(g_l + t)  +  delta_e^T H_ll delta_e / 2
 // with t = sum Jl^T a, g_l = sum Jl^T r, H_ll = sum Jl^T Jl, so one sweep over the Jacobian chunks is enough (the generic
 // kernel above sweeps twice: once for t, once for m after delta_e is known).
+template <int LPP>
 __global__ void __launch_bounds__(256) backsub_rows_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr, const uint4* __restrict__ grp,
                                                             const int32_t* __restrict__ grp_f, const uint8_t* __restrict__ regular,
                                                             const double* __restrict__ dpose, const double* __restrict__ x,
                                                             double* __restrict__ x_cand, double* __restrict__ delta_e,
                                                             double* __restrict__ scalars) {
   __shared__ double s_mc[8], s_s2[8];
-  const int e = blockIdx.x * 32 + (threadIdx.x >> 3);
-  const int sub = threadIdx.x & 7;
+  const int e = blockIdx.x * (256 / LPP) + threadIdx.x / LPP;
+  const int sub = threadIdx.x % LPP;
   const bool act = e < A.ne && regular[e];
   uint32_t g0 = 0, g1 = 0;
   if (act) { g0 = grp_ptr[e]; g1 = grp_ptr[e + 1]; }
   double H[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0}, t[3] = {0, 0, 0}, sa = 0.0;
-  for (uint32_t gi = g0 + sub; gi < g1; gi += 8) {
+  for (uint32_t gi = g0 + sub; gi < g1; gi += LPP) {
     const uint4 G = grp[gi];
     const int fi = grp_f[gi];
     double dp[6];
@@ -1718,7 +1720,7 @@ __global__ void __launch_bounds__(256) backsub_rows_kernel(EArgs A, const uint32
     }
   }
 #pragma unroll
-  for (int d = 1; d < 8; d <<= 1) {
+  for (int d = 1; d < LPP; d <<= 1) {
 #pragma unroll
     for (int a = 0; a < 6; a++) H[a] += __shfl_xor_sync(0xffffffffu, H[a], d);
 #pragma unroll

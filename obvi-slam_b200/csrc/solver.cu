@@ -202,6 +202,7 @@ struct Solver {
   bool resident_ok = false;
   DBuf<double> rs_dbl;        // [16 reduction slots | nsb * 96 forward accumulators]
   DBuf<unsigned int> rs_u32;  // [4 reduction counters | nsb arrival counters | nsb z epochs]
+  int lanes_per_point = 8;   // OBVI_LPP=16: sixteen lanes per point in point_prep / backsub_rows (measured slower: 359 / 200 us vs 329 / 165)
   bool bt_v1 = false;   // OBVI_BT=v1: first-generation factorisation kernels (scalar-pivot Gauss-Jordan, FMA GEMM)
   // The factorisation is reused across LM iterations while it still preconditions well: it is redone when the
   // trust-region radius moved by more than 2x since it was computed or the last PCG needed more than
@@ -256,6 +257,7 @@ struct Solver {
     if (pcg_bt_blocks_per_sm < 1) throw std::runtime_error("pcg_bt_kernel cannot be made resident");
     if (const char* e = getenv("OBVI_PRECOND")) use_bt = std::string(e) != "jacobi";
     if (const char* e = getenv("OBVI_BT")) bt_v1 = std::string(e) == "v1";
+    if (const char* e = getenv("OBVI_LPP")) lanes_per_point = std::string(e) == "16" ? 16 : 8;
     if (const char* e = getenv("OBVI_PCG")) pcg_resident = std::string(e) != "grid";
     CUDA_OK(cudaFuncSetAttribute(pcg_bt_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentSmem));
     if (const char* e = getenv("OBVI_PROFILE")) prof.on = std::string(e) == "1";
@@ -557,7 +559,8 @@ struct Solver {
     if (S.n_obs && S.nf) { pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag); launches++; }
     prof.end("pose_accum", pt0, stream); pt0 = prof.begin(stream);
     if (schur_mode == 3) {
-      if (S.P) { point_prep_kernel<<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
+      if (S.P && lanes_per_point == 8) { point_prep_kernel<8><<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
+      else if (S.P) { point_prep_kernel<16><<<nblk(S.P, 16), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
       prof.end("point_prep", pt0, stream); pt0 = prof.begin(stream);
       if (n_row_items) { schur_rows_kernel<<<nblk(n_row_items, kRowWarps), 32 * kRowWarps, 0, stream>>>(reinterpret_cast<const uint4*>(pr_items.p), n_row_items, pr_ent.p, WZ.p, pr_rowblk.p, kRowSpan, S_upper, b_schur); launches++; }
       if (n_row_fallback) {
@@ -639,7 +642,8 @@ struct Solver {
     if (S.nf) { pose_step_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(S.nf, pose_of_f.p, pscale.p, y.p, poses[cur].p, poses[cand].p, dpose.p, rank == 0, scalars.p); launches++; }
     fork();
     if (S.P && schur_mode == 3) {
-      backsub_rows_kernel<<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_grp_f.p, pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
+      if (lanes_per_point == 8) backsub_rows_kernel<8><<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_grp_f.p, pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
+      else backsub_rows_kernel<16><<<nblk(S.P, 16), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_grp_f.p, pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
       launches++;
       if (n_row_fallback) {   // points outside the row-owner path: generic kernel on the fallback list
         EArgs a = eargs(pts, J.p); a.elist = pr_fallback.p;
