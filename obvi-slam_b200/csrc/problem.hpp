@@ -8,6 +8,9 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -197,7 +200,10 @@ inline void count_reduced(const Problem& pb, Structure& S) {
 // ---- structure build ---------------------------------------------------------------------------
 // rank/world: e-blocks (points, objects) are dealt to ranks in contiguous ranges of the internal
 // (first-observing-keyframe) order, balanced by observation count; rank 0 also owns the pose-only factors.
+#define OBVI_TMARK(name) do { if (tm_on) { auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "[build] before %s: +%.1f ms\n", name, std::chrono::duration<double, std::milli>(t1 - tm_t0).count()); tm_t0 = t1; } } while (0)
 inline bool build_structure(const Problem& pb, Structure& S, int rank, int world, std::string& err) {
+  const bool tm_on = getenv("OBVI_BUILD_TIMING") != nullptr;
+  auto tm_t0 = std::chrono::steady_clock::now();
   { const bool wb = S.want_batches; S = Structure(); S.want_batches = wb; }
   const int nb = (int)pb.blocks.size();
   std::vector<int32_t> pose_of_block(nb, -1), point_of_block(nb, -1), obj_of_block(nb, -1);
@@ -262,6 +268,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     return (uint32_t)(S.classes.size() - 1);
   };
 
+  OBVI_TMARK("0");
   // ---- reprojection observations: counting sort by pose, then (camera, point) inside each pose
   {
     std::vector<uint32_t> cnt(S.K + 1, 0);
@@ -292,24 +299,25 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
       S.obs_user[cur[k]] = (uint32_t)n;
       cur[k]++;
     }
-    // sort inside each pose segment by (camera, point)
-    std::vector<uint32_t> idx;
-    std::vector<ObsRec> tmp; std::vector<uint32_t> tmpu;
-    for (int k = 0; k < S.K; k++) {
-      const uint32_t b = S.pose_ptr[k], e = S.pose_ptr[k + 1];
-      if (e - b < 2) continue;
-      idx.resize(e - b); std::iota(idx.begin(), idx.end(), 0u);
-      const ObsRec* ob = &S.obs[b];
-      std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {
-        const int cx = S.classes[ob[x].cls].cam, cy = S.classes[ob[y].cls].cam;
-        if (cx != cy) return cx < cy;
-        if (ob[x].point != ob[y].point) return ob[x].point < ob[y].point;
-        return x < y; });
-      tmp.assign(S.obs.begin() + b, S.obs.begin() + e); tmpu.assign(S.obs_user.begin() + b, S.obs_user.begin() + e);
-      for (uint32_t i = 0; i < e - b; i++) { S.obs[b + i] = tmp[idx[i]]; S.obs_user[b + i] = tmpu[idx[i]]; }
+    // sort inside each pose segment by (camera, point): 64-bit keys, segments in parallel
+    std::vector<uint64_t> key(S.n_obs);
+    for (int64_t q = 0; q < S.n_obs; q++) key[q] = ((uint64_t)S.classes[S.obs[q].cls].cam << 32) | S.obs[q].point;
+    std::vector<ObsRec> sorted_obs(S.n_obs); std::vector<uint32_t> sorted_user(S.n_obs);
+#pragma omp parallel
+    {
+      std::vector<std::pair<uint64_t, uint32_t>> kv;
+#pragma omp for schedule(dynamic, 16)
+      for (int k = 0; k < S.K; k++) {
+        const uint32_t b = S.pose_ptr[k], e = S.pose_ptr[k + 1];
+        kv.resize(e - b);
+        for (uint32_t i = 0; i < e - b; i++) kv[i] = {key[b + i], i};     // ties keep the order of addition
+        std::sort(kv.begin(), kv.end());
+        for (uint32_t i = 0; i < e - b; i++) { sorted_obs[b + i] = S.obs[b + kv[i].second]; sorted_user[b + i] = S.obs_user[b + kv[i].second]; }
+      }
     }
+    S.obs.swap(sorted_obs); S.obs_user.swap(sorted_user);
   }
-
+  OBVI_TMARK("1");
   // ---- bbox observations, object-major (object, pose, camera)
   {
     std::vector<uint32_t> ids;
@@ -354,6 +362,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
   }
   S.n_unary = (int64_t)S.unary.size();
 
+  OBVI_TMARK("2");
   // ---- e-block lists + reduced-system structure (bitmap over f x f)
   const int nf = S.nf;
   const int W = (nf + 63) / 64;
@@ -399,6 +408,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
       for (int a = 0; a < ns; a++) for (int b = a; b < ns; b++) setbit(sf[a], sf[b]);
     }
   }
+  OBVI_TMARK("3");
   // relative-pose factors
   for (size_t n = 0; n < pb.rel.size(); n++) {
     const RelPoseFactor& f = pb.rel[n];
@@ -424,6 +434,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     }
     for (const auto& f : pb.rel) if (f.alive) { const int f1 = S.f_of_pose[pose_of_block[f.p1]], f2 = S.f_of_pose[pose_of_block[f.p2]]; if (f1 >= 0 && f2 >= 0) setbit(std::min(f1, f2), std::max(f1, f2)); }
   }
+  OBVI_TMARK("4");
   // upper BSR + O(1) rank lookup
   std::vector<uint32_t> wpre((size_t)nf * W + 1, 0);  // blocks before word w of row i (global)
   S.su_ptr.assign(nf + 1, 0);
@@ -454,6 +465,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
       for (int a = 0; a < ns; a++) for (int b = a; b < ns; b++) L->pair_blk[w++] = cst[e] ? 0u : blk_of(sf[a], sf[b]);
     }
   }
+  OBVI_TMARK("5");
   // ---- point batches: consecutive points (first-observing-keyframe order) whose poses fit a 64-wide window
   //      (only the batched kernels use them; the default row-owner path skips this pass)
   if (S.want_batches) {
@@ -501,6 +513,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     close_batch();
     (void)cur_pairs;
   }
+  OBVI_TMARK("6");
   // ---- row-owner structure.  Slots are DENSE per point: one record for every f index between the point's first and
   // last variable pose (gap poses keep an all-zero record), so the column at offset d of slot gs is simply slot gs + d.
   {
@@ -566,6 +579,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     r.blk12 = -1; r.swap12 = 0;
     if (r.f1 >= 0 && r.f2 >= 0 && r.f1 != r.f2) { r.swap12 = r.f1 > r.f2; r.blk12 = (int32_t)blk_of(std::min(r.f1, r.f2), std::max(r.f1, r.f2)); }
   }
+  OBVI_TMARK("7");
   // full symmetric BSR
   {
     std::vector<uint32_t> cnt(nf + 1, 0);
@@ -581,6 +595,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     }
     for (int i = 0; i < nf; i++) for (uint32_t q = S.su_ptr[i]; q < S.su_ptr[i + 1]; q++) { S.sf_col[cur[i]] = S.su_col[q]; S.sf_src[cur[i]] = q; cur[i]++; }
   }
+  OBVI_TMARK("8");
   count_reduced(pb, S);
   return true;
 }
