@@ -209,7 +209,7 @@ struct Solver {
   // kRefactorPcgIters iterations.  (A stale preconditioner changes the PCG iteration count, never its answer.)
   double bt_radius = -1.0;
   int last_pcg_iters = 0;
-  static constexpr int kRefactorPcgIters = 8;
+  int kRefactorPcgIters = 8;   // OBVI_REFACTOR_ITERS
   int64_t bt_factorizations = 0;
   double* h_scalars = nullptr;  // pinned
   std::vector<double> h_poses, h_points, h_objects;
@@ -257,6 +257,7 @@ struct Solver {
     if (pcg_bt_blocks_per_sm < 1) throw std::runtime_error("pcg_bt_kernel cannot be made resident");
     if (const char* e = getenv("OBVI_PRECOND")) use_bt = std::string(e) != "jacobi";
     if (const char* e = getenv("OBVI_BT")) bt_v1 = std::string(e) == "v1";
+    if (const char* e = getenv("OBVI_REFACTOR_ITERS")) kRefactorPcgIters = std::max(1, atoi(e));
     if (const char* e = getenv("OBVI_LPP")) lanes_per_point = std::string(e) == "16" ? 16 : 8;
     if (const char* e = getenv("OBVI_PCG")) pcg_resident = std::string(e) != "grid";
     CUDA_OK(cudaFuncSetAttribute(pcg_bt_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentSmem));
