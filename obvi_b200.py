@@ -11,5 +11,6 @@ if _ROOT not in sys.path:
 _pkg = importlib.import_module("obvi-slam_b200")
 synth = importlib.import_module("obvi-slam_b200.synth")
 schedule = importlib.import_module("obvi-slam_b200.schedule")
+pg_state_io = importlib.import_module("obvi-slam_b200.pg_state_io")
 
 globals().update({k: v for k, v in vars(_pkg).items() if not k.startswith("__")})

@@ -1,0 +1,116 @@
+"""Pose-graph-state JSON: the dialect of object_and_reprojection_feature_pose_graph_file_storage_io.h.
+OpenCV is not available here, so these tests pin the structure against the labels transcribed from that header and check
+the round trip (the reference's own test for this format is a write -> read round trip as well,
+test/file_io/cv_file_storage/object_and_reprojection_feature_pose_graph_file_storage_io_tests.cc)."""
+import json
+
+import numpy as np
+import pytest
+
+LOW_KEYS = {"camera_extrinsics_by_camera", "camera_intrinsics_by_camera", "visual_factor_type", "min_frame_id", "max_frame_id",
+            "max_feature_factor_id", "max_pose_factor_id", "robot_poses", "pose_factors_by_frame", "visual_feature_factors_by_frame",
+            "visual_factors_by_feature", "pose_factors", "factors", "last_observed_frame_by_feature", "first_observed_frame_by_feature"}
+OBJ_KEYS = {"mean_and_cov_by_semantic_class", "min_object_id", "max_object_id", "ellipsoid_estimates", "semantic_class_for_object",
+            "last_observed_frame_by_object", "first_observed_frame_by_object", "min_object_observation_factor",
+            "max_object_observation_factor", "min_obj_specific_factor", "max_obj_specific_factor", "long_term_map_object_ids",
+            "object_observation_factors", "shape_dim_prior_factors", "observation_factors_by_frame", "observation_factors_by_object",
+            "object_only_factors_by_object"}
+
+
+def graph(ob):
+    return ob.synth.make_graph(K=8, P=60, O=3, seed=91, objects_on=True, relpose="all", n_const_poses=1, min_obj_obs=3, min_point_obs=3)
+
+
+def test_written_structure_follows_the_reference_labels(ob, tmp_path):
+    g = graph(ob)
+    path = str(tmp_path / "pg.json")
+    ob.pg_state_io.write_pose_graph_state(path, g, semantic_classes={0: "chair"}, class_priors={"chair": (np.array([0.6, 0.6, 1.0]), np.eye(3) * 0.01)})
+    d = json.load(open(path))
+    assert set(d) == {"pose_graph"} and set(d["pose_graph"]) == {"reprojection_low_level_feature_pose_graph_state", "obj_only_pose_graph_state_"}
+    rs = d["pose_graph"]["reprojection_low_level_feature_pose_graph_state"]
+    assert set(rs) == {"low_level_pg_state", "min_feature_id", "max_feature_id", "feature_positions"}
+    assert set(rs["low_level_pg_state"]) == LOW_KEYS and set(d["pose_graph"]["obj_only_pose_graph_state_"]) == OBJ_KEYS
+    low = rs["low_level_pg_state"]
+    # maps are lists of {k, v}; ids are decimal strings; matrices are {Rows, Cols, Data} row-major
+    e = low["robot_poses"][0]
+    assert set(e) == {"k", "v"} and isinstance(e["k"], str) and e["v"]["Rows"] == 6 and e["v"]["Cols"] == 1 and len(e["v"]["Data"]) == 6
+    f = low["factors"][0]["v"]
+    assert set(f) == {"frame_id", "feature_id", "camera_id", "feature_pos", "reprojection_error_std_dev"} and f["feature_pos"]["Rows"] == 2
+    pf = low["pose_factors"][0]["v"]
+    assert set(pf) == {"frame_id_1", "frame_id_2", "measured_pose_deviation", "pose_deviation_cov"}
+    assert set(pf["measured_pose_deviation"]) == {"transl", "rot"} and set(pf["measured_pose_deviation"]["rot"]) == {"angle", "axis"}
+    assert pf["pose_deviation_cov"]["Rows"] == 6 and len(pf["pose_deviation_cov"]["Data"]) == 36
+    assert low["visual_factor_type"] == 0
+    vf = low["visual_feature_factors_by_frame"][0]["v"][0]
+    assert set(vf) == {"i", "v"} and set(vf["v"]) == {"f", "s"} and vf["v"]["f"] == 0 and isinstance(vf["v"]["s"], str)
+    assert set(low["pose_factors_by_frame"][0]["v"][0]) == {"f", "s"} and low["pose_factors_by_frame"][0]["v"][0]["f"] == 5
+    oo = d["pose_graph"]["obj_only_pose_graph_state_"]
+    of = oo["object_observation_factors"][0]["v"]
+    assert set(of) == {"frame_id", "camera_id", "object_id", "bounding_box_corners", "bounding_box_corners_covariance", "detection_confidence"}
+    assert of["bounding_box_corners"]["Rows"] == 4 and oo["ellipsoid_estimates"][0]["v"]["Rows"] == 7
+    assert set(oo["shape_dim_prior_factors"][0]["v"]) == {"object_id", "mean_shape_dim", "shape_dim_cov"}
+    assert oo["observation_factors_by_object"][0]["v"][0]["f"] == 2 and oo["object_only_factors_by_object"][0]["v"][0]["f"] == 3
+    cp = oo["mean_and_cov_by_semantic_class"][0]
+    assert cp["k"] == "chair" and set(cp["v"]) == {"f", "s"} and cp["v"]["s"]["Rows"] == 3
+
+
+def test_round_trip_preserves_the_graph_and_ids(ob, tmp_path):
+    g = graph(ob)
+    ids = dict(frame=np.arange(len(g.poses)) * 3 + 10, feature=np.arange(len(g.points)) + 1000, object=np.arange(len(g.objects)) * 2 + 7,
+               camera=np.array([1, 2]), ltm_objects=[7])
+    p1, p2 = str(tmp_path / "a.json"), str(tmp_path / "b.json")
+    ob.pg_state_io.write_pose_graph_state(p1, g, ids)
+    g2, ids2, _ = ob.pg_state_io.read_pose_graph_state(p1)
+    for k in ("frame", "feature", "object", "camera"):
+        assert np.array_equal(ids2[k], ids[k])
+    assert ids2["ltm_objects"] == [7]
+    assert np.allclose(g2.poses, g.poses, rtol=0, atol=1e-15) and np.allclose(g2.points, g.points, atol=1e-15) and np.allclose(g2.objects, g.objects, atol=1e-15)
+    for name, keys in (("reproj", ("pose", "point", "cam", "px", "sigma")), ("bbox", ("obj", "pose", "cam", "corners", "cov")),
+                       ("shape", ("obj", "mean", "cov")), ("relpose", ("p1", "p2", "t", "cov"))):
+        for k in keys:
+            assert np.allclose(getattr(g2, name)[k], getattr(g, name)[k], rtol=0, atol=1e-12), (name, k)
+    assert np.allclose(g2.relpose["Rm"], g.relpose["Rm"], atol=1e-12)     # through angle / axis
+    for c2, c in zip(g2.cams, g.cams):
+        assert np.allclose(c2["intr"], c["intr"]) and np.allclose(c2["R"], c["R"], atol=1e-12) and np.allclose(c2["t"], c["t"])
+    ob.pg_state_io.write_pose_graph_state(p2, g2, ids2)
+
+    def same(x, y):       # identical structure; numbers equal to rounding (rotations pass through angle / axis <-> matrix)
+        if isinstance(x, dict):
+            return isinstance(y, dict) and set(x) == set(y) and all(same(x[k], y[k]) for k in x)
+        if isinstance(x, list):
+            return isinstance(y, list) and len(x) == len(y) and all(same(u, v) for u, v in zip(x, y))
+        if isinstance(x, float):
+            return isinstance(y, float) and abs(x - y) <= 1e-12 * max(1.0, abs(x))
+        return x == y
+    assert same(json.load(open(p1)), json.load(open(p2)))
+
+
+def test_reader_accepts_numeric_ids_and_ignores_index_maps(ob, tmp_path):
+    g = graph(ob)
+    path = str(tmp_path / "pg.json")
+    ob.pg_state_io.write_pose_graph_state(path, g)
+    d = json.load(open(path))
+    low = d["pose_graph"]["reprojection_low_level_feature_pose_graph_state"]["low_level_pg_state"]
+    for e in low["robot_poses"]:
+        e["k"] = int(e["k"])
+    for k in ("pose_factors_by_frame", "visual_feature_factors_by_frame", "visual_factors_by_feature"):
+        low[k] = []
+    json.dump(d, open(path, "w"))
+    g2, _, _ = ob.pg_state_io.read_pose_graph_state(path)
+    assert np.allclose(g2.poses, g.poses) and len(g2.reproj["pose"]) == len(g.reproj["pose"])
+
+
+@pytest.mark.gpu
+def test_run_opt_from_pg_state_cli(ob, tmp_path):
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = ob.synth.make_graph(K=20, P=600, O=4, seed=92, objects_on=True, relpose="all", n_const_poses=1, min_obj_obs=4)
+    pin, pout = str(tmp_path / "in.json"), str(tmp_path / "out.json")
+    ob.pg_state_io.write_pose_graph_state(pin, g)
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "run_opt_from_pg_state.py"), "--pg-state", pin, "--out", pout], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["frames"] == [0, 19] and r["lm_steps"] > 0 and r["excluded"] > 0
+    g2, _, _ = ob.pg_state_io.read_pose_graph_state(pout)
+    assert np.array_equal(g2.poses[0], g.poses[0]) and np.abs(g2.poses[1:] - g.poses[1:]).max() > 1e-6
+    assert len(g2.reproj["pose"]) == len(g.reproj["pose"])      # the file keeps every factor; exclusion is per optimisation
