@@ -14,7 +14,8 @@ two-phase schedule -- can be run and parity-checked end to end):
                                      offline_problem_runner.h:438-520, pose_graph_plus_objects_optimizer.h:24-353
 
 The numerical work of every solve is done by `backend` (GpuBackend: the CUDA path through the C ABI, with the outlier
-ranking on the device and the exclusion done in place; tests also plug in the CPU oracle to check the composition).
+ranking on the device and the exclusion done in place).  A backend is any object with solve(sub, opts) and
+two_phase(sub, opts1, opts2, fraction); tests/helpers.py holds one that runs the CPU oracle to check the composition.
 Graphs are synth.FactorGraph objects; a window is optimised on an extracted sub-graph whose arrays are the parameter
 blocks, and the results are copied back -- the analogue of the reference's pose-graph nodes being updated in place.
 """
@@ -226,50 +227,6 @@ class GpuBackend:
         self.stats["structure_builds"] += p.num_structure_builds(); self.stats["excluded"] += len(out)
         self.stats["wall_s"] += time.time() - t
         return [s1.final_cost, s2.final_cost]
-
-
-class OracleBackend:
-    """TEST ONLY: the same composition on the CPU oracle (tests compare the two trajectories)."""
-
-    def __init__(self, oracle):
-        self.oracle = oracle
-
-    @staticmethod
-    def _o(opts):
-        return dict(max_num_iterations=opts["max_num_iterations"], function_tolerance=opts["function_tolerance"],
-                    gradient_tolerance=opts["gradient_tolerance"], parameter_tolerance=opts["parameter_tolerance"],
-                    initial_radius=opts["initial_trust_region_radius"], max_radius=opts["max_trust_region_radius"],
-                    use_nonmonotonic_steps=bool(opts["use_nonmonotonic_steps"]))
-
-    def solve(self, sub, opts):
-        return [self.oracle.solve(sub, **self._o(opts))["final_cost"]]
-
-    @staticmethod
-    def _topk(sq, frac):
-        by_err = {}
-        for i, e in enumerate(sq):            # std::map<double, id, greater>: equal keys overwrite
-            by_err[e] = i
-        order = sorted(by_err, reverse=True)
-        return [by_err[e] for e in order[:int(len(order) * frac)]]
-
-    def two_phase(self, sub, opts1, opts2, frac):
-        x0 = (sub.poses.copy(), sub.points.copy(), sub.objects.copy())
-        c1 = self.oracle.solve(sub, **self._o(opts1))["final_cost"]
-        ev = self.oracle.evaluate(sub, apply_loss=False)
-        keep_rp = np.ones(len(sub.reproj["pose"]), bool); keep_bb = np.ones(len(sub.bbox["obj"]), bool)
-        if len(keep_rp):
-            r = ev["r_reproj"]; keep_rp[self._topk(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1], frac)] = False
-        if len(keep_bb):
-            r = ev["r_bbox"]; keep_bb[self._topk(((r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1]) + r[:, 2] * r[:, 2]) + r[:, 3] * r[:, 3], frac)] = False
-        s2 = sub.copy()
-        s2.poses[:], s2.points[:], s2.objects[:] = x0
-        for k in ("pose", "point", "cam", "px", "sigma"):
-            s2.reproj[k] = s2.reproj[k][keep_rp]
-        for k in ("obj", "pose", "cam", "corners", "cov"):
-            s2.bbox[k] = s2.bbox[k][keep_bb]
-        c2 = self.oracle.solve(s2, **self._o(opts2))["final_cost"]
-        sub.poses[:], sub.points[:], sub.objects[:] = s2.poses, s2.points, s2.objects
-        return [c1, c2]
 
 
 # ----------------------------------------------------------------------------- the runner

@@ -24,3 +24,49 @@ def graph_from_npz(ob, d):
 def rel_err(a, b):
     a, b = np.asarray(a), np.asarray(b)
     return float(np.abs(a - b).max() / (1.0 + np.abs(b).max())) if a.size else 0.0
+
+
+class OracleBackend:
+    """Schedule backend (obvi-slam_b200/schedule.py) that runs every solve on the CPU oracle: the checker for the GPU backend."""
+
+    def __init__(self, oracle):
+        self.oracle = oracle
+
+    @staticmethod
+    def _o(opts):
+        return dict(max_num_iterations=opts["max_num_iterations"], function_tolerance=opts["function_tolerance"],
+                    gradient_tolerance=opts["gradient_tolerance"], parameter_tolerance=opts["parameter_tolerance"],
+                    initial_radius=opts["initial_trust_region_radius"], max_radius=opts["max_trust_region_radius"],
+                    use_nonmonotonic_steps=bool(opts["use_nonmonotonic_steps"]))
+
+    def solve(self, sub, opts):
+        return [self.oracle.solve(sub, **self._o(opts))["final_cost"]]
+
+    @staticmethod
+    def _topk(sq, frac):
+        by_err = {}
+        for i, e in enumerate(sq):            # std::map<double, id, greater>: equal keys overwrite
+            by_err[e] = i
+        order = sorted(by_err, reverse=True)
+        return [by_err[e] for e in order[:int(len(order) * frac)]]
+
+    def two_phase(self, sub, opts1, opts2, frac):
+        x0 = (sub.poses.copy(), sub.points.copy(), sub.objects.copy())
+        c1 = self.oracle.solve(sub, **self._o(opts1))["final_cost"]
+        ev = self.oracle.evaluate(sub, apply_loss=False)
+        keep_rp = np.ones(len(sub.reproj["pose"]), bool); keep_bb = np.ones(len(sub.bbox["obj"]), bool)
+        if len(keep_rp):
+            r = ev["r_reproj"]; keep_rp[self._topk(r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1], frac)] = False
+        if len(keep_bb):
+            r = ev["r_bbox"]; keep_bb[self._topk(((r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1]) + r[:, 2] * r[:, 2]) + r[:, 3] * r[:, 3], frac)] = False
+        s2 = sub.copy()
+        s2.poses[:], s2.points[:], s2.objects[:] = x0
+        for k in ("pose", "point", "cam", "px", "sigma"):
+            s2.reproj[k] = s2.reproj[k][keep_rp]
+        for k in ("obj", "pose", "cam", "corners", "cov"):
+            s2.bbox[k] = s2.bbox[k][keep_bb]
+        c2 = self.oracle.solve(s2, **self._o(opts2))["final_cost"]
+        sub.poses[:], sub.points[:], sub.objects[:] = s2.poses, s2.points, s2.objects
+        return [c1, c2]
+
+

@@ -6,6 +6,8 @@ CPU: window rule, scope selection and the composition on the CPU oracle.  GPU: t
 import numpy as np
 import pytest
 
+from helpers import OracleBackend
+
 
 def small_params(ob, **kw):
     S = ob.schedule
@@ -64,7 +66,7 @@ def test_pose_algebra_roundtrip(ob):
 def test_schedule_on_oracle_runs_every_step_kind(ob, oracle):
     S = ob.schedule
     g = session(ob, K=16, seed=42)
-    log = S.run_schedule(g, S.OracleBackend(oracle), small_params(ob))
+    log = S.run_schedule(g, OracleBackend(oracle), small_params(ob))
     kinds = [e["kind"] for e in log]
     assert kinds.count("lba") >= 8 and "pgo" in kinds and "points_only" in kinds and kinds[-1] == "final"
     assert all(len(e["costs"]) >= 2 and e["costs"][1] <= e["costs"][0] * 1.5 for e in log if e["kind"] in ("lba", "final"))
@@ -81,7 +83,7 @@ def test_schedule_gpu_matches_oracle(ob, oracle):
     p = small_params(ob)
     be = S.GpuBackend(ob)
     log_gpu = S.run_schedule(g_gpu, be, p)
-    log_cpu = S.run_schedule(g_cpu, S.OracleBackend(oracle), p)
+    log_cpu = S.run_schedule(g_cpu, OracleBackend(oracle), p)
     assert [(e["frame"], e["start"], e["kind"]) for e in log_gpu] == [(e["frame"], e["start"], e["kind"]) for e in log_cpu]
     for a, b in zip(log_gpu, log_cpu):
         assert len(a["costs"]) == len(b["costs"])
@@ -103,7 +105,7 @@ def test_multi_session_ltm_chain_matches_oracle(ob, oracle):
     from oracle import py_oracle as po
     opts = dict(max_num_iterations=12, function_tolerance=1e-6, gradient_tolerance=1e-10, parameter_tolerance=1e-8,
                 initial_trust_region_radius=100.0, max_trust_region_radius=1e4, use_nonmonotonic_steps=0)
-    o_opts = ob.schedule.OracleBackend._o(opts)
+    o_opts = OracleBackend._o(opts)
 
     def sessions():
         return [ob.synth.make_graph(K=14, P=350, O=5, seed=71, objects_on=True, relpose="all", n_const_poses=1, min_obj_obs=4) for _ in range(3)]
