@@ -241,7 +241,7 @@ def complex_step_jacobian(fun, blocks, h=1e-30):
 def huber_rho(s, a):
     """Ceres HuberLoss::Evaluate -> (rho, rho', rho'')."""
     b = a * a
-    if s > b:
+    if np.isfinite(b) and s > b:
         r = np.sqrt(s)
         rho1 = max(np.finfo(np.float64).tiny, a / r)
         return 2.0 * a * r - b, rho1, -rho1 / (2.0 * s)
@@ -292,6 +292,13 @@ def residual_blocks(g):
     for n in range(len(rl["p1"])):
         f = (lambda t, R, c: lambda a, b: relpose_residual(a, b, t, R, c))(rl["t"][n], rl["Rm"][n], rl["cov"][n])
         out.append(("relpose", rl["huber"], f, [("pose", int(rl["p1"][n])), ("pose", int(rl["p2"][n]))]))
+    # ParameterPrior (parameter_prior.h:27-34), used by the long-term-map rank repair: optional `g.prior` =
+    # dict(kind ("pose" | "point" | "obj"), index, idx, mean, std (N,)); added with no loss function
+    pr = getattr(g, "prior", None)
+    if pr is not None:
+        for n in range(len(pr["index"])):
+            f = (lambda i, m, sd: lambda block: param_prior_residual(block, i, m, sd))(int(pr["idx"][n]), float(pr["mean"][n]), float(pr["std"][n]))
+            out.append(("prior", np.inf, f, [(pr["kind"][n], int(pr["index"][n]))]))
     return out
 
 

@@ -456,3 +456,41 @@ def test_jacobian_crs_export_matches_dense_oracle(ob):
             ref_row = J[nb_rp + 4 * b + a]
             want = np.concatenate([ref_row[off[("obj", o)]:off[("obj", o)] + 7] if ("obj", o) in off else np.zeros(7) for o in objs])
             assert np.abs(got - want).max() <= 1e-9 * (1 + np.abs(want).max())
+
+
+def test_parameter_priors_on_poses_points_objects(ob):
+    """ParameterPrior<N> (parameter_prior.h:27-45), the factor the long-term-map rank repair adds on single coordinates of
+    poses, features and ellipsoids (long_term_object_map_extraction.cpp:817,869,916), no loss function: residual, Jacobian
+    and the LM trajectory against the NumPy oracle.  Priors on points exercise the prior path of the point elimination."""
+    from oracle import py_oracle as po
+    g = ob.synth.make_graph(K=8, P=80, O=3, seed=95, objects_on=True, relpose="all", n_const_poses=0, min_obj_obs=3, min_point_obs=3)
+    seen_pts = np.unique(g.reproj["point"]); seen_obj = np.unique(g.bbox["obj"])
+    kinds = ["pose"] * 6 + ["point"] * 12 + ["obj"] * 4
+    index = [0] * 6 + [int(p) for p in seen_pts[:12]] + [int(seen_obj[0])] * 4
+    idx = list(range(6)) + [i % 3 for i in range(12)] + [3, 4, 5, 6]
+    arrs = dict(pose=g.poses, point=g.points, obj=g.objects)
+    mean = [float(arrs[k][i][c]) + 0.01 * (n % 5 - 2) for n, (k, i, c) in enumerate(zip(kinds, index, idx))]
+    std = [0.05 + 0.01 * (n % 3) for n in range(len(kinds))]
+    g.prior = dict(kind=kinds, index=index, idx=idx, mean=mean, std=std)
+    g_ref = g.copy(); g_ref.prior = g.prior
+    p = ob.problem_from_graph(g)
+    for k, i, c, m, sd in zip(kinds, index, idx, mean, std):
+        p.add_parameter_prior(arrs[k][i], c, m, sd)
+    # the 6 priors on pose 0 fix the gauge (no constant pose): residuals / Jacobian / gradient through the CRS export
+    off, n = po._layout(g_ref)
+    cost, r, J = po.evaluate(g_ref, apply_loss=True)
+    blocks = [g.poses[i] for i in range(len(g.poses))] + [g.points[i] for i in range(len(g.points))] + [g.objects[i] for i in range(len(g.objects))]
+    rows, cols, vals, shape, grad = p.evaluate_jacobian(True, None, blocks)
+    assert shape == (J.shape[0], n)
+    D = np.zeros(shape)
+    for i in range(shape[0]):
+        D[i, cols[rows[i]:rows[i + 1]]] = vals[rows[i]:rows[i + 1]]
+    assert rel_err(D, J[:, :n]) < 1e-9
+    c_gpu, r_gpu = p.evaluate(apply_loss_function=True)
+    assert abs(c_gpu - cost) <= 1e-10 * cost and rel_err(r_gpu, r) < 1e-9
+    s = p.solve(**dict(OPTS, max_num_iterations=8))
+    ref = po.solve_lm_dense(g_ref, max_num_iterations=8, function_tolerance=1e-6, initial_radius=100.0, max_radius=1e4, use_nonmonotonic_steps=True)
+    assert s.num_iterations == len(ref["iterations"])
+    for a, b in zip(s.iterations, ref["iterations"]):
+        assert a["successful"] == b["successful"] and abs(a["cost"] - b["cost"]) <= 1e-5 * abs(b["cost"])
+    assert np.abs(g.poses[:, :3] - g_ref.poses[:, :3]).max() < 1e-4 and np.abs(g.points - g_ref.points).max() < 1e-3
