@@ -1764,29 +1764,35 @@ __global__ void bbox_kernel(const BBoxRec* __restrict__ rec, int64_t n, const Po
                             const double* __restrict__ objs, int mode, int apply_loss, double* __restrict__ J,
                             double* __restrict__ scalars) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const BBoxRec& R = rec[i];
-  const PoseCam& pc = pcam[(size_t)R.pose * C + R.cam];
-  double ell[7];
+  double cost = 0.0, fixed = 0.0;
+  if (i < n) {
+    const BBoxRec& R = rec[i];
+    const PoseCam& pc = pcam[(size_t)R.pose * C + R.cam];
+    double ell[7];
 #pragma unroll
-  for (int a = 0; a < 7; a++) ell[a] = objs[7 * (size_t)R.obj + a];
-  double r[4];
-  double* ch = J + (size_t)i * kBBoxChunk;
-  if (mode == 0) bbox_residual_jacobian(pc, ell, R.A4, R.brect, R.invalid_err, r, ch + 24, ch);
-  else bbox_residual_jacobian(pc, ell, R.A4, R.brect, R.invalid_err, r, nullptr, nullptr);
-  const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
-  double sc = 1.0, c = 0.5 * s;
-  if (apply_loss && R.huber > 0.0) c = huber(R.huber, s, &sc);
-  if (R.flags & kObsMasked) {   // removed in place: an all-zero block, no cost
-    if (mode == 0) for (int a = 0; a < kBBoxChunk; a++) ch[a] = 0.0;
-    return;
+    for (int a = 0; a < 7; a++) ell[a] = objs[7 * (size_t)R.obj + a];
+    double r[4];
+    double* ch = J + (size_t)i * kBBoxChunk;
+    if (mode == 0) bbox_residual_jacobian(pc, ell, R.A4, R.brect, R.invalid_err, r, ch + 24, ch);
+    else bbox_residual_jacobian(pc, ell, R.A4, R.brect, R.invalid_err, r, nullptr, nullptr);
+    const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3];
+    double sc = 1.0, c = 0.5 * s;
+    if (apply_loss && R.huber > 0.0) c = huber(R.huber, s, &sc);
+    if (R.flags & kObsMasked) {   // removed in place: an all-zero block, no cost
+      if (mode == 0) for (int a = 0; a < kBBoxChunk; a++) ch[a] = 0.0;
+    } else {
+      if (mode == 0) {
+        for (int a = 0; a < 52; a++) ch[a] *= sc;
+        for (int a = 0; a < 4; a++) ch[52 + a] = sc * r[a];
+      }
+      if ((R.flags & 3u) == 3u) fixed = c; else cost = c;
+    }
   }
-  if (mode == 0) {
-    for (int a = 0; a < 52; a++) ch[a] *= sc;
-    for (int a = 0; a < 4; a++) ch[52 + a] = sc * r[a];
-    atomicAdd(&scalars[(R.flags & 3u) == 3u ? SC_FIXED : SC_COST], c);
-  } else {
-    atomicAdd(&scalars[(R.flags & 3u) == 3u ? SC_CAND_FIXED : SC_CAND], c);
+  // one atomic per warp instead of one per observation (they all hit the same two scalars)
+  cost = warp_sum(cost); fixed = warp_sum(fixed);
+  if ((threadIdx.x & 31) == 0) {
+    if (cost != 0.0) atomicAdd(&scalars[mode == 0 ? SC_COST : SC_CAND], cost);
+    if (fixed != 0.0) atomicAdd(&scalars[mode == 0 ? SC_FIXED : SC_CAND_FIXED], fixed);
   }
 }
 
@@ -1971,10 +1977,16 @@ __global__ void finish_kernel(int nf, const uint32_t* __restrict__ sf_ptr, const
     }
     row[t] = v;
   }
-  if (lane < 6) {
-    const double g = gp[6 * i + lane];
-    rhs[6 * i + lane] = pscale[6 * i + lane] * (g + b_schur[6 * i + lane]);
-    atomic_max_nonneg(&scalars[SC_GMAX], fabs(g));
+  if (lane < 32) {   // first warp: rhs + one gradient-max atomic per row
+    double ga = 0.0;
+    if (lane < 6) {
+      const double g = gp[6 * i + lane];
+      rhs[6 * i + lane] = pscale[6 * i + lane] * (g + b_schur[6 * i + lane]);
+      ga = fabs(g);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) ga = fmax(ga, __shfl_xor_sync(0xffffffffu, ga, o));
+    if (lane == 0 && ga > 0.0) atomic_max_nonneg(&scalars[SC_GMAX], ga);
   }
 }
 
