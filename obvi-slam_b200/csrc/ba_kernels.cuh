@@ -63,7 +63,7 @@ __device__ __forceinline__ void atomic_max_nonneg(double* slot, double v) {
 // One thread per (pose, camera): R_cw, t_cw and the rotation-derivative matrices shared by every
 // observation of that pose (the reference recomputes them per observation on 9-wide Jets).
 __global__ void pose_cam_kernel(const double* __restrict__ poses, int K, const Camera* __restrict__ cams, int C, int jac,
-                                PoseCam* __restrict__ out, PoseCamR* __restrict__ out_r = nullptr) {
+                                PoseCam* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K * C) return;
   const int k = i / C, c = i % C;
@@ -74,7 +74,6 @@ __global__ void pose_cam_kernel(const double* __restrict__ poses, int K, const C
   make_pose_cam(p, cams[c].Rinv, cams[c].tinv, jac != 0, &pc);
   if (jac) {
     out[i] = pc;
-    if (out_r) compact_pose_cam(pc, p, &out_r[i]);
   } else {
 #pragma unroll
     for (int a = 0; a < 9; a++) out[i].Rcw[a] = pc.Rcw[a];
@@ -248,212 +247,6 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const Ob
   }
 }
 
-// Variant of reproj_jac_tma_kernel on the compact pose/camera entries (16-byte shared-memory loads) with optional
-// conflict-free staging of the output tile.
-template <bool ROT, int STORE = 0>
-__global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma2_kernel(const ObsRec* __restrict__ obs, int64_t n,
-                                                                         const PoseCamR* __restrict__ pcam, const Camera* __restrict__ cams, int C,
-                                                                         const CalibClass* __restrict__ cls, int ncls,
-                                                                         const double* __restrict__ points, int apply_loss,
-                                                                         const uint2* __restrict__ tile_pc,
-                                                                         double* __restrict__ J, double* __restrict__ scalars) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ double red[33];
-  __shared__ CalibClass cls_s[kJacMaxCls];
-  double* out_tile = reinterpret_cast<double*>(smem);
-  PoseCamR* pc_s = reinterpret_cast<PoseCamR*>(smem + kJacTileBytes);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kJacTileBytes + kJacMaxPc * sizeof(PoseCamR));
-  __shared__ double cam_tinv[16][3];
-  const int64_t i0 = (int64_t)blockIdx.x * kJacThreads;
-  const int nt = (int)min((int64_t)kJacThreads, n - i0);
-  const uint2 tp = tile_pc[blockIdx.x];  // first pose/camera entry of the tile, number of entries staged
-  const int64_t i = i0 + threadIdx.x;
-  const bool active = (int)threadIdx.x < nt;
-  double2 uv = make_double2(0.0, 0.0);
-  uint4 id = make_uint4(0, 0, 0, 0);
-  if (active) {  // issue the record loads first: they head the longest dependency chain (record -> point)
-    uv = reinterpret_cast<const double2*>(obs)[2 * i];
-    id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];
-  }
-  if (threadIdx.x == 0) mbar_init(bar, 1);
-  if ((int)threadIdx.x < ncls * 4) reinterpret_cast<double*>(cls_s)[threadIdx.x] = reinterpret_cast<const double*>(cls)[threadIdx.x];
-  if ((int)threadIdx.x < C * 3) cam_tinv[threadIdx.x / 3][threadIdx.x % 3] = cams[threadIdx.x / 3].tinv[threadIdx.x % 3];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, tp.y * (uint32_t)sizeof(PoseCamR));
-    tma_load_1d(pc_s, pcam + tp.x, tp.y * (uint32_t)sizeof(PoseCamR), bar);
-  }
-  double cost = 0.0, fixed = 0.0;
-  double X[3] = {0.0, 0.0, 0.0};
-  if (active) {
-    X[0] = points[3 * (size_t)id.y]; X[1] = points[3 * (size_t)id.y + 1]; X[2] = points[3 * (size_t)id.y + 2];
-  }
-  const CalibClass cc = cls_s[id.z];
-  mbar_wait(bar, 0);
-  if (active) {
-    const uint32_t camidx = (id.w >> 8) & 0xffu;
-    const uint32_t pci = id.x * (uint32_t)C + camidx;
-    const uint32_t rel = pci - tp.x;
-    const PoseCamR* pcr = rel < tp.y ? &pc_s[rel] : &pcam[pci];
-    double r[2], Jp[12], Jl[6];
-    reproj_residual_jacobian_compact(pcr, cam_tinv[camidx], X, uv.x, uv.y, cc.mx, cc.my, r, Jp, Jl);
-    const double s = r[0] * r[0] + r[1] * r[1];
-    double sc = 1.0, c = 0.5 * s;
-    if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
-    if ((id.w & 3u) == 3u) fixed = c; else cost = c;
-    double2* out = reinterpret_cast<double2*>(out_tile + (size_t)threadIdx.x * kChunk);
-    double2 pc10[10];
-#pragma unroll
-    for (int a = 0; a < 6; a++) pc10[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
-#pragma unroll
-    for (int a = 0; a < 3; a++) pc10[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
-    pc10[9] = make_double2(sc * r[0], sc * r[1]);
-    // 160 B per thread = 40 banks: the 8 lanes of one store phase would collide pairwise; lanes with an odd (lane >> 2)
-    // write their ten 16-byte pieces rotated by one, which makes every phase conflict-free
-    if (ROT && ((threadIdx.x >> 2) & 1)) {
-#pragma unroll
-      for (int a = 0; a < 10; a++) out[(a + 1) % 10] = pc10[(a + 1) % 10];
-    } else {
-#pragma unroll
-      for (int a = 0; a < 10; a++) out[a] = pc10[a];
-    }
-  }
-  fence_proxy_async_smem();
-  cost = block_sum_all<kJacThreads>(cost, red);     // contains __syncthreads: the tile image is complete after it
-  fixed = block_sum_all<kJacThreads>(fixed, red);
-  if (STORE == 1) {
-    // cooperative copy-out: consecutive threads store consecutive 16-byte pieces (512 B per warp instruction)
-    const double2* src = reinterpret_cast<const double2*>(out_tile);
-    double2* dst = reinterpret_cast<double2*>(J + (size_t)i0 * kChunk);
-    for (int p = threadIdx.x; p < nt * 10; p += kJacThreads) dst[p] = src[p];
-    if (threadIdx.x == 0) {
-      if (cost != 0.0) atomicAdd(&scalars[SC_COST], cost);
-      if (fixed != 0.0) atomicAdd(&scalars[SC_FIXED], fixed);
-    }
-  } else if (threadIdx.x == 0) {
-    tma_store_1d(J + (size_t)i0 * kChunk, out_tile, (uint32_t)nt * kChunk * 8);
-    if (cost != 0.0) atomicAdd(&scalars[SC_COST], cost);
-    if (fixed != 0.0) atomicAdd(&scalars[SC_FIXED], fixed);
-    tma_store_wait_read();
-  }
-}
-
-// ------------------------------------------------------------------------------------------ reprojection Jacobians, persistent + pipelined
-// Third revision of the Jacobian-evaluation kernel.  The per-tile arithmetic is the one of reproj_jac_tma_kernel;
-// the difference is that a CTA is PERSISTENT (2 per SM, grid-stride over the 256-observation tiles) and the tile loop is
-// software-pipelined so that the DRAM latencies of consecutive tiles overlap instead of adding up:
-//   iteration t:  [records of tile t+2 -> registers]  [points of tile t+1 -> registers]  [PoseCam range of tile t+1 by TMA]
-//                 compute tile t from registers / shared memory -> shared-memory image of the output tile (double-buffered)
-//                 one elected thread issues the TMA bulk store; its completion is only awaited two tiles later.
-// The cost is reduced once per CTA at the end (one atomic per CTA) instead of once per tile.
-constexpr int kJacPersistSmem = 2 * kJacTileBytes + 2 * kJacMaxPc * (int)sizeof(PoseCamR) + 32;
-constexpr int kJacSmemBytes2 = kJacTileBytes + kJacMaxPc * (int)sizeof(PoseCamR) + 16;
-constexpr int kJacMaxCam = 16;
-
-template <bool ROT>
-__global__ void __launch_bounds__(kJacThreads, 2) reproj_jac_persistent_kernel(const ObsRec* __restrict__ obs, int64_t n,
-                                                                               const PoseCamR* __restrict__ pcam, const Camera* __restrict__ cams, int C,
-                                                                               const CalibClass* __restrict__ cls, int ncls,
-                                                                               const double* __restrict__ points, int apply_loss,
-                                                                               const uint2* __restrict__ tile_pc, int ntiles,
-                                                                               double* __restrict__ J, double* __restrict__ scalars) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ double red[33];
-  __shared__ CalibClass cls_s[kJacMaxCls];
-  auto out_tile = [&](int b) { return reinterpret_cast<double*>(smem + (size_t)b * kJacTileBytes); };
-  auto pc_stage = [&](int b) { return reinterpret_cast<PoseCamR*>(smem + 2 * kJacTileBytes + (size_t)b * kJacMaxPc * sizeof(PoseCamR)); };
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * kJacTileBytes + 2 * kJacMaxPc * sizeof(PoseCamR));  // bar[0], bar[1]
-  __shared__ double cam_tinv[kJacMaxCam][3];
-  const int tid = threadIdx.x;
-  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
-  if (tid < ncls * 4) reinterpret_cast<double*>(cls_s)[tid] = reinterpret_cast<const double*>(cls)[tid];
-  if (tid < C * 3) cam_tinv[tid / 3][tid % 3] = cams[tid / 3].tinv[tid % 3];
-  __syncthreads();
-
-  auto rec_load = [&](int t, double2& uv, uint4& id) {
-    uv = make_double2(0.0, 0.0); id = make_uint4(0u, 0u, 0u, 0xffffffffu);   // flags = ~0 marks "no observation"
-    const int64_t i = (int64_t)t * kJacThreads + tid;
-    if (t < ntiles && i < n) { uv = reinterpret_cast<const double2*>(obs)[2 * i]; id = reinterpret_cast<const uint4*>(obs)[2 * i + 1]; }
-  };
-  auto pt_load = [&](const uint4& id, double* X) {
-    X[0] = X[1] = X[2] = 0.0;
-    if (id.w != 0xffffffffu) { X[0] = points[3 * (size_t)id.y]; X[1] = points[3 * (size_t)id.y + 1]; X[2] = points[3 * (size_t)id.y + 2]; }
-  };
-  auto pc_issue = [&](int t, int buf) {   // thread 0 only
-    if (t < ntiles) {
-      const uint2 tp = tile_pc[t];
-      mbar_expect_tx(&bar[buf], tp.y * (uint32_t)sizeof(PoseCamR));
-      tma_load_1d(pc_stage(buf), pcam + tp.x, tp.y * (uint32_t)sizeof(PoseCamR), &bar[buf]);
-    }
-  };
-
-  const int t0 = blockIdx.x, stride = gridDim.x;
-  double2 uv0, uv1, uv2; uint4 id0, id1, id2; double X0[3], X1[3];
-  rec_load(t0, uv0, id0);
-  rec_load(t0 + stride, uv1, id1);
-  if (tid == 0) pc_issue(t0, 0);
-  pt_load(id0, X0);
-  double cost = 0.0, fixed = 0.0;
-  uint32_t phase_bits = 0u;   // bit b = parity to wait for on bar[b]
-  int it = 0;
-  for (int t = t0; t < ntiles; t += stride, it++) {
-    const int buf = it & 1;
-    // ---- prefetch for the next two tiles
-    rec_load(t + 2 * stride, uv2, id2);
-    pt_load(id1, X1);
-    if (tid == 0) pc_issue(t + stride, buf ^ 1);
-    // ---- the output buffer was handed to a TMA store two tiles ago: make sure it has been read
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-    __syncthreads();
-    const uint2 tp = tile_pc[t];
-    mbar_wait(&bar[buf], (phase_bits >> buf) & 1u);
-    phase_bits ^= 1u << buf;
-    const int64_t i0 = (int64_t)t * kJacThreads;
-    const int nt = (int)min((int64_t)kJacThreads, n - i0);
-    if (id0.w != 0xffffffffu) {
-      const CalibClass cc = cls_s[id0.z];
-      const uint32_t camidx = (id0.w >> 8) & 0xffu;
-      const uint32_t pci = id0.x * (uint32_t)C + camidx;
-      const uint32_t rel = pci - tp.x;
-      const PoseCamR* pcr = rel < tp.y ? &pc_stage(buf)[rel] : &pcam[pci];
-      double r[2], Jp[12], Jl[6];
-      reproj_residual_jacobian_compact(pcr, cam_tinv[camidx], X0, uv0.x, uv0.y, cc.mx, cc.my, r, Jp, Jl);
-      const double s = r[0] * r[0] + r[1] * r[1];
-      double sc = 1.0, c = 0.5 * s;
-      if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
-      if ((id0.w & 3u) == 3u) fixed += c; else cost += c;
-      double2* out = reinterpret_cast<double2*>(out_tile(buf) + (size_t)tid * kChunk);
-      double2 pc10[10];
-#pragma unroll
-      for (int a = 0; a < 6; a++) pc10[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
-#pragma unroll
-      for (int a = 0; a < 3; a++) pc10[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
-      pc10[9] = make_double2(sc * r[0], sc * r[1]);
-      // A thread's chunk is 160 B = 40 banks: the 8 lanes of one store phase would collide pairwise.  Lanes with an odd
-      // (lane >> 2) therefore write their ten 16-byte pieces rotated by one, which makes every phase conflict-free.
-      if (ROT && ((tid >> 2) & 1)) {
-#pragma unroll
-        for (int a = 0; a < 10; a++) out[(a + 1) % 10] = pc10[(a + 1) % 10];
-      } else {
-#pragma unroll
-        for (int a = 0; a < 10; a++) out[a] = pc10[a];
-      }
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) tma_store_1d(J + (size_t)i0 * kChunk, out_tile(buf), (uint32_t)nt * kChunk * 8);
-    // ---- rotate the pipeline registers
-    uv0 = uv1; id0 = id1; X0[0] = X1[0]; X0[1] = X1[1]; X0[2] = X1[2];
-    uv1 = uv2; id1 = id2;
-  }
-  if (tid == 0) tma_store_wait_read();
-  cost = block_sum_all<kJacThreads>(cost, red);
-  fixed = block_sum_all<kJacThreads>(fixed, red);
-  if (tid == 0) {
-    if (cost != 0.0) atomicAdd(&scalars[SC_COST], cost);
-    if (fixed != 0.0) atomicAdd(&scalars[SC_FIXED], fixed);
-  }
-}
 
 // Residual-only evaluation at the candidate point (cost only; nothing is stored).
 __global__ void __launch_bounds__(kJacThreads) reproj_cost_kernel(const ObsRec* __restrict__ obs, int64_t n,
@@ -768,502 +561,9 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
 }
 
 
-// ------------------------------------------------------------------------------------------ points: batched elimination
-// Owner-computes Schur elimination of points.  A CTA takes a batch of consecutive points (they are ordered by
-// first-observing keyframe, so the batch touches a narrow window of <= 64 poses) and every thread OWNS one 6x6
-// block of the reduced matrix for the whole batch: the per-point products Z_a W_b^T are accumulated in registers
-// and flushed with one set of atomics per batch instead of one per point (40x fewer global atomics).
-//   phase 1 (a warp per point, 16 points per pass): H_ll, g_l by warp-shuffle reduction, damping, 3x3 inverse,
-//            W = sum Jp^T Jl and Z = W Hinv per merged pose slot, staged in shared memory;
-//   phase 2 (a thread per block pair): for every staged point that observes both poses of the pair, acc += Z_a W_b^T.
-struct BatchArgs {
-  const uint32_t* first; const uint32_t* count; const int32_t* win_f; const uint32_t* nwin; const uint64_t* mask;
-  const uint32_t* pair_ptr; const uint32_t* pair_info; const uint32_t* pair_blk;
-};
-constexpr int kBatchThreads = 256;
-constexpr int kSubPts = kBatchThreads / 32;   // 16 points per pass
-constexpr int kStageSlots = 16;
-constexpr int kSlotStride = 37;               // 36 doubles (Z 6x3, W 6x3) + 1 pad: conflict-free across slots
-constexpr int kPtStride = kStageSlots * kSlotStride;
-
-// USE_MMA = true: phase 2 runs on the fp64 tensor-core path (mma.sync m8n8k4, SASS DMMA): warp w owns the block rows
-// wa = w (mod 8) of the window; for every staged point that observes wa it walks the point's later slots and issues
-// one DMMA per block pair, A = Z_a (6x3 in an 8x4 fragment), B = W_b^T, C = the pair's 6x6 accumulator kept in shared
-// memory (the warp is the only writer of its rows, so plain load / store, no atomics).  ~12 instructions per
-// (point, pair) instead of ~170 on the scalar path.
-constexpr int kMmaMaxWin = 20;
-constexpr int kMmaMaxPairs = kMmaMaxWin * (kMmaMaxWin + 1) / 2;
+// fp64 tensor-core product D (8x8) += A (8x4) B (4x8): lane holds A[lane/4][lane%4], B[lane%4][lane/4], D[lane/4][2 (lane%4) + {0,1}]
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-
-template <bool USE_MMA>
-__global__ void __launch_bounds__(kBatchThreads, 2) schur_points_batched_kernel(EArgs A, BatchArgs B, LMParams lm,
-                                                                              double* __restrict__ S_upper,
-                                                                              double* __restrict__ b_schur,
-                                                                              double* __restrict__ scalars) {
-  extern __shared__ double stage[];          // [kSubPts][kStageSlots][kSlotStride] (+ [kMmaMaxPairs][36] accumulators)
-  double* accs = stage + kSubPts * kPtStride;
-  __shared__ unsigned long long s_mask[kSubPts];
-  __shared__ double s_g[kSubPts][3];
-  __shared__ double s_gmax[kSubPts];
-  __shared__ unsigned char s_wb[kSubPts][kStageSlots];   // window index of each staged slot
-  const int batch = blockIdx.x;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t p_first = B.first[batch], np = B.count[batch];
-  const uint32_t pr0 = B.pair_ptr[batch];
-  const int npairs = (int)(B.pair_ptr[batch + 1] - pr0);
-  const int nwin = (int)B.nwin[batch];
-  int wa = 0, wb = 0;
-  const bool own_pair = (int)threadIdx.x < npairs;
-  if (own_pair) { const uint32_t info = B.pair_info[pr0 + threadIdx.x]; wa = info & 0xff; wb = (info >> 8) & 0xff; }
-  const bool own_b = (int)threadIdx.x < nwin * 6;
-  const int bw = threadIdx.x / 6, brow = threadIdx.x - 6 * bw;
-  double acc[USE_MMA ? 1 : 36];
-#pragma unroll
-  for (int a = 0; a < (USE_MMA ? 1 : 36); a++) acc[a] = 0.0;
-  double bacc = 0.0, gmax = 0.0;
-  if (USE_MMA) {
-    for (int t = threadIdx.x; t < kMmaMaxPairs * 36; t += kBatchThreads) accs[t] = 0.0;
-    // (the first __syncthreads of the pass loop orders this before any accumulation)
-  }
-
-  for (uint32_t s0 = 0; s0 < np; s0 += kSubPts) {
-    // ---------------- phase 1: warp `wib` handles point p_first + s0 + wib, lane = observation (<= 32 per point).
-    // All global loads are issued up front (index entries, then the whole 160-byte chunk of the lane's observation);
-    // observations of the same keyframe (stereo) are merged with warp shuffles, so there is no dependent reload.
-    {
-      const uint32_t pi = s0 + wib;
-      unsigned long long mk = 0ull;
-      double g[3] = {0.0, 0.0, 0.0};
-      if (pi < np) {
-        const int e = (int)(p_first + pi);
-        const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
-        if (!A.cst[e] && b1 > b0) {
-          const uint32_t q = b0 + lane;
-          const bool have = q < b1;
-          uint16_t sl = 0xFFFF;
-          double jp[12], jl[6], r0 = 0.0, r1 = 0.0;
-#pragma unroll
-          for (int a = 0; a < 12; a++) jp[a] = 0.0;
-#pragma unroll
-          for (int a = 0; a < 6; a++) jl[a] = 0.0;
-          if (have) {
-            sl = A.slot[q];
-            const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)A.pos[q] * kChunk);
-#pragma unroll
-            for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
-#pragma unroll
-            for (int a = 0; a < 3; a++) { const double2 v = ch[6 + a]; jl[2 * a] = v.x; jl[2 * a + 1] = v.y; }
-            const double2 rv = ch[9]; r0 = rv.x; r1 = rv.y;
-          }
-          const unsigned long long my_mask = B.mask[e];
-          double s[3];
-          if (!lm.compute_scale) { s[0] = A.escale[(size_t)e * 3]; s[1] = A.escale[(size_t)e * 3 + 1]; s[2] = A.escale[(size_t)e * 3 + 2]; }
-          double H[6];
-          {
-            int t = 0;
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-              g[a] = jl[a] * r0 + jl[3 + a] * r1;
-#pragma unroll
-              for (int b = a; b < 3; b++) H[t++] = jl[a] * jl[b] + jl[3 + a] * jl[3 + b];
-            }
-          }
-#pragma unroll
-          for (int a = 0; a < 6; a++) H[a] = warp_sum(H[a]);
-#pragma unroll
-          for (int a = 0; a < 3; a++) g[a] = warp_sum(g[a]);
-          if (A.prior_H) {
-            const double* ph = A.prior_H + (size_t)e * 9;
-            H[0] += ph[0]; H[1] += ph[1]; H[2] += ph[2]; H[3] += ph[4]; H[4] += ph[5]; H[5] += ph[8];
-#pragma unroll
-            for (int a = 0; a < 3; a++) g[a] += A.prior_g[(size_t)e * 3 + a];
-          }
-          const double hd[3] = {H[0], H[3], H[5]};
-#pragma unroll
-          for (int a = 0; a < 3; a++) {
-            if (lm.compute_scale) s[a] = 1.0 / (1.0 + sqrt(hd[a]));
-            gmax = fmax(gmax, fabs(g[a]));
-          }
-          double Hs[9], hinv[9];
-          Hs[0] = s[0] * H[0] * s[0]; Hs[1] = Hs[3] = s[0] * H[1] * s[1]; Hs[2] = Hs[6] = s[0] * H[2] * s[2];
-          Hs[4] = s[1] * H[3] * s[1]; Hs[5] = Hs[7] = s[1] * H[4] * s[2]; Hs[8] = s[2] * H[5] * s[2];
-#pragma unroll
-          for (int a = 0; a < 3; a++) Hs[4 * a] += fmin(fmax(Hs[4 * a], lm.min_diag), lm.max_diag) * lm.inv_radius;
-          const bool ok = spd_inverse3_cofactor(Hs, hinv);
-          // W = Jp^T Jl of the lane's observation, then merge runs of equal slot (same keyframe, several cameras)
-          double Wm[18];
-#pragma unroll
-          for (int a = 0; a < 6; a++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) Wm[3 * a + c] = jp[a] * jl[c] + jp[6 + a] * jl[3 + c];
-          const uint32_t sl_prev = __shfl_up_sync(0xffffffffu, (uint32_t)sl, 1);
-          const bool head = have && sl != 0xFFFF && (lane == 0 || sl_prev != (uint32_t)sl);
-          // run length is bounded by the number of cameras; loop until no lane has a longer run
-          for (int d = 1; d < 32; d++) {
-            const uint32_t sl_d = __shfl_down_sync(0xffffffffu, (uint32_t)sl, d);
-            const bool take = head && (lane + d < 32) && sl_d == (uint32_t)sl;
-            if (!__any_sync(0xffffffffu, take)) break;
-#pragma unroll
-            for (int a = 0; a < 18; a++) {
-              const double v = __shfl_down_sync(0xffffffffu, Wm[a], d);
-              if (take) Wm[a] += v;
-            }
-          }
-          if (!ok) {
-            if (lane == 0) atomicAdd(&scalars[SC_FAIL], 1.0);
-          } else {
-#pragma unroll
-            for (int a = 0; a < 3; a++)
-#pragma unroll
-              for (int b = 0; b < 3; b++) hinv[3 * a + b] *= s[a] * s[b];
-            if (lane == 0) {
-              if (lm.compute_scale) { A.escale[(size_t)e * 3] = s[0]; A.escale[(size_t)e * 3 + 1] = s[1]; A.escale[(size_t)e * 3 + 2] = s[2]; }
-#pragma unroll
-              for (int a = 0; a < 9; a++) A.einv[(size_t)e * 9 + a] = hinv[a];
-#pragma unroll
-              for (int a = 0; a < 3; a++) A.eg[(size_t)e * 3 + a] = g[a];
-            }
-            mk = my_mask;
-            if (head) {
-              if (USE_MMA) s_wb[wib][sl] = (unsigned char)__fns((unsigned int)my_mask, 0, (int)sl + 1);
-              double* st = stage + (size_t)wib * kPtStride + (size_t)sl * kSlotStride;
-#pragma unroll
-              for (int a = 0; a < 6; a++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                  st[3 * a + c] = Wm[3 * a] * hinv[c] + Wm[3 * a + 1] * hinv[3 + c] + Wm[3 * a + 2] * hinv[6 + c];
-                  st[18 + 3 * a + c] = Wm[3 * a + c];
-                }
-            }
-          }
-        }
-      }
-      if (lane == 0) { s_mask[wib] = mk; s_g[wib][0] = g[0]; s_g[wib][1] = g[1]; s_g[wib][2] = g[2]; }
-    }
-    __syncthreads();
-    // ---------------- phase 2: owner-computes accumulation over the staged points
-    if (USE_MMA) {
-      const int frag = 3 * (lane >> 2) + (lane & 3);                // element of a 6x3 matrix held by this lane (A and B alike)
-      const bool fvalid = (lane >> 2) < 6 && (lane & 3) < 3;
-      const int coff = 6 * (lane >> 2) + 2 * (lane & 3);            // first of the lane's two accumulator elements
-      const bool cvalid = fvalid;
-      for (int pt = 0; pt < kSubPts; pt++) {
-        const unsigned int m = (unsigned int)s_mask[pt];
-        // rows of this warp that the point observes
-        unsigned int rows = m & (0x01010101u << wib);
-        if (rows == 0u) continue;
-        const int ns = __popc(m);
-        const double* st_pt = stage + (size_t)pt * kPtStride + frag;
-        const unsigned char* wbt = s_wb[pt];
-        while (rows) {
-          const int wa_ = __ffs(rows) - 1;
-          rows &= rows - 1;
-          const int sa = __popc(m & ((1u << wa_) - 1u));
-          const double a = fvalid ? st_pt[(size_t)sa * kSlotStride] : 0.0;
-          double* Crow = accs + (size_t)(wa_ * nwin - (wa_ * (wa_ - 1)) / 2 - wa_) * 36 + coff;  // pair (wa, wb) at Crow + 36 wb
-          const double* bp = st_pt + (size_t)sa * kSlotStride + 18;
-#pragma unroll 2
-          for (int sb = sa; sb < ns; sb++, bp += kSlotStride) {
-            const double b = fvalid ? *bp : 0.0;
-            double* C = Crow + 36 * (int)wbt[sb];
-            double2 c = cvalid ? *reinterpret_cast<double2*>(C) : make_double2(0.0, 0.0);
-            dmma_m8n8k4(c.x, c.y, a, b);
-            if (cvalid) *reinterpret_cast<double2*>(C) = c;
-          }
-        }
-      }
-    } else if (own_pair) {
-#pragma unroll 1
-      for (int pt = 0; pt < kSubPts; pt++) {
-        const unsigned long long m = s_mask[pt];
-        if (((m >> wa) & (m >> wb) & 1ull) == 0ull) continue;
-        const int sa = __popcll(m & ((1ull << wa) - 1ull)), sb = __popcll(m & ((1ull << wb) - 1ull));
-        const double* Za = stage + (size_t)pt * kPtStride + (size_t)sa * kSlotStride;
-        const double* Wb = stage + (size_t)pt * kPtStride + (size_t)sb * kSlotStride + 18;
-        double wv[18];
-#pragma unroll
-        for (int a = 0; a < 18; a++) wv[a] = Wb[a];
-#pragma unroll
-        for (int a = 0; a < 6; a++) {
-          const double z0 = Za[3 * a], z1 = Za[3 * a + 1], z2 = Za[3 * a + 2];
-#pragma unroll
-          for (int c = 0; c < 6; c++) acc[6 * a + c] += z0 * wv[3 * c] + z1 * wv[3 * c + 1] + z2 * wv[3 * c + 2];
-        }
-      }
-    }
-    if (own_b) {
-#pragma unroll 1
-      for (int pt = 0; pt < kSubPts; pt++) {
-        const unsigned long long m = s_mask[pt];
-        if (((m >> bw) & 1ull) == 0ull) continue;
-        const int sa = __popcll(m & ((1ull << bw) - 1ull));
-        const double* Za = stage + (size_t)pt * kPtStride + (size_t)sa * kSlotStride + 3 * brow;
-        bacc += Za[0] * s_g[pt][0] + Za[1] * s_g[pt][1] + Za[2] * s_g[pt][2];
-      }
-    }
-    __syncthreads();
-  }
-  // ---------------- flush: one set of atomics per batch
-  if (USE_MMA) {
-    __syncwarp();
-    // (the last pass ended with __syncthreads: every warp's accumulators are visible)
-    for (int t = threadIdx.x; t < npairs * 36; t += kBatchThreads) {
-      const int pr = t / 36, el = t - 36 * pr;
-      const uint32_t info = B.pair_info[pr0 + pr];
-      const int a_ = info & 0xff, b_ = (info >> 8) & 0xff;
-      const double v = accs[(size_t)(a_ * nwin - (a_ * (a_ - 1)) / 2 + (b_ - a_)) * 36 + el];
-      if (v != 0.0) atomicAdd(&S_upper[(size_t)B.pair_blk[pr0 + pr] * 36 + el], -v);
-    }
-  } else if (own_pair) {
-    double* Sb = S_upper + (size_t)B.pair_blk[pr0 + threadIdx.x] * 36;
-#pragma unroll
-    for (int a = 0; a < 36; a++) atomicAdd(&Sb[a], -acc[a]);
-  }
-  if (own_b) {
-    const int f = B.win_f[(size_t)batch * 64 + bw];
-    if (bacc != 0.0) atomicAdd(&b_schur[6 * f + brow], -bacc);
-  }
-  gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 16));  // every lane of a warp holds the same value already
-  if (lane == 0) s_gmax[wib] = gmax;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double m = 0.0;
-    for (int i = 0; i < kSubPts; i++) m = fmax(m, s_gmax[i]);
-    atomic_max_nonneg(&scalars[SC_GMAX], m);
-  }
-}
-
-// ------------------------------------------------------------------------------------------ points: pipelined tensor-core elimination
-// Second-generation point elimination (replaces schur_points_batched_kernel<true> on the fast path).  Same
-// owner-computes idea -- a CTA takes a batch of consecutive points, warp w owns the block rows wa = w (mod 8) of the
-// batch's pose window and accumulates Z_a W_b^T with DMMA into shared-memory 6x6 accumulators -- restructured as a
-// software pipeline so that the three latencies no longer add up:
-//   * only W (6x3 per merged slot) and the point's Hinv / Hinv g are staged (Z = W Hinv is rebuilt in the A fragment),
-//     which halves the staging footprint and pays for DOUBLE BUFFERING: one block barrier per pass instead of two;
-//   * the global loads of the NEXT pass (index entries two passes ahead, the 160-byte chunk one pass ahead) are issued
-//     before the tensor-core phase of the current pass and consumed after it.
-constexpr int kPipeThreads = 256;
-constexpr int kPipePts = kPipeThreads / 32;        // points per pass (one warp each)
-constexpr int kWStride = 19;                       // 18 doubles of W + 1 pad: conflict-free across slots
-constexpr int kWPt = kStageSlots * kWStride;       // doubles per staged point
-constexpr int kPipeSmemDoubles = 2 * kPipePts * kWPt + kMmaMaxPairs * 36;
-
-struct PipePoint {   // per-lane registers of a point whose loads are in flight (lane = observation)
-  int e; uint32_t b0, b1; bool act, have; uint32_t sl; uint32_t pos;
-  double jp[12], jl[6], r0, r1;
-};
-
-__global__ void __launch_bounds__(kPipeThreads, 2) schur_points_mma_kernel(EArgs A, BatchArgs B, LMParams lm,
-                                                                            double* __restrict__ S_upper,
-                                                                            double* __restrict__ b_schur,
-                                                                            double* __restrict__ scalars) {
-  extern __shared__ double smem_d[];
-  double* stW = smem_d;                                   // [2][kPipePts][kStageSlots][kWStride]
-  double* accs = smem_d + 2 * kPipePts * kWPt;            // [kMmaMaxPairs][36]
-  __shared__ unsigned int s_mask[2][kPipePts];
-  __shared__ double s_hinv[2][kPipePts][9];
-  __shared__ double s_hg[2][kPipePts][3];
-  __shared__ unsigned char s_wb[2][kPipePts][kStageSlots];
-  __shared__ double s_b[kMmaMaxWin][6];
-  __shared__ double s_gmax[kPipePts];
-  const int batch = blockIdx.x;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t p_first = B.first[batch], np = B.count[batch];
-  const uint32_t pr0 = B.pair_ptr[batch];
-  const int npairs = (int)(B.pair_ptr[batch + 1] - pr0);
-  const int nwin = (int)B.nwin[batch];
-  const int npass = (int)((np + kPipePts - 1) / kPipePts);
-  double gmax = 0.0;
-  for (int t = threadIdx.x; t < kMmaMaxPairs * 36; t += kPipeThreads) accs[t] = 0.0;
-  if (threadIdx.x < kMmaMaxWin * 6) (&s_b[0][0])[threadIdx.x] = 0.0;
-
-  // index entries of the point this warp handles in pass `ps` (ptr -> slot / pos)
-  auto load_index = [&](int ps, PipePoint& P) {
-    const uint32_t pi = (uint32_t)ps * kPipePts + wib;
-    P.act = false; P.have = false; P.sl = 0xFFFFu; P.pos = 0; P.e = 0; P.b0 = P.b1 = 0;
-    if (ps < npass && pi < np) {
-      P.e = (int)(p_first + pi);
-      P.b0 = A.ptr[P.e]; P.b1 = A.ptr[P.e + 1];
-      P.act = !A.cst[P.e] && P.b1 > P.b0;
-      const uint32_t q = P.b0 + lane;
-      P.have = P.act && q < P.b1;
-      if (P.have) { P.sl = A.slot[q]; P.pos = A.pos[q]; }
-    }
-  };
-  auto load_chunk = [&](PipePoint& P) {
-#pragma unroll
-    for (int a = 0; a < 12; a++) P.jp[a] = 0.0;
-#pragma unroll
-    for (int a = 0; a < 6; a++) P.jl[a] = 0.0;
-    P.r0 = P.r1 = 0.0;
-    if (P.have) {
-      const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)P.pos * kChunk);
-#pragma unroll
-      for (int a = 0; a < 6; a++) { const double2 v = ch[a]; P.jp[2 * a] = v.x; P.jp[2 * a + 1] = v.y; }
-#pragma unroll
-      for (int a = 0; a < 3; a++) { const double2 v = ch[6 + a]; P.jl[2 * a] = v.x; P.jl[2 * a + 1] = v.y; }
-      const double2 rv = ch[9]; P.r0 = rv.x; P.r1 = rv.y;
-    }
-  };
-  // reductions, damping, inverse, merged W per slot -> staging buffer `buf`
-  auto finish_point = [&](const PipePoint& P, int buf) {
-    unsigned int mk = 0u;
-    if (P.act) {
-      const int e = P.e;
-      const unsigned int my_mask = (unsigned int)B.mask[e];
-      double s[3];
-      if (!lm.compute_scale) { s[0] = A.escale[(size_t)e * 3]; s[1] = A.escale[(size_t)e * 3 + 1]; s[2] = A.escale[(size_t)e * 3 + 2]; }
-      double H[6], g[3];
-      {
-        int t = 0;
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-          g[a] = P.jl[a] * P.r0 + P.jl[3 + a] * P.r1;
-#pragma unroll
-          for (int b = a; b < 3; b++) H[t++] = P.jl[a] * P.jl[b] + P.jl[3 + a] * P.jl[3 + b];
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < 6; a++) H[a] = warp_sum(H[a]);
-#pragma unroll
-      for (int a = 0; a < 3; a++) g[a] = warp_sum(g[a]);
-      if (A.prior_H) {
-        const double* ph = A.prior_H + (size_t)e * 9;
-        H[0] += ph[0]; H[1] += ph[1]; H[2] += ph[2]; H[3] += ph[4]; H[4] += ph[5]; H[5] += ph[8];
-#pragma unroll
-        for (int a = 0; a < 3; a++) g[a] += A.prior_g[(size_t)e * 3 + a];
-      }
-      const double hd[3] = {H[0], H[3], H[5]};
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        if (lm.compute_scale) s[a] = 1.0 / (1.0 + sqrt(hd[a]));
-        gmax = fmax(gmax, fabs(g[a]));
-      }
-      double Hs[9], hinv[9];
-      Hs[0] = s[0] * H[0] * s[0]; Hs[1] = Hs[3] = s[0] * H[1] * s[1]; Hs[2] = Hs[6] = s[0] * H[2] * s[2];
-      Hs[4] = s[1] * H[3] * s[1]; Hs[5] = Hs[7] = s[1] * H[4] * s[2]; Hs[8] = s[2] * H[5] * s[2];
-#pragma unroll
-      for (int a = 0; a < 3; a++) Hs[4 * a] += fmin(fmax(Hs[4 * a], lm.min_diag), lm.max_diag) * lm.inv_radius;
-      const bool ok = spd_inverse3_cofactor(Hs, hinv);
-      double Wm[18];
-#pragma unroll
-      for (int a = 0; a < 6; a++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) Wm[3 * a + c] = P.jp[a] * P.jl[c] + P.jp[6 + a] * P.jl[3 + c];
-      const uint32_t sl = P.sl;
-      const uint32_t sl_prev = __shfl_up_sync(0xffffffffu, sl, 1);
-      const bool head = P.have && sl != 0xFFFFu && (lane == 0 || sl_prev != sl);
-      for (int d = 1; d < 32; d++) {   // merge the observations of one keyframe (stereo: one trip)
-        const uint32_t sl_d = __shfl_down_sync(0xffffffffu, sl, d);
-        const bool take = head && (lane + d < 32) && sl_d == sl;
-        if (!__any_sync(0xffffffffu, take)) break;
-#pragma unroll
-        for (int a = 0; a < 18; a++) {
-          const double v = __shfl_down_sync(0xffffffffu, Wm[a], d);
-          if (take) Wm[a] += v;
-        }
-      }
-      if (!ok) {
-        if (lane == 0) atomicAdd(&scalars[SC_FAIL], 1.0);
-      } else {
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-          for (int b = 0; b < 3; b++) hinv[3 * a + b] *= s[a] * s[b];
-        if (lane == 0) {
-          if (lm.compute_scale) { A.escale[(size_t)e * 3] = s[0]; A.escale[(size_t)e * 3 + 1] = s[1]; A.escale[(size_t)e * 3 + 2] = s[2]; }
-#pragma unroll
-          for (int a = 0; a < 9; a++) { A.einv[(size_t)e * 9 + a] = hinv[a]; s_hinv[buf][wib][a] = hinv[a]; }
-#pragma unroll
-          for (int a = 0; a < 3; a++) {
-            A.eg[(size_t)e * 3 + a] = g[a];
-            s_hg[buf][wib][a] = hinv[3 * a] * g[0] + hinv[3 * a + 1] * g[1] + hinv[3 * a + 2] * g[2];
-          }
-        }
-        mk = my_mask;
-        if (head) {
-          s_wb[buf][wib][sl] = (unsigned char)__fns(my_mask, 0, (int)sl + 1);
-          double* st = stW + ((size_t)(buf * kPipePts + wib) * kStageSlots + sl) * kWStride;
-#pragma unroll
-          for (int a = 0; a < 18; a++) st[a] = Wm[a];
-        }
-      }
-    }
-    if (lane == 0) s_mask[buf][wib] = mk;
-  };
-  // tensor-core accumulation over the points staged in `buf`
-  const int frow = lane >> 2, fk = lane & 3;
-  const bool fvalid = frow < 6 && fk < 3;
-  const int coff = 6 * frow + 2 * fk;
-  auto accumulate = [&](int buf) {
-    for (int pt = 0; pt < kPipePts; pt++) {
-      const unsigned int m = s_mask[buf][pt];
-      unsigned int rows = m & (0x01010101u << wib);
-      if (rows == 0u) continue;
-      const int ns = __popc(m);
-      const double* Wp = stW + (size_t)(buf * kPipePts + pt) * kWPt;
-      const unsigned char* wbt = s_wb[buf][pt];
-      // column fk of Hinv (for the A fragment) and Hinv g
-      const double h0 = fvalid ? s_hinv[buf][pt][fk] : 0.0, h1 = fvalid ? s_hinv[buf][pt][3 + fk] : 0.0, h2 = fvalid ? s_hinv[buf][pt][6 + fk] : 0.0;
-      const double hg0 = s_hg[buf][pt][0], hg1 = s_hg[buf][pt][1], hg2 = s_hg[buf][pt][2];
-      while (rows) {
-        const int wa_ = __ffs(rows) - 1;
-        rows &= rows - 1;
-        const int sa = __popc(m & ((1u << wa_) - 1u));
-        const double* Wa = Wp + (size_t)sa * kWStride;
-        double a = 0.0;
-        if (fvalid) a = Wa[3 * frow] * h0 + Wa[3 * frow + 1] * h1 + Wa[3 * frow + 2] * h2;   // (W_a Hinv)[frow][fk]
-        if (lane < 6) s_b[wa_][lane] += Wa[3 * lane] * hg0 + Wa[3 * lane + 1] * hg1 + Wa[3 * lane + 2] * hg2;
-        double* Crow = accs + (size_t)(wa_ * nwin - (wa_ * (wa_ - 1)) / 2 - wa_) * 36 + coff;
-        const double* bp = Wa + 3 * frow + fk;
-#pragma unroll 2
-        for (int sb = sa; sb < ns; sb++, bp += kWStride) {
-          const double b = fvalid ? *bp : 0.0;
-          double* C = Crow + 36 * (int)wbt[sb];
-          double2 c = fvalid ? *reinterpret_cast<double2*>(C) : make_double2(0.0, 0.0);
-          dmma_m8n8k4(c.x, c.y, a, b);
-          if (fvalid) *reinterpret_cast<double2*>(C) = c;
-        }
-      }
-    }
-  };
-
-  PipePoint cur, nxt;
-  load_index(0, cur);
-  load_chunk(cur);
-  load_index(1, nxt);
-  finish_point(cur, 0);
-  __syncthreads();
-  for (int ps = 0; ps < npass; ps++) {
-    cur = nxt;
-    load_chunk(cur);            // chunk of pass ps + 1: in flight during the tensor-core phase
-    load_index(ps + 2, nxt);    // index entries of pass ps + 2
-    accumulate(ps & 1);
-    if (ps + 1 < npass) finish_point(cur, (ps + 1) & 1);
-    __syncthreads();
-  }
-  // ---------------- flush: one set of atomics per batch
-  for (int t = threadIdx.x; t < npairs * 36; t += kPipeThreads) {
-    const int pr = t / 36, el = t - 36 * pr;
-    const uint32_t info = B.pair_info[pr0 + pr];
-    const int a_ = info & 0xff, b_ = (info >> 8) & 0xff;
-    const double v = accs[(size_t)(a_ * nwin - (a_ * (a_ - 1)) / 2 + (b_ - a_)) * 36 + el];
-    if (v != 0.0) atomicAdd(&S_upper[(size_t)B.pair_blk[pr0 + pr] * 36 + el], -v);
-  }
-  if ((int)threadIdx.x < nwin * 6) {
-    const int bw = threadIdx.x / 6, brow = threadIdx.x - 6 * bw;
-    const double v = s_b[bw][brow];
-    if (v != 0.0) atomicAdd(&b_schur[6 * B.win_f[(size_t)batch * 64 + bw] + brow], -v);
-  }
-  if (lane == 0) s_gmax[wib] = gmax;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double mx = 0.0;
-    for (int i = 0; i < kPipePts; i++) mx = fmax(mx, s_gmax[i]);
-    atomic_max_nonneg(&scalars[SC_GMAX], mx);
-  }
 }
 
 // ------------------------------------------------------------------------------------------ points: row-owner elimination

@@ -92,18 +92,6 @@ struct Structure {
     std::vector<uint32_t> slot_ptr;  // ne+1
     int max_slots = 0;
   } pts, objs;
-  // batches of consecutive points for the owner-computes Schur kernel (see schur_points_batched_kernel)
-  bool want_batches = false;
-  struct PointBatches {
-    std::vector<uint32_t> first, count;     // per batch: first point, number of points
-    std::vector<int32_t> win_f;             // 64 per batch: f index of each window pose, ascending, -1 padded
-    std::vector<uint32_t> nwin;             // per batch
-    std::vector<uint64_t> mask;             // per point: window poses it observes (bit = window index)
-    std::vector<uint32_t> pair_ptr;         // per batch + 1
-    std::vector<uint32_t> pair_info;        // wa | wb << 8  (f[wa] <= f[wb])
-    std::vector<uint32_t> pair_blk;         // S_upper block of the pair
-    std::vector<uint32_t> fallback;         // points handled by the generic per-e-block kernel instead
-  } pbatch;
   // Row-owner point elimination (point_prep_kernel + schur_rows_kernel).  A point is "regular" when its variable poses
   // span fewer than kRowSpan consecutive f indices; every other point goes to the generic per-e-block kernel.
   //   groups : per point, one record per run of observations taken from the same pose (stereo pair = one group)
@@ -204,7 +192,7 @@ inline void count_reduced(const Problem& pb, Structure& S) {
 inline bool build_structure(const Problem& pb, Structure& S, int rank, int world, std::string& err) {
   const bool tm_on = getenv("OBVI_BUILD_TIMING") != nullptr;
   auto tm_t0 = std::chrono::steady_clock::now();
-  { const bool wb = S.want_batches; S = Structure(); S.want_batches = wb; }
+  S = Structure();
   const int nb = (int)pb.blocks.size();
   std::vector<int32_t> pose_of_block(nb, -1), point_of_block(nb, -1), obj_of_block(nb, -1);
   std::vector<uint8_t> used(nb, 0);
@@ -464,54 +452,6 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
       const std::vector<uint8_t>& cst = (L == &S.pts) ? S.point_const : S.obj_const;
       for (int a = 0; a < ns; a++) for (int b = a; b < ns; b++) L->pair_blk[w++] = cst[e] ? 0u : blk_of(sf[a], sf[b]);
     }
-  }
-  OBVI_TMARK("5");
-  // ---- point batches: consecutive points (first-observing-keyframe order) whose poses fit a 64-wide window
-  //      (only the batched kernels use them; the default row-owner path skips this pass)
-  if (S.want_batches) {
-    constexpr int kMaxPts = 128, kMaxWin = 20, kMaxPairs = 256, kMaxSlots = 16;  // kMaxWin: window of the tensor-core path (u32 masks, 210 pair accumulators)
-    Structure::PointBatches& B = S.pbatch;
-    B.mask.assign(S.P, 0); B.pair_ptr.push_back(0);
-    std::vector<int32_t> win; std::vector<uint32_t> members;
-    auto close_batch = [&]() {
-      if (members.empty()) return;
-      std::sort(win.begin(), win.end());
-      uint64_t pm[kMaxWin];
-      for (int a = 0; a < kMaxWin; a++) pm[a] = 0;
-      for (uint32_t e : members) {
-        const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]]; const int ns = S.pts.nslots[e];
-        uint64_t m = 0; int wi[kMaxSlots];
-        for (int a = 0; a < ns; a++) { wi[a] = (int)(std::lower_bound(win.begin(), win.end(), sf[a]) - win.begin()); m |= 1ull << wi[a]; }
-        B.mask[e] = m;
-        for (int a = 0; a < ns; a++) for (int b = a; b < ns; b++) pm[wi[a]] |= 1ull << wi[b];
-      }
-      B.first.push_back(members.front()); B.count.push_back((uint32_t)(members.back() - members.front() + 1));
-      B.nwin.push_back((uint32_t)win.size());
-      for (int a = 0; a < 64; a++) B.win_f.push_back(a < (int)win.size() ? win[a] : -1);  // fixed stride of 64 per batch
-      for (int a = 0; a < (int)win.size(); a++) for (int b = a; b < (int)win.size(); b++) if ((pm[a] >> b) & 1) {
-        B.pair_info.push_back((uint32_t)a | ((uint32_t)b << 8)); B.pair_blk.push_back(blk_of(win[a], win[b]));
-      }
-      B.pair_ptr.push_back((uint32_t)B.pair_info.size());
-      win.clear(); members.clear();
-    };
-    uint64_t cur_pairs = 0;  // upper bound on the batch's distinct pairs (sum over points; exact count is <=)
-    for (int e = 0; e < S.P; e++) {
-      if (S.point_const[e] || S.pts.ptr[e] == S.pts.ptr[e + 1]) { continue; }
-      const int ns = S.pts.nslots[e];
-      if (ns > kMaxSlots || S.pts.ptr[e + 1] - S.pts.ptr[e] > 32) { close_batch(); cur_pairs = 0; B.fallback.push_back((uint32_t)e); continue; }
-      const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]];
-      int add = 0;
-      for (int a = 0; a < ns; a++) if (std::find(win.begin(), win.end(), sf[a]) == win.end()) add++;
-      // points in between that were skipped (constant / empty) keep their mask 0 and are ignored by the kernel,
-      // but a batch must be a contiguous point range
-      const size_t wnew = win.size() + add;
-      if (!members.empty() && ((int)members.size() >= kMaxPts || (int)(e - members.front() + 1) > kMaxPts || wnew > kMaxWin ||
-                               wnew * (wnew + 1) / 2 > kMaxPairs)) { close_batch(); cur_pairs = 0; }
-      for (int a = 0; a < ns; a++) if (std::find(win.begin(), win.end(), sf[a]) == win.end()) win.push_back(sf[a]);
-      members.push_back((uint32_t)e);
-    }
-    close_batch();
-    (void)cur_pairs;
   }
   OBVI_TMARK("6");
   // ---- row-owner structure.  Slots are DENSE per point: one record for every f index between the point's first and

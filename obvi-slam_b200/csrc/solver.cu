@@ -149,20 +149,11 @@ struct Solver {
   DBuf<int32_t> f_of_pose, pose_of_f;
   DBuf<uint8_t> pose_skip, point_skip, obj_skip;
   DBuf<uint2> jac_tile;  // per 256-observation tile: first pose/camera entry, entries staged by TMA
-  bool use_tma_jac = true;
-  bool jac_rot = false;
-  int jac_mode = 1;  // 0 plain, 1 TMA per tile (default), 2 persistent + pipelined + compact entries (measured slower: 170 vs 128 us at C3)
+  int jac_mode = 1;  // 1: TMA-staged tile kernel (default), 0: plain loads / stores (OBVI_JAC=plain)
   DBuf<BBoxRec> bbox;
   DBuf<UnaryRec> unary;
   DBuf<RelRec> rel;
   EListDev pts, objs;
-  // point batches (schur_points_batched_kernel)
-  DBuf<uint32_t> pb_first, pb_count, pb_nwin, pb_pair_ptr, pb_pair_info, pb_pair_blk, pb_fallback;
-  DBuf<int32_t> pb_win_f;
-  DBuf<uint64_t> pb_mask;
-  int n_batches = 0, n_fallback = 0;
-  bool use_mma_schur = true;
-  int schur_mode = 3;  // 3: row-owner kernels (default), 2: pipelined batched tensor-core kernel, 1: two-barrier one, 0: scalar
   // row-owner point elimination (point_prep_kernel + schur_rows_kernel)
   DBuf<uint32_t> pr_grp_ptr, pr_rowblk, pr_fallback;
   DBuf<Structure::RowGroup> pr_grp;
@@ -182,7 +173,6 @@ struct Solver {
   DBuf<double> poses[3], points[3], objects[3];  // cur, cand, best
   int cur = 0;
   DBuf<PoseCam> pcam, pcam_cand;
-  DBuf<PoseCamR> pcam_r;  // compact entries for the persistent Jacobian kernel
   DBuf<double> J, Jb;
   DBuf<UnaryOut> unary_out;
   DBuf<RelOut> rel_out;
@@ -247,10 +237,6 @@ struct Solver {
     CUDA_OK(cudaMallocHost((void**)&h_scalars, SC_COUNT * sizeof(double)));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_blocks_per_sm, pcg_kernel, kPcgThreads, 0));
     if (pcg_blocks_per_sm < 1) throw std::runtime_error("pcg_kernel cannot be made resident");
-    CUDA_OK(cudaFuncSetAttribute(schur_points_batched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubPts * kPtStride * 8));
-    CUDA_OK(cudaFuncSetAttribute(schur_points_batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kSubPts * kPtStride + kMmaMaxPairs * 36) * 8));
-    if (const char* e = getenv("OBVI_SCHUR")) { const std::string v(e); use_mma_schur = v != "scalar"; schur_mode = v == "scalar" ? 0 : (v == "mma1" ? 1 : (v == "mma" ? 2 : 3)); }
-    CUDA_OK(cudaFuncSetAttribute(schur_points_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmemDoubles * 8));
     CUDA_OK(cudaFuncSetAttribute(bt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBB * 8));
     CUDA_OK(cudaFuncSetAttribute(bt_gemm_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_bt_blocks_per_sm, pcg_bt_kernel, kPcgThreads, 0));
@@ -262,13 +248,7 @@ struct Solver {
     if (const char* e = getenv("OBVI_PCG")) pcg_resident = std::string(e) != "grid";
     CUDA_OK(cudaFuncSetAttribute(pcg_bt_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentSmem));
     if (const char* e = getenv("OBVI_PROFILE")) prof.on = std::string(e) == "1";
-    if (const char* e = getenv("OBVI_JAC")) { const std::string v(e); jac_mode = v == "plain" ? 0 : (v == "persistent" ? 2 : (v == "tma2" ? 3 : (v == "tma2rot" ? 4 : (v == "tma2stg" ? 5 : 1)))); use_tma_jac = jac_mode > 0; }
-    CUDA_OK(cudaFuncSetAttribute(reproj_jac_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacPersistSmem));
-    CUDA_OK(cudaFuncSetAttribute(reproj_jac_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacPersistSmem));
-    if (const char* e = getenv("OBVI_JAC_ROT")) jac_rot = std::string(e) == "1";
-    CUDA_OK(cudaFuncSetAttribute(reproj_jac_tma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes2));
-    CUDA_OK(cudaFuncSetAttribute(reproj_jac_tma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes2));
-    CUDA_OK((cudaFuncSetAttribute(reproj_jac_tma2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes2)));
+    if (const char* e = getenv("OBVI_JAC")) jac_mode = std::string(e) == "plain" ? 0 : 1;
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes));
   }
 
@@ -308,18 +288,11 @@ struct Solver {
     upload_elist(pts, S.pts, S.point_const, 3, 16);
     upload_elist(objs, S.objs, S.obj_const, 7, 64);
     {
-      const Structure::PointBatches& B = S.pbatch;
-      n_batches = (int)B.first.size(); n_fallback = (int)B.fallback.size();
-      pb_first.upload(B.first, stream); pb_count.upload(B.count, stream); pb_nwin.upload(B.nwin, stream); pb_win_f.upload(B.win_f, stream);
-      pb_mask.upload(B.mask, stream); pb_pair_ptr.upload(B.pair_ptr, stream); pb_pair_info.upload(B.pair_info, stream);
-      pb_pair_blk.upload(B.pair_blk, stream); pb_fallback.upload(B.fallback, stream);
-    }
-    {
       const Structure::PointRows& R = S.prow;
       n_row_items = (int)R.items.size(); n_row_fallback = (int)R.fallback.size();
       pr_grp_ptr.upload(R.grp_ptr, stream); pr_grp.upload(R.grp, stream); pr_grp_f.upload(R.grp_f, stream); pr_regular.upload(R.regular, stream);
       pr_ent.upload(R.ent, stream); pr_items.upload(R.items, stream); pr_rowblk.upload(R.rowblk, stream); pr_fallback.upload(R.fallback, stream);
-      if (schur_mode == 3) { WZ.alloc((size_t)std::max<int64_t>(R.n_slots, 1) * kWZ); WZ.zero(stream); }  // gap slots stay zero
+      WZ.alloc((size_t)std::max<int64_t>(R.n_slots, 1) * kWZ); WZ.zero(stream);   // gap slots stay zero
     }
     inv_rp.assign(pb.reproj.size(), 0xFFFFFFFFu); inv_bb.assign(pb.bbox.size(), 0xFFFFFFFFu);
     for (int64_t q = 0; q < S.n_obs; q++) inv_rp[S.obs_user[q]] = (uint32_t)q;
@@ -336,7 +309,7 @@ struct Solver {
     for (int i = 0; i < S.O; i++) ob[i] = S.obj_const[i] || !owns_object(i);
     pose_skip.upload(ps, stream); point_skip.upload(pt, stream); obj_skip.upload(ob, stream);
     for (int b = 0; b < 3; b++) { poses[b].alloc((size_t)S.K * 6); points[b].alloc((size_t)S.P * 3); objects[b].alloc((size_t)S.O * 7); }
-    pcam.alloc((size_t)S.K * std::max(S.C, 1)); pcam_cand.alloc((size_t)S.K * std::max(S.C, 1)); pcam_r.alloc((size_t)S.K * std::max(S.C, 1));
+    pcam.alloc((size_t)S.K * std::max(S.C, 1)); pcam_cand.alloc((size_t)S.K * std::max(S.C, 1));
     J.alloc((size_t)S.n_obs * kChunk); Jb.alloc((size_t)S.n_bbox * kBBoxChunk);
     unary_out.alloc(S.n_unary); rel_out.alloc(S.n_rel);
     const size_t nf6 = (size_t)S.nf * 6;
@@ -492,7 +465,7 @@ struct Solver {
     const Structure& S = st;
     const size_t pt0 = prof.begin(stream);
     zero_scalars(SC_COST, 3);
-    if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p, pcam_r.p); launches++; }
+    if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p); launches++; }
     fork();
     prof.end("lin: pose_cam", pt0, stream);
     CUDA_OK(cudaStreamWaitEvent(s3, ev_fork, 0));
@@ -515,16 +488,7 @@ struct Solver {
     const Structure& S = st;
     const bool tma_ok = (int)S.classes.size() <= kJacMaxCls && S.C <= 256;
     const int ntiles = nblk(S.n_obs, kJacThreads);
-    const bool any_masked = n_masked_rp > 0;   // only the plain and the default TMA kernel honour the mask bit
-    if (jac_mode == 2 && tma_ok && S.C <= kJacMaxCam && !any_masked) {
-      const int grid = std::min(ntiles, 2 * num_sms);
-      if (jac_rot) reproj_jac_persistent_kernel<true><<<grid, kJacThreads, kJacPersistSmem, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, ntiles, J.p, scalars.p);
-      else reproj_jac_persistent_kernel<false><<<grid, kJacThreads, kJacPersistSmem, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, ntiles, J.p, scalars.p);
-    } else if (jac_mode >= 3 && tma_ok && S.C <= 16 && !any_masked) {
-      if (jac_mode == 5) reproj_jac_tma2_kernel<false, 1><<<ntiles, kJacThreads, kJacSmemBytes2, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
-      else if (jac_mode == 4) reproj_jac_tma2_kernel<true><<<ntiles, kJacThreads, kJacSmemBytes2, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
-      else reproj_jac_tma2_kernel<false><<<ntiles, kJacThreads, kJacSmemBytes2, stream>>>(obs.p, S.n_obs, pcam_r.p, cams.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
-    } else if (jac_mode >= 1 && tma_ok) {
+    if (jac_mode >= 1 && tma_ok) {
       reproj_jac_tma_kernel<<<ntiles, kJacThreads, kJacSmemBytes, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
     } else {
       reproj_jac_kernel<<<ntiles, kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, pts_dev, apply_loss, J.p, scalars.p);
@@ -559,7 +523,7 @@ struct Solver {
     prof.end("zero", pt0, stream); pt0 = prof.begin(stream);
     if (S.n_obs && S.nf) { pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag); launches++; }
     prof.end("pose_accum", pt0, stream); pt0 = prof.begin(stream);
-    if (schur_mode == 3) {
+    {
       if (S.P && lanes_per_point == 8) { point_prep_kernel<8><<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
       else if (S.P) { point_prep_kernel<16><<<nblk(S.P, 16), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
       prof.end("point_prep", pt0, stream); pt0 = prof.begin(stream);
@@ -569,18 +533,6 @@ struct Solver {
         schur_eblock_kernel<3, 2, 32, 16, false><<<n_row_fallback, 32, 0, stream>>>(a, lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p);
         launches++;
       }
-    } else if (n_batches) {
-      BatchArgs B; B.first = pb_first.p; B.count = pb_count.p; B.win_f = pb_win_f.p; B.nwin = pb_nwin.p; B.mask = pb_mask.p;
-      B.pair_ptr = pb_pair_ptr.p; B.pair_info = pb_pair_info.p; B.pair_blk = pb_pair_blk.p;
-      if (schur_mode == 2) schur_points_mma_kernel<<<n_batches, kPipeThreads, kPipeSmemDoubles * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
-      else if (use_mma_schur) schur_points_batched_kernel<true><<<n_batches, kBatchThreads, (kSubPts * kPtStride + kMmaMaxPairs * 36) * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
-      else schur_points_batched_kernel<false><<<n_batches, kBatchThreads, kSubPts * kPtStride * 8, stream>>>(eargs(pts, J.p), B, lm, S_upper, b_schur, scalars.p);
-      launches++;
-    }
-    if (schur_mode != 3 && n_fallback) {
-      EArgs a = eargs(pts, J.p); a.elist = pb_fallback.p;
-      schur_eblock_kernel<3, 2, 32, 16, false><<<n_fallback, 32, 0, stream>>>(a, lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p);
-      launches++;
     }
     prof.end("schur_points", pt0, stream); pt0 = prof.begin(stream);
     join();
@@ -642,7 +594,7 @@ struct Solver {
     zero_scalars(SC_MODEL, 2);
     if (S.nf) { pose_step_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(S.nf, pose_of_f.p, pscale.p, y.p, poses[cur].p, poses[cand].p, dpose.p, rank == 0, scalars.p); launches++; }
     fork();
-    if (S.P && schur_mode == 3) {
+    if (S.P) {
       if (lanes_per_point == 8) backsub_rows_kernel<8><<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_grp_f.p, pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
       else backsub_rows_kernel<16><<<nblk(S.P, 16), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_grp_f.p, pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
       launches++;
@@ -651,7 +603,7 @@ struct Solver {
         backsub_points_kernel<<<nblk(n_row_fallback, 4), 128, 0, stream>>>(a, n_row_fallback, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
         launches++;
       }
-    } else if (S.P) { backsub_points_kernel<<<nblk(S.P, 4), 128, 0, stream>>>(eargs(pts, J.p), S.P, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p); launches++; }
+    }
     if (S.O) { backsub_eblock_kernel<7, 4, 128><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), dpose.p, objects[cur].p, objects[cand].p, objs.delta.p, scalars.p); launches++; }
     if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 2, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
     join();
@@ -743,7 +695,6 @@ struct Solver {
     const auto t0 = std::chrono::steady_clock::now();
     if (pb.dirty || !uploaded) {
       std::string err;
-      st.want_batches = schur_mode != 3;
       if (!build_structure(pb, st, rank, world, err)) throw std::runtime_error(err);
       upload_structure();
       structure_builds++;
@@ -1614,7 +1565,7 @@ int obvi_profile_jacobian(obvi_problem* p, int reps, double* sec, int64_t* bytes
   s.gather_params();
   const Structure& S = s.st;
   if (!S.n_obs) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "no reprojection observations");
-  pose_cam_kernel<<<Solver::nblk((int64_t)S.K * S.C, 128), 128, 0, s.stream>>>(s.poses[0].p, S.K, s.cams.p, S.C, 1, s.pcam.p, s.pcam_r.p);
+  pose_cam_kernel<<<Solver::nblk((int64_t)S.K * S.C, 128), 128, 0, s.stream>>>(s.poses[0].p, S.K, s.cams.p, S.C, 1, s.pcam.p);
   auto launch = [&]() { s.launch_jacobian(1, s.points[0].p); };
   for (int i = 0; i < 3; i++) launch();
   CUDA_OK(cudaEventRecord(s.ev[0], s.stream));
@@ -1643,14 +1594,13 @@ int obvi_debug_partition(obvi_problem* p, int rank, int world, int64_t* stats) {
   if (!p || !stats || world < 1 || rank < 0 || rank >= world) return OBVI_ERR_INVALID_ARGUMENT;
   try {
     Structure S;
-    S.want_batches = true;
     std::string err;
     if (!build_structure(p->s.pb, S, rank, world, err)) return fail(p, OBVI_ERR_INVALID_ARGUMENT, err.c_str());
     int64_t np = 0, no = 0, ck = 0;
     for (int i = 0; i < S.P; i++) np += S.pts.ptr[i + 1] > S.pts.ptr[i];
     for (int i = 0; i < S.O; i++) no += S.objs.ptr[i + 1] > S.objs.ptr[i];
     for (uint32_t c : S.sf_col) ck += c;
-    const int64_t v[12] = {S.n_obs, S.n_bbox, S.n_unary, S.n_rel, S.nf, S.n_upper, np, no, (int64_t)S.pbatch.first.size(), ck,
+    const int64_t v[12] = {S.n_obs, S.n_bbox, S.n_unary, S.n_rel, S.nf, S.n_upper, np, no, (int64_t)S.prow.items.size(), ck,
                            S.num_params_reduced, S.num_residual_blocks_reduced};
     std::memcpy(stats, v, sizeof(v));
     return OBVI_OK;
