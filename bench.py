@@ -26,7 +26,7 @@ UNIT = "LM it/s"
 WORKLOAD = dict(workload="C3: 2000 keyframes / 200k points / 500 objects, full residual set (reproj + bbox + shape-prior + rel-pose)",
                 generator="obvi-slam_b200/synth.py make_config('C3', seed=0)",
                 solver="LM (Ceres semantics), radius 100 / max 1e4, non-monotonic, Huber 1.0/0.5/10/1.0, tolerances disabled for timing",
-                l2="working set per iteration (0.09 GB observations + 0.44 GB Jacobian chunks) exceeds the 126 MB L2: no flush needed")
+                l2="working set per iteration (0.09 GB observations + 0.36 GB Jacobian chunks) exceeds the 126 MB L2: no flush needed")
 
 
 def solver_opts(iters):

@@ -15,6 +15,7 @@
 #pragma once
 
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -87,7 +88,47 @@ __global__ void pose_cam_kernel(const double* __restrict__ poses, int K, const C
 // the pose/camera entry (uniform across most of a warp: observations are pose-major), the point (gather through
 // L2), writes the 160-byte chunk [Jp | Jl | r] with the Huber corrector applied, and reduces the cost.
 constexpr int kJacThreads = 256;
-constexpr int kChunk = 20;  // doubles per reprojection observation
+// Reprojection chunk, 128 bytes per observation: [Jr 2x3 | Jl 2x3 | r 2 | pad 2], loss-corrected.  The translation block
+// of the pose Jacobian is EXACTLY -Jl (d X_cam / d t = -R_cw = -d X_cam / d X, reproj_residual_jacobian), so only the
+// rotation block Jr is stored and the full 2x6 pose Jacobian [-Jl | Jr] is rebuilt in registers by the consumers:
+// 20 % less HBM traffic for the Jacobian kernel and for every kernel that re-reads the chunks, bit-identical values.
+constexpr int kChunk = 16;     // doubles per reprojection observation
+constexpr int kChunkJl = 6;    // offset of Jl
+constexpr int kChunkR = 12;    // offset of r
+__host__ __device__ __forceinline__ void decode_chunk(const double* ch, double* jp /*2x6*/, double* jl /*2x3*/, double* r /*2*/) {
+#pragma unroll
+  for (int a = 0; a < 6; a++) jl[a] = ch[kChunkJl + a];
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+#pragma unroll
+    for (int a = 0; a < 3; a++) { jp[6 * k + a] = -jl[3 * k + a]; jp[6 * k + 3 + a] = ch[3 * k + a]; }
+  r[0] = ch[kChunkR]; r[1] = ch[kChunkR + 1];
+}
+// 16-byte loads (device): the chunk is 16-byte aligned
+__device__ __forceinline__ void load_chunk(const double* chunk, double* jp, double* jl, double& r0, double& r1) {
+  const double2* c = reinterpret_cast<const double2*>(chunk);
+  double raw[14];
+#pragma unroll
+  for (int a = 0; a < 7; a++) { const double2 v = c[a]; raw[2 * a] = v.x; raw[2 * a + 1] = v.y; }
+  double rr[2];
+  decode_chunk(raw, jp, jl, rr);
+  r0 = rr[0]; r1 = rr[1];
+}
+__device__ __forceinline__ void store_chunk(double* chunk, const double* Jp, const double* Jl, const double* r, double sc, bool masked) {
+  double2* out = reinterpret_cast<double2*>(chunk);
+  if (masked) {   // removed in place (obvi_factor_remove without a structure rebuild): an all-zero block
+#pragma unroll
+    for (int a = 0; a < 8; a++) out[a] = make_double2(0.0, 0.0);
+    return;
+  }
+  out[0] = make_double2(sc * Jp[3], sc * Jp[4]);
+  out[1] = make_double2(sc * Jp[5], sc * Jp[9]);
+  out[2] = make_double2(sc * Jp[10], sc * Jp[11]);
+#pragma unroll
+  for (int a = 0; a < 3; a++) out[3 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
+  out[6] = make_double2(sc * r[0], sc * r[1]);
+  out[7] = make_double2(0.0, 0.0);
+}
 constexpr uint32_t kObsMasked = 4u;  // flag bit 2 of ObsRec / BBoxRec: residual block removed in place (two-phase outlier exclusion)
 
 __global__ void __launch_bounds__(kJacThreads) reproj_jac_kernel(const ObsRec* __restrict__ obs, int64_t n,
@@ -109,18 +150,9 @@ __global__ void __launch_bounds__(kJacThreads) reproj_jac_kernel(const ObsRec* _
     const double s = r[0] * r[0] + r[1] * r[1];
     double sc = 1.0, c = 0.5 * s;
     if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
-    double2* out = reinterpret_cast<double2*>(J + (size_t)i * kChunk);
-    if (id.w & kObsMasked) {   // removed in place (obvi_factor_remove without a structure rebuild): an all-zero block
-#pragma unroll
-      for (int a = 0; a < 10; a++) out[a] = make_double2(0.0, 0.0);
-    } else {
-      if ((id.w & 3u) == 3u) fixed = c; else cost = c;
-#pragma unroll
-      for (int a = 0; a < 6; a++) out[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
-#pragma unroll
-      for (int a = 0; a < 3; a++) out[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
-      out[9] = make_double2(sc * r[0], sc * r[1]);
-    }
+    const bool masked = (id.w & kObsMasked) != 0u;
+    if (!masked) { if ((id.w & 3u) == 3u) fixed = c; else cost = c; }
+    store_chunk(J + (size_t)i * kChunk, Jp, Jl, r, sc, masked);
   }
   cost = block_sum_all<kJacThreads>(cost, red);
   fixed = block_sum_all<kJacThreads>(fixed, red);
@@ -164,26 +196,57 @@ __device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_sme
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 2-D tensor-map TMA store (shared -> global) of a [rows x 128 B] box; the box is written into shared memory in the 128-byte
+// swizzle pattern of the tensor map (16-byte piece a of row r lives at piece a ^ (r & 7)), so the 256 threads of a CTA --
+// each writing the eight pieces of its own 128-byte row -- never collide on a bank, and the TMA unit undoes the swizzle.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* src_smem) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_addr(src_smem)) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void store_chunk_swz(double* tile, int row, const double* Jp, const double* Jl, const double* r, double sc, bool masked) {
+  double2* base = reinterpret_cast<double2*>(tile) + (size_t)row * 8;
+  const int x = row & 7;
+  double2 v[8];
+  if (masked) {
+#pragma unroll
+    for (int a = 0; a < 8; a++) v[a] = make_double2(0.0, 0.0);
+  } else {
+    v[0] = make_double2(sc * Jp[3], sc * Jp[4]);
+    v[1] = make_double2(sc * Jp[5], sc * Jp[9]);
+    v[2] = make_double2(sc * Jp[10], sc * Jp[11]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) v[3 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
+    v[6] = make_double2(sc * r[0], sc * r[1]);
+    v[7] = make_double2(0.0, 0.0);
+  }
+#pragma unroll
+  for (int a = 0; a < 8; a++) base[a ^ x] = v[a];
+}
+
 // ------------------------------------------------------------------------------------------ reprojection Jacobians, TMA-staged
 // Same arithmetic as reproj_jac_kernel, restructured around the memory system:
 //   * observations are pose-major, so the pose/camera entries a 256-observation tile needs are a short CONTIGUOUS range
 //     of the table: one 1-D TMA bulk copy stages them in shared memory (no per-thread 384-byte reloads);
-//   * each thread writes its 160-byte chunk into a shared-memory image of the output tile, and one elected thread
-//     stores the whole contiguous 40 KB tile with a single TMA bulk store: full-line HBM writes, no LSU store traffic.
+//   * each thread writes its 128-byte chunk into a (swizzled, bank-conflict-free) shared-memory image of the output tile,
+//     and one elected thread stores the whole 32 KB tile with a single TMA tensor store: full-line HBM writes, no LSU
+//     store traffic.  (Without a tensor map -- `tmap_ok == 0` -- the image is linear and goes out as a 1-D bulk copy.)
 constexpr int kJacMaxPc = 6;                       // staged pose/camera entries per tile
 constexpr int kJacMaxCls = 16;                     // calibration classes staged in shared memory
 constexpr int kJacTileBytes = kJacThreads * kChunk * 8;
-constexpr int kJacSmemBytes = kJacTileBytes + kJacMaxPc * (int)sizeof(PoseCam) + 16;
+constexpr int kJacSmemBytes = kJacTileBytes + kJacMaxPc * (int)sizeof(PoseCam) + 16 + 1024;   // + slack to align the tile to 1 KB
 
-__global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const ObsRec* __restrict__ obs, int64_t n,
+__global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const __grid_constant__ CUtensorMap tmap, int tmap_ok,
+                                                                         const ObsRec* __restrict__ obs, int64_t n,
                                                                          const PoseCam* __restrict__ pcam, int C,
                                                                          const CalibClass* __restrict__ cls, int ncls,
                                                                          const double* __restrict__ points, int apply_loss,
                                                                          const uint2* __restrict__ tile_pc,
                                                                          double* __restrict__ J, double* __restrict__ scalars) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double red[33];
   __shared__ CalibClass cls_s[kJacMaxCls];
+  // the swizzled tile must sit on a 1 KB boundary of the shared-memory window
+  unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
   double* out_tile = reinterpret_cast<double*>(smem);
   PoseCam* pc_s = reinterpret_cast<PoseCam*>(smem + kJacTileBytes);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kJacTileBytes + kJacMaxPc * sizeof(PoseCam));
@@ -223,24 +286,17 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const Ob
     const double s = r[0] * r[0] + r[1] * r[1];
     double sc = 1.0, c = 0.5 * s;
     if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
-    double2* out = reinterpret_cast<double2*>(out_tile + (size_t)threadIdx.x * kChunk);
-    if (id.w & kObsMasked) {   // removed in place: an all-zero block, no cost
-#pragma unroll
-      for (int a = 0; a < 10; a++) out[a] = make_double2(0.0, 0.0);
-    } else {
-      if ((id.w & 3u) == 3u) fixed = c; else cost = c;
-#pragma unroll
-      for (int a = 0; a < 6; a++) out[a] = make_double2(sc * Jp[2 * a], sc * Jp[2 * a + 1]);
-#pragma unroll
-      for (int a = 0; a < 3; a++) out[6 + a] = make_double2(sc * Jl[2 * a], sc * Jl[2 * a + 1]);
-      out[9] = make_double2(sc * r[0], sc * r[1]);
-    }
+    const bool masked = (id.w & kObsMasked) != 0u;
+    if (!masked) { if ((id.w & 3u) == 3u) fixed = c; else cost = c; }
+    if (tmap_ok) store_chunk_swz(out_tile, (int)threadIdx.x, Jp, Jl, r, sc, masked);
+    else store_chunk(out_tile + (size_t)threadIdx.x * kChunk, Jp, Jl, r, sc, masked);
   }
   fence_proxy_async_smem();
   cost = block_sum_all<kJacThreads>(cost, red);     // contains __syncthreads: the tile image is complete after it
   fixed = block_sum_all<kJacThreads>(fixed, red);
   if (threadIdx.x == 0) {
-    tma_store_1d(J + (size_t)i0 * kChunk, out_tile, (uint32_t)nt * kChunk * 8);
+    if (tmap_ok) tma_store_2d(&tmap, 0, (int)i0, out_tile);     // rows beyond n are clipped by the tensor map
+    else tma_store_1d(J + (size_t)i0 * kChunk, out_tile, (uint32_t)nt * kChunk * 8);
     if (cost != 0.0) atomicAdd(&scalars[SC_COST], cost);
     if (fixed != 0.0) atomicAdd(&scalars[SC_FIXED], fixed);
     tma_store_wait_read();
@@ -299,11 +355,9 @@ __global__ void __launch_bounds__(kPoseAccThreads) pose_accum_kernel(const doubl
 #pragma unroll
   for (int a = 0; a < 27; a++) acc[a] = 0.0;
   for (uint32_t i = b0 + threadIdx.x; i < b1; i += kPoseAccThreads) {
-    const double2* ch = reinterpret_cast<const double2*>(J + (size_t)i * kChunk);
-    double jp[12];
-#pragma unroll
-    for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
-    const double2 r = ch[9];
+    double jp[12], jl_[6];
+    double2 r;
+    load_chunk(J + (size_t)i * kChunk, jp, jl_, r.x, r.y);
     int t = 0;
 #pragma unroll
     for (int a = 0; a < 6; a++) {
@@ -336,6 +390,105 @@ __global__ void __launch_bounds__(kPoseAccThreads) pose_accum_kernel(const doubl
     } else {
       atomicAdd(&gp[6 * f + (threadIdx.x - 21)], s);
     }
+  }
+}
+
+// pose_accum_tma_kernel: the same reduction with the keyframe's Jacobian tile STAGED BY TMA.  The chunk array is viewed
+// through the tensor map of the Jacobian kernel ([n_obs x 128 B], 128-byte swizzle); a CTA walks its keyframe's contiguous
+// rows in boxes of 256, double-buffered: while the threads reduce box t out of shared memory (thread = row, the eight
+// 16-byte pieces at their swizzled positions: conflict free), the TMA unit is already fetching box t + 1 with full-line
+// reads.  Rows of the box that belong to the next keyframe are skipped; rows past the end of the array arrive zero-filled.
+constexpr int kPoseAccTmaSmem = 2 * kPoseAccThreads * kChunk * 8 + 1024 + 64;
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_addr(dst_smem)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_addr(bar)) : "memory");
+}
+__global__ void __launch_bounds__(kPoseAccThreads) pose_accum_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                          const uint32_t* __restrict__ pose_ptr,
+                                                                          const int32_t* __restrict__ f_of_pose,
+                                                                          const uint32_t* __restrict__ su_ptr,
+                                                                          double* __restrict__ S_upper, double* __restrict__ gp,
+                                                                          double* __restrict__ hpp_diag) {
+  extern __shared__ __align__(128) unsigned char pa_raw[];
+  const int k = blockIdx.x;
+  const int f = f_of_pose[k];
+  if (f < 0) return;
+  const uint32_t b0 = pose_ptr[k], b1 = pose_ptr[k + 1];
+  if (b0 == b1) return;
+  unsigned char* base = pa_raw + ((1024u - (smem_addr(pa_raw) & 1023u)) & 1023u);
+  constexpr int kBoxBytes = kPoseAccThreads * kChunk * 8;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 2 * kBoxBytes);
+  const int nbox = (int)((b1 - b0 + kPoseAccThreads - 1) / kPoseAccThreads);
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+  __syncthreads();
+  if (threadIdx.x == 0) { mbar_expect_tx(&bar[0], kBoxBytes); tma_load_2d(base, &tmap, 0, (int)b0, &bar[0]); }
+  double acc[27];
+#pragma unroll
+  for (int a = 0; a < 27; a++) acc[a] = 0.0;
+  const int x = threadIdx.x & 7;
+  for (int t = 0; t < nbox; t++) {
+    if (t + 1 < nbox && threadIdx.x == 0) {
+      const int nb = (t + 1) & 1;
+      mbar_expect_tx(&bar[nb], kBoxBytes);
+      tma_load_2d(base + nb * kBoxBytes, &tmap, 0, (int)(b0 + (uint32_t)(t + 1) * kPoseAccThreads), &bar[nb]);
+    }
+    mbar_wait(&bar[t & 1], (uint32_t)((t >> 1) & 1));
+    const uint32_t row = b0 + (uint32_t)t * kPoseAccThreads + threadIdx.x;
+    if (row < b1) {
+      const double2* c = reinterpret_cast<const double2*>(base + (t & 1) * kBoxBytes) + (size_t)threadIdx.x * 8;
+      double raw[14], jp[12], jl[6], r[2];
+#pragma unroll
+      for (int a = 0; a < 7; a++) { const double2 v = c[a ^ x]; raw[2 * a] = v.x; raw[2 * a + 1] = v.y; }
+      decode_chunk(raw, jp, jl, r);
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+#pragma unroll
+        for (int b = a; b < 6; b++) acc[q++] += jp[a] * jp[b] + jp[6 + a] * jp[6 + b];
+      }
+#pragma unroll
+      for (int a = 0; a < 6; a++) acc[21 + a] += jp[a] * r[0] + jp[6 + a] * r[1];
+    }
+    fence_proxy_async_smem();
+    __syncthreads();   // box t is consumed: its buffer may be refilled (by the load issued in iteration t + 1)
+  }
+  __shared__ double red[27][kPoseAccThreads / 32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int a = 0; a < 27; a++) {
+    const double v = warp_sum(acc[a]);
+    if (l == 0) red[a][w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < kPoseAccThreads / 32; i++) s += red[threadIdx.x][i];
+    double* Sd = S_upper + (size_t)su_ptr[f] * 36;
+    if (threadIdx.x < 21) {
+      int a = 0, t = threadIdx.x;
+      while (t >= 6 - a) { t -= 6 - a; a++; }
+      const int b = a + t;
+      atomicAdd(&Sd[a * 6 + b], s);
+      if (a != b) atomicAdd(&Sd[b * 6 + a], s);
+      else atomicAdd(&hpp_diag[6 * f + a], s);
+    } else {
+      atomicAdd(&gp[6 * f + (threadIdx.x - 21)], s);
+    }
+  }
+}
+
+// The generic e-block kernels below index a chunk as [Jp KRx6 | Je KRxNE | r KR].  Object chunks (bounding boxes) are stored that
+// way; point chunks are stored compact (see kChunk) and expanded into a register image of the same layout.
+template <int NE, int KR>
+__device__ __forceinline__ const double* chunk_full(const double* J, size_t pos, double* tmp /* KR (6 + NE + 1) */) {
+  if constexpr (NE == 3 && KR == 2) {
+    double rr[2];
+    decode_chunk(J + pos * kChunk, tmp, tmp + 12, rr);
+    tmp[18] = rr[0]; tmp[19] = rr[1];
+    return tmp;
+  } else {
+    return J + pos * (size_t)(KR * (6 + NE + 1));
   }
 }
 
@@ -380,7 +533,8 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
 #pragma unroll
   for (int a = 0; a < NE; a++) g[a] = 0.0;
   for (uint32_t q = b0 + threadIdx.x; q < b1; q += T) {
-    const double* ch = A.J + (size_t)A.pos[q] * CH;
+    double chunk_tmp_1[CH];
+    const double* ch = chunk_full<NE, KR>(A.J, (size_t)A.pos[q], chunk_tmp_1);
     const double* Je = ch + KR * 6;
     const double* r = ch + KR * (6 + NE);
 #pragma unroll
@@ -477,7 +631,8 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
       for (int a = 0; a < 6; a++) gq[a] = 0.0;
     }
     for (uint32_t q2 = q; q2 < b1 && A.slot[q2] == sl; q2++) {
-      const double* ch = A.J + (size_t)A.pos[q2] * CH;
+      double chunk_tmp_2[CH];
+      const double* ch = chunk_full<NE, KR>(A.J, (size_t)A.pos[q2], chunk_tmp_2);
 #pragma unroll
       for (int k = 0; k < KR; k++) {
         double jp[6], je[NE];
@@ -600,13 +755,9 @@ __global__ void __launch_bounds__(256, 2) point_prep_kernel(EArgs A, const uint3
   auto sweep = [&](const uint4 G, double* W) {
     for (uint32_t k = 0; k < G.w; k++) {
       const uint32_t pos = k == 0 ? G.x : (G.w <= 2 ? G.y : A.pos[G.y + k]);
-      const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)pos * kChunk);
       double jp[12], jl[6];
-#pragma unroll
-      for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
-#pragma unroll
-      for (int a = 0; a < 3; a++) { const double2 v = ch[6 + a]; jl[2 * a] = v.x; jl[2 * a + 1] = v.y; }
-      const double2 rv = ch[9];
+      double2 rv;
+      load_chunk(A.J + (size_t)pos * kChunk, jp, jl, rv.x, rv.y);
       int t = 0;
 #pragma unroll
       for (int a = 0; a < 3; a++) {
@@ -821,7 +972,8 @@ __global__ void __launch_bounds__(T) backsub_eblock_kernel(EArgs A, const double
     for (uint32_t q = b0 + threadIdx.x; q < b1; q += T) {
       const int fi = A.f[q];
       if (fi < 0) continue;
-      const double* ch = A.J + (size_t)A.pos[q] * CH;
+      double chunk_tmp_3[CH];
+      const double* ch = chunk_full<NE, KR>(A.J, (size_t)A.pos[q], chunk_tmp_3);
       double dp[6];
 #pragma unroll
       for (int a = 0; a < 6; a++) dp[a] = dpose[6 * fi + a];
@@ -859,7 +1011,8 @@ __global__ void __launch_bounds__(T) backsub_eblock_kernel(EArgs A, const double
   for (uint32_t q = b0 + threadIdx.x; q < b1; q += T) {
     const int fi = A.f[q];
     if (cst && fi < 0) continue;
-    const double* ch = A.J + (size_t)A.pos[q] * CH;
+    double chunk_tmp_4[CH];
+    const double* ch = chunk_full<NE, KR>(A.J, (size_t)A.pos[q], chunk_tmp_4);
     double dp[6];
 #pragma unroll
     for (int a = 0; a < 6; a++) dp[a] = fi >= 0 ? dpose[6 * fi + a] : 0.0;
@@ -899,12 +1052,7 @@ __global__ void __launch_bounds__(128) backsub_points_kernel(EArgs A, int n_e, c
       if (have) {
         const uint32_t q = b0 + lane;
         fi = A.f[q];
-        const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)A.pos[q] * kChunk);
-#pragma unroll
-        for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
-#pragma unroll
-        for (int a = 0; a < 3; a++) { const double2 v = ch[6 + a]; jl[2 * a] = v.x; jl[2 * a + 1] = v.y; }
-        const double2 rv = ch[9]; r[0] = rv.x; r[1] = rv.y;
+        load_chunk(A.J + (size_t)A.pos[q] * kChunk, jp, jl, r[0], r[1]);
 #pragma unroll
         for (int a = 0; a < 6; a++) dp[a] = fi >= 0 ? dpose[6 * fi + a] : 0.0;
       }
@@ -919,11 +1067,11 @@ __global__ void __launch_bounds__(128) backsub_points_kernel(EArgs A, int n_e, c
         for (uint32_t q = b0 + 32 + lane; q < b1; q += 32) {
           const int f2 = A.f[q];
           if (f2 < 0) continue;
-          const double* ch = A.J + (size_t)A.pos[q] * kChunk;
-          double d2[6];
+          double jp2[12], jl2[6], r2[2], d2[6];
+          load_chunk(A.J + (size_t)A.pos[q] * kChunk, jp2, jl2, r2[0], r2[1]);
 #pragma unroll
           for (int a = 0; a < 6; a++) d2[a] = dpose[6 * f2 + a];
-          accum_t(ch, ch + 12, d2);
+          accum_t(jp2, jl2, d2);
         }
       }
       double de[3] = {0.0, 0.0, 0.0};
@@ -955,11 +1103,11 @@ __global__ void __launch_bounds__(128) backsub_points_kernel(EArgs A, int n_e, c
       for (uint32_t q = b0 + 32 + lane; q < b1; q += 32) {
         const int f2 = A.f[q];
         if (cst && f2 < 0) continue;
-        const double* ch = A.J + (size_t)A.pos[q] * kChunk;
-        double d2[6];
+        double jp2[12], jl2[6], r2[2], d2[6];
+        load_chunk(A.J + (size_t)A.pos[q] * kChunk, jp2, jl2, r2[0], r2[1]);
 #pragma unroll
         for (int a = 0; a < 6; a++) d2[a] = f2 >= 0 ? dpose[6 * f2 + a] : 0.0;
-        accum_m(ch, ch + 12, ch + 18, d2);
+        accum_m(jp2, jl2, r2, d2);
       }
     }
   }
@@ -999,13 +1147,9 @@ __global__ void __launch_bounds__(256) backsub_rows_kernel(EArgs A, const uint32
     for (int a = 0; a < 6; a++) dp[a] = fi >= 0 ? dpose[6 * fi + a] : 0.0;
     for (uint32_t k = 0; k < G.w; k++) {
       const uint32_t pos = k == 0 ? G.x : (G.w <= 2 ? G.y : A.pos[G.y + k]);
-      const double2* ch = reinterpret_cast<const double2*>(A.J + (size_t)pos * kChunk);
       double jp[12], jl[6];
-#pragma unroll
-      for (int a = 0; a < 6; a++) { const double2 v = ch[a]; jp[2 * a] = v.x; jp[2 * a + 1] = v.y; }
-#pragma unroll
-      for (int a = 0; a < 3; a++) { const double2 v = ch[6 + a]; jl[2 * a] = v.x; jl[2 * a + 1] = v.y; }
-      const double2 rv = ch[9];
+      double2 rv;
+      load_chunk(A.J + (size_t)pos * kChunk, jp, jl, rv.x, rv.y);
       const double a0 = jp[0] * dp[0] + jp[1] * dp[1] + jp[2] * dp[2] + jp[3] * dp[3] + jp[4] * dp[4] + jp[5] * dp[5];
       const double a1 = jp[6] * dp[0] + jp[7] * dp[1] + jp[8] * dp[2] + jp[9] * dp[3] + jp[10] * dp[4] + jp[11] * dp[5];
       sa += a0 * (rv.x + 0.5 * a0) + a1 * (rv.y + 0.5 * a1);

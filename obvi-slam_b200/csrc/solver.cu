@@ -150,6 +150,8 @@ struct Solver {
   DBuf<uint8_t> pose_skip, point_skip, obj_skip;
   DBuf<uint2> jac_tile;  // per 256-observation tile: first pose/camera entry, entries staged by TMA
   int jac_mode = 1;  // 1: TMA-staged tile kernel (default), 0: plain loads / stores (OBVI_JAC=plain)
+  CUtensorMap jac_tmap;     // [n_obs x 128 B] view of J for the swizzled tile store of the Jacobian kernel
+  int jac_tmap_ok = 0;
   DBuf<BBoxRec> bbox;
   DBuf<UnaryRec> unary;
   DBuf<RelRec> rel;
@@ -250,6 +252,7 @@ struct Solver {
     if (const char* e = getenv("OBVI_PROFILE")) prof.on = std::string(e) == "1";
     if (const char* e = getenv("OBVI_JAC")) jac_mode = std::string(e) == "plain" ? 0 : 1;
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes));
+    CUDA_OK(cudaFuncSetAttribute(pose_accum_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoseAccTmaSmem));
   }
 
   void upload_elist(EListDev& D, const Structure::EList& L, const std::vector<uint8_t>& cst, int NE, int maxs) {
@@ -311,6 +314,7 @@ struct Solver {
     for (int b = 0; b < 3; b++) { poses[b].alloc((size_t)S.K * 6); points[b].alloc((size_t)S.P * 3); objects[b].alloc((size_t)S.O * 7); }
     pcam.alloc((size_t)S.K * std::max(S.C, 1)); pcam_cand.alloc((size_t)S.K * std::max(S.C, 1));
     J.alloc((size_t)S.n_obs * kChunk); Jb.alloc((size_t)S.n_bbox * kBBoxChunk);
+    encode_jac_tmap();
     unary_out.alloc(S.n_unary); rel_out.alloc(S.n_rel);
     const size_t nf6 = (size_t)S.nf * 6;
     redbuf.alloc((size_t)S.n_upper * 36 + 3 * nf6);
@@ -484,12 +488,30 @@ struct Solver {
     prof.end("lin: side join", pt2, stream);
   }
   // the reprojection Jacobian-evaluation kernel (three revisions, selectable with OBVI_JAC = plain | tma | persistent)
+  // Tensor map of the chunk array for the Jacobian kernel's tile store (128-byte rows, 256-row boxes, 128-byte swizzle).
+  void encode_jac_tmap() {
+    jac_tmap_ok = 0;
+    std::memset(&jac_tmap, 0, sizeof(jac_tmap));
+    if (st.n_obs == 0 || getenv("OBVI_JAC_LINEAR")) return;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) { cudaGetLastError(); return; }
+    const cuuint64_t gdim[2] = {(cuuint64_t)kChunk, (cuuint64_t)st.n_obs};
+    const cuuint64_t gstride[1] = {(cuuint64_t)kChunk * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)kJacThreads};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = ((EncodeFn)fn)(&jac_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, J.p, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    jac_tmap_ok = rc == CUDA_SUCCESS;
+  }
   void launch_jacobian(int apply_loss, const double* pts_dev) {
     const Structure& S = st;
     const bool tma_ok = (int)S.classes.size() <= kJacMaxCls && S.C <= 256;
     const int ntiles = nblk(S.n_obs, kJacThreads);
     if (jac_mode >= 1 && tma_ok) {
-      reproj_jac_tma_kernel<<<ntiles, kJacThreads, kJacSmemBytes, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
+      reproj_jac_tma_kernel<<<ntiles, kJacThreads, kJacSmemBytes, stream>>>(jac_tmap, jac_tmap_ok, obs.p, S.n_obs, pcam.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
     } else {
       reproj_jac_kernel<<<ntiles, kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, pts_dev, apply_loss, J.p, scalars.p);
     }
@@ -521,7 +543,11 @@ struct Solver {
     if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 1, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
     if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
     prof.end("zero", pt0, stream); pt0 = prof.begin(stream);
-    if (S.n_obs && S.nf) { pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag); launches++; }
+    if (S.n_obs && S.nf) {
+      if (jac_tmap_ok && !getenv("OBVI_POSE_ACCUM_PLAIN")) pose_accum_tma_kernel<<<S.K, kPoseAccThreads, kPoseAccTmaSmem, stream>>>(jac_tmap, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
+      else pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
+      launches++;
+    }
     prof.end("pose_accum", pt0, stream); pt0 = prof.begin(stream);
     {
       if (S.P && lanes_per_point == 8) { point_prep_kernel<8><<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
@@ -1264,10 +1290,11 @@ int obvi_evaluate_factor_type(obvi_problem* p, int type, int apply_loss, double*
     for (int64_t q = 0; q < S.n_obs; q++) {
       const int64_t u = live_rank[S.obs_user[q]];
       if (u < 0) continue;   // removed in place
-      const double* ch = &h[(size_t)q * kChunk];
-      if (J0) std::memcpy(J0 + 12 * u, ch, 96);
-      if (J1) std::memcpy(J1 + 6 * u, ch + 12, 48);
-      if (r) std::memcpy(r + 2 * u, ch + 18, 16);
+      double jp[12], jl[6], rr[2];
+      decode_chunk(&h[(size_t)q * kChunk], jp, jl, rr);
+      if (J0) std::memcpy(J0 + 12 * u, jp, 96);
+      if (J1) std::memcpy(J1 + 6 * u, jl, 48);
+      if (r) std::memcpy(r + 2 * u, rr, 16);
     }
   } else if (type == OBVI_FACTOR_BBOX) {
     std::vector<double> h((size_t)S.n_bbox * kBBoxChunk);
@@ -1351,7 +1378,7 @@ int obvi_evaluate(obvi_problem* p, int apply_loss, double* cost, double* residua
     const uint64_t i = id_index(id);
     const double* src;
     switch (id_type(id)) {
-      case OBVI_FACTOR_REPROJECTION: src = &hJ[(size_t)inv_rp[i] * kChunk + 18]; break;
+      case OBVI_FACTOR_REPROJECTION: src = &hJ[(size_t)inv_rp[i] * kChunk + kChunkR]; break;
       case OBVI_FACTOR_BBOX: src = &hB[(size_t)inv_bb[i] * kBBoxChunk + 52]; break;
       case OBVI_FACTOR_REL_POSE: src = hR[inv_rl[i]].r; break;
       default: src = hU[inv_un[i]].r; break;
@@ -1416,11 +1443,11 @@ int obvi_evaluate_jacobian(obvi_problem* p, int apply_loss, const obvi_factor_id
     struct Part { int32_t b; int w; const double* J; int ld; int off; double scale; };
     Part parts[2]; int np = 0;
     const double* r = nullptr;
-    double unaryJ[49];
+    double unaryJ[49], rp_jp[12], rp_jl[6], rp_r[2];
     switch (id_type(ids[n])) {
       case OBVI_FACTOR_REPROJECTION: {
-        const double* ch = &hJ[(size_t)s.inv_rp[i] * kChunk];
-        parts[np++] = {pb.reproj[i].pose, 6, ch, 6, 0, 1.0}; parts[np++] = {pb.reproj[i].point, 3, ch + 12, 3, 0, 1.0}; r = ch + 18; break; }
+        decode_chunk(&hJ[(size_t)s.inv_rp[i] * kChunk], rp_jp, rp_jl, rp_r);
+        parts[np++] = {pb.reproj[i].pose, 6, rp_jp, 6, 0, 1.0}; parts[np++] = {pb.reproj[i].point, 3, rp_jl, 3, 0, 1.0}; r = rp_r; break; }
       case OBVI_FACTOR_BBOX: {
         const double* ch = &hB[(size_t)s.inv_bb[i] * kBBoxChunk];
         parts[np++] = {pb.bbox[i].obj, 7, ch + 24, 7, 0, 1.0}; parts[np++] = {pb.bbox[i].pose, 6, ch, 6, 0, 1.0}; r = ch + 52; break; }
@@ -1495,7 +1522,7 @@ int obvi_topk_outliers(obvi_problem* p, int type, double fraction, obvi_factor_i
     DBuf<int64_t> d_count;
     d_rank.upload(rank, s.stream);
     d_vals.alloc(nb); d_vals_sorted.alloc(nb); d_sel.alloc(nb); d_keys.alloc(nb); d_keys_sorted.alloc(nb); d_flags.alloc(nb); d_count.alloc(1);
-    if (rp) block_sqnorm_kernel<<<Solver::nblk(nb, 256), 256, 0, s.stream>>>(s.J.p, nb, kChunk, 18, 2, d_rank.p, d_keys.p, d_vals.p);
+    if (rp) block_sqnorm_kernel<<<Solver::nblk(nb, 256), 256, 0, s.stream>>>(s.J.p, nb, kChunk, kChunkR, 2, d_rank.p, d_keys.p, d_vals.p);
     else block_sqnorm_kernel<<<Solver::nblk(nb, 256), 256, 0, s.stream>>>(s.Jb.p, nb, kBBoxChunk, 52, 4, d_rank.p, d_keys.p, d_vals.p);
     size_t tmp1 = 0, tmp2 = 0;
     cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp1, d_keys.p, d_keys_sorted.p, d_vals.p, d_vals_sorted.p, (int)nb, 0, 64, s.stream);
