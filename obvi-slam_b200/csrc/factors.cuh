@@ -141,55 +141,6 @@ OBVI_HD void reproj_residual_jacobian(const PoseCam& pc, const double* X, double
   }
 }
 
-// Compact per-(pose, camera) entry used by the hot reprojection kernel: 42 doubles laid out so that every piece the
-// kernel consumes starts on a 16-byte boundary (21 x 16-byte shared-memory loads instead of 48 x 8-byte ones).
-//   X_cam = Rcw (X - t) + te_inv,   d X_cam / d omega_k = M[k] (X - t)
-struct PoseCamR {
-  double Rcw[9];
-  double t[3];
-  double M[3][10];   // 9 entries + 1 pad each
-};  // 336 B
-OBVI_HD void compact_pose_cam(const PoseCam& pc, const double* pose, PoseCamR* out) {
-  for (int i = 0; i < 9; i++) out->Rcw[i] = pc.Rcw[i];
-  for (int i = 0; i < 3; i++) out->t[i] = pose[i];
-  for (int k = 0; k < 3; k++) {
-    for (int i = 0; i < 9; i++) out->M[k][i] = pc.M[9 * k + i];
-    out->M[k][9] = 0.0;
-  }
-}
-struct OBVI_ALIGN16 Dbl2 { double x, y; };
-// Same residual / Jacobian as reproj_residual_jacobian, from the compact entry, read as 16-byte pieces and consumed
-// piece by piece (at most 12 + 10 values live), so that shared-memory reads compile to 128-bit loads.
-OBVI_HD void reproj_residual_jacobian_compact(const PoseCamR* pcr, const double* te_inv, const double* X, double ur, double vr,
-                                              double mx, double my, double* r, double* Jp, double* Jl) {
-  const Dbl2* q2 = reinterpret_cast<const Dbl2*>(pcr);
-  double q[12];
-  for (int a = 0; a < 6; a++) { const Dbl2 v = q2[a]; q[2 * a] = v.x; q[2 * a + 1] = v.y; }
-  const double v0 = X[0] - q[9], v1 = X[1] - q[10], v2 = X[2] - q[11];
-  const double x = q[0] * v0 + q[1] * v1 + q[2] * v2 + te_inv[0];
-  const double y = q[3] * v0 + q[4] * v1 + q[5] * v2 + te_inv[1];
-  const double z = q[6] * v0 + q[7] * v1 + q[8] * v2 + te_inv[2];
-  const double iz = 1.0 / z, u = x * iz, v = y * iz;
-  r[0] = mx * (u - ur);
-  r[1] = my * (v - vr);
-  const double a0 = mx * iz, a2 = -mx * u * iz, b1 = my * iz, b2 = -my * v * iz;
-  for (int j = 0; j < 3; j++) {
-    Jl[j] = a0 * q[j] + a2 * q[6 + j];
-    Jl[3 + j] = b1 * q[3 + j] + b2 * q[6 + j];
-    Jp[j] = -Jl[j];
-    Jp[6 + j] = -Jl[3 + j];
-  }
-  for (int k = 0; k < 3; k++) {
-    double Mk[10];
-    for (int a = 0; a < 5; a++) { const Dbl2 w = q2[6 + 5 * k + a]; Mk[2 * a] = w.x; Mk[2 * a + 1] = w.y; }
-    const double dx = Mk[0] * v0 + Mk[1] * v1 + Mk[2] * v2;
-    const double dy = Mk[3] * v0 + Mk[4] * v1 + Mk[5] * v2;
-    const double dz = Mk[6] * v0 + Mk[7] * v1 + Mk[8] * v2;
-    Jp[3 + k] = a0 * dx + a2 * dz;
-    Jp[9 + k] = b1 * dy + b2 * dz;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Bounding-box residual -- BoundingBoxFactor::operator() (bounding_box_factor.h:68-136) via
 // getCornerLocationsVectorRectified (ellipsoid_utils.h:159-273).  ell = (x y z yaw dx dy dz);

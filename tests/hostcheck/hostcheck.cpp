@@ -21,18 +21,6 @@ void hc_reproj(const double* pose, const double* point, const double* px, const 
   if (r2[0] != r[0] || r2[1] != r[1]) r[0] = NAN;
 }
 
-void hc_reproj_compact(const double* pose, const double* point, const double* px, const double* intr, const double* Re,
-                       const double* te, double sigma, double* r, double* Jp, double* Jl) {
-  double Ri[9], ti[3];
-  invert_extrinsics(Re, te, Ri, ti);
-  PoseCam pc;
-  make_pose_cam(pose, Ri, ti, true, &pc);
-  alignas(16) PoseCamR pr;
-  compact_pose_cam(pc, pose, &pr);
-  const double ur = (px[0] - intr[2]) / intr[0], vr = (px[1] - intr[3]) / intr[1];
-  reproj_residual_jacobian_compact(&pr, ti, point, ur, vr, intr[0] / sigma, intr[1] / sigma, r, Jp, Jl);
-}
-
 void hc_bbox(const double* ell, const double* pose, const double* corners, const double* cov4, const double* intr,
              const double* Re, const double* te, double invalid_err, double* r, double* Jo, double* Jp) {
   double Ri[9], ti[3];
