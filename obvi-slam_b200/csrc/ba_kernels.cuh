@@ -512,7 +512,9 @@ struct EArgs {
 // One CTA (T threads) per e-block.  Phase A: H_ee, g_e (shuffle reductions), damping, inverse.
 // Phase B: per merged pose slot W = sum Jp^T Je and Z = W Hinv, staged in shared memory.
 // Phase C: S_ab -= Z_a W_b^T for every slot pair, spread over the threads by block row.
-template <int NE, int KR, int T, int MAXS, bool POSE_SIDE>
+// PREP_ONLY: stop after phase A (einv / eg / escale written; an all-zero einv on a failed inverse) -- the first half of the
+// split object path, whose phases B and C run in obj_schur_kernel.
+template <int NE, int KR, int T, int MAXS, bool POSE_SIDE, bool PREP_ONLY = false>
 __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, const uint32_t* __restrict__ su_ptr,
                                                           double* __restrict__ S_upper, double* __restrict__ gp,
                                                           double* __restrict__ hpp_diag, double* __restrict__ b_schur,
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
   constexpr int NH = NE * (NE + 1) / 2;
   constexpr int SL = 12 * NE;  // doubles per slot in the staging buffer: Z (6xNE) then W (6xNE)
   __shared__ double red[33];
-  __shared__ double stage_s[MAXS * SL];
+  __shared__ double stage_s[PREP_ONLY ? 1 : MAXS * SL];
   const int e = A.elist ? (int)A.elist[blockIdx.x] : (int)blockIdx.x;
   if (A.cst[e]) return;
   const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
@@ -598,7 +600,15 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
     for (int a = 0; a < NE; a++) Hs[a * NE + a] += fmin(fmax(Hs[a * NE + a], lm.min_diag), lm.max_diag) / lm.radius;
   }
   if (!spd_inverse<NE>(Hs, hinv)) {
-    if (threadIdx.x == 0) atomicAdd(&scalars[SC_FAIL], 1.0);
+    if (threadIdx.x == 0) {
+      atomicAdd(&scalars[SC_FAIL], 1.0);
+      if (PREP_ONLY) {
+#pragma unroll
+        for (int a = 0; a < NE * NE; a++) A.einv[(size_t)e * NE * NE + a] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NE; a++) A.eg[(size_t)e * NE + a] = g[a];
+      }
+    }
     return;
   }
 #pragma unroll
@@ -612,6 +622,7 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
 #pragma unroll
     for (int a = 0; a < NE; a++) A.eg[(size_t)e * NE + a] = g[a];
   }
+  if (PREP_ONLY) return;
   // ---- phase B
   const int ns = A.nslots[e];
   if (ns == 0) return;
@@ -687,6 +698,103 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
           else atomicAdd(&hpp_diag[6 * fi + a], v);
         }
       }
+    }
+  }
+  if (ns > MAXS) __threadfence_block();
+  __syncthreads();
+  // ---- phase C
+  const int items = ns * (ns + 1) / 2 * 6;
+  const uint32_t* pb = A.pair_blk + A.pair_ptr[e];
+  for (int it = threadIdx.x; it < items; it += T) {
+    const int pr = it / 6, row = it - 6 * pr;
+    int a = 0, t = pr;
+    while (t >= ns - a) { t -= ns - a; a++; }
+    const int b = a + t;
+    const double* Za = stage + (size_t)a * SL + row * NE;
+    const double* Wb = stage + (size_t)b * SL + 6 * NE;
+    double z[NE];
+#pragma unroll
+    for (int d = 0; d < NE; d++) z[d] = Za[d];
+    double* Sb = S_upper + (size_t)pb[pr] * 36 + row * 6;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      double v = 0.0;
+#pragma unroll
+      for (int d = 0; d < NE; d++) v += z[d] * Wb[c * NE + d];
+      atomicAdd(&Sb[c], -v);
+    }
+  }
+}
+
+// Second half of the split object path (objects: NE = 7, bbox chunks [Jp 4x6 | Je 4x7 | r 4]); H_e^-1 and g_e come from
+// schur_eblock_kernel<7, 4, 32, ., true, PREP_ONLY>.  Phase B is spread over (pose slot, row a of the 6x7 block W) instead of
+// one thread per slot, so a thread keeps 7 + 6 accumulators instead of 42 + 21 + the 49-entry inverse (which lives in shared
+// memory here): ~64 registers instead of 254, i.e. the CTAs of this latency-bound kernel no longer take the whole register
+// file away from the pose-accumulation kernel they run beside.  Sums are formed in the same order as in the one-kernel
+// version.  Phase C (S_ab -= Z_a W_b^T over slot pairs) is unchanged.
+template <int T, int MAXS>
+__global__ void __launch_bounds__(T) obj_schur_kernel(EArgs A, const uint32_t* __restrict__ su_ptr, double* __restrict__ S_upper,
+                                                       double* __restrict__ gp, double* __restrict__ hpp_diag,
+                                                       double* __restrict__ b_schur) {
+  constexpr int NE = 7, KR = 4, CH = KR * (6 + NE + 1), SL = 12 * NE;
+  __shared__ double hinv_s[NE * NE];
+  __shared__ double g_s[NE];
+  __shared__ double stage_s[MAXS * SL];
+  const int e = (int)blockIdx.x;
+  if (A.cst[e]) return;
+  const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
+  const int ns = A.nslots[e];
+  if (b0 == b1 || ns == 0) return;
+  if (threadIdx.x < NE * NE) hinv_s[threadIdx.x] = A.einv[(size_t)e * NE * NE + threadIdx.x];
+  if (threadIdx.x < NE) g_s[threadIdx.x] = A.eg[(size_t)e * NE + threadIdx.x];
+  __syncthreads();
+  double* stage = (ns <= MAXS) ? stage_s : (A.overflow + A.overflow_off[e]);
+  // ---- phase B
+  const uint32_t nitems = (b1 - b0) * 6;
+  for (uint32_t it = threadIdx.x; it < nitems; it += T) {
+    const uint32_t q = b0 + it / 6;
+    const int a = (int)(it % 6);
+    const uint16_t sl = A.slot[q];
+    if (sl == 0xFFFF) continue;
+    if (q > b0 && A.slot[q - 1] == sl) continue;  // not the head of its run
+    double Wm[NE], hp[6], gq = 0.0;
+#pragma unroll
+    for (int c = 0; c < NE; c++) Wm[c] = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; b++) hp[b] = 0.0;
+    for (uint32_t q2 = q; q2 < b1 && A.slot[q2] == sl; q2++) {
+      const double* ch = A.J + (size_t)A.pos[q2] * CH;
+#pragma unroll
+      for (int k = 0; k < KR; k++) {
+        const double jpa = ch[k * 6 + a];
+#pragma unroll
+        for (int c = 0; c < NE; c++) Wm[c] += jpa * ch[KR * 6 + k * NE + c];
+        gq += jpa * ch[KR * (6 + NE) + k];
+#pragma unroll
+        for (int b = 0; b < 6; b++) hp[b] += jpa * ch[k * 6 + b];
+      }
+    }
+    const int fi = A.f[q];
+    double* st = stage + (size_t)sl * SL;
+    double zg = 0.0;
+#pragma unroll
+    for (int c = 0; c < NE; c++) {
+      double z = 0.0;
+#pragma unroll
+      for (int d = 0; d < NE; d++) z += Wm[d] * hinv_s[d * NE + c];
+      st[a * NE + c] = z;
+      st[6 * NE + a * NE + c] = Wm[c];
+      zg += z * g_s[c];
+    }
+    atomicAdd(&b_schur[6 * fi + a], -zg);
+    atomicAdd(&gp[6 * fi + a], gq);
+    double* Sd = S_upper + (size_t)su_ptr[fi] * 36;
+#pragma unroll
+    for (int b = 0; b < 6; b++) {
+      if (b < a) continue;
+      atomicAdd(&Sd[a * 6 + b], hp[b]);
+      if (a != b) atomicAdd(&Sd[b * 6 + a], hp[b]);
+      else atomicAdd(&hpp_diag[6 * fi + a], hp[b]);
     }
   }
   if (ns > MAXS) __threadfence_block();

@@ -194,6 +194,9 @@ struct Solver {
   bool resident_ok = false;
   DBuf<double> rs_dbl;        // [16 reduction slots | nsb * 96 forward accumulators]
   DBuf<unsigned int> rs_u32;  // [4 reduction counters | nsb arrival counters | nsb z epochs]
+  bool defer_sync = false;       // OBVI_DEFER_SYNC=1: one host synchronisation per accepted LM iteration instead of two
+  bool pose_accum_side = false;  // OBVI_POSE_ACCUM_SIDE=1 (experiment)
+  bool obj_split = true;      // OBVI_OBJ_SPLIT=0: one-kernel object elimination (254 registers; kept for A/B runs and tests)
   int lanes_per_point = 8;   // OBVI_LPP=16: sixteen lanes per point in point_prep / backsub_rows (measured slower: 359 / 200 us vs 329 / 165)
   bool bt_v1 = false;   // OBVI_BT=v1: first-generation factorisation kernels (scalar-pivot Gauss-Jordan, FMA GEMM)
   // The factorisation is reused across LM iterations while it still preconditions well: it is redone when the
@@ -246,6 +249,9 @@ struct Solver {
     if (const char* e = getenv("OBVI_PRECOND")) use_bt = std::string(e) != "jacobi";
     if (const char* e = getenv("OBVI_BT")) bt_v1 = std::string(e) == "v1";
     if (const char* e = getenv("OBVI_REFACTOR_ITERS")) kRefactorPcgIters = std::max(1, atoi(e));
+    if (const char* e = getenv("OBVI_DEFER_SYNC")) defer_sync = std::string(e) == "1";
+    if (const char* e = getenv("OBVI_POSE_ACCUM_SIDE")) pose_accum_side = std::string(e) == "1";
+    if (const char* e = getenv("OBVI_OBJ_SPLIT")) obj_split = std::string(e) != "0";
     if (const char* e = getenv("OBVI_LPP")) lanes_per_point = std::string(e) == "16" ? 16 : 8;
     if (const char* e = getenv("OBVI_PCG")) pcg_resident = std::string(e) != "grid";
     CUDA_OK(cudaFuncSetAttribute(pcg_bt_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentSmem));
@@ -541,12 +547,21 @@ struct Solver {
     // side stream: priors, rel-pose and the object elimination (all accumulate with atomics); enqueued first, high priority
     if (S.n_unary && !pts.has_prior) launch_unary(1, 1, cur, s2);
     if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 1, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
-    if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
+    if (S.O && obj_split) {
+      // split object elimination: a warp per object for H_e^-1 / g_e, then the low-register slot / pair kernel
+      schur_eblock_kernel<7, 4, 32, 64, true, true><<<S.O, 32, 0, s2>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p);
+      obj_schur_kernel<128, 64><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), su_ptr.p, S_upper, gp, hpp_diag, b_schur);
+      launches += 2;
+    } else if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
     prof.end("zero", pt0, stream); pt0 = prof.begin(stream);
     if (S.n_obs && S.nf) {
-      if (jac_tmap_ok && !getenv("OBVI_POSE_ACCUM_PLAIN")) pose_accum_tma_kernel<<<S.K, kPoseAccThreads, kPoseAccTmaSmem, stream>>>(jac_tmap, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
-      else pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
+      // OBVI_POSE_ACCUM_SIDE=1: the (bandwidth-bound) pose accumulation on the second side stream, beside the (latency-bound) point kernels
+      cudaStream_t ps = pose_accum_side ? s3 : stream;
+      if (pose_accum_side) CUDA_OK(cudaStreamWaitEvent(s3, ev_fork, 0));
+      if (jac_tmap_ok && !getenv("OBVI_POSE_ACCUM_PLAIN")) pose_accum_tma_kernel<<<S.K, kPoseAccThreads, kPoseAccTmaSmem, ps>>>(jac_tmap, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
+      else pose_accum_kernel<<<S.K, kPoseAccThreads, 0, ps>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
       launches++;
+      if (pose_accum_side) CUDA_OK(cudaEventRecord(ev_join3, s3));
     }
     prof.end("pose_accum", pt0, stream); pt0 = prof.begin(stream);
     {
@@ -561,6 +576,7 @@ struct Solver {
       }
     }
     prof.end("schur_points", pt0, stream); pt0 = prof.begin(stream);
+    if (pose_accum_side && S.n_obs && S.nf) CUDA_OK(cudaStreamWaitEvent(stream, ev_join3, 0));
     join();
     prof.end("join(objects,rel)", pt0, stream); pt0 = prof.begin(stream);
     if (world > 1) { allreduce_sum(redbuf.p, redbuf.n); prof.end("allreduce S", pt0, stream); pt0 = prof.begin(stream); }
@@ -650,12 +666,15 @@ struct Solver {
     join();
   }
   // stage 0: after linearize () + build_reduced (); stage 1: after take_step () + candidate_cost ()
-  void fetch_scalars(int stage) {
+  void reduce_scalars(int stage) {
     if (world > 1) {
       // replicated pose contributions (|x|^2, |delta|^2) are added by rank 0 only
       if (stage == 0) allreduce_sum(scalars.p + SC_COST, 3); else allreduce_sum(scalars.p + SC_CAND, 4);
       allreduce_max(scalars.p + SC_GMAX, 2);
     }
+  }
+  void fetch_scalars(int stage, bool reduce = true) {
+    if (reduce) reduce_scalars(stage);
     CUDA_OK(cudaMemcpyAsync(h_scalars, scalars.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
     CUDA_OK(cudaGetLastError());
@@ -884,6 +903,22 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
   double decrease = 2.0;
   bool need_build = false;
   int64_t pcg_total = 0;
+  // an accepted step whose new cost / gradient norm / |x| have not been read back yet (see defer_sync)
+  struct { int iter, pcg_it; double cost_change, step_norm, rho, radius; } pend = {0, 0, 0, 0, 0, 0};
+  bool pending0 = false;
+  // needs h_scalars from a fetch made after that step's build_reduced (); returns true when the gradient tolerance is met
+  auto finish_pending = [&]() {
+    CUDA_OK(cudaEventElapsedTime(&ms, ev[0], ev[1])); t_jac += ms * 1e-3;
+    CUDA_OK(cudaEventElapsedTime(&ms, ev[1], ev[5])); t_lin += ms * 1e-3;
+    x_cost = h_scalars[SC_COST];
+    gmax = h_scalars[SC_GMAX];
+    x_norm = std::sqrt(h_scalars[SC_XNORM2]);
+    build_failed = h_scalars[SC_FAIL] != 0.0;
+    if (x_cost < minimum_cost) { minimum_cost = x_cost; best = cur; }
+    push(pend.iter, true, true, pend.pcg_it, x_cost + fixed_cost, pend.cost_change, gmax, pend.step_norm, pend.rho, pend.radius);
+    pending0 = false;
+    return gmax <= o.gradient_tolerance;
+  };
   const bool finite0 = std::isfinite(x_cost);
   if (!finite0) termination = OBVI_FAILURE;
   else if (S.num_params_reduced == 0 || gmax <= o.gradient_tolerance) termination = OBVI_CONVERGENCE;
@@ -904,6 +939,12 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
     fetch_scalars(1);
     CUDA_OK(cudaEventElapsedTime(&ms, ev[2], ev[3])); t_lin += ms * 1e-3;
     CUDA_OK(cudaEventElapsedTime(&ms, ev[3], ev[4])); t_res += ms * 1e-3;
+    if (pending0 && finish_pending()) {
+      // the previous (accepted) iterate already met the gradient tolerance: the step enqueued speculatively is dropped
+      iter--; lm_steps--;
+      termination = OBVI_CONVERGENCE;
+      break;
+    }
     if (h_scalars[SC_PCG_BREAK] == 2.0) {
       // the block-tridiagonal factorisation hit a non-positive pivot: redo this step with block-Jacobi PCG
       minv_kernel<<<nblk(S.nf, 64), 64, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, Sf.p, Minv.p, scalars.p); launches++;
@@ -957,21 +998,21 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
       CUDA_OK(cudaEventRecord(ev[1], stream));
       build_reduced(lm);
       CUDA_OK(cudaEventRecord(ev[5], stream));
-      fetch_scalars(0);
-      CUDA_OK(cudaEventElapsedTime(&ms, ev[0], ev[1])); t_jac += ms * 1e-3;
-      CUDA_OK(cudaEventElapsedTime(&ms, ev[1], ev[5])); t_lin += ms * 1e-3;
-      x_cost = h_scalars[SC_COST];
-      gmax = h_scalars[SC_GMAX];
-      x_norm = std::sqrt(h_scalars[SC_XNORM2]);
-      build_failed = h_scalars[SC_FAIL] != 0.0;
       ev_cur = cand_cost; acc_cand += model_change; acc_ref += model_change;
       if (ev_cur < ev_min) { ev_min = ev_cur; n_nonmono = 0; ev_cand = ev_cur; acc_cand = 0; }
       else { n_nonmono++; if (ev_cur > ev_cand) { ev_cand = ev_cur; acc_cand = 0; } }
       if (n_nonmono == max_nonmono) { ev_ref = ev_cand; acc_ref = acc_cand; }
       n_ok++;
-      if (x_cost < minimum_cost) { minimum_cost = x_cost; best = cur; }
-      push(iter, true, true, pcg_it, x_cost + fixed_cost, cost_change, gmax, step_norm, rho, lm.radius);
-      if (gmax <= o.gradient_tolerance) { termination = OBVI_CONVERGENCE; break; }
+      pend = {iter, pcg_it, cost_change, step_norm, rho, lm.radius};
+      pending0 = true;
+      if (defer_sync) {
+        // no host synchronisation here: the cost / gradient norm of the new point ride along with the next step's
+        // scalars, and the next step is enqueued right away (it is dropped if this point turns out to be converged)
+        reduce_scalars(0);
+      } else {
+        fetch_scalars(0);
+        if (finish_pending()) { termination = OBVI_CONVERGENCE; break; }
+      }
     } else {
       lm.radius /= decrease; decrease *= 2.0;
       need_build = true;
@@ -979,6 +1020,10 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
       push(iter, true, false, pcg_it, cand_cost + fixed_cost, cost_change, gmax, step_norm, rho, lm.radius);
     }
     if (lm.radius <= o.min_trust_region_radius) { termination = OBVI_CONVERGENCE; break; }
+  }
+  if (pending0) {   // the loop ended (iteration limit, minimum radius, failure) with an accepted step still unread
+    fetch_scalars(0, false);   // its cross-rank reduction was enqueued when the step was accepted
+    if (finish_pending() && termination == OBVI_NO_CONVERGENCE) termination = OBVI_CONVERGENCE;
   }
   CUDA_OK(cudaEventRecord(ev[7], stream));
   CUDA_OK(cudaStreamSynchronize(stream));

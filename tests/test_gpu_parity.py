@@ -395,12 +395,14 @@ def test_row_owner_edge_cases(ob, oracle):
     assert p.num_structure_builds() == 1 and s2.final_cost < s2.initial_cost
 
 
-@pytest.mark.parametrize("env", [dict(OBVI_PCG="grid"), dict(OBVI_BT="v1", OBVI_LPP="16"), dict(OBVI_PRECOND="jacobi", OBVI_JAC="plain")])
+@pytest.mark.parametrize("env", [dict(OBVI_PCG="grid"), dict(OBVI_BT="v1", OBVI_LPP="16"), dict(OBVI_PRECOND="jacobi", OBVI_JAC="plain"),
+                                 dict(OBVI_OBJ_SPLIT="0")])
 def test_alternate_kernel_paths_agree(ob, env, tmp_path):
     """The kernels that are not on the default path must keep working: pcg_bt_kernel (grid-barrier PCG) is the fallback
     for problems with more super-blocks than SMs (> 2368 keyframes), the first factorisation kernels and the 16-lane
     point kernels are kept for A/B measurements, block-Jacobi PCG is the fallback after a failed factorisation, the plain
-    Jacobian kernel the fallback when the TMA-staged one does not apply (> 16 calibration classes)."""
+    Jacobian kernel the fallback when the TMA-staged one does not apply (> 16 calibration classes), the one-kernel object
+    elimination the predecessor of the split (warp-per-object prep + low-register slot / pair kernel) default."""
     import json, os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "alt.py"
