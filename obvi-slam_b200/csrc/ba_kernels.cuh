@@ -56,6 +56,9 @@ __device__ __forceinline__ double block_sum_all(double v, double* red) {
   for (int i = 0; i < T / 32; i++) s += red[i];
   return s;
 }
+// Fire-and-forget fp64 reduction (SASS REDG).  In the e-block kernels nvcc turns a result-less atomicAdd into ATOMG (an atomic
+// WITH a response: every one of them occupies a scoreboard slot until L2 answers), so the reduction is spelled out there.
+__device__ __forceinline__ void red_add(double* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v)); }
 __device__ __forceinline__ void atomic_max_nonneg(double* slot, double v) {
   atomicMax(reinterpret_cast<unsigned long long*>(slot), (unsigned long long)__double_as_longlong(v));
 }
@@ -682,20 +685,20 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
         st[6 * NE + a * NE + c] = Wm[a * NE + c];
         zg += z * g[c];
       }
-      atomicAdd(&b_schur[6 * fi + a], -zg);
+      red_add(&b_schur[6 * fi + a], -zg);
     }
     if (POSE_SIDE) {
       double* Sd = S_upper + (size_t)su_ptr[fi] * 36;
       int t = 0;
 #pragma unroll
       for (int a = 0; a < 6; a++) {
-        atomicAdd(&gp[6 * fi + a], gq[a]);
+        red_add(&gp[6 * fi + a], gq[a]);
 #pragma unroll
         for (int b = a; b < 6; b++) {
           const double v = hp[t++];
-          atomicAdd(&Sd[a * 6 + b], v);
-          if (a != b) atomicAdd(&Sd[b * 6 + a], v);
-          else atomicAdd(&hpp_diag[6 * fi + a], v);
+          red_add(&Sd[a * 6 + b], v);
+          if (a != b) red_add(&Sd[b * 6 + a], v);
+          else red_add(&hpp_diag[6 * fi + a], v);
         }
       }
     }
@@ -721,7 +724,7 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
       double v = 0.0;
 #pragma unroll
       for (int d = 0; d < NE; d++) v += z[d] * Wb[c * NE + d];
-      atomicAdd(&Sb[c], -v);
+      red_add(&Sb[c], -v);
     }
   }
 }
@@ -729,26 +732,19 @@ __global__ void __launch_bounds__(T) schur_eblock_kernel(EArgs A, LMParams lm, c
 // Second half of the split object path (objects: NE = 7, bbox chunks [Jp 4x6 | Je 4x7 | r 4]); H_e^-1 and g_e come from
 // schur_eblock_kernel<7, 4, 32, ., true, PREP_ONLY>.  Phase B is spread over (pose slot, row a of the 6x7 block W) instead of
 // one thread per slot, so a thread keeps 7 + 6 accumulators instead of 42 + 21 + the 49-entry inverse (which lives in shared
-// memory here): ~64 registers instead of 254, i.e. the CTAs of this latency-bound kernel no longer take the whole register
+// memory here): 64 registers instead of 254, i.e. the CTAs of this latency-bound kernel no longer take the whole register
 // file away from the pose-accumulation kernel they run beside.  Sums are formed in the same order as in the one-kernel
-// version.  Phase C (S_ab -= Z_a W_b^T over slot pairs) is unchanged.
-template <int T, int MAXS>
-__global__ void __launch_bounds__(T) obj_schur_kernel(EArgs A, const uint32_t* __restrict__ su_ptr, double* __restrict__ S_upper,
-                                                       double* __restrict__ gp, double* __restrict__ hpp_diag,
-                                                       double* __restrict__ b_schur) {
+// version.  Phase C (S_ab -= Z_a W_b^T over slot pairs): the pair index is inverted with a square root instead of a loop.
+constexpr int kObjMaxSlots = 56;   // pose slots staged on chip: 56 x 84 doubles + the 1596-entry pair table = 43 KB of static shared memory
+constexpr int kObjThreads = 256, kObjMinBlocks = 4;   // 8 warps per object, <= 64 registers: every object CTA of C3 is resident at once
+// `stage` is passed by the caller either as the shared-memory array itself (so that, after inlining, the accesses compile to
+// LDS / STS) or as the global overflow area of an object with more than MAXS pose slots.
+template <int T>
+__device__ __forceinline__ void obj_schur_body(const EArgs& A, int e, uint32_t b0, uint32_t b1, int ns, double* stage, const uint32_t* pb,
+                                               const double* hinv_s, const double* g_s, const uint32_t* __restrict__ su_ptr,
+                                               double* __restrict__ S_upper, double* __restrict__ gp,
+                                               double* __restrict__ hpp_diag, double* __restrict__ b_schur, bool fence) {
   constexpr int NE = 7, KR = 4, CH = KR * (6 + NE + 1), SL = 12 * NE;
-  __shared__ double hinv_s[NE * NE];
-  __shared__ double g_s[NE];
-  __shared__ double stage_s[MAXS * SL];
-  const int e = (int)blockIdx.x;
-  if (A.cst[e]) return;
-  const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
-  const int ns = A.nslots[e];
-  if (b0 == b1 || ns == 0) return;
-  if (threadIdx.x < NE * NE) hinv_s[threadIdx.x] = A.einv[(size_t)e * NE * NE + threadIdx.x];
-  if (threadIdx.x < NE) g_s[threadIdx.x] = A.eg[(size_t)e * NE + threadIdx.x];
-  __syncthreads();
-  double* stage = (ns <= MAXS) ? stage_s : (A.overflow + A.overflow_off[e]);
   // ---- phase B
   const uint32_t nitems = (b1 - b0) * 6;
   for (uint32_t it = threadIdx.x; it < nitems; it += T) {
@@ -786,27 +782,31 @@ __global__ void __launch_bounds__(T) obj_schur_kernel(EArgs A, const uint32_t* _
       st[6 * NE + a * NE + c] = Wm[c];
       zg += z * g_s[c];
     }
-    atomicAdd(&b_schur[6 * fi + a], -zg);
-    atomicAdd(&gp[6 * fi + a], gq);
+    red_add(&b_schur[6 * fi + a], -zg);
+    red_add(&gp[6 * fi + a], gq);
     double* Sd = S_upper + (size_t)su_ptr[fi] * 36;
 #pragma unroll
     for (int b = 0; b < 6; b++) {
       if (b < a) continue;
-      atomicAdd(&Sd[a * 6 + b], hp[b]);
-      if (a != b) atomicAdd(&Sd[b * 6 + a], hp[b]);
-      else atomicAdd(&hpp_diag[6 * fi + a], hp[b]);
+      red_add(&Sd[a * 6 + b], hp[b]);
+      if (a != b) red_add(&Sd[b * 6 + a], hp[b]);
+      else red_add(&hpp_diag[6 * fi + a], hp[b]);
     }
   }
-  if (ns > MAXS) __threadfence_block();
+  if (fence) __threadfence_block();
+  asm volatile("cp.async.wait_all;" ::: "memory");   // the pair -> S-block table staged by the caller (shared-memory path)
   __syncthreads();
-  // ---- phase C
+  // ---- phase C: pair p = (a, b >= a) in row-major order of the upper triangle, six threads (rows of the 6x6 block) per pair
   const int items = ns * (ns + 1) / 2 * 6;
-  const uint32_t* pb = A.pair_blk + A.pair_ptr[e];
+  const double tn = 2.0 * ns + 1.0;
   for (int it = threadIdx.x; it < items; it += T) {
     const int pr = it / 6, row = it - 6 * pr;
-    int a = 0, t = pr;
-    while (t >= ns - a) { t -= ns - a; a++; }
-    const int b = a + t;
+    // first pair of row a has index a (2 ns - a + 1) / 2: invert with a square root, then correct the rounding
+    int a = (int)((tn - sqrt(tn * tn - 8.0 * pr)) * 0.5);
+    a = max(0, min(a, ns - 1));
+    while (a > 0 && a * (2 * ns - a + 1) / 2 > pr) a--;
+    while ((a + 1) * (2 * ns - a) / 2 <= pr) a++;
+    const int b = a + pr - a * (2 * ns - a + 1) / 2;
     const double* Za = stage + (size_t)a * SL + row * NE;
     const double* Wb = stage + (size_t)b * SL + 6 * NE;
     double z[NE];
@@ -818,9 +818,38 @@ __global__ void __launch_bounds__(T) obj_schur_kernel(EArgs A, const uint32_t* _
       double v = 0.0;
 #pragma unroll
       for (int d = 0; d < NE; d++) v += z[d] * Wb[c * NE + d];
-      atomicAdd(&Sb[c], -v);
+      red_add(&Sb[c], -v);
     }
   }
+}
+
+template <int T, int MAXS, int MINB>
+__global__ void __launch_bounds__(T, MINB) obj_schur_kernel(EArgs A, const uint32_t* __restrict__ su_ptr, double* __restrict__ S_upper,
+                                                             double* __restrict__ gp, double* __restrict__ hpp_diag,
+                                                             double* __restrict__ b_schur) {
+  constexpr int NE = 7, SL = 12 * NE;
+  __shared__ double hinv_s[NE * NE];
+  __shared__ double g_s[NE];
+  __shared__ double stage_s[MAXS * SL];
+  __shared__ uint32_t pb_s[MAXS * (MAXS + 1) / 2];
+  const int e = (int)blockIdx.x;
+  if (A.cst[e]) return;
+  const uint32_t b0 = A.ptr[e], b1 = A.ptr[e + 1];
+  const int ns = A.nslots[e];
+  if (b0 == b1 || ns == 0) return;
+  const uint32_t* pb = A.pair_blk + A.pair_ptr[e];
+  if (ns <= MAXS) {
+    // the S-block index of every slot pair is needed only in phase C: fetch the table asynchronously now (LDGSTS), so that
+    // its DRAM latency is hidden behind phase B instead of being paid by every phase-C iteration
+    const int npairs = ns * (ns + 1) / 2;
+    for (int i = threadIdx.x; i < npairs; i += T)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(&pb_s[i])), "l"(pb + i) : "memory");
+  }
+  if (threadIdx.x < NE * NE) hinv_s[threadIdx.x] = A.einv[(size_t)e * NE * NE + threadIdx.x];
+  if (threadIdx.x < NE) g_s[threadIdx.x] = A.eg[(size_t)e * NE + threadIdx.x];
+  __syncthreads();
+  if (ns <= MAXS) obj_schur_body<T>(A, e, b0, b1, ns, stage_s, pb_s, hinv_s, g_s, su_ptr, S_upper, gp, hpp_diag, b_schur, false);
+  else obj_schur_body<T>(A, e, b0, b1, ns, A.overflow + A.overflow_off[e], pb, hinv_s, g_s, su_ptr, S_upper, gp, hpp_diag, b_schur, true);
 }
 
 

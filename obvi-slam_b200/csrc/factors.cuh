@@ -347,34 +347,52 @@ OBVI_HD void relpose_residual_jacobian(const double* p1, const double* p2, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// Small SPD inverse by Cholesky (n <= 7), row-major full storage.  Returns false if not SPD.
+// Small SPD inverse by Cholesky (n <= 7), row-major full storage.  Returns false if not SPD.  Fully unrolled (the factor
+// stays in registers) and with ONE division per pivot -- an fp64 division is ~35 instructions on the GPU and the textbook
+// form needs N (N + 1) / 2 + 2 N^2 of them in a serial chain: inv = L^-T L^-1 with L^-1 built from the pivot reciprocals.
 template <int N>
 OBVI_HD bool spd_inverse(const double* A, double* inv) {
-  double L[N * N];
-  for (int i = 0; i < N * N; i++) L[i] = A[i];
+  double L[N * N], rd[N];
+#pragma unroll
   for (int j = 0; j < N; j++) {
-    double dj = L[j * N + j];
+    double dj = A[j * N + j];
+#pragma unroll
     for (int k = 0; k < j; k++) dj -= L[j * N + k] * L[j * N + k];
     if (!(dj > 0.0)) return false;
     dj = sqrt(dj);
     L[j * N + j] = dj;
+    rd[j] = 1.0 / dj;
+#pragma unroll
     for (int i = j + 1; i < N; i++) {
-      double s = L[i * N + j];
+      double s = A[i * N + j];
+#pragma unroll
       for (int k = 0; k < j; k++) s -= L[i * N + k] * L[j * N + k];
-      L[i * N + j] = s / dj;
+      L[i * N + j] = s * rd[j];
     }
   }
+  // M = L^-1 (lower triangular), column by column: M[c][c] = 1 / L[c][c], M[i][c] = -(sum_{k=c}^{i-1} L[i][k] M[k][c]) / L[i][i]
+  double M[N * N];
+#pragma unroll
   for (int c = 0; c < N; c++) {
-    double y[N];
-    for (int i = 0; i < N; i++) {
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = 0; k < i; k++) s -= L[i * N + k] * y[k];
-      y[i] = s / L[i * N + i];
+    M[c * N + c] = rd[c];
+#pragma unroll
+    for (int i = c + 1; i < N; i++) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = c; k < i; k++) s -= L[i * N + k] * M[k * N + c];
+      M[i * N + c] = s * rd[i];
     }
-    for (int i = N - 1; i >= 0; i--) {
-      double s = y[i];
-      for (int k = i + 1; k < N; k++) s -= L[k * N + i] * inv[k * N + c];
-      inv[i * N + c] = s / L[i * N + i];
+  }
+  // inv = M^T M (symmetric): inv[a][b] = sum_{k >= max(a, b)} M[k][a] M[k][b]
+#pragma unroll
+  for (int a = 0; a < N; a++) {
+#pragma unroll
+    for (int b = a; b < N; b++) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = b; k < N; k++) s += M[k * N + a] * M[k * N + b];
+      inv[a * N + b] = s;
+      inv[b * N + a] = s;
     }
   }
   return true;

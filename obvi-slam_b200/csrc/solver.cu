@@ -194,8 +194,7 @@ struct Solver {
   bool resident_ok = false;
   DBuf<double> rs_dbl;        // [16 reduction slots | nsb * 96 forward accumulators]
   DBuf<unsigned int> rs_u32;  // [4 reduction counters | nsb arrival counters | nsb z epochs]
-  bool defer_sync = false;       // OBVI_DEFER_SYNC=1: one host synchronisation per accepted LM iteration instead of two
-  bool pose_accum_side = false;  // OBVI_POSE_ACCUM_SIDE=1 (experiment)
+  bool defer_sync = true;        // OBVI_DEFER_SYNC=0: two host synchronisations per accepted LM iteration instead of one
   bool obj_split = true;      // OBVI_OBJ_SPLIT=0: one-kernel object elimination (254 registers; kept for A/B runs and tests)
   int lanes_per_point = 8;   // OBVI_LPP=16: sixteen lanes per point in point_prep / backsub_rows (measured slower: 359 / 200 us vs 329 / 165)
   bool bt_v1 = false;   // OBVI_BT=v1: first-generation factorisation kernels (scalar-pivot Gauss-Jordan, FMA GEMM)
@@ -249,8 +248,7 @@ struct Solver {
     if (const char* e = getenv("OBVI_PRECOND")) use_bt = std::string(e) != "jacobi";
     if (const char* e = getenv("OBVI_BT")) bt_v1 = std::string(e) == "v1";
     if (const char* e = getenv("OBVI_REFACTOR_ITERS")) kRefactorPcgIters = std::max(1, atoi(e));
-    if (const char* e = getenv("OBVI_DEFER_SYNC")) defer_sync = std::string(e) == "1";
-    if (const char* e = getenv("OBVI_POSE_ACCUM_SIDE")) pose_accum_side = std::string(e) == "1";
+    if (const char* e = getenv("OBVI_DEFER_SYNC")) defer_sync = std::string(e) != "0";
     if (const char* e = getenv("OBVI_OBJ_SPLIT")) obj_split = std::string(e) != "0";
     if (const char* e = getenv("OBVI_LPP")) lanes_per_point = std::string(e) == "16" ? 16 : 8;
     if (const char* e = getenv("OBVI_PCG")) pcg_resident = std::string(e) != "grid";
@@ -295,7 +293,7 @@ struct Solver {
       jac_tile.upload(tp, stream);
     }
     upload_elist(pts, S.pts, S.point_const, 3, 16);
-    upload_elist(objs, S.objs, S.obj_const, 7, 64);
+    upload_elist(objs, S.objs, S.obj_const, 7, kObjMaxSlots);   // overflow areas for every object the split kernel cannot stage on chip
     {
       const Structure::PointRows& R = S.prow;
       n_row_items = (int)R.items.size(); n_row_fallback = (int)R.fallback.size();
@@ -550,18 +548,14 @@ struct Solver {
     if (S.O && obj_split) {
       // split object elimination: a warp per object for H_e^-1 / g_e, then the low-register slot / pair kernel
       schur_eblock_kernel<7, 4, 32, 64, true, true><<<S.O, 32, 0, s2>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p);
-      obj_schur_kernel<128, 64><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), su_ptr.p, S_upper, gp, hpp_diag, b_schur);
+      obj_schur_kernel<kObjThreads, kObjMaxSlots, kObjMinBlocks><<<S.O, kObjThreads, 0, s2>>>(eargs(objs, Jb.p), su_ptr.p, S_upper, gp, hpp_diag, b_schur);
       launches += 2;
     } else if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
     prof.end("zero", pt0, stream); pt0 = prof.begin(stream);
     if (S.n_obs && S.nf) {
-      // OBVI_POSE_ACCUM_SIDE=1: the (bandwidth-bound) pose accumulation on the second side stream, beside the (latency-bound) point kernels
-      cudaStream_t ps = pose_accum_side ? s3 : stream;
-      if (pose_accum_side) CUDA_OK(cudaStreamWaitEvent(s3, ev_fork, 0));
-      if (jac_tmap_ok && !getenv("OBVI_POSE_ACCUM_PLAIN")) pose_accum_tma_kernel<<<S.K, kPoseAccThreads, kPoseAccTmaSmem, ps>>>(jac_tmap, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
-      else pose_accum_kernel<<<S.K, kPoseAccThreads, 0, ps>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
+      if (jac_tmap_ok && !getenv("OBVI_POSE_ACCUM_PLAIN")) pose_accum_tma_kernel<<<S.K, kPoseAccThreads, kPoseAccTmaSmem, stream>>>(jac_tmap, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
+      else pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
       launches++;
-      if (pose_accum_side) CUDA_OK(cudaEventRecord(ev_join3, s3));
     }
     prof.end("pose_accum", pt0, stream); pt0 = prof.begin(stream);
     {
@@ -576,7 +570,6 @@ struct Solver {
       }
     }
     prof.end("schur_points", pt0, stream); pt0 = prof.begin(stream);
-    if (pose_accum_side && S.n_obs && S.nf) CUDA_OK(cudaStreamWaitEvent(stream, ev_join3, 0));
     join();
     prof.end("join(objects,rel)", pt0, stream); pt0 = prof.begin(stream);
     if (world > 1) { allreduce_sum(redbuf.p, redbuf.n); prof.end("allreduce S", pt0, stream); pt0 = prof.begin(stream); }

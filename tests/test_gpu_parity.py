@@ -89,6 +89,17 @@ def test_solve_reproj_only(ob, oracle):
     check_solve(ob, oracle, g, OPTS)
 
 
+def test_objects_with_more_pose_slots_than_fit_on_chip(ob, oracle):
+    """An ellipsoid seen from 66 keyframes: more pose slots than the object kernels stage in shared memory (56 / 64), so its
+    W / Z blocks and the pair table go through the global staging area.  The named configs cap an object at 40 keyframes."""
+    g = ob.synth.make_graph(K=120, P=1500, O=8, seed=3, objects_on=True, relpose="all", n_const_poses=1, min_obj_obs=4, max_obj_kf=100)
+    per = {}
+    for o, k in zip(g.bbox["obj"], g.bbox["pose"]):
+        per.setdefault(int(o), set()).add(int(k))
+    assert max(len(v) for v in per.values()) > 64
+    check_solve(ob, oracle, g, dict(OPTS, max_num_iterations=8))
+
+
 def test_solve_monotonic_default_radius(ob, oracle):
     o = dict(OPTS, use_nonmonotonic_steps=0, initial_trust_region_radius=1e4, max_trust_region_radius=1e16)
     check_solve(ob, oracle, small_graph(ob, seed=4), o)
@@ -396,13 +407,14 @@ def test_row_owner_edge_cases(ob, oracle):
 
 
 @pytest.mark.parametrize("env", [dict(OBVI_PCG="grid"), dict(OBVI_BT="v1", OBVI_LPP="16"), dict(OBVI_PRECOND="jacobi", OBVI_JAC="plain"),
-                                 dict(OBVI_OBJ_SPLIT="0")])
+                                 dict(OBVI_OBJ_SPLIT="0", OBVI_DEFER_SYNC="0")])
 def test_alternate_kernel_paths_agree(ob, env, tmp_path):
     """The kernels that are not on the default path must keep working: pcg_bt_kernel (grid-barrier PCG) is the fallback
     for problems with more super-blocks than SMs (> 2368 keyframes), the first factorisation kernels and the 16-lane
     point kernels are kept for A/B measurements, block-Jacobi PCG is the fallback after a failed factorisation, the plain
     Jacobian kernel the fallback when the TMA-staged one does not apply (> 16 calibration classes), the one-kernel object
-    elimination the predecessor of the split (warp-per-object prep + low-register slot / pair kernel) default."""
+    elimination the predecessor of the split (warp-per-object prep + low-register slot / pair kernel) default, and the LM loop
+    with a host synchronisation after every linearisation the predecessor of the deferred read-back."""
     import json, os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "alt.py"
