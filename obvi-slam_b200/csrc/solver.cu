@@ -204,6 +204,7 @@ struct Solver {
   double bt_radius = -1.0;
   int last_pcg_iters = 0;
   int kRefactorPcgIters = 8;   // OBVI_REFACTOR_ITERS
+  double kRefactorRatio = 2.0; // OBVI_REFACTOR_RATIO
   int64_t bt_factorizations = 0;
   double* h_scalars = nullptr;  // pinned
   std::vector<double> h_poses, h_points, h_objects;
@@ -248,6 +249,7 @@ struct Solver {
     if (const char* e = getenv("OBVI_PRECOND")) use_bt = std::string(e) != "jacobi";
     if (const char* e = getenv("OBVI_BT")) bt_v1 = std::string(e) == "v1";
     if (const char* e = getenv("OBVI_REFACTOR_ITERS")) kRefactorPcgIters = std::max(1, atoi(e));
+    if (const char* e = getenv("OBVI_REFACTOR_RATIO")) kRefactorRatio = std::max(1.0, atof(e));
     if (const char* e = getenv("OBVI_DEFER_SYNC")) defer_sync = std::string(e) != "0";
     if (const char* e = getenv("OBVI_OBJ_SPLIT")) obj_split = std::string(e) != "0";
     if (const char* e = getenv("OBVI_LPP")) lanes_per_point = std::string(e) == "16" ? 16 : 8;
@@ -476,6 +478,12 @@ struct Solver {
     if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p); launches++; }
     fork();
     prof.end("lin: pose_cam", pt0, stream);
+    // The Jacobian kernel is enqueued FIRST: linearize () usually follows a host synchronisation, so every API call made
+    // before this launch is time the device sits idle.  The side kernels wait on the fork event only and, coming from
+    // high-priority streams, are placed as soon as the first Jacobian CTAs retire.
+    const size_t pt1 = prof.begin(stream);
+    if (S.n_obs) launch_jacobian(apply_loss, points[cur].p);
+    prof.end("lin: jacobian", pt1, stream);
     CUDA_OK(cudaStreamWaitEvent(s3, ev_fork, 0));
     if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, s2>>>(bbox.p, S.n_bbox, pcam.p, S.C, objects[cur].p, 0, apply_loss, Jb.p, scalars.p); launches++; }
     if (S.n_unary) { launch_unary(0, apply_loss, cur, s3); }
@@ -483,9 +491,6 @@ struct Solver {
     if (S.K) { xnorm_kernel<<<nblk((int64_t)S.K * 6, 256), 256, 0, s3>>>(poses[cur].p, pose_skip.p, S.K, 6, scalars.p); launches++; }
     if (S.P) { xnorm_kernel<<<nblk((int64_t)S.P * 3, 256), 256, 0, s3>>>(points[cur].p, point_skip.p, S.P, 3, scalars.p); launches++; }
     if (S.O) { xnorm_kernel<<<nblk((int64_t)S.O * 7, 256), 256, 0, s3>>>(objects[cur].p, obj_skip.p, S.O, 7, scalars.p); launches++; }
-    const size_t pt1 = prof.begin(stream);
-    if (S.n_obs) launch_jacobian(apply_loss, points[cur].p);
-    prof.end("lin: jacobian", pt1, stream);
     const size_t pt2 = prof.begin(stream);
     CUDA_OK(cudaEventRecord(ev_join3, s3)); CUDA_OK(cudaStreamWaitEvent(stream, ev_join3, 0));
     join();
@@ -579,7 +584,7 @@ struct Solver {
       launches++;
       if (!use_bt) { minv_kernel<<<nblk(S.nf, 64), 64, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, Sf.p, Minv.p, scalars.p); launches++; }
       prof.end("finish", pt0, stream); pt0 = prof.begin(stream);
-      const bool stale = bt_radius <= 0.0 || lm.radius > 2.0 * bt_radius || lm.radius < 0.5 * bt_radius || last_pcg_iters > kRefactorPcgIters;
+      const bool stale = bt_radius <= 0.0 || lm.radius > kRefactorRatio * bt_radius || lm.radius * kRefactorRatio < bt_radius || last_pcg_iters > kRefactorPcgIters;
       if (stale) { factor_bt(); bt_radius = lm.radius; bt_factorizations++; prof.end("factor_bt", pt0, stream); }
     }
   }
@@ -979,9 +984,11 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
       if (best == old) {
         // `old` becomes the candidate buffer of the next step and will be overwritten: save it
         const size_t np = (size_t)S.K * 6 * 8, nq = (size_t)S.P * 3 * 8, no = (size_t)S.O * 7 * 8;
-        if (np) CUDA_OK(cudaMemcpyAsync(poses[2].p, poses[old].p, np, cudaMemcpyDeviceToDevice, stream));
-        if (nq) CUDA_OK(cudaMemcpyAsync(points[2].p, points[old].p, nq, cudaMemcpyDeviceToDevice, stream));
-        if (no) CUDA_OK(cudaMemcpyAsync(objects[2].p, objects[old].p, no, cudaMemcpyDeviceToDevice, stream));
+        // on the second side stream: the main stream was synchronised by fetch_scalars (1), so `old` is final; linearize ()
+        // below joins s3 back into the main stream before anything can overwrite `old`
+        if (np) CUDA_OK(cudaMemcpyAsync(poses[2].p, poses[old].p, np, cudaMemcpyDeviceToDevice, s3));
+        if (nq) CUDA_OK(cudaMemcpyAsync(points[2].p, points[old].p, nq, cudaMemcpyDeviceToDevice, s3));
+        if (no) CUDA_OK(cudaMemcpyAsync(objects[2].p, objects[old].p, no, cudaMemcpyDeviceToDevice, s3));
         best = 2;
       }
       lm.radius = std::min(o.max_trust_region_radius, lm.radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
