@@ -70,3 +70,57 @@ class OracleBackend:
         return [c1, c2]
 
 
+
+
+class OracleLtmBackend:
+    """Twin of obvi-slam_b200/ltm_extraction.py:GpuLtmBackend on the dense NumPy oracle (small graphs): evaluation, marginal
+    covariance blocks with ceres::Covariance's failure on a rank-deficient Jacobian, block-structured CRS export in a given
+    block order, ParameterPrior insertion.  The checker for the GPU backend of the long-term-map extraction."""
+
+    def __init__(self, po, ltm, g):
+        self.po, self.ltm, self.g = po, ltm, g
+        if not hasattr(g, "prior"):
+            g.prior = dict(kind=[], index=[], idx=[], mean=[], std=[])
+
+    def evaluate(self):
+        return self.po.evaluate(self.g, want_jac=False, apply_loss=True)[0]
+
+    def _dense(self):
+        off, n = self.po._layout(self.g)
+        _, _, J = self.po.evaluate(self.g, apply_loss=True)
+        return off, n, J[:, :n]
+
+    def _structure(self, J, off):
+        """Stored-entry mask: a residual row stores every column of a block it touches (Ceres' CRS is block structured)."""
+        width = dict(pose=6, point=3, obj=7)
+        mask = np.zeros(J.shape, bool)
+        for (kind, _), o in off.items():
+            w = width[kind]
+            mask[:, o:o + w] = (J[:, o:o + w] != 0).any(axis=1)[:, None]
+        return mask
+
+    def covariances(self, objs):
+        off, n, J = self._dense()
+        used = self._structure(J, off).any(axis=0)
+        Ju = J[:, used]
+        m, k = Ju.shape
+        rows = np.arange(0, (m + 1) * k, k); cols = np.tile(np.arange(k), m)
+        if self.ltm.rank_deficiency_dense(rows, cols, Ju.ravel(), (m, k), 10 ** 9) > 0:
+            return False, None
+        cov = np.zeros((n, n))
+        cov[np.ix_(used, used)] = np.linalg.inv(Ju.T @ Ju)
+        return True, np.stack([cov[off[("obj", o)]:off[("obj", o)] + 7, off[("obj", o)]:off[("obj", o)] + 7] for o in objs])
+
+    def jacobian(self, blocks):
+        off, n, J = self._dense()
+        mask = self._structure(J, off)
+        width = dict(pose=6, point=3, obj=7)
+        sel = np.concatenate([np.arange(off[b], off[b] + width[b[0]]) for b in blocks]) if blocks else np.zeros(0, int)
+        Jb, Mb = J[:, sel], mask[:, sel]
+        rows = np.concatenate([[0], np.cumsum(Mb.sum(axis=1))]).astype(np.int64)
+        r, c = np.nonzero(Mb)
+        return rows, c.astype(np.int64), Jb[r, c], Jb.shape
+
+    def add_param_prior(self, kind, index, param_idx, mean, std):
+        pr = self.g.prior
+        pr["kind"].append(kind); pr["index"].append(int(index)); pr["idx"].append(int(param_idx)); pr["mean"].append(float(mean)); pr["std"].append(float(std))
