@@ -3,9 +3,9 @@
 // and the candidate-cost evaluation.  Everything is float64 (the reference is all-double).
 //
 // Data layout:
-//   * reprojection observations are sorted pose-major; the Jacobian kernel writes one 160-byte chunk per
-//     observation  [Jp 2x6 | Jl 2x3 | r 2]  (row-major, loss-corrected), so a keyframe's Jacobian tile is one
-//     contiguous range;
+//   * reprojection observations are sorted pose-major; the Jacobian kernel writes one 128-byte chunk per
+//     observation  [Jr 2x3 | Jl 2x3 | r 2 | pad]  (row-major, loss-corrected; the translation block of the pose
+//     Jacobian is -Jl and is not stored), so a keyframe's Jacobian tile is one contiguous range;
 //   * bbox observations are sorted object-major with 448-byte chunks [Jp 4x6 | Jo 4x7 | r 4];
 //   * every e-block (point or object) has a CSR list of its observations (position, f index, merged pose slot)
 //     and the precomputed index of the reduced-matrix block of every slot pair;
@@ -89,7 +89,7 @@ __global__ void pose_cam_kernel(const double* __restrict__ poses, int K, const C
 // ------------------------------------------------------------------------------------------ reprojection: residual + Jacobian
 // THE Jacobian-evaluation kernel.  One thread per observation.  Reads the 32-byte record (coalesced 2 x 16 B),
 // the pose/camera entry (uniform across most of a warp: observations are pose-major), the point (gather through
-// L2), writes the 160-byte chunk [Jp | Jl | r] with the Huber corrector applied, and reduces the cost.
+// L2), writes the 128-byte chunk [Jr | Jl | r] with the Huber corrector applied, and reduces the cost.
 constexpr int kJacThreads = 256;
 // Reprojection chunk, 128 bytes per observation: [Jr 2x3 | Jl 2x3 | r 2 | pad 2], loss-corrected.  The translation block
 // of the pose Jacobian is EXACTLY -Jl (d X_cam / d t = -R_cw = -d X_cam / d X, reproj_residual_jacobian), so only the
