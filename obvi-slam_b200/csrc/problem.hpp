@@ -14,6 +14,9 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <unordered_map>
 #include <vector>
 
@@ -196,7 +199,9 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
   const int nb = (int)pb.blocks.size();
   std::vector<int32_t> pose_of_block(nb, -1), point_of_block(nb, -1), obj_of_block(nb, -1);
   std::vector<uint8_t> used(nb, 0);
-  for (const auto& f : pb.reproj) if (f.alive) { used[f.pose] = 1; used[f.point] = 1; }
+  const int64_t n_reproj = (int64_t)pb.reproj.size();
+#pragma omp parallel for schedule(static)
+  for (int64_t n = 0; n < n_reproj; n++) { const ReprojFactor& f = pb.reproj[n]; if (f.alive) { used[f.pose] = 1; used[f.point] = 1; } }   // every writer stores 1
   for (const auto& f : pb.bbox) if (f.alive) { used[f.obj] = 1; used[f.pose] = 1; }
   for (const auto& f : pb.unary) if (f.alive) used[f.block] = 1;
   for (const auto& f : pb.rel) if (f.alive) { used[f.p1] = 1; used[f.p2] = 1; }
@@ -212,7 +217,14 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
   // points: internal order = (first observing pose, block id)
   {
     std::vector<int32_t> first(nb, INT32_MAX);
-    for (const auto& f : pb.reproj) if (f.alive) first[f.point] = std::min(first[f.point], pose_of_block[f.pose]);
+#pragma omp parallel for schedule(static)
+    for (int64_t n = 0; n < n_reproj; n++) {
+      const ReprojFactor& f = pb.reproj[n];
+      if (!f.alive) continue;
+      const int32_t k = pose_of_block[f.pose];
+      int32_t seen = __atomic_load_n(&first[f.point], __ATOMIC_RELAXED);
+      while (k < seen && !__atomic_compare_exchange_n(&first[f.point], &seen, k, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    }
     std::vector<int32_t> ids;
     for (int b = 0; b < nb; b++) if (used[b] && pb.blocks[b].size == 3) ids.push_back(b);
     std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return first[a] < first[b]; });
@@ -227,7 +239,8 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
 
   // ownership ranges (multi-GPU): by cumulative observation count
   std::vector<uint32_t> pt_cnt(S.P, 0), ob_cnt(S.O, 0);
-  for (const auto& f : pb.reproj) if (f.alive) pt_cnt[point_of_block[f.point]]++;
+#pragma omp parallel for schedule(static)
+  for (int64_t n = 0; n < n_reproj; n++) { const ReprojFactor& f = pb.reproj[n]; if (f.alive) __atomic_fetch_add(&pt_cnt[point_of_block[f.point]], 1u, __ATOMIC_RELAXED); }
   for (const auto& f : pb.bbox) if (f.alive) ob_cnt[obj_of_block[f.obj]]++;
   auto owner_range = [&](const std::vector<uint32_t>& cnt, int& lo, int& hi) {
     const int n = (int)cnt.size();
@@ -257,53 +270,101 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
   };
 
   OBVI_TMARK("0");
-  // ---- reprojection observations: counting sort by pose, then (camera, point) inside each pose
+  // ---- reprojection observations: stable counting sort by pose, then (camera, point) inside each pose.  The factors are
+  // split into contiguous chunks, one per thread; chunk t's share of a pose segment follows chunk t - 1's, so the scatter is
+  // the one a serial pass would produce.  Calibration classes are numbered in order of first appearance (per-chunk lists
+  // merged in chunk order give exactly that order).
   {
-    std::vector<uint32_t> cnt(S.K + 1, 0);
-    for (const auto& f : pb.reproj) {
-      if (!f.alive) continue;
-      const int pt = point_of_block[f.point];
-      if (pt < p_lo || pt >= p_hi) continue;
-      cnt[pose_of_block[f.pose] + 1]++;
+    const int64_t nfac = (int64_t)pb.reproj.size();
+    int nt = 1;
+#ifdef _OPENMP
+    nt = std::max(1, omp_get_max_threads());
+#endif
+    nt = (int)std::min<int64_t>(nt, std::max<int64_t>(1, nfac / 4096));
+    struct ClsKey { int cam; double sigma, huber; };
+    std::vector<std::vector<uint32_t>> hist(nt, std::vector<uint32_t>(S.K, 0));
+    std::vector<std::vector<ClsKey>> local_cls(nt);
+    auto chunk = [&](int t, int64_t& b, int64_t& e) { b = nfac * t / nt; e = nfac * (t + 1) / nt; };
+    auto mine = [&](const ReprojFactor& f, int& pt) {
+      if (!f.alive) return false;
+      pt = point_of_block[f.point];
+      return pt >= p_lo && pt < p_hi;
+    };
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+    for (int t = 0; t < nt; t++) {
+      int64_t b, e; chunk(t, b, e);
+      std::vector<uint32_t>& h = hist[t];
+      std::vector<ClsKey>& lc = local_cls[t];
+      int last_cam = -1; double last_sigma = 0, last_huber = 0;
+      for (int64_t n = b; n < e; n++) {
+        const ReprojFactor& f = pb.reproj[n];
+        int pt;
+        if (!mine(f, pt)) continue;
+        h[pose_of_block[f.pose]]++;
+        if (f.cam != last_cam || f.sigma != last_sigma || f.huber != last_huber) {
+          last_cam = f.cam; last_sigma = f.sigma; last_huber = f.huber;
+          bool seen = false;
+          for (const ClsKey& c : lc) if (c.cam == f.cam && c.sigma == f.sigma && c.huber == f.huber) { seen = true; break; }
+          if (!seen) lc.push_back({f.cam, f.sigma, f.huber});
+        }
+      }
     }
-    for (int k = 0; k < S.K; k++) cnt[k + 1] += cnt[k];
-    S.pose_ptr = cnt;
-    S.n_obs = cnt[S.K];
-    S.obs.resize(S.n_obs); S.obs_user.resize(S.n_obs);
-    std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
-    uint32_t last_cls = 0; int last_cam = -1; double last_sigma = 0, last_huber = 0;
-    for (size_t n = 0; n < pb.reproj.size(); n++) {
-      const ReprojFactor& f = pb.reproj[n];
-      if (!f.alive) continue;
-      const int pt = point_of_block[f.point];
-      if (pt < p_lo || pt >= p_hi) continue;
-      const int k = pose_of_block[f.pose];
-      if (f.cam != last_cam || f.sigma != last_sigma || f.huber != last_huber) { last_cls = class_of(f.cam, f.sigma, f.huber); last_cam = f.cam; last_sigma = f.sigma; last_huber = f.huber; }
-      const Camera& c = pb.cams[f.cam];
-      ObsRec& o = S.obs[cur[k]];
-      o.ur = (f.px - c.intr[2]) / c.intr[0]; o.vr = (f.py - c.intr[3]) / c.intr[1];
-      o.pose = k; o.point = pt; o.cls = last_cls;
-      o.flags = (S.f_of_pose[k] < 0 ? 1u : 0u) | (S.point_const[pt] ? 2u : 0u) | ((uint32_t)f.cam << 8);
-      S.obs_user[cur[k]] = (uint32_t)n;
-      cur[k]++;
+    for (int t = 0; t < nt; t++) for (const ClsKey& c : local_cls[t]) class_of(c.cam, c.sigma, c.huber);
+    // segment starts, and the start of every chunk's share inside each segment
+    S.pose_ptr.assign(S.K + 1, 0);
+    for (int k = 0; k < S.K; k++) {
+      uint32_t acc = S.pose_ptr[k];
+      for (int t = 0; t < nt; t++) { const uint32_t c = hist[t][k]; hist[t][k] = acc; acc += c; }
+      S.pose_ptr[k + 1] = acc;
     }
-    // sort inside each pose segment by (camera, point): 64-bit keys, segments in parallel
+    S.n_obs = S.pose_ptr[S.K];
+    // scatter (key, factor index); the key orders a pose segment by (camera, point)
     std::vector<uint64_t> key(S.n_obs);
-    for (int64_t q = 0; q < S.n_obs; q++) key[q] = ((uint64_t)S.classes[S.obs[q].cls].cam << 32) | S.obs[q].point;
-    std::vector<ObsRec> sorted_obs(S.n_obs); std::vector<uint32_t> sorted_user(S.n_obs);
+    std::vector<uint32_t> fac(S.n_obs);
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+    for (int t = 0; t < nt; t++) {
+      int64_t b, e; chunk(t, b, e);
+      std::vector<uint32_t>& cur = hist[t];
+      for (int64_t n = b; n < e; n++) {
+        const ReprojFactor& f = pb.reproj[n];
+        int pt;
+        if (!mine(f, pt)) continue;
+        const uint32_t q = cur[pose_of_block[f.pose]]++;
+        key[q] = ((uint64_t)(uint32_t)f.cam << 32) | (uint32_t)pt;
+        fac[q] = (uint32_t)n;
+      }
+    }
+    // sort inside each pose segment (ties keep the order of addition), then write the records in their final place
+    S.obs.resize(S.n_obs); S.obs_user.resize(S.n_obs);
 #pragma omp parallel
     {
       std::vector<std::pair<uint64_t, uint32_t>> kv;
+      uint32_t last_cls = 0; int last_cam = -1; double last_sigma = 0, last_huber = 0;
 #pragma omp for schedule(dynamic, 16)
       for (int k = 0; k < S.K; k++) {
         const uint32_t b = S.pose_ptr[k], e = S.pose_ptr[k + 1];
         kv.resize(e - b);
-        for (uint32_t i = 0; i < e - b; i++) kv[i] = {key[b + i], i};     // ties keep the order of addition
+        for (uint32_t i = 0; i < e - b; i++) kv[i] = {key[b + i], i};
         std::sort(kv.begin(), kv.end());
-        for (uint32_t i = 0; i < e - b; i++) { sorted_obs[b + i] = S.obs[b + kv[i].second]; sorted_user[b + i] = S.obs_user[b + kv[i].second]; }
+        for (uint32_t i = 0; i < e - b; i++) {
+          const uint32_t n = fac[b + kv[i].second];
+          const ReprojFactor& f = pb.reproj[n];
+          if (f.cam != last_cam || f.sigma != last_sigma || f.huber != last_huber) {
+            const double mx = pb.cams[f.cam].intr[0] / f.sigma, my = pb.cams[f.cam].intr[1] / f.sigma;
+            for (size_t c = 0; c < S.classes.size(); c++)
+              if (S.classes[c].cam == f.cam && S.classes[c].mx == mx && S.classes[c].my == my && S.classes[c].huber == f.huber) { last_cls = (uint32_t)c; break; }
+            last_cam = f.cam; last_sigma = f.sigma; last_huber = f.huber;
+          }
+          const Camera& c = pb.cams[f.cam];
+          const int pt = (int)(uint32_t)kv[i].first;
+          ObsRec& o = S.obs[b + i];
+          o.ur = (f.px - c.intr[2]) / c.intr[0]; o.vr = (f.py - c.intr[3]) / c.intr[1];
+          o.pose = k; o.point = pt; o.cls = last_cls;
+          o.flags = (S.f_of_pose[k] < 0 ? 1u : 0u) | (S.point_const[pt] ? 2u : 0u) | ((uint32_t)f.cam << 8);
+          S.obs_user[b + i] = n;
+        }
       }
     }
-    S.obs.swap(sorted_obs); S.obs_user.swap(sorted_user);
   }
   OBVI_TMARK("1");
   // ---- bbox observations, object-major (object, pose, camera)
@@ -366,6 +427,8 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     std::vector<uint32_t> cur(L.ptr.begin(), L.ptr.end() - 1);
     for (int64_t q = 0; q < n_entries; q++) { const uint32_t d = cur[entry_e(q)]++; L.pos[d] = (uint32_t)q; L.f[d] = S.f_of_pose[entry_pose(q)]; }
     L.nslots.assign(ne, 0); L.pair_ptr.assign(ne + 1, 0); L.slot_ptr.assign(ne + 1, 0);
+    int max_slots = L.max_slots;
+#pragma omp parallel for schedule(static, 1024) reduction(max : max_slots)
     for (int e = 0; e < ne; e++) {
       int ns = 0, lastf = -1;
       for (uint32_t d = L.ptr[e]; d < L.ptr[e + 1]; d++) {
@@ -374,11 +437,16 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
         L.slot[d] = (uint16_t)(ns - 1);
       }
       L.nslots[e] = (uint16_t)ns;
-      L.max_slots = std::max(L.max_slots, ns);
+      max_slots = std::max(max_slots, ns);
+    }
+    L.max_slots = max_slots;
+    for (int e = 0; e < ne; e++) {
+      const int ns = L.nslots[e];
       L.pair_ptr[e + 1] = L.pair_ptr[e] + (uint32_t)(ns * (ns + 1) / 2);
       L.slot_ptr[e + 1] = L.slot_ptr[e] + ns;
     }
     L.slot_f.resize(L.slot_ptr[ne]);
+#pragma omp parallel for schedule(static, 1024)
     for (int e = 0; e < ne; e++) {
       uint32_t w = L.slot_ptr[e]; int lastf = -1;
       for (uint32_t d = L.ptr[e]; d < L.ptr[e + 1]; d++) if (L.f[d] >= 0 && L.f[d] != lastf) { L.slot_f[w++] = L.f[d]; lastf = L.f[d]; }
@@ -390,10 +458,15 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
   for (Structure::EList* L : {&S.pts, &S.objs}) {
     const int ne = (int)L->nslots.size();
     const std::vector<uint8_t>& cst = (L == &S.pts) ? S.point_const : S.obj_const;
+#pragma omp parallel for schedule(static, 1024)
     for (int e = 0; e < ne; e++) {
       if (cst[e]) continue;
       const int32_t* sf = &L->slot_f[L->slot_ptr[e]]; const int ns = L->nslots[e];
-      for (int a = 0; a < ns; a++) for (int b = a; b < ns; b++) setbit(sf[a], sf[b]);
+      for (int a = 0; a < ns; a++) for (int b = a; b < ns; b++) {
+        uint64_t* word = &bits[(size_t)sf[a] * W + (sf[b] >> 6)];
+        const uint64_t m = 1ull << (sf[b] & 63);
+        if (!(__atomic_load_n(word, __ATOMIC_RELAXED) & m)) __atomic_fetch_or(word, m, __ATOMIC_RELAXED);
+      }
     }
   }
   OBVI_TMARK("3");
@@ -446,10 +519,11 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
   for (Structure::EList* L : {&S.pts, &S.objs}) {
     const int ne = (int)L->nslots.size();
     L->pair_blk.resize(L->pair_ptr[ne]);
+    const std::vector<uint8_t>& cst = (L == &S.pts) ? S.point_const : S.obj_const;
+#pragma omp parallel for schedule(static, 1024)
     for (int e = 0; e < ne; e++) {
       const int32_t* sf = &L->slot_f[L->slot_ptr[e]]; const int ns = L->nslots[e];
       uint32_t w = L->pair_ptr[e];
-      const std::vector<uint8_t>& cst = (L == &S.pts) ? S.point_const : S.obj_const;
       for (int a = 0; a < ns; a++) for (int b = a; b < ns; b++) L->pair_blk[w++] = cst[e] ? 0u : blk_of(sf[a], sf[b]);
     }
   }
@@ -464,31 +538,50 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     std::vector<uint32_t> dptr(S.P + 1, 0);
     std::vector<uint8_t> pt_has_prior(S.P, 0);
     for (const UnaryRec& u : S.unary) if (u.kind == 1) pt_has_prior[u.idx] = 1;
+    // pass A (parallel): classify every point, count its dense slots and its groups
+    std::vector<uint8_t> kind(S.P, 0);          // 0: nothing to do, 1: generic kernels (fallback), 2: row-owner kernels
+    std::vector<uint32_t> span_of(S.P, 0), ngs_of(S.P, 0);
+#pragma omp parallel for schedule(static, 1024)
     for (int e = 0; e < S.P; e++) {
-      R.grp_ptr[e + 1] = R.grp_ptr[e]; dptr[e + 1] = dptr[e];
       // constant points with observations (they still carry model-cost terms) and prior-only points keep the generic kernels
-      if (S.pts.ptr[e] == S.pts.ptr[e + 1]) { if (!S.point_const[e] && pt_has_prior[e]) R.fallback.push_back((uint32_t)e); continue; }
-      if (S.point_const[e]) { R.fallback.push_back((uint32_t)e); continue; }
+      if (S.pts.ptr[e] == S.pts.ptr[e + 1]) { if (!S.point_const[e] && pt_has_prior[e]) kind[e] = 1; continue; }
+      if (S.point_const[e]) { kind[e] = 1; continue; }
       const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]]; const int ns = S.pts.nslots[e];
-      if (ns > 0 && sf[ns - 1] - sf[0] >= kRowSpan) { R.fallback.push_back((uint32_t)e); continue; }
-      R.regular[e] = 1;
-      const int span = ns ? sf[ns - 1] - sf[0] + 1 : 0;
-      dptr[e + 1] = dptr[e] + (uint32_t)span;
-      int ngs = 0;
+      if (ns > 0 && sf[ns - 1] - sf[0] >= kRowSpan) { kind[e] = 1; continue; }
+      kind[e] = 2;
+      span_of[e] = ns ? (uint32_t)(sf[ns - 1] - sf[0] + 1) : 0u;
+      uint32_t ngs = 0;
       for (uint32_t d = S.pts.ptr[e]; d < S.pts.ptr[e + 1];) {
         uint32_t d2 = d + 1;
-        // a run of entries from the same pose (constant poses: one group per entry is fine, they carry no slot)
+        while (d2 < S.pts.ptr[e + 1] && S.pts.slot[d] != 0xFFFF && S.pts.slot[d2] == S.pts.slot[d]) d2++;
+        ngs++; d = d2;
+      }
+      ngs_of[e] = ngs;
+      for (int a = 0; a < ns; a++) {
+        const int ncol = sf[ns - 1] - sf[a] + 1;
+        for (int r = 0; 5 * r < ncol; r++) __atomic_fetch_add(&cnt[(size_t)sf[a] * kRanges + r + 1], 1u, __ATOMIC_RELAXED);
+      }
+    }
+    for (int e = 0; e < S.P; e++) {
+      R.grp_ptr[e + 1] = R.grp_ptr[e] + ngs_of[e]; dptr[e + 1] = dptr[e] + span_of[e];
+      if (kind[e] == 1) R.fallback.push_back((uint32_t)e);
+      R.regular[e] = kind[e] == 2;
+    }
+    R.grp.resize(R.grp_ptr[S.P]); R.grp_f.resize(R.grp_ptr[S.P]);
+    // pass B (parallel): one record per run of entries from the same pose (constant poses: one group per entry, no slot)
+#pragma omp parallel for schedule(static, 1024)
+    for (int e = 0; e < S.P; e++) {
+      if (kind[e] != 2) continue;
+      const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]];
+      uint32_t w = R.grp_ptr[e];
+      for (uint32_t d = S.pts.ptr[e]; d < S.pts.ptr[e + 1];) {
+        uint32_t d2 = d + 1;
         while (d2 < S.pts.ptr[e + 1] && S.pts.slot[d] != 0xFFFF && S.pts.slot[d2] == S.pts.slot[d]) d2++;
         Structure::RowGroup G;
         G.cnt = d2 - d; G.pos0 = S.pts.pos[d]; G.pos1 = G.cnt == 2 ? S.pts.pos[d + 1] : (G.cnt > 2 ? d : 0u);
         G.gs = S.pts.slot[d] == 0xFFFF ? 0xFFFFFFFFu : dptr[e] + (uint32_t)(S.pts.f[d] - sf[0]);
-        R.grp.push_back(G); R.grp_f.push_back(S.pts.f[d]); ngs++;
+        R.grp[w] = G; R.grp_f[w] = S.pts.f[d]; w++;
         d = d2;
-      }
-      R.grp_ptr[e + 1] = R.grp_ptr[e] + (uint32_t)ngs;
-      for (int a = 0; a < ns; a++) {
-        const int ncol = sf[ns - 1] - sf[a] + 1;
-        for (int r = 0; 5 * r < ncol; r++) cnt[(size_t)sf[a] * kRanges + r + 1]++;
       }
     }
     R.n_slots = dptr[S.P];

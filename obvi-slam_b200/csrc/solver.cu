@@ -1682,6 +1682,44 @@ int obvi_debug_partition(obvi_problem* p, int rank, int world, int64_t* stats) {
   }
 }
 
+int obvi_debug_structure_hash(obvi_problem* p, int rank, int world, uint64_t* hash) {
+  if (!p || !hash || world < 1 || rank < 0 || rank >= world) return OBVI_ERR_INVALID_ARGUMENT;
+  try {
+    Structure S;
+    std::string err;
+    if (!build_structure(p->s.pb, S, rank, world, err)) return fail(p, OBVI_ERR_INVALID_ARGUMENT, err.c_str());
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* data, size_t bytes) {
+      const unsigned char* c = static_cast<const unsigned char*>(data);
+      for (size_t i = 0; i < bytes; i++) { h ^= c[i]; h *= 1099511628211ull; }
+      h ^= bytes; h *= 1099511628211ull;
+    };
+    auto vec = [&](const auto& v) { if (!v.empty()) mix(v.data(), v.size() * sizeof(v[0])); else mix(nullptr, 0); };
+    const int64_t scal[] = {S.K, S.P, S.O, S.C, S.nf, S.n_obs, S.n_bbox, S.n_unary, S.n_rel, S.num_residual_blocks_reduced, S.num_residuals_reduced,
+                            S.num_param_blocks_reduced, S.num_params_reduced, S.n_upper, S.pts.max_slots, S.objs.max_slots, S.prow.n_slots};
+    mix(scal, sizeof(scal));
+    vec(S.pose_block); vec(S.point_block); vec(S.obj_block); vec(S.f_of_pose); vec(S.point_const); vec(S.obj_const);
+    vec(S.obs); vec(S.obs_user); vec(S.pose_ptr);
+    for (const CalibClass& c : S.classes) { mix(&c.mx, 8); mix(&c.my, 8); mix(&c.huber, 8); mix(&c.cam, 4); }
+    for (const Structure::EList* L : {&S.pts, &S.objs}) {
+      vec(L->ptr); vec(L->pos); vec(L->f); vec(L->slot); vec(L->pair_ptr); vec(L->nslots); vec(L->pair_blk); vec(L->slot_f); vec(L->slot_ptr);
+    }
+    vec(S.prow.grp_ptr); vec(S.prow.grp); vec(S.prow.grp_f); vec(S.prow.regular); vec(S.prow.ent); vec(S.prow.items); vec(S.prow.rowblk); vec(S.prow.fallback);
+    for (const BBoxRec& r : S.bbox) { mix(r.brect, sizeof(r.brect)); mix(r.A4, sizeof(r.A4)); mix(&r.invalid_err, 8); mix(&r.huber, 8); mix(&r.obj, 16); }
+    vec(S.bbox_user);
+    for (const UnaryRec& r : S.unary) { mix(r.A, sizeof(r.A)); mix(r.mean, sizeof(r.mean)); mix(&r.huber, 8); mix(&r.kind, 16); mix(&r.flags, 4); }
+    vec(S.unary_user);
+    for (const RelRec& r : S.rel) { mix(r.tm, sizeof(r.tm)); mix(r.Rm_inv, sizeof(r.Rm_inv)); mix(r.A6, sizeof(r.A6)); mix(&r.huber, 8); mix(&r.p1, 32); }
+    vec(S.rel_user);
+    vec(S.su_ptr); vec(S.su_col); vec(S.sf_ptr); vec(S.sf_col); vec(S.sf_src);
+    *hash = h;
+    return OBVI_OK;
+  } catch (const std::exception& e) {
+    p->s.pb.error = e.what();
+    return OBVI_ERR_INVALID_ARGUMENT;
+  }
+}
+
 int obvi_comm_unique_id(void* out) {
   if (!out) return OBVI_ERR_INVALID_ARGUMENT;
   std::string err;

@@ -63,3 +63,39 @@ def test_sharding_world_size_2_gloo():
     for o in out:
         for k in ("nf", "n_upper", "structure_checksum", "num_parameters_reduced", "num_residual_blocks_reduced"):
             assert o[k] == alone[k], k
+
+
+def test_structure_build_is_independent_of_thread_count(tmp_path):
+    """The structure build (csrc/problem.hpp) runs its passes over the factors in parallel (chunked stable counting sort,
+    atomic min / or / add); every array it produces must be bit-identical to the one-thread build, for the whole problem and for
+    every rank's share of a sharded one.  obvi_debug_structure_hash hashes exactly the bytes the solver would upload."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "hash.py"
+    script.write_text(f"""
+import sys, json
+sys.path.insert(0, {root!r})
+import numpy as np
+import obvi_b200 as ob
+out = []
+g1 = ob.synth.make_graph(K=120, P=6000, O=12, seed=3, objects_on=True, relpose="starved", n_const_poses=5, min_obj_obs=4, ltm_frac=0.3, max_obj_kf=100)
+g1.const_point[::7] = True; g1.const_obj[1] = True
+g2 = ob.synth.make_graph(K=40, P=1500, O=6, seed=61, objects_on=True, relpose="all", n_const_poses=1, min_obj_obs=4)
+perm = np.random.default_rng(0).permutation(len(g2.reproj["pose"]))
+for k in ("pose", "point", "cam", "px", "sigma"):
+    g2.reproj[k] = np.ascontiguousarray(g2.reproj[k][perm])
+for g in (g1, g2):
+    p = ob.problem_from_graph(g, device=-1)
+    out.append([p.debug_structure_hash(0, 1)] + [p.debug_structure_hash(r, 3) for r in range(3)])
+    for fid in p.factor_ids["reproj"][::13][:200]:
+        p.remove_residual_block(fid)
+    out[-1].append(p.debug_structure_hash(0, 1))
+print("RESULT " + json.dumps(out))
+""")
+    def run(threads):
+        r = subprocess.run([sys.executable, str(script)], env=dict(os.environ, OMP_NUM_THREADS=str(threads)), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        return json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    one, many = run(1), run(5)
+    assert one == many
+    assert len(set(one[0])) == len(one[0])          # different ranks / edits give different structures
