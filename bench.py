@@ -194,9 +194,11 @@ def run_ours(args, rank, world, local_rank):
                     data="synthetic", config=dict(WORKLOAD, parallelism=f"e-blocks sharded over {world} rank(s), reduced system all-reduced" if world > 1 else "single GPU",
                                                   counts=g.counts(), seed=args.seed),
                     clocks=clocks,
-                    e2e=dict(value=steps / wall_t, unit=UNIT, h2d_bytes_per_step=nparam / steps, d2h_bytes_per_step=nparam / steps,
-                             note="obvi_solve through the C ABI with host parameter blocks: gather + H2D, K iterations, D2H + scatter; "
-                                  "factor records are device-resident from the first solve, as in a persistent ceres::Problem",
+                    e2e=dict(value=steps / wall_t, unit=UNIT, h2d_bytes_per_step=nparam / steps, d2h_bytes_per_step=nparam / steps + 16 * 8,
+                             note="obvi_solve through the C ABI with host parameter blocks: gather + H2D of every block, K iterations "
+                                  "(each reads its 16-double result block -- cost, model change, norms, flags -- back through pinned "
+                                  "memory and decides accept / reject on the host), D2H + scatter of every block; factor records are "
+                                  "device-resident from the first solve, as in a persistent ceres::Problem",
                              first_call_preprocess_s=s_first.preprocessor_time_in_seconds),
                     gpu_launches=int(s.kernel_launches), roofline=roof, cpu_baseline=cpu, parity=parity,
                     final_cost=gpu_cost, pcg_iterations=int(s.pcg_iterations_total),
