@@ -13,5 +13,6 @@ synth = importlib.import_module("obvi-slam_b200.synth")
 schedule = importlib.import_module("obvi-slam_b200.schedule")
 pg_state_io = importlib.import_module("obvi-slam_b200.pg_state_io")
 ltm_extraction = importlib.import_module("obvi-slam_b200.ltm_extraction")
+vslam_dataset_io = importlib.import_module("obvi-slam_b200.vslam_dataset_io")
 
 globals().update({k: v for k, v in vars(_pkg).items() if not k.startswith("__")})
