@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- see ba_oracle.hpp.  PARITY UNPINNED (no Ceres binary, no reference
-// golden vectors); checked against oracle/py_oracle.py.
+// golden vectors); checked against oracle/py_oracle.py.  (The projection model of the reprojection factor
+// alone is pinned by the reference's simulated sequences, tests/test_vslam_dataset.py.)
 //
 // What is restated, and from where (paths relative to /root/reference):
 //   * residual functors, evaluated on forward-mode dual numbers exactly as ceres::AutoDiffCostFunction

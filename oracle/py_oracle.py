@@ -2,6 +2,8 @@
 
 PARITY UNPINNED: the reference holds no golden vectors for this path and its solver
 arithmetic lives in Ceres/SuiteSparse, which are absent here.
+(Only the projection model of the reprojection factor is pinned by reference material:
+the simulated sequences under /root/reference/data, see tests/test_vslam_dataset.py.)
 This file restates the reference's *residual formulas* (what Ceres autodiff evaluates)
 in float64 NumPy, differentiates them by the complex-step method (exact to rounding),
 and restates Ceres' Levenberg-Marquardt semantics with a *dense* normal-equation solve.
