@@ -1,7 +1,7 @@
 """A/B timing diagnostics (not a test): one C3 graph, one Problem per environment variant (the OBVI_* switches are read when
 the problem is created), 2 solves each; prints LM it/s and, with OBVI_PROFILE=1, the in-situ phase table on stderr.
 
-  python tests/gpu_ab.py 50 "" OBVI_OBJ_SPLIT=0 OBVI_DEFER_SYNC=1,OBVI_POSE_ACCUM_SIDE=1
+  python tests/gpu_ab.py 50 "" OBVI_OBJ_SPLIT=0 OBVI_DEFER_SYNC=0,OBVI_REFACTOR_RATIO=4
 """
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
