@@ -29,6 +29,14 @@ WORKLOAD = dict(workload="C3: 2000 keyframes / 200k points / 500 objects, full r
                 l2="working set per iteration (0.09 GB observations + 0.36 GB Jacobian chunks) exceeds the 126 MB L2: no flush needed")
 
 
+def workload(args):
+    """`config` of the JSON line; the named workload is C3 (BASELINE.json configs[2]) -- say so when another one was asked for."""
+    if args.config == "C3":
+        return dict(WORKLOAD)
+    return dict(WORKLOAD, workload=f"{args.config} (NOT the benchmark workload; obvi-slam_b200/synth.py make_config('{args.config}'))",
+                generator=f"obvi-slam_b200/synth.py make_config('{args.config}', seed={args.seed})")
+
+
 def solver_opts(iters):
     return dict(max_num_iterations=iters, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
                 initial_trust_region_radius=100.0, max_trust_region_radius=1e4, use_nonmonotonic_steps=1)
@@ -102,9 +110,9 @@ def run_reference(args, rank):
     cores = r["num_threads"]
     line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=r["lm_steps"], warmup=args.warmup,
                 ms_per_step=1e3 * loop / r["lm_steps"], higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
-                data="synthetic", config=WORKLOAD,
+                data="synthetic", config=workload(args),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
-                                  sample=f"{r['lm_steps']} LM iterations of the full C3 graph, Ceres-semantics restatement "
+                                  sample=f"{r['lm_steps']} LM iterations of the full {args.config} graph, Ceres-semantics restatement "
                                          f"(dual-number autodiff, Schur, sparse Cholesky), OpenMP {cores} threads; "
                                          f"jac {r['jacobian_time']:.2f}s lin {r['linear_solver_time']:.2f}s res {r['residual_time']:.2f}s"),
                 e2e=dict(value=r["lm_steps"] / (time.time() - t0), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -191,7 +199,7 @@ def run_ours(args, rank, world, local_rank):
         nparam = (g.poses.size + g.points.size + g.objects.size) * 8
         line = dict(metric=METRIC, value=steps / dev_t, unit=UNIT, n_gpus=world, steps=steps, warmup=args.warmup,
                     ms_per_step=1e3 * dev_t / steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
-                    data="synthetic", config=dict(WORKLOAD, parallelism=f"e-blocks sharded over {world} rank(s), reduced system all-reduced" if world > 1 else "single GPU",
+                    data="synthetic", config=dict(workload(args), parallelism=f"e-blocks sharded over {world} rank(s), reduced system all-reduced" if world > 1 else "single GPU",
                                                   counts=g.counts(), seed=args.seed),
                     clocks=clocks,
                     e2e=dict(value=steps / wall_t, unit=UNIT, h2d_bytes_per_step=nparam / steps, d2h_bytes_per_step=nparam / steps + 16 * 8,
