@@ -29,6 +29,25 @@ WORKLOAD = dict(workload="C3: 2000 keyframes / 200k points / 500 objects, full r
                 l2="working set per iteration (0.09 GB observations + 0.36 GB Jacobian chunks) exceeds the 126 MB L2: no flush needed")
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to stdout when
+    NCCL_DEBUG is set in the environment, as it is on the GPU boxes), so file descriptor 1 is pointed at stderr for the whole run
+    and the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def workload(args):
     """`config` of the JSON line; the named workload is C3 (BASELINE.json configs[2]) -- say so when another one was asked for."""
     if args.config == "C3":
@@ -117,7 +136,7 @@ def run_reference(args, rank):
                                          f"jac {r['jacobian_time']:.2f}s lin {r['linear_solver_time']:.2f}s res {r['residual_time']:.2f}s"),
                 e2e=dict(value=r["lm_steps"] / (time.time() - t0), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 note="Ceres + SuiteSparse are not installable here (SURVEY.md 8c): this arm is the CPU restatement, not a Ceres binary")
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -213,7 +232,7 @@ def run_ours(args, rank, world, local_rank):
                     phases_ms_per_step=dict(jacobian=1e3 * s.jacobian_evaluation_time_in_seconds / steps,
                                             linear=1e3 * s.linear_solver_time_in_seconds / steps,
                                             residual=1e3 * s.residual_evaluation_time_in_seconds / steps))
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -231,6 +250,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    claim_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
