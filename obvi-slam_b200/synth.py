@@ -139,10 +139,99 @@ def odom_cov(t, R, k=0.025):
     return cov
 
 
+
+def _object_visibility(ell1, R_gt, t_gt, min_bbox_px):
+    """Keyframes (ascending) that see the ellipsoid with BOTH cameras under the generator's detection gates, and the
+    exact bounding boxes [cam][keyframe] (pixels)."""
+    d2 = np.sum((t_gt[:, :2] - ell1[:2]) ** 2, axis=1)
+    near = np.nonzero(d2 < 20.0 ** 2)[0]
+    if len(near) == 0:
+        return near, [np.zeros((0, 4)), np.zeros((0, 4))]
+    ell = np.repeat(ell1[None, :], len(near), axis=0)
+    vis = []
+    for cam in range(2):
+        px, ok, zc = _bbox_exact(ell, R_gt[near], t_gt[near], cam)
+        ctr_u, ctr_v = 0.5 * (px[:, 0] + px[:, 1]), 0.5 * (px[:, 2] + px[:, 3])
+        ok &= (zc > 1.5) & (ctr_u > 0) & (ctr_u < IMG_W) & (ctr_v > 0) & (ctr_v < IMG_H)
+        ok &= (np.abs(px[:, 1] - px[:, 0]) < 2.0 * IMG_W) & (np.abs(px[:, 3] - px[:, 2]) < 2.0 * IMG_H)
+        # detections smaller than min_bbox_px carry no shape information at 10 px noise
+        ok &= (np.abs(px[:, 1] - px[:, 0]) >= min_bbox_px) & (np.abs(px[:, 3] - px[:, 2]) >= min_bbox_px)
+        vis.append((px, ok))
+    both = np.nonzero(vis[0][1] & vis[1][1])[0]
+    return near[both], [vis[0][0][both], vis[1][0][both]]
+
+
+def _fill_points(rng, K, P, R_gt, t_gt, min_parallax_deg, n_starved):
+    """Candidate points drawn 3x; P of those whose whole track (L keyframes x 2 cameras) stays inside the images and
+    passes the parallax gate are kept, with per-length quotas: L uniform on 5..15, tilted by the smallest linear factor
+    that brings the total to 20 P observations AFTER the feature-starved keyframes have dropped theirs."""
+    fx, fy, cx, cy = INTR
+    Pc = 3 * P
+    anchor = rng.integers(0, K, Pc)
+    L = rng.integers(5, 16, Pc)
+    depth = rng.uniform(2.0, 30.0, Pc)
+    upx = rng.uniform(20.0, IMG_W - 20.0, Pc)
+    vpx = rng.uniform(20.0, IMG_H - 20.0, Pc)
+    Xc = np.stack([(upx - cx) / fx * depth, (vpx - cy) / fy * depth, depth], -1)
+    Xr = Xc @ R_EXTR.T + T_EXTR[0][None, :]
+    X = np.einsum("nij,nj->ni", R_gt[anchor], Xr) + t_gt[anchor]
+    ok = anchor + L <= K
+    rep = np.repeat(np.arange(Pc), L)
+    kf = np.minimum(anchor[rep] + (np.arange(L.sum()) - np.repeat(np.cumsum(L) - L, L)), K - 1)
+    for cam in range(2):
+        Xo = _project(R_gt[kf], t_gt[kf], cam, X[rep])
+        z = Xo[:, 2]
+        zz = np.where(z > 0.1, z, 1.0)
+        u, v = fx * Xo[:, 0] / zz + cx, fy * Xo[:, 1] / zz + cy
+        inside = (z > 0.1) & (u >= 0) & (u < IMG_W) & (v >= 0) & (v < IMG_H)
+        ok &= np.bincount(rep, weights=~inside, minlength=Pc) == 0
+    if min_parallax_deg > 0:
+        la = np.minimum(anchor + L - 1, K - 1)
+        c0 = t_gt[anchor] + np.einsum("nij,j->ni", R_gt[anchor], T_EXTR[0])
+        c1 = t_gt[la] + np.einsum("nij,j->ni", R_gt[la], T_EXTR[1])
+        v0, v1 = X - c0, X - c1
+        cosang = np.einsum("ni,ni->n", v0, v1) / (np.linalg.norm(v0, axis=1) * np.linalg.norm(v1, axis=1))
+        ok &= np.degrees(np.arccos(np.clip(cosang, -1.0, 1.0))) >= min_parallax_deg
+    lens = np.arange(5, 16)
+    avail = np.array([int(np.sum(ok & (L == l))) for l in lens])
+    target = 20.0 * P + n_starved * max(0.0, 20.0 * P / K - 30.0)   # the starved keyframes drop all but 30 observations
+
+    def quotas(alpha):
+        w = np.clip(1.0 + alpha * (lens - 10.0), 0.0, None)
+        q = np.floor(P * w / w.sum()).astype(np.int64)
+        q[np.argmax(w)] += P - q.sum()
+        return q
+
+    lo, hi = 0.0, 0.2
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        if float(np.sum(2 * lens * quotas(mid))) < target:
+            lo = mid
+        else:
+            hi = mid
+    q = np.minimum(quotas(hi), avail)
+    # hand what a short supply of some length leaves over to the lengths that still have candidates, longest first
+    short = P - int(q.sum())
+    for i in np.argsort(-lens):
+        if short <= 0:
+            break
+        extra = min(short, int(avail[i] - q[i]))
+        q[i] += extra
+        short -= extra
+    keep = np.zeros(Pc, dtype=bool)
+    for l, n in zip(lens, q):
+        keep[np.nonzero(ok & (L == l))[0][:n]] = True
+    idx = np.nonzero(keep)[0]
+    if len(idx) < P:    # not enough eligible tracks (tiny K): top up with any candidate
+        idx = np.sort(np.concatenate([idx, np.setdiff1d(np.arange(Pc), idx)[:P - len(idx)]]))
+    return anchor[idx], L[idx], depth[idx], upx[idx], vpx[idx]
+
+
 # ----------------------------------------------------------------------------- generator
 def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_poses=1,
                sigma_px=1.5, outlier_frac=0.05, min_point_obs=5, min_obj_obs=10, ltm_frac=0.0,
-               pose_noise=True, min_parallax_deg=1.0, symmetric_priors=False, min_bbox_px=30.0, max_obj_kf=40):
+               pose_noise=True, min_parallax_deg=1.0, symmetric_priors=False, min_bbox_px=30.0, max_obj_kf=40,
+               fill=False, starved_every=20):
     """Build S(K, P, O, seed).
 
     relpose: "starved" -> rel-pose factors only into feature-starved keyframes (reference rule,
@@ -154,6 +243,13 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
     min_parallax_deg: tracks whose first/last rays subtend less than this at the point are dropped.
     max_obj_kf: cap on the keyframes that observe one object (40 in the named configs; tests raise it to reach the
              kernels' off-chip staging path for objects with more pose slots than fit in shared memory).
+    fill:    reach the factor counts SURVEY.md 8(d) pins for S(K, P, O) -- 20 P reprojection blocks, 80 O bounding-box
+             blocks, O shape priors -- by OVERSAMPLING candidates: points are drawn 3x, only tracks that stay inside
+             both images for all of their L keyframes and pass the parallax gate are eligible, and P of them are picked
+             with per-length quotas (L uniform on 5..15, tilted just enough to make up for the observations the
+             feature-starved keyframes drop); objects are drawn 8x and the first O seen from >= max_obj_kf keyframes by
+             both cameras are kept.  Without it the gates simply thin the graph (the round-1 "C3-gated" workload).
+    starved_every: every n-th keyframe keeps at most 30 feature observations (and so gets a relative-pose factor).
     """
     rng = np.random.default_rng(seed)
     g = FactorGraph()
@@ -171,12 +267,18 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
     poses_gt = np.concatenate([t_gt, mat_to_rotvec(R_gt)], axis=1)
 
     # --- points: anchored to a keyframe, inside camera 0's frustum there
-    anchor = rng.integers(0, K, P)
-    L = rng.integers(5, 16, P)
-    depth = rng.uniform(2.0, 30.0, P)
-    upx = rng.uniform(20.0, IMG_W - 20.0, P)
-    vpx = rng.uniform(20.0, IMG_H - 20.0, P)
     fx, fy, cx, cy = INTR
+    starved = np.zeros(K, dtype=bool)
+    if relpose == "starved":
+        starved[np.arange(starved_every - 1, K, starved_every)] = True
+    if fill:
+        anchor, L, depth, upx, vpx = _fill_points(rng, K, P, R_gt, t_gt, min_parallax_deg, int(starved.sum()))
+    else:
+        anchor = rng.integers(0, K, P)
+        L = rng.integers(5, 16, P)
+        depth = rng.uniform(2.0, 30.0, P)
+        upx = rng.uniform(20.0, IMG_W - 20.0, P)
+        vpx = rng.uniform(20.0, IMG_H - 20.0, P)
     Xc = np.stack([(upx - cx) / fx * depth, (vpx - cy) / fy * depth, depth], -1)
     Xr = Xc @ R_EXTR.T + T_EXTR[0][None, :]
     X_gt = np.einsum("nij,nj->ni", R_gt[anchor], Xr) + t_gt[anchor]
@@ -200,9 +302,7 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
     obs_pose = np.concatenate(obs_pose); obs_point = np.concatenate(obs_point)
     obs_cam = np.concatenate(obs_cam); obs_px = np.concatenate(obs_px)
     # feature-starved keyframes (every 20th): keep at most 30 observations
-    starved = np.zeros(K, dtype=bool)
     if relpose == "starved":
-        starved[np.arange(19, K, 20)] = True
         drop = np.zeros(len(obs_pose), dtype=bool)
         for kk in np.nonzero(starved)[0]:
             idx = np.nonzero(obs_pose == kk)[0]
@@ -245,49 +345,46 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
     g.ltm = dict(obj=np.zeros(0, np.int64), mean=np.zeros((0, 7)), cov=np.zeros((0, 7, 7)), huber=1.0)
     obj_gt = np.zeros((O, 7))
     if O > 0:
-        cls = rng.integers(0, len(SHAPE_PRIORS), O)
-        okf = rng.integers(0, K, O)
-        side = rng.choice([-1.0, 1.0], O)
-        lat = rng.uniform(2.5, 7.0, O) * side
-        fwd = rng.uniform(3.0, 8.0, O)
+        Oc = 8 * O if (fill and objects_on) else O      # candidates
+        cls = rng.integers(0, len(SHAPE_PRIORS), Oc)
+        okf = rng.integers(0, K, Oc)
+        side = rng.choice([-1.0, 1.0], Oc)
+        lat = rng.uniform(2.5, 7.0, Oc) * side
+        fwd = rng.uniform(3.0, 8.0, Oc)
         mean = np.array([SHAPE_PRIORS[c][0] for c in cls])
         var = np.array([SHAPE_PRIORS[c][1] for c in cls])
+        obj_gt = np.zeros((Oc, 7))
         if not symmetric_priors:
             # Five of the six class means have dx == dy, which makes the ellipsoid's yaw a pure gauge freedom
             # (the tight dimension priors pull dx, dy back to the symmetric mean): LM -- Ceres' too -- then takes
             # yaw steps of thousands of radians and the iteration sequence becomes chaotic, useless for parity
             # checks.  The synthetic classes therefore use the config's means with dy scaled by 1.5.
             mean = mean * np.array([1.0, 1.5, 1.0])
-        dims = np.clip(mean + rng.normal(0.0, 1.0, (O, 3)) * np.minimum(np.sqrt(var), 0.15 * mean), 0.1, None)
+        dims = np.clip(mean + rng.normal(0.0, 1.0, (Oc, 3)) * np.minimum(np.sqrt(var), 0.15 * mean), 0.1, None)
         ca, sa = np.cos(yaw[okf]), np.sin(yaw[okf])
         obj_gt[:, 0] = t_gt[okf, 0] + ca * fwd - sa * lat
         obj_gt[:, 1] = t_gt[okf, 1] + sa * fwd + ca * lat
         obj_gt[:, 2] = dims[:, 2] / 2.0 - 0.3  # standing on the ground, robot origin 0.3 m above it
-        obj_gt[:, 3] = rng.uniform(-np.pi, np.pi, O)
+        obj_gt[:, 3] = rng.uniform(-np.pi, np.pi, Oc)
         obj_gt[:, 4:7] = dims
+        if Oc != O:
+            # keep the first O candidates that max_obj_kf keyframes see with both cameras (then the best of the rest)
+            nvis = np.array([len(_object_visibility(obj_gt[o], R_gt, t_gt, min_bbox_px)[0]) for o in range(Oc)])
+            full = np.nonzero(nvis >= max_obj_kf)[0][:O]
+            if len(full) < O:
+                rest = np.setdiff1d(np.arange(Oc), full)
+                full = np.sort(np.concatenate([full, rest[np.argsort(-nvis[rest], kind="stable")][:O - len(full)]]))
+            cls, okf, mean, var, obj_gt = cls[full], okf[full], mean[full], var[full], np.ascontiguousarray(obj_gt[full])
     if O > 0 and objects_on:
         bo, bp, bc, bcr, bcv = [], [], [], [], []
         for o in range(O):
-            d2 = np.sum((t_gt[:, :2] - obj_gt[o, :2]) ** 2, axis=1)
-            near = np.nonzero(d2 < 20.0 ** 2)[0]
-            if len(near) == 0:
+            kfs, vis_px = _object_visibility(obj_gt[o], R_gt, t_gt, min_bbox_px)
+            kfs = kfs[:max_obj_kf]  # cap: 40 keyframes x 2 cameras
+            if 2 * len(kfs) < min_obj_obs:
                 continue
-            ell = np.repeat(obj_gt[o][None, :], len(near), axis=0)
-            vis = []
+            near, sel = kfs, np.arange(len(kfs))
             for cam in range(2):
-                px, ok, zc = _bbox_exact(ell, R_gt[near], t_gt[near], cam)
-                ctr_u, ctr_v = 0.5 * (px[:, 0] + px[:, 1]), 0.5 * (px[:, 2] + px[:, 3])
-                ok &= (zc > 1.5) & (ctr_u > 0) & (ctr_u < IMG_W) & (ctr_v > 0) & (ctr_v < IMG_H)
-                ok &= (np.abs(px[:, 1] - px[:, 0]) < 2.0 * IMG_W) & (np.abs(px[:, 3] - px[:, 2]) < 2.0 * IMG_H)
-                # detections smaller than min_bbox_px carry no shape information at 10 px noise
-                ok &= (np.abs(px[:, 1] - px[:, 0]) >= min_bbox_px) & (np.abs(px[:, 3] - px[:, 2]) >= min_bbox_px)
-                vis.append((px, ok))
-            both = vis[0][1] & vis[1][1]
-            sel = np.nonzero(both)[0][:max_obj_kf]  # cap: 40 keyframes x 2 cameras
-            if 2 * len(sel) < min_obj_obs:
-                continue
-            for cam in range(2):
-                px = vis[cam][0][sel]
+                px = vis_px[cam][:max_obj_kf]
                 # reference corner order is (xmin, xmax, ymin, ymax); the functor's prediction order is
                 # (q13+sqrt, q13-sqrt, ...)/q33 which equals that order for q33 < 0.
                 lo_x, hi_x = np.minimum(px[:, 0], px[:, 1]), np.maximum(px[:, 0], px[:, 1])
@@ -376,7 +473,10 @@ CONFIGS = {
     "C1": dict(K=50, P=2000, O=20, objects_on=False, relpose="starved", n_const_poses=5),
     "C1obj": dict(K=50, P=2000, O=20, objects_on=True, relpose="starved", n_const_poses=5),
     "C2": dict(K=500, P=50000, O=100, objects_on=False, relpose="all", n_const_poses=1),
-    "C3": dict(K=2000, P=200000, O=500, objects_on=True, relpose="starved", n_const_poses=1),
+    # C3 reaches the factor counts SURVEY.md 8(d) pins (4.0 M reprojection / 40 k bbox / 500 shape / ~200 rel-pose);
+    # C3-gated is the round-1 workload (the same shape thinned by the generator's gates to 2.77 M / 19 k / 352 / 100)
+    "C3": dict(K=2000, P=200000, O=500, objects_on=True, relpose="starved", n_const_poses=1, fill=True, starved_every=10),
+    "C3-gated": dict(K=2000, P=200000, O=500, objects_on=True, relpose="starved", n_const_poses=1),
 }
 
 
