@@ -226,3 +226,115 @@ def read_pose_graph_state(path, huber=None):
     extras = dict(semantic_classes={_id(k): v for k, v in _unmap(os_.get("semantic_class_for_object"))},
                   class_priors={k: (_unmat(v["f"]).ravel(), _unmat(v["s"])) for k, v in _unmap(os_.get("mean_and_cov_by_semantic_class"))})
     return g, ids, extras
+
+
+# ----------------------------------------------------------------------------- state-level API
+# The file as the reference's own structs hold it (ObjectAndReprojectionFeaturePoseGraphState =
+# ReprojectionLowLevelFeaturePoseGraphState{LowLevelFeaturePoseGraphState} + ObjOnlyPoseGraphState), without the
+# consistency a FactorGraph needs: ids are arbitrary uint64, factors may reference frames / features that have no estimate,
+# a Pose3D keeps its (angle, axis) pair verbatim (Eigen::AngleAxis does not normalise).  Python mirror:
+#   uint64-keyed maps -> dict[int, ...];  sets of (factor type, factor id) -> set[tuple[int, int]];  the one vector of such
+#   pairs -> list[tuple];  matrices -> numpy arrays;  Pose3D -> dict(transl, angle, axis);  factor structs -> dicts with the
+#   reference's field names (trailing underscore dropped).
+# This is what the reference's round-trip test exercises with hand-made values
+# (test/file_io/cv_file_storage/object_and_reprojection_feature_pose_graph_file_storage_io_tests.cc:9-262).
+def _enc_pose3d(p):
+    return {"transl": _vec(p["transl"]), "rot": {"angle": float(p["angle"]), "axis": _vec(p["axis"])}}
+
+
+def _dec_pose3d(n):
+    return dict(transl=_unmat(n["transl"]).ravel(), angle=float(n["rot"]["angle"]), axis=_unmat(n["rot"]["axis"]).ravel())
+
+
+def _enc_idmap(m, enc):
+    return _map((_uid(k), enc(v)) for k, v in m.items())
+
+
+def _dec_idmap(n, dec):
+    return {_id(k): dec(v) for k, v in _unmap(n)}
+
+
+def _dec_fset(n):
+    return {(int(e["f"]), _id(e["s"])) for e in (n or [])}
+
+
+_RELPOSE_F = (("frame_id_1", _uid, _id), ("frame_id_2", _uid, _id), ("measured_pose_deviation", _enc_pose3d, _dec_pose3d),
+              ("pose_deviation_cov", _mat, _unmat))
+_REPROJ_F = (("frame_id", _uid, _id), ("feature_id", _uid, _id), ("camera_id", _uid, _id), ("feature_pos", _vec, lambda n: _unmat(n).ravel()),
+             ("reprojection_error_std_dev", float, float))
+_BBOX_F = (("frame_id", _uid, _id), ("camera_id", _uid, _id), ("object_id", _uid, _id), ("bounding_box_corners", _vec, lambda n: _unmat(n).ravel()),
+           ("bounding_box_corners_covariance", _mat, _unmat), ("detection_confidence", float, float))
+_SHAPE_F = (("object_id", _uid, _id), ("mean_shape_dim", _vec, lambda n: _unmat(n).ravel()), ("shape_dim_cov", _mat, _unmat))
+
+
+def _enc_struct(fields):
+    return lambda d: {k: enc(d[k]) for k, enc, _ in fields}
+
+
+def _dec_struct(fields):
+    return lambda n: {k: dec(n[k]) for k, _, dec in fields}
+
+
+_vec_dec = lambda n: _unmat(n).ravel()
+_fset_map = (lambda m: _enc_idmap(m, lambda s: _fset(sorted(s))), lambda n: _dec_idmap(n, _dec_fset))
+_id_map = (lambda m: _enc_idmap(m, _uid), lambda n: _dec_idmap(n, _id))
+# (key, encoder, decoder) in the order the reference writes them (…file_storage_io.h:270-352, 604-616, 681-760)
+_LOW_FIELDS = (
+    ("camera_extrinsics_by_camera", lambda m: _enc_idmap(m, _enc_pose3d), lambda n: _dec_idmap(n, _dec_pose3d)),
+    ("camera_intrinsics_by_camera", lambda m: _enc_idmap(m, _mat), lambda n: _dec_idmap(n, _unmat)),
+    ("visual_factor_type", int, int), ("min_frame_id", _uid, _id), ("max_frame_id", _uid, _id),
+    ("max_feature_factor_id", _uid, _id), ("max_pose_factor_id", _uid, _id),
+    ("robot_poses", lambda m: _enc_idmap(m, _vec), lambda n: _dec_idmap(n, _vec_dec)),
+    ("pose_factors_by_frame",) + _fset_map,
+    ("visual_feature_factors_by_frame", lambda m: _enc_idmap(m, lambda v: [{"i": i, "v": e} for i, e in enumerate(_fset(v))]),
+     lambda n: _dec_idmap(n, lambda v: [(int(e["v"]["f"]), _id(e["v"]["s"])) for e in sorted(v, key=lambda e: int(e["i"]))])),
+    ("visual_factors_by_feature",) + _fset_map,
+    ("pose_factors", lambda m: _enc_idmap(m, _enc_struct(_RELPOSE_F)), lambda n: _dec_idmap(n, _dec_struct(_RELPOSE_F))),
+    ("factors", lambda m: _enc_idmap(m, _enc_struct(_REPROJ_F)), lambda n: _dec_idmap(n, _dec_struct(_REPROJ_F))),
+    ("last_observed_frame_by_feature",) + _id_map, ("first_observed_frame_by_feature",) + _id_map,
+)
+_OBJ_FIELDS = (
+    ("mean_and_cov_by_semantic_class", lambda m: _map((str(c), {"f": _vec(v[0]), "s": _mat(v[1])}) for c, v in m.items()),
+     lambda n: {k: (_vec_dec(v["f"]), _unmat(v["s"])) for k, v in _unmap(n)}),
+    ("min_object_id", _uid, _id), ("max_object_id", _uid, _id),
+    ("ellipsoid_estimates", lambda m: _enc_idmap(m, _vec), lambda n: _dec_idmap(n, _vec_dec)),
+    ("semantic_class_for_object", lambda m: _enc_idmap(m, str), lambda n: _dec_idmap(n, str)),
+    ("last_observed_frame_by_object",) + _id_map, ("first_observed_frame_by_object",) + _id_map,
+    ("min_object_observation_factor", _uid, _id), ("max_object_observation_factor", _uid, _id),
+    ("min_obj_specific_factor", _uid, _id), ("max_obj_specific_factor", _uid, _id),
+    ("long_term_map_object_ids", lambda s: [_uid(o) for o in sorted(s)], lambda n: {_id(o) for o in (n or [])}),
+    ("object_observation_factors", lambda m: _enc_idmap(m, _enc_struct(_BBOX_F)), lambda n: _dec_idmap(n, _dec_struct(_BBOX_F))),
+    ("shape_dim_prior_factors", lambda m: _enc_idmap(m, _enc_struct(_SHAPE_F)), lambda n: _dec_idmap(n, _dec_struct(_SHAPE_F))),
+    ("observation_factors_by_frame",) + _fset_map, ("observation_factors_by_object",) + _fset_map,
+    ("object_only_factors_by_object",) + _fset_map,
+)
+
+
+def write_state(path, state):
+    """state = dict(low=..., min_feature_id=, max_feature_id=, feature_positions={id: xyz}, obj=...) -- see the comment above."""
+    low = {k: enc(state["low"][k]) for k, enc, _ in _LOW_FIELDS}
+    rs = {"low_level_pg_state": low, "min_feature_id": _uid(state["min_feature_id"]), "max_feature_id": _uid(state["max_feature_id"]),
+          "feature_positions": _enc_idmap(state["feature_positions"], _vec)}
+    obj = {k: enc(state["obj"][k]) for k, enc, _ in _OBJ_FIELDS}
+    with open(path, "w") as f:
+        json.dump({TOP: {K_LOW: rs, K_OBJ: obj}}, f)
+
+
+def read_state(path):
+    with open(path) as f:
+        root = json.load(f)[TOP]
+    rs = root[K_LOW]
+    return dict(low={k: dec(rs["low_level_pg_state"][k]) for k, _, dec in _LOW_FIELDS}, min_feature_id=_id(rs["min_feature_id"]),
+                max_feature_id=_id(rs["max_feature_id"]), feature_positions=_dec_idmap(rs["feature_positions"], _vec_dec),
+                obj={k: dec(root[K_OBJ][k]) for k, _, dec in _OBJ_FIELDS})
+
+
+def states_equal(a, b):
+    """Field-by-field equality (exact, as the reference's operator== on these structs)."""
+    if isinstance(a, dict):
+        return isinstance(b, dict) and set(a) == set(b) and all(states_equal(a[k], b[k]) for k in a)
+    if isinstance(a, (list, tuple)) and not (a and isinstance(a[0], (int, float)) and isinstance(a, tuple)):
+        return isinstance(b, (list, tuple)) and len(a) == len(b) and all(states_equal(x, y) for x, y in zip(a, b))
+    if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        return np.shape(a) == np.shape(b) and bool(np.array_equal(np.asarray(a), np.asarray(b)))
+    return a == b

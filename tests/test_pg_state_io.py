@@ -114,3 +114,38 @@ def test_run_opt_from_pg_state_cli(ob, tmp_path):
     g2, _, _ = ob.pg_state_io.read_pose_graph_state(pout)
     assert np.array_equal(g2.poses[0], g.poses[0]) and np.abs(g2.poses[1:] - g.poses[1:]).max() > 1e-6
     assert len(g2.reproj["pose"]) == len(g.reproj["pose"])      # the file keeps every factor; exclusion is per optimisation
+
+
+def test_reference_round_trip_values(ob, tmp_path):
+    """The reference's own test for this format: its hand-made state (tests/golden/pg_state_reference_values.py, values from
+    ..._pose_graph_file_storage_io_tests.cc) written, read back, and equal field for field -- plus the on-disk dialect of a few
+    of those entries (ids as decimal strings, maps as [{k, v}], Pose3D as transl + angle + axis kept verbatim)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import pg_state_reference_values as ref
+    st = ref.state()
+    path = str(tmp_path / "ref_state.json")
+    ob.pg_state_io.write_state(path, st)
+    back = ob.pg_state_io.read_state(path)
+    assert ob.pg_state_io.states_equal(st, back)
+    back["low"]["pose_factors"][123]["pose_deviation_cov"][0, 0] += 1e-12
+    assert not ob.pg_state_io.states_equal(st, back)          # the comparison is exact
+    d = json.load(open(path))["pose_graph"]
+    assert set(d) == {"reprojection_low_level_feature_pose_graph_state", "obj_only_pose_graph_state_"}
+    low = d["reprojection_low_level_feature_pose_graph_state"]["low_level_pg_state"]
+    assert set(low) == LOW_KEYS and set(d["obj_only_pose_graph_state_"]) == OBJ_KEYS
+    pf = {e["k"]: e["v"] for e in low["pose_factors"]}["123"]
+    assert pf["frame_id_1"] == "1" and pf["measured_pose_deviation"]["rot"]["angle"] == -np.pi
+    assert pf["measured_pose_deviation"]["rot"]["axis"] == {"Rows": 3, "Cols": 1, "Data": [0.4, -19.3, 48.2]}      # not normalised
+    assert pf["pose_deviation_cov"]["Data"][:6] == [1.2, 4.0, 3.5, 10.4, -0.3, -20.3]                              # row-major
+    f = {e["k"]: e["v"] for e in low["factors"]}["832"]
+    assert f == {"frame_id": "4", "feature_id": "3", "camera_id": "49", "feature_pos": {"Rows": 2, "Cols": 1, "Data": [-38.4, 39.4]},
+                 "reprojection_error_std_dev": 1.3}
+    oo = d["obj_only_pose_graph_state_"]
+    assert sorted(oo["long_term_map_object_ids"]) == ["13", "472", "493", "846"]
+    bb = {e["k"]: e["v"] for e in oo["object_observation_factors"]}["32"]
+    assert bb["object_id"] == "43" and bb["bounding_box_corners"]["Data"] == [1.2, 2.3, 3.4, 1.4] and bb["detection_confidence"] == 13.4
+    assert {e["k"]: e["v"] for e in oo["ellipsoid_estimates"]}["94"]["Data"] == [9.4, -184.4, 4.2, 18.3, -10.3, 4.2, 0.3]
+    # the same file goes through the graph-level writer's key set: a file this module writes from a FactorGraph has these keys too
+    vf = {e["k"]: e["v"] for e in low["visual_feature_factors_by_frame"]}["344"]
+    assert [(e["i"], e["v"]["f"], e["v"]["s"]) for e in vf] == [(0, 4, "42"), (1, 2, "3"), (2, 5, "948")]
