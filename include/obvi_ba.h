@@ -138,6 +138,14 @@ typedef struct {
   /* reduced-camera-system solver (block-Jacobi preconditioned CG on the Schur complement) */
   int32_t pcg_max_iterations;   /* 2000 */
   double pcg_relative_tolerance; /* |r| <= tol * |b|; 1e-12 keeps the LM trajectory on the direct-solve one */
+  /* ceres::IterationCallback + Solver::Options::update_state_every_iteration (object_pose_graph_optimizer.h:651-659): called on
+   * the calling thread after every iteration summary, in order.  Return 0 to continue (SOLVER_CONTINUE), 1 to abort
+   * (SOLVER_ABORT -> OBVI_USER_FAILURE), 2 to stop successfully (SOLVER_TERMINATE_SUCCESSFULLY -> OBVI_USER_SUCCESS).  With
+   * update_state_every_iteration the caller's parameter blocks hold the current iterate when the callback runs (one extra
+   * device->host copy per iteration; single-rank problems only).  NULL: no callback, the loop never leaves the device queue. */
+  int32_t (*iteration_callback)(void* user, const void* iteration_summary /* obvi_iteration_summary */);
+  void* iteration_callback_user;
+  int32_t update_state_every_iteration;
 } obvi_solver_options;
 
 /* Ceres defaults + the struct defaults of optimization_solver_params.h:17-23 (radius 1e4 / 1e16). */
@@ -158,7 +166,7 @@ typedef struct {
 } obvi_iteration_summary;
 
 /* ceres::TerminationType values */
-enum obvi_termination { OBVI_CONVERGENCE = 0, OBVI_NO_CONVERGENCE = 1, OBVI_FAILURE = 2 };
+enum obvi_termination { OBVI_CONVERGENCE = 0, OBVI_NO_CONVERGENCE = 1, OBVI_FAILURE = 2, OBVI_USER_SUCCESS = 3, OBVI_USER_FAILURE = 4 };
 
 /* ceres::Solver::Summary subset consumed by optimization_logger.h:192-203 and solveOptimization. */
 typedef struct {
@@ -228,6 +236,11 @@ int obvi_object_covariances(obvi_problem* p, int64_t n_pairs, double* const* obj
  *      produced by obvi_comm_unique_id on rank 0 and distributed by the caller. */
 int obvi_comm_unique_id(void* unique_id_128_bytes);
 int obvi_comm_init(obvi_problem* p, const void* unique_id_128_bytes, int rank, int world_size);
+/* Single-process variant: joins `world_size` handles of THIS process (handle i = rank i; same device or peer-accessible
+ * devices) through host barriers + a plain reduction kernel instead of NCCL.  Each handle must then be driven by its own host
+ * thread, all making the same sequence of obvi_solve / obvi_evaluate calls.  It exists so that the sharded code path can be
+ * run and checked on a single-GPU box (NCCL refuses two ranks on one device); the multi-process path is obvi_comm_init. */
+int obvi_comm_init_local(obvi_problem** handles, int world_size);
 
 /* ---- measurement hook (bench.py): times `reps` back-to-back launches of the reprojection Jacobian-evaluation
  *      kernel at the current host values with CUDA events on the solver's stream (after 3 warm-up launches) and

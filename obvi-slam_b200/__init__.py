@@ -21,7 +21,8 @@ _d = C.POINTER(C.c_double)
 _pp = C.POINTER(C.c_void_p)
 
 FACTOR_REPROJECTION, FACTOR_BBOX, FACTOR_SHAPE_PRIOR, FACTOR_LTM_PRIOR, FACTOR_REL_POSE, FACTOR_PARAM_PRIOR = 0, 2, 3, 4, 5, 6
-TERMINATION = {0: "CONVERGENCE", 1: "NO_CONVERGENCE", 2: "FAILURE"}
+TERMINATION = {0: "CONVERGENCE", 1: "NO_CONVERGENCE", 2: "FAILURE", 3: "USER_SUCCESS", 4: "USER_FAILURE"}
+ITERATION_CALLBACK = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p)
 
 
 class ObviError(RuntimeError):
@@ -36,7 +37,9 @@ class SolverOptions(C.Structure):
                 ("max_trust_region_radius", C.c_double), ("min_trust_region_radius", C.c_double),
                 ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
                 ("max_consecutive_nonmonotonic_steps", C.c_int32), ("max_num_consecutive_invalid_steps", C.c_int32),
-                ("pcg_max_iterations", C.c_int32), ("pcg_relative_tolerance", C.c_double)]
+                ("pcg_max_iterations", C.c_int32), ("pcg_relative_tolerance", C.c_double),
+                ("iteration_callback", ITERATION_CALLBACK), ("iteration_callback_user", C.c_void_p),
+                ("update_state_every_iteration", C.c_int32)]
 
     def __init__(self, **kw):
         super().__init__()
@@ -128,6 +131,7 @@ def lib():
         "obvi_debug_structure_hash": ([vp, C.c_int, C.c_int, C.POINTER(C.c_uint64)], C.c_int),
         "obvi_comm_unique_id": ([vp], C.c_int),
         "obvi_comm_init": ([vp, vp, C.c_int, C.c_int], C.c_int),
+        "obvi_comm_init_local": ([C.POINTER(vp), C.c_int], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here means the library does not export what obvi_ba.h declares
@@ -144,7 +148,7 @@ EXPORTED_SYMBOLS = [
     "obvi_factor_add_shape_prior", "obvi_factor_add_ltm_prior", "obvi_factor_add_rel_pose", "obvi_factor_add_param_prior",
     "obvi_factor_remove", "obvi_num_factors", "obvi_num_structure_builds", "obvi_residual_blocks", "obvi_solver_options_init", "obvi_solve",
     "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_evaluate_jacobian", "obvi_object_covariances", "obvi_profile_jacobian", "obvi_debug_partition", "obvi_debug_structure_hash", "obvi_comm_unique_id",
-    "obvi_comm_init",
+    "obvi_comm_init", "obvi_comm_init_local",
 ]
 
 
@@ -296,8 +300,17 @@ class Problem:
         return ids, types, sizes
 
     # ---- solve / evaluate
-    def solve(self, options=None, **kw):
+    def solve(self, options=None, callback=None, **kw):
+        """callback(dict) -> 0 continue | 1 abort | 2 terminate successfully: ceres::IterationCallback."""
         opt = options if options is not None else SolverOptions(**kw)
+        if callback is not None:
+            def tramp(_user, it_ptr):
+                i = C.cast(it_ptr, C.POINTER(IterationSummary)).contents
+                return int(callback(dict(iteration=i.iteration, cost=i.cost, cost_change=i.cost_change, step_norm=i.step_norm,
+                                         successful=bool(i.step_is_successful), radius=i.trust_region_radius,
+                                         gradient_max_norm=i.gradient_max_norm)) or 0)
+            opt._cb = ITERATION_CALLBACK(tramp)     # keep the thunk alive for the duration of the call
+            opt.iteration_callback = opt._cb
         summ = Summary()
         cap = opt.max_num_iterations + 2
         its = (IterationSummary * cap)()
@@ -391,6 +404,14 @@ class Problem:
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._ck(self._lib.obvi_comm_init(self._h, buf, rank, world))
+
+    @staticmethod
+    def comm_init_local(problems):
+        """Join problems of this process into one sharded solve (problems[i] = rank i); drive each from its own thread."""
+        arr = (C.c_void_p * len(problems))(*[p._h for p in problems])
+        rc = lib().obvi_comm_init_local(arr, len(problems))
+        if rc != 0:
+            raise ObviError(f"obvi_comm_init_local failed ({rc})")
 
 
 def problem_from_graph(g, device=0):

@@ -36,6 +36,23 @@ enum : int {
 
 struct LMParams { double radius, min_diag, max_diag; int compute_scale; double inv_radius; };
 
+// ---- sharded runs: scalars that ride along with the collectives -------------------------------------------------
+constexpr int kStage0Sums = 3;   // SC_COST, SC_FIXED, SC_XNORM2
+constexpr int kPcgStatus = 5;    // SC_PCG_IT .. SC_BT_FAIL, appended to y for the broadcast of rank 0's solution
+// tail of the all-reduced buffer: [cost, fixed, |x|^2 | (gradient max, failures) per rank].  `local` != 0: scalars 0-2 are this
+// rank's partial sums (fresh linearisation); otherwise they already hold the global values and only rank 0 contributes them.
+__global__ void pack_stage0_kernel(const double* __restrict__ scalars, double* __restrict__ tail, int rank, int world, int local) {
+  const int i = threadIdx.x;
+  if (i < kStage0Sums) tail[i] = (local || rank == 0) ? scalars[SC_COST + i] : 0.0;
+  if (i < 2) tail[kStage0Sums + 2 * rank + i] = scalars[SC_GMAX + i];   // the other ranks' slots stay zero
+}
+__global__ void unpack_stage0_kernel(double* __restrict__ scalars, const double* __restrict__ tail, int world) {
+  const int i = threadIdx.x;
+  if (i < kStage0Sums) scalars[SC_COST + i] = tail[i];
+  if (i == 0) { double g = 0.0, f = 0.0; for (int r = 0; r < world; r++) { g = fmax(g, tail[kStage0Sums + 2 * r]); f += tail[kStage0Sums + 2 * r + 1]; } scalars[SC_GMAX] = g; scalars[SC_FAIL] = f; }
+}
+__global__ void set_scalar_kernel(double* p, double v) { *p = v; }
+
 // ------------------------------------------------------------------------------------------ reductions
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -156,15 +156,37 @@ struct Problem {
   int32_t add_block(double* ptr, int size) {
     int32_t id = find_block(ptr);
     if (id >= 0) {
-      if (blocks[id].size != size) return -2;
-      if (!blocks[id].alive) { blocks[id].alive = 1; blocks[id].constant = 0; dirty = true; }
-      return id;
+      if (!blocks[id].alive) {
+        // a removed block: the address may have been recycled for a block of another size (Ceres accepts that sequence)
+        if (blocks[id].size == size) { blocks[id].alive = 1; blocks[id].constant = 0; dirty = true; return id; }
+        if (single.count(ptr)) {   // replace the dead entry; a dead element of a registered ARRAY keeps its slot (and its size)
+          single.erase(ptr);
+          id = -1;
+        } else {
+          return -2;
+        }
+      } else {
+        if (blocks[id].size != size) return -2;
+        return id;
+      }
     }
     id = (int32_t)blocks.size();
     blocks.push_back({ptr, size, 0, 1});
     single.emplace(ptr, id);
     dirty = true;
     return id;
+  }
+  // true when a singly registered block (alive or not) starts inside [base, base + count * size)
+  bool array_overlaps_single(const double* base, int size, int64_t count) const {
+    const double* end = base + count * size;
+    if ((int64_t)single.size() < count) { for (const auto& kv : single) if (kv.first >= base && kv.first < end) return true; return false; }
+    for (int64_t i = 0; i < count * size; i++) if (single.count(base + i)) return true;
+    return false;
+  }
+  bool array_overlaps_array(const double* base, int size, int64_t count) const {
+    const double* end = base + count * size;
+    for (const ParamArray& a : arrays) if (base < a.base + a.count * a.size && a.base < end) return true;
+    return false;
   }
   int add_array(double* base, int size, int64_t count) {
     ParamArray a{base, size, count, (int64_t)blocks.size()};

@@ -14,7 +14,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <condition_variable>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -64,6 +67,76 @@ struct Nccl {
   }
 };
 static Nccl g_nccl;
+
+// ---- communicators ------------------------------------------------------------------------------------------
+// The sharded solve needs three collectives on device buffers of doubles: all-reduce (sum), all-reduce (max), broadcast
+// from rank 0.  NcclComm is the multi-process path (one process per GPU, NVLink / NVSwitch).  LocalComm joins several
+// problem handles of ONE process (each driven by its own host thread, on the same or on peer-accessible devices): the
+// ranks rendezvous on a host barrier and reduce each other's buffers with a plain kernel.  It exists so that the sharded
+// code path -- structure partitioning, every sharded kernel, the merged write-back -- can be run and checked on a box
+// with a single GPU, where NCCL refuses two ranks on one device.
+struct Comm {
+  virtual ~Comm() {}
+  virtual void allreduce_sum(double* p, size_t n, cudaStream_t s, int rank) = 0;
+  virtual void allreduce_max(double* p, size_t n, cudaStream_t s, int rank) = 0;
+  virtual void broadcast0(double* p, size_t n, cudaStream_t s, int rank) = 0;
+};
+struct NcclComm : Comm {
+  ncclComm_t comm = nullptr;
+  ~NcclComm() override { if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm); }
+  static void ck(ncclResult_t r, const char* what) { if (r != ncclSuccess) throw std::runtime_error(std::string(what) + ": " + g_nccl.GetErrorString(r)); }
+  void allreduce_sum(double* p, size_t n, cudaStream_t s, int) override { ck(g_nccl.AllReduce(p, p, n, ncclDouble, ncclSum, comm, s), "ncclAllReduce"); }
+  void allreduce_max(double* p, size_t n, cudaStream_t s, int) override { ck(g_nccl.AllReduce(p, p, n, ncclDouble, ncclMax, comm, s), "ncclAllReduce"); }
+  void broadcast0(double* p, size_t n, cudaStream_t s, int) override { ck(g_nccl.Broadcast(p, p, n, ncclDouble, 0, comm, s), "ncclBroadcast"); }
+};
+__global__ void local_reduce_kernel(double* __restrict__ out, const double* const* __restrict__ in, int world, size_t n, int is_max) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = in[0][i];
+  for (int r = 1; r < world; r++) v = is_max ? fmax(v, in[r][i]) : v + in[r][i];   // fixed rank order: every rank gets the same bits
+  out[i] = v;
+}
+struct LocalComm : Comm {
+  int world;
+  std::mutex m;
+  std::condition_variable cv;
+  int arrived = 0;
+  uint64_t gen = 0;
+  std::vector<double*> ptr;
+  explicit LocalComm(int w) : world(w), ptr(w, nullptr) {}
+  void barrier() {
+    std::unique_lock<std::mutex> lk(m);
+    const uint64_t g = gen;
+    if (++arrived == world) { arrived = 0; gen++; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != g; });
+  }
+  void reduce(double* p, size_t n, cudaStream_t s, int rank, int is_max) {
+    if (n == 0) return;
+    CUDA_OK(cudaStreamSynchronize(s));          // p is final on this rank
+    ptr[rank] = p;
+    barrier();                                  // ... and on every other rank
+    double* tmp = nullptr; const double** d_in = nullptr;
+    CUDA_OK(cudaMalloc((void**)&tmp, n * sizeof(double)));
+    CUDA_OK(cudaMalloc((void**)&d_in, world * sizeof(double*)));
+    CUDA_OK(cudaMemcpyAsync(d_in, ptr.data(), world * sizeof(double*), cudaMemcpyHostToDevice, s));
+    local_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tmp, d_in, world, n, is_max);
+    CUDA_OK(cudaStreamSynchronize(s));
+    barrier();                                  // everybody has read everybody's input
+    CUDA_OK(cudaMemcpyAsync(p, tmp, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    cudaFree(tmp); cudaFree(d_in);
+  }
+  void allreduce_sum(double* p, size_t n, cudaStream_t s, int rank) override { reduce(p, n, s, rank, 0); }
+  void allreduce_max(double* p, size_t n, cudaStream_t s, int rank) override { reduce(p, n, s, rank, 1); }
+  void broadcast0(double* p, size_t n, cudaStream_t s, int rank) override {
+    if (n == 0) return;
+    CUDA_OK(cudaStreamSynchronize(s));
+    ptr[rank] = p;
+    barrier();
+    if (rank != 0) { CUDA_OK(cudaMemcpyAsync(p, ptr[0], n * sizeof(double), cudaMemcpyDefault, s)); CUDA_OK(cudaStreamSynchronize(s)); }
+    barrier();
+  }
+};
 
 // ---- small RAII device buffer ---------------------------------------------------------------------------
 template <class T>
@@ -139,8 +212,9 @@ struct Solver {
   int num_sms = 0;
   int pcg_blocks_per_sm = 0;
   // communicator
-  ncclComm_t comm = nullptr;
+  std::shared_ptr<Comm> comm;
   int rank = 0, world = 1;
+  int debug_bt_fail_rank = -1;   // OBVI_DEBUG_BT_FAIL_RANK: this rank reports a failed factorisation (tests of the fallback path)
   // device structure
   DBuf<Camera> cams;
   DBuf<CalibClass> classes;
@@ -179,7 +253,8 @@ struct Solver {
   DBuf<UnaryOut> unary_out;
   DBuf<RelOut> rel_out;
   DBuf<double> redbuf;  // [S_upper | gp | b_schur | hpp_diag]
-  double *S_upper = nullptr, *gp = nullptr, *b_schur = nullptr, *hpp_diag = nullptr;
+  double *S_upper = nullptr, *gp = nullptr, *b_schur = nullptr, *hpp_diag = nullptr, *red_tail = nullptr;
+  bool stage0_local = false;   // sharded run: scalars 0-2 hold this rank's partial sums (set by linearize (), cleared by the reduction)
   DBuf<double> pscale, Sf, rhs, Minv, y, cg_r, cg_z, cg_p, cg_q, cg_acc, dpose, scalars;
   // block-tridiagonal preconditioner (bt_precond.cuh)
   int nsb = 0, nlev = 0, pcg_bt_blocks_per_sm = 0;
@@ -211,7 +286,6 @@ struct Solver {
   int64_t launches = 0;
 
   ~Solver() {
-    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     if (h_scalars) cudaFreeHost(h_scalars);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -256,6 +330,7 @@ struct Solver {
     if (const char* e = getenv("OBVI_PCG")) pcg_resident = std::string(e) != "grid";
     CUDA_OK(cudaFuncSetAttribute(pcg_bt_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentSmem));
     if (const char* e = getenv("OBVI_PROFILE")) prof.on = std::string(e) == "1";
+    if (const char* e = getenv("OBVI_DEBUG_BT_FAIL_RANK")) debug_bt_fail_rank = atoi(e);
     if (const char* e = getenv("OBVI_JAC")) jac_mode = std::string(e) == "plain" ? 0 : 1;
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes));
     CUDA_OK(cudaFuncSetAttribute(pose_accum_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoseAccTmaSmem));
@@ -323,10 +398,12 @@ struct Solver {
     encode_jac_tmap();
     unary_out.alloc(S.n_unary); rel_out.alloc(S.n_rel);
     const size_t nf6 = (size_t)S.nf * 6;
-    redbuf.alloc((size_t)S.n_upper * 36 + 3 * nf6);
-    S_upper = redbuf.p; gp = S_upper + (size_t)S.n_upper * 36; b_schur = gp + nf6; hpp_diag = b_schur + nf6;
+    // a sharded run all-reduces this buffer once per build; its tail carries the linearisation's scalars along
+    // (cost, fixed cost, |x|^2 as sums; one (gradient max, failure count) slot pair per rank): see pack_stage0_kernel
+    redbuf.alloc((size_t)S.n_upper * 36 + 3 * nf6 + kStage0Sums + 2 * (size_t)world);
+    S_upper = redbuf.p; gp = S_upper + (size_t)S.n_upper * 36; b_schur = gp + nf6; hpp_diag = b_schur + nf6; red_tail = hpp_diag + nf6;
     pscale.alloc(nf6); Sf.alloc((size_t)S.sf_col.size() * 36); rhs.alloc(nf6); Minv.alloc((size_t)S.nf * 36);
-    y.alloc(nf6); cg_r.alloc(nf6); cg_z.alloc(nf6); cg_p.alloc(nf6); cg_q.alloc(nf6); cg_acc.alloc(16); dpose.alloc(nf6);
+    y.alloc(nf6 + kPcgStatus); cg_r.alloc(nf6); cg_z.alloc(nf6); cg_p.alloc(nf6); cg_q.alloc(nf6); cg_acc.alloc(16); dpose.alloc(nf6);
     scalars.alloc(SC_COUNT);
     setup_bt();
     uploaded = true;
@@ -411,6 +488,7 @@ struct Solver {
     if (bt_v1) bt_invert_kernel<<<1, kInvThreads, 0, stream>>>(bt_idx.p + bt_last_inv_off, bt_D.p, bt_Dinv.p, scalars.p);
     else bt_invert8_kernel<<<1, kInvThreads, 0, stream>>>(bt_idx.p + bt_last_inv_off, bt_D.p, bt_Dinv.p, scalars.p);
     launches++;
+    if (debug_bt_fail_rank == rank) { set_scalar_kernel<<<1, 1, 0, stream>>>(scalars.p + SC_BT_FAIL, 1.0); launches++; }
   }
   bool owns_object(int o) const {
     // an object is "owned" when this rank holds its observations or (no observations) rank 0
@@ -474,6 +552,7 @@ struct Solver {
   void linearize(int apply_loss) {
     const Structure& S = st;
     const size_t pt0 = prof.begin(stream);
+    stage0_local = world > 1;
     zero_scalars(SC_COST, 3);
     if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p); launches++; }
     fork();
@@ -577,7 +656,15 @@ struct Solver {
     prof.end("schur_points", pt0, stream); pt0 = prof.begin(stream);
     join();
     prof.end("join(objects,rel)", pt0, stream); pt0 = prof.begin(stream);
-    if (world > 1) { allreduce_sum(redbuf.p, redbuf.n); prof.end("allreduce S", pt0, stream); pt0 = prof.begin(stream); }
+    if (world > 1) {
+      // ONE collective per build: the partial reduced system and, in its tail, the scalars of this linearisation
+      pack_stage0_kernel<<<1, 32, 0, stream>>>(scalars.p, red_tail, rank, world, stage0_local ? 1 : 0);
+      allreduce_sum(redbuf.p, (size_t)S.n_upper * 36 + 3 * (size_t)S.nf * 6 + kStage0Sums + 2 * (size_t)world);
+      unpack_stage0_kernel<<<1, 32, 0, stream>>>(scalars.p, red_tail, world);
+      launches += 2;
+      stage0_local = false;
+      prof.end("allreduce S", pt0, stream); pt0 = prof.begin(stream);
+    }
     if (S.nf) {
       if (lm.compute_scale) { pose_scale_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(hpp_diag, S.nf * 6, pscale.p); launches++; }
       finish_kernel<<<S.nf, 128, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, sf_src.p, S_upper, pscale.p, hpp_diag, gp, b_schur, lm, Sf.p, rhs.p, scalars.p);
@@ -603,7 +690,7 @@ struct Solver {
       void* args[] = {&nf, &a1, &a2, &a3, &a4, &P, &Y, &a6, &a7, &a9, &max_iter, &tol, &a14};
       CUDA_OK(cudaLaunchCooperativeKernel((void*)pcg_bt_resident_kernel, dim3(nsb), dim3(kPcgThreads), args, kResidentSmem, stream));
       launches++;
-      if (world > 1) broadcast0(y.p, (size_t)nf * 6);
+      share_solution();
       return;
     }
     if (use_bt && !force_jacobi) {
@@ -615,7 +702,7 @@ struct Solver {
       void* args[] = {&nf, &a1, &a2, &a3, &a4, &P, &a6, &a7, &a9, &a10, &a11, &max_iter, &tol, &a14};
       CUDA_OK(cudaLaunchCooperativeKernel((void*)pcg_bt_kernel, dim3(grid), dim3(kPcgThreads), args, 0, stream));
       launches++;
-      if (world > 1) broadcast0(y.p, (size_t)nf * 6);
+      share_solution();
       return;
     }
     int grid = std::min(num_sms * pcg_blocks_per_sm, std::max(1, nblk(nf, kPcgThreads / 32)));
@@ -625,7 +712,17 @@ struct Solver {
     void* args[] = {&nf, &a1, &a2, &a3, &a4, &a5, &a6, &a7, &a8, &a9, &a10, &a11, &max_iter, &tol, &a14};
     CUDA_OK(cudaLaunchCooperativeKernel((void*)pcg_kernel, dim3(grid), dim3(kPcgThreads), args, 0, stream));
     launches++;
-    if (world > 1) broadcast0(y.p, (size_t)nf * 6);
+    share_solution();
+  }
+  // Sharded run: every rank solved the (identical) reduced system; rank 0's solution AND its solver status travel in one
+  // broadcast, so that every host decision that depends on them -- fallback to block-Jacobi, invalid step, refactorisation
+  // -- is the same on every rank (the PCG sums with atomics: iteration counts may differ from rank to rank).
+  void share_solution() {
+    if (world <= 1) return;
+    const size_t nf6 = (size_t)st.nf * 6;
+    CUDA_OK(cudaMemcpyAsync(y.p + nf6, scalars.p + SC_PCG_IT, kPcgStatus * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    broadcast0(y.p, nf6 + kPcgStatus);
+    CUDA_OK(cudaMemcpyAsync(scalars.p + SC_PCG_IT, y.p + nf6, kPcgStatus * sizeof(double), cudaMemcpyDeviceToDevice, stream));
   }
   // step, model cost change, candidate point
   void take_step() {
@@ -665,10 +762,14 @@ struct Solver {
   }
   // stage 0: after linearize () + build_reduced (); stage 1: after take_step () + candidate_cost ()
   void reduce_scalars(int stage) {
-    if (world > 1) {
-      // replicated pose contributions (|x|^2, |delta|^2) are added by rank 0 only
-      if (stage == 0) allreduce_sum(scalars.p + SC_COST, 3); else allreduce_sum(scalars.p + SC_CAND, 4);
-      allreduce_max(scalars.p + SC_GMAX, 2);
+    if (world <= 1) return;
+    // replicated pose contributions (|x|^2, |delta|^2) are added by rank 0 only
+    if (stage == 0) {
+      // normally folded into the all-reduce of the reduced system (build_reduced); only an evaluation without a build
+      // (obvi_evaluate) still has rank-local values here
+      if (stage0_local) { allreduce_sum(scalars.p + SC_COST, 3); allreduce_max(scalars.p + SC_GMAX, 2); stage0_local = false; }
+    } else {
+      allreduce_sum(scalars.p + SC_CAND, 4);   // candidate cost, its fixed part, model cost change, |delta|^2
     }
   }
   void fetch_scalars(int stage, bool reduce = true) {
@@ -677,18 +778,9 @@ struct Solver {
     CUDA_OK(cudaStreamSynchronize(stream));
     CUDA_OK(cudaGetLastError());
   }
-  void allreduce_sum(double* p, size_t n) {
-    ncclResult_t r = g_nccl.AllReduce(p, p, n, ncclDouble, ncclSum, comm, stream);
-    if (r != ncclSuccess) throw std::runtime_error(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
-  }
-  void allreduce_max(double* p, size_t n) {
-    ncclResult_t r = g_nccl.AllReduce(p, p, n, ncclDouble, ncclMax, comm, stream);
-    if (r != ncclSuccess) throw std::runtime_error(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
-  }
-  void broadcast0(double* p, size_t n) {
-    ncclResult_t r = g_nccl.Broadcast(p, p, n, ncclDouble, 0, comm, stream);
-    if (r != ncclSuccess) throw std::runtime_error(std::string("ncclBroadcast: ") + g_nccl.GetErrorString(r));
-  }
+  void allreduce_sum(double* p, size_t n) { comm->allreduce_sum(p, n, stream, rank); }
+  void allreduce_max(double* p, size_t n) { comm->allreduce_max(p, n, stream, rank); }
+  void broadcast0(double* p, size_t n) { comm->broadcast0(p, n, stream, rank); }
 
   // Remove a reprojection / bbox block without rebuilding the structure: its record is flagged, the Jacobian kernels then
   // write an all-zero block and no cost, so every downstream kernel sees a factor that contributes nothing
@@ -860,14 +952,21 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
   bt_radius = -1.0; last_pcg_iters = 0;
 
   int n_log = 0;
+  int user_stop = 0;   // first non-zero return of the iteration callback: 1 abort, 2 terminate successfully
   auto push = [&](int iter, bool valid, bool ok, int lin_it, double cost, double cc, double gmax, double sn, double rd, double radius) {
-    if (its && n_log < cap) {
-      obvi_iteration_summary& s = its[n_log];
-      s.iteration = iter; s.step_is_valid = valid; s.step_is_successful = ok; s.linear_solver_iterations = lin_it;
-      s.cost = cost; s.cost_change = cc; s.gradient_max_norm = gmax; s.step_norm = sn; s.relative_decrease = rd; s.trust_region_radius = radius;
-    }
+    obvi_iteration_summary s;
+    s.iteration = iter; s.step_is_valid = valid; s.step_is_successful = ok; s.linear_solver_iterations = lin_it;
+    s.cost = cost; s.cost_change = cc; s.gradient_max_norm = gmax; s.step_norm = sn; s.relative_decrease = rd; s.trust_region_radius = radius;
+    if (its && n_log < cap) its[n_log] = s;
     n_log++;
+    if (o.iteration_callback && !user_stop) {
+      // `cur` holds the iterate this summary describes (an accepted step is logged once its linearisation has been read back)
+      if (o.update_state_every_iteration && world == 1 && (ok || iter == 0)) scatter_params(cur);
+      const int r = o.iteration_callback(o.iteration_callback_user, &s);
+      if (r == 1 || r == 2) user_stop = r;
+    }
   };
+  auto user_termination = [&]() { return user_stop == 2 ? OBVI_USER_SUCCESS : OBVI_USER_FAILURE; };
   float ms = 0;
   double t_jac = 0, t_lin = 0, t_res = 0;
   LMParams lm;
@@ -915,12 +1014,13 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
     if (x_cost < minimum_cost) { minimum_cost = x_cost; best = cur; }
     push(pend.iter, true, true, pend.pcg_it, x_cost + fixed_cost, pend.cost_change, gmax, pend.step_norm, pend.rho, pend.radius);
     pending0 = false;
-    return gmax <= o.gradient_tolerance;
+    return gmax <= o.gradient_tolerance || user_stop != 0;
   };
   const bool finite0 = std::isfinite(x_cost);
   if (!finite0) termination = OBVI_FAILURE;
   else if (S.num_params_reduced == 0 || gmax <= o.gradient_tolerance) termination = OBVI_CONVERGENCE;
   else while (true) {
+    if (user_stop) { termination = user_termination(); break; }
     if (iter >= o.max_num_iterations) { termination = OBVI_NO_CONVERGENCE; break; }
     iter++; lm_steps++;
     CUDA_OK(cudaEventRecord(ev[2], stream));
@@ -938,9 +1038,10 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
     CUDA_OK(cudaEventElapsedTime(&ms, ev[2], ev[3])); t_lin += ms * 1e-3;
     CUDA_OK(cudaEventElapsedTime(&ms, ev[3], ev[4])); t_res += ms * 1e-3;
     if (pending0 && finish_pending()) {
-      // the previous (accepted) iterate already met the gradient tolerance: the step enqueued speculatively is dropped
+      // the previous (accepted) iterate already met the gradient tolerance (or the callback stopped the solve there): the
+      // step enqueued speculatively is dropped
       iter--; lm_steps--;
-      termination = OBVI_CONVERGENCE;
+      termination = user_stop ? user_termination() : OBVI_CONVERGENCE;
       break;
     }
     if (h_scalars[SC_PCG_BREAK] == 2.0) {
@@ -960,7 +1061,7 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
     build_failed = false;
     if (!valid) {
       if (++n_invalid >= o.max_num_consecutive_invalid_steps) { termination = OBVI_FAILURE; break; }
-      lm.radius *= 0.5;  // LevenbergMarquardtStrategy::StepIsInvalid
+      lm.radius /= decrease; decrease *= 2.0;  // LevenbergMarquardtStrategy::StepIsInvalid () = StepRejected (0): same rule as a rejected step
       need_build = true;
       n_bad++;
       push(iter, false, false, pcg_it, x_cost + fixed_cost, 0, gmax, 0, 0, lm.radius);
@@ -1011,7 +1112,7 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
         reduce_scalars(0);
       } else {
         fetch_scalars(0);
-        if (finish_pending()) { termination = OBVI_CONVERGENCE; break; }
+        if (finish_pending()) { termination = user_stop ? user_termination() : OBVI_CONVERGENCE; break; }
       }
     } else {
       lm.radius /= decrease; decrease *= 2.0;
@@ -1023,17 +1124,18 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
   }
   if (pending0) {   // the loop ended (iteration limit, minimum radius, failure) with an accepted step still unread
     fetch_scalars(0, false);   // its cross-rank reduction was enqueued when the step was accepted
-    if (finish_pending() && termination == OBVI_NO_CONVERGENCE) termination = OBVI_CONVERGENCE;
+    if (finish_pending() && termination == OBVI_NO_CONVERGENCE) termination = user_stop ? user_termination() : OBVI_CONVERGENCE;
   }
+  if (user_stop && termination != OBVI_FAILURE) termination = user_termination();   // a stop requested on the very last summary
   CUDA_OK(cudaEventRecord(ev[7], stream));
   CUDA_OK(cudaStreamSynchronize(stream));
   CUDA_OK(cudaEventElapsedTime(&ms, ev[6], ev[7]));
   sum->minimizer_device_time_in_seconds = ms * 1e-3;
   prof.report(lm_steps);
   // write the minimum-cost iterate back to the caller's blocks (on FAILURE the initial values stay)
-  if (termination != OBVI_FAILURE) scatter_params(best);
+  sum->is_solution_usable = termination == OBVI_CONVERGENCE || termination == OBVI_NO_CONVERGENCE || termination == OBVI_USER_SUCCESS;
+  if (sum->is_solution_usable) scatter_params(best);
   sum->termination_type = termination;
-  sum->is_solution_usable = termination == OBVI_CONVERGENCE || termination == OBVI_NO_CONVERGENCE;
   sum->num_iterations = n_log; sum->num_lm_steps = lm_steps; sum->num_successful_steps = n_ok; sum->num_unsuccessful_steps = n_bad;
   sum->final_cost = minimum_cost + fixed_cost;
   sum->linear_solver_time_in_seconds = t_lin; sum->jacobian_evaluation_time_in_seconds = t_jac; sum->residual_evaluation_time_in_seconds = t_res;
@@ -1101,7 +1203,10 @@ int obvi_param_add(obvi_problem* p, double* host, int size) {
 int obvi_param_add_array(obvi_problem* p, double* base, int size, int64_t count) {
   if (!p || !base || count < 0 || (size != 3 && size != 6 && size != 7)) return OBVI_ERR_INVALID_ARGUMENT;
   if (count == 0) return OBVI_OK;
-  if (p->s.pb.find_block(base) >= 0 || p->s.pb.find_block(base + (count - 1) * size) >= 0) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "array overlaps registered blocks");
+  // every address of the range is checked, not just its ends: a block registered singly in the MIDDLE of the range would
+  // otherwise keep its old id in the factors that reference it while later look-ups resolve to the array's id
+  if (p->s.pb.array_overlaps_array(base, size, count) || p->s.pb.array_overlaps_single(base, size, count))
+    return fail(p, OBVI_ERR_INVALID_ARGUMENT, "array overlaps registered blocks");
   p->s.pb.add_array(base, size, count);
   return OBVI_OK;
 }
@@ -1297,6 +1402,7 @@ void obvi_solver_options_init(obvi_solver_options* o) {
   o->min_trust_region_radius = 1e-32; o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->max_consecutive_nonmonotonic_steps = 5; o->max_num_consecutive_invalid_steps = 5;
   o->pcg_max_iterations = 2000; o->pcg_relative_tolerance = 1e-12;
+  o->iteration_callback = nullptr; o->iteration_callback_user = nullptr; o->update_state_every_iteration = 0;
 }
 
 int obvi_solve(obvi_problem* p, const obvi_solver_options* o, obvi_summary* sum, obvi_iteration_summary* its, int32_t cap) {
@@ -1740,11 +1846,22 @@ int obvi_comm_init(obvi_problem* p, const void* uid, int rank, int world) {
   if (!g_nccl.load(err)) return fail(p, OBVI_ERR_COMM, err.c_str());
   ncclUniqueId id;
   std::memcpy(&id, uid, 128);
-  ncclResult_t r = g_nccl.CommInitRank(&s.comm, world, id, rank);
+  auto nc = std::make_shared<NcclComm>();
+  ncclResult_t r = g_nccl.CommInitRank(&nc->comm, world, id, rank);
   if (r != ncclSuccess) return fail(p, OBVI_ERR_COMM, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclCommInitRank failed");
-  s.rank = rank; s.world = world; s.pb.dirty = true;
+  s.comm = nc; s.rank = rank; s.world = world; s.pb.dirty = true;
   return OBVI_OK;
   API_END(p)
+}
+
+// Join `world` problem handles of THIS process into one sharded solve (handle i becomes rank i).  Every handle must then
+// be driven by its own host thread, all of them making the same sequence of collective calls (obvi_solve, obvi_evaluate).
+int obvi_comm_init_local(obvi_problem** handles, int world) {
+  if (!handles || world < 1) return OBVI_ERR_INVALID_ARGUMENT;
+  for (int r = 0; r < world; r++) if (!handles[r] || handles[r]->s.pb.device < 0) return OBVI_ERR_INVALID_ARGUMENT;
+  auto lc = std::make_shared<LocalComm>(world);
+  for (int r = 0; r < world; r++) { Solver& s = handles[r]->s; s.comm = lc; s.rank = r; s.world = world; s.pb.dirty = true; }
+  return OBVI_OK;
 }
 
 }  // extern "C"

@@ -247,16 +247,22 @@ class Problem {
     }
     obvi_factor_id id = 0;
     check(cost->obvi_add(handle_, x, loss ? loss->obvi_huber_parameter() : 0.0, &id), "AddResidualBlock");
+    cost_refs_[cost]++;
+    if (loss) loss_refs_[loss]++;
     std::unique_ptr<ResidualBlock> rb(new ResidualBlock{id, std::vector<double*>(x, x + n), cost, loss});
     ResidualBlockId out = rb.get();
     blocks_[id] = std::move(rb);
     return out;
   }
+  // Ceres reference-counts the cost / loss objects it owns: one LossFunction (or CostFunction) may be shared by many residual
+  // blocks and is deleted when the last of them goes.
   void release(ResidualBlock* rb) {
-    if (options_.cost_function_ownership == TAKE_OWNERSHIP) { delete rb->cost; }
-    if (options_.loss_function_ownership == TAKE_OWNERSHIP) { delete rb->loss; }
+    if (rb->cost && options_.cost_function_ownership == TAKE_OWNERSHIP && --cost_refs_[rb->cost] == 0) { cost_refs_.erase(rb->cost); delete rb->cost; }
+    if (rb->loss && options_.loss_function_ownership == TAKE_OWNERSHIP && --loss_refs_[rb->loss] == 0) { loss_refs_.erase(rb->loss); delete rb->loss; }
     rb->cost = nullptr; rb->loss = nullptr;
   }
+  std::unordered_map<const CostFunction*, int> cost_refs_;
+  std::unordered_map<const LossFunction*, int> loss_refs_;
   Options options_;
   obvi_problem* handle_ = nullptr;
   std::unordered_map<obvi_factor_id, std::unique_ptr<ResidualBlock>> blocks_;
@@ -337,6 +343,30 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
   o.min_relative_decrease = options.min_relative_decrease; o.min_lm_diagonal = options.min_lm_diagonal; o.max_lm_diagonal = options.max_lm_diagonal;
   o.max_consecutive_nonmonotonic_steps = options.max_consecutive_nonmonotonic_steps;
   o.max_num_consecutive_invalid_steps = options.max_num_consecutive_invalid_steps;
+  // Iteration callbacks run on this thread after every iteration summary, in order; SOLVER_ABORT / SOLVER_TERMINATE_SUCCESSFULLY
+  // stop the solve there (USER_FAILURE / USER_SUCCESS), and with update_state_every_iteration the parameter blocks hold the
+  // current iterate when they run (object_pose_graph_optimizer.h:651-659).
+  struct Trampoline {
+    const Solver::Options* opt;
+    static int32_t call(void* user, const void* it_) {
+      const Solver::Options& op = *static_cast<Trampoline*>(user)->opt;
+      const obvi_iteration_summary& in = *static_cast<const obvi_iteration_summary*>(it_);
+      IterationSummary it;
+      it.iteration = in.iteration; it.step_is_valid = in.step_is_valid != 0; it.step_is_successful = in.step_is_successful != 0;
+      it.cost = in.cost; it.cost_change = in.cost_change; it.gradient_max_norm = in.gradient_max_norm; it.step_norm = in.step_norm;
+      it.relative_decrease = in.relative_decrease; it.trust_region_radius = in.trust_region_radius; it.linear_solver_iterations = in.linear_solver_iterations;
+      for (IterationCallback* cb : op.callbacks) {
+        const CallbackReturnType r = (*cb)(it);
+        if (r == SOLVER_ABORT) return 1;
+        if (r == SOLVER_TERMINATE_SUCCESSFULLY) return 2;
+      }
+      return 0;
+    }
+  } tramp{&options};
+  if (!options.callbacks.empty()) {
+    o.iteration_callback = &Trampoline::call; o.iteration_callback_user = &tramp;
+    o.update_state_every_iteration = options.update_state_every_iteration ? 1 : 0;
+  }
   obvi_summary s;
   std::vector<obvi_iteration_summary> its(options.max_num_iterations + 2);
   *summary = Solver::Summary();
@@ -365,11 +395,9 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
     it.linear_solver_iterations = its[i].linear_solver_iterations;
     summary->iterations.push_back(it);
   }
-  summary->message = summary->termination_type == CONVERGENCE ? "Convergence" : summary->termination_type == NO_CONVERGENCE ? "Maximum number of iterations reached" : "Failure";
-  // Callbacks: the whole LM loop runs on the device; the per-iteration summaries are replayed to the callbacks after it
-  // (the reference's production callback list is empty, run_opt_utils.h:34-40).  They cannot abort the solve.
-  for (IterationCallback* cb : options.callbacks)
-    for (const IterationSummary& it : summary->iterations) (*cb)(it);
+  summary->message = summary->termination_type == CONVERGENCE ? "Convergence" : summary->termination_type == NO_CONVERGENCE ? "Maximum number of iterations reached"
+                     : summary->termination_type == USER_SUCCESS ? "User callback returned SOLVER_TERMINATE_SUCCESSFULLY"
+                     : summary->termination_type == USER_FAILURE ? "User callback returned SOLVER_ABORT" : "Failure";
 }
 
 // ---------------------------------------------------------------------------------------------- covariance

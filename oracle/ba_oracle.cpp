@@ -910,7 +910,7 @@ extern "C" int oracle_solve(oracle_graph* g, const oracle_options* opt, oracle_s
     t_lin += now_s() - t0;
     if (!ok) {
       if (++n_invalid >= 5) { termination = 2; break; }
-      radius *= 0.5;  // LevenbergMarquardtStrategy::StepIsInvalid
+      radius /= decrease; decrease *= 2.0; reuse_diag = true;  // LevenbergMarquardtStrategy::StepIsInvalid () = StepRejected (0)
       push_log(iter, x_cost + fixed_cost, 0, 0, 0, radius, gmax);
       continue;
     }

@@ -434,7 +434,8 @@ def solve_lm_dense(g, max_num_iterations=50, function_tolerance=1e-6, gradient_t
             if n_invalid >= 5:
                 out["termination"] = "FAILURE"
                 break
-            radius *= 0.5  # LevenbergMarquardtStrategy::StepIsInvalid
+            radius /= decrease  # LevenbergMarquardtStrategy::StepIsInvalid () = StepRejected (0)
+            decrease *= 2.0
             reuse_diag = True
             continue
         n_invalid = 0

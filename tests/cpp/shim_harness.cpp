@@ -84,12 +84,14 @@ int main(int argc, char** argv) {
     Covariance<double, 7> cov; for (int i = 0; i < 49; i++) cov.v[i] = v[8 + i];
     block_info[problem.AddResidualBlock(IndependentObjectMapFactor::createIndependentObjectMapFactor(e, cov), new ceres::HuberLoss(hub_lt), objs[(int)v[0]].get())] = {4, n};
   }
+  // ONE loss object shared by every relative-pose block: legal in Ceres (the Problem reference-counts what it owns)
+  ceres::LossFunction* shared_rel_loss = new ceres::HuberLoss(hub_rl);
   for (int n = 0; n < n_rl; n++) {
     const double* v = take(50);
     Pose3D<double> meas; for (int i = 0; i < 3; i++) meas.transl_(i) = v[2 + i];
     for (int i = 0; i < 9; i++) meas.orientation_.R.v[i] = v[5 + i];
     Covariance<double, 6> cov; for (int i = 0; i < 36; i++) cov.v[i] = v[14 + i];
-    block_info[problem.AddResidualBlock(RelativePoseFactor::createRelativePoseFactor(meas, cov), new ceres::HuberLoss(hub_rl), poses[(int)v[0]].get(), poses[(int)v[1]].get())] = {5, n};
+    block_info[problem.AddResidualBlock(RelativePoseFactor::createRelativePoseFactor(meas, cov), shared_rel_loss, poses[(int)v[0]].get(), poses[(int)v[1]].get())] = {5, n};
   }
   for (int k = 0; k < K; k++) {
     problem.AddParameterBlock(poses[k].get(), 6);  // object_pose_graph_optimizer.h:417-422
@@ -158,6 +160,26 @@ int main(int argc, char** argv) {
   for (int k = 0; k < K; k++) out.insert(out.end(), poses[k].get(), poses[k].get() + 6);
   for (int k = 0; k < P; k++) out.insert(out.end(), points[k].get(), points[k].get() + 3);
   for (int k = 0; k < O; k++) out.insert(out.end(), objs[k].get(), objs[k].get() + 7);
+  // ---- iteration callback with update_state_every_iteration (object_pose_graph_optimizer.h:651-659): stop after iteration 2
+  {
+    struct StopAt2 : ceres::IterationCallback {
+      const double* watched; std::vector<double> seen; int calls = 0;
+      ceres::CallbackReturnType operator()(const ceres::IterationSummary& it) override {
+        calls++; seen.push_back(watched[0]);
+        return it.iteration >= 2 ? ceres::SOLVER_TERMINATE_SUCCESSFULLY : ceres::SOLVER_CONTINUE;
+      }
+    } cb;
+    // perturb one variable pose so that the first iterations move it visibly
+    double* wp = poses[K - 1].get(); wp[0] += 0.05; cb.watched = wp;
+    ceres::Solver::Options o3 = options;
+    o3.callbacks.push_back(&cb); o3.update_state_every_iteration = true;
+    ceres::Solver::Summary s3;
+    ceres::Solve(o3, &problem, &s3);
+    std::printf("%s\n", s3.BriefReport().c_str());
+    bool moved = cb.seen.size() >= 3 && cb.seen[1] != cb.seen[0] && cb.seen[2] != cb.seen[1];
+    out.push_back((double)s3.termination_type); out.push_back((double)s3.iterations.size()); out.push_back((double)cb.calls);
+    out.push_back(moved ? 1.0 : 0.0); out.push_back(s3.IsSolutionUsable() ? 1.0 : 0.0);
+  }
   FILE* f = std::fopen(argv[2], "wb");
   std::fwrite(out.data(), 8, out.size(), f);
   std::fclose(f);

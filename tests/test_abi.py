@@ -76,3 +76,35 @@ def test_problem_bookkeeping_host_only(ob):
         p.add_relative_pose(poses[0], poses[1], np.zeros(3), np.eye(3), np.full((6, 6), np.nan), 1.0)
     st = p.debug_partition(0, 1)
     assert st["nf"] == 3 and st["n_obs"] == 3 and st["n_bbox"] == 1 and st["n_rel"] == 1 and st["n_unary"] == 2
+
+
+def test_recycled_block_address_and_array_overlap(ob):
+    """ADVICE r1 (problem.hpp): a removed block's address may come back with another size (Ceres accepts the sequence); an array
+    may not be registered over a block that is already registered singly anywhere inside its range."""
+    p = ob.Problem(-1)
+    buf = np.zeros(8)
+    pose, cam_pts = np.zeros(6), np.ones((2, 3))
+    p.add_parameter_block(buf[:6])                 # a 6-block at this address ...
+    p.remove_parameter_block(buf[:6])
+    p.add_parameter_block(buf[:3])                 # ... recycled as a 3-block
+    cam = p.add_camera((400, 400, 320, 240), np.eye(3), np.zeros(3))
+    p.add_parameter_block(pose)
+    p.add_reprojection(pose, buf[:3], cam, (300.0, 200.0), 1.5, 1.0)
+    assert p.debug_partition(0, 1)["n_obs"] == 1
+    with pytest.raises(ob.ObviError):              # a LIVE block keeps its size
+        p.add_parameter_block(buf[:7])
+    # one row registered singly, referenced by a factor, then the whole array: refused (the factor would keep the old id)
+    q = ob.Problem(-1)
+    pts = np.ones((5, 3)); pose2 = np.zeros(6)
+    cam = q.add_camera((400, 400, 320, 240), np.eye(3), np.zeros(3))
+    q.add_parameter_block(pts[2]); q.add_parameter_block(pose2)
+    q.add_reprojection(pose2, pts[2], cam, (300.0, 200.0), 1.5, 1.0)
+    with pytest.raises(ob.ObviError, match="overlaps"):
+        q.add_parameter_array(pts)
+    q.set_parameter_block_constant(pts[2])
+    assert q.is_parameter_block_constant(pts[2])
+    other = np.ones((4, 3))
+    q.add_parameter_array(other)                   # disjoint arrays are fine; so is re-adding rows of a registered array
+    q.add_parameter_block(other[1])
+    with pytest.raises(ob.ObviError, match="overlaps"):
+        q.add_parameter_array(other[1:3])

@@ -29,6 +29,14 @@ def test_reference_arm_prints_one_json_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["unit"] == d["unit"]
 
 
+def test_reference_arm_uses_every_host_core_under_torchrun():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm must not inherit it (round-1 SCALE ratios were against one thread)."""
+    r = _run(dict(OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0"))
+    assert r.returncode == 0, r.stderr[-1500:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+
+
 def test_reference_arm_is_silent_on_other_ranks():
     r = _run(dict(RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert r.returncode == 0 and r.stdout.strip() == ""

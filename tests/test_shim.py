@@ -76,7 +76,10 @@ def test_shim_matches_c_abi_two_phase(ob, tmp_path):
     cov_py = p.object_covariances([g.objects[o] for o in used], [g.objects[o] for o in used])
     for a, b in zip(cov_shim, cov_py):
         assert np.abs(a - b).max() <= 1e-3 * np.abs(np.diag(b)).max()
-    res = np.concatenate([res[:11], res[12 + 49 * ncov:]])
+    # trailing five values: the callback section (terminate successfully at iteration 2, state updated every iteration)
+    term3, n_it3, calls3, moved3, usable3 = res[-5:]
+    assert int(term3) == 3 and int(n_it3) == 3 and int(calls3) == 3 and moved3 == 1.0 and usable3 == 1.0      # USER_SUCCESS
+    res = np.concatenate([res[:11], res[12 + 49 * ncov:-5]])
     assert np.abs(res[11:11 + 6 * K].reshape(K, 6) - g.poses).max() < 1e-5
     assert np.abs(res[11 + 6 * K:11 + 6 * K + 3 * P].reshape(P, 3) - g.points).max() < 1e-3
     assert np.abs(res[11 + 6 * K + 3 * P:].reshape(-1, 7) - g.objects).max() < 1e-3
