@@ -102,7 +102,7 @@ def test_sharded_solve_on_one_device_matches_unsharded(ob, world):
         s = out[r]
         assert s.termination == s1.termination and len(s.iterations) == len(s1.iterations)
         for a, b in zip(s.iterations, s1.iterations):
-            assert abs(a["cost"] - b["cost"]) <= 1e-7 * abs(b["cost"]) and a["step_is_successful"] == b["step_is_successful"]
+            assert abs(a["cost"] - b["cost"]) <= 1e-7 * abs(b["cost"]) and a["successful"] == b["successful"]
         assert abs(s.final_cost - s1.final_cost) <= 1e-7 * s1.final_cost
         # every rank writes back the full, merged solution
         import numpy as np
