@@ -151,6 +151,12 @@ __device__ __forceinline__ void store_chunk(double* chunk, const double* Jp, con
 }
 constexpr uint32_t kObsMasked = 4u;  // flag bit 2 of ObsRec / BBoxRec: residual block removed in place (two-phase outlier exclusion)
 
+// Pose-side sums of the reprojection blocks, kept apart from the reduced system (which is rebuilt for every trust-region
+// radius while these only change with the linearisation point): per variable pose f the 6x6 block H_pp = sum Jp^T Jp
+// (36, row-major), g_p = sum Jp^T r (6) and a spare 6 -> kPoseAcc doubles.  Filled by the Jacobian kernel, added into the
+// reduced system by pose_acc_add_kernel.
+constexpr int kPoseAcc = 48;
+
 __global__ void __launch_bounds__(kJacThreads) reproj_jac_kernel(const ObsRec* __restrict__ obs, int64_t n,
                                                                   const PoseCam* __restrict__ pcam, int C,
                                                                   const CalibClass* __restrict__ cls,
@@ -161,8 +167,8 @@ __global__ void __launch_bounds__(kJacThreads) reproj_jac_kernel(const ObsRec* _
   double cost = 0.0, fixed = 0.0;
   if (i < n) {
     const double2 uv = reinterpret_cast<const double2*>(obs)[2 * i];
-    const uint4 id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];  // pose, point, cls, flags
-    const CalibClass cc = cls[id.z];
+    const uint4 id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];  // pose, point, chunk position, flags
+    const CalibClass cc = cls[id.w >> 16];
     const PoseCam& pc = pcam[(size_t)id.x * C + cc.cam];
     const double X[3] = {points[3 * (size_t)id.y], points[3 * (size_t)id.y + 1], points[3 * (size_t)id.y + 2]};
     double r[2], Jp[12], Jl[6];
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(kJacThreads) reproj_jac_kernel(const ObsRec* _
     if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
     const bool masked = (id.w & kObsMasked) != 0u;
     if (!masked) { if ((id.w & 3u) == 3u) fixed = c; else cost = c; }
-    store_chunk(J + (size_t)i * kChunk, Jp, Jl, r, sc, masked);
+    store_chunk(J + (size_t)id.z * kChunk, Jp, Jl, r, sc, masked);
   }
   cost = block_sum_all<kJacThreads>(cost, red);
   fixed = block_sum_all<kJacThreads>(fixed, red);
@@ -216,13 +222,13 @@ __device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_sme
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// 2-D tensor-map TMA store (shared -> global) of a [rows x 128 B] box; the box is written into shared memory in the 128-byte
-// swizzle pattern of the tensor map (16-byte piece a of row r lives at piece a ^ (r & 7)), so the 256 threads of a CTA --
-// each writing the eight pieces of its own 128-byte row -- never collide on a bank, and the TMA unit undoes the swizzle.
-__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* src_smem) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_addr(src_smem)) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+// fp64 tensor-core product D (8x8) += A (8x4) B (4x8): lane holds A[lane/4][lane%4], B[lane%4][lane/4], D[lane/4][2 (lane%4) + {0,1}]
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+
+// A row's chunk in the swizzled shared-memory tile image: 16-byte piece a of row r lives at piece a ^ (r & 7), so the 256
+// threads of a CTA -- each writing the eight pieces of its own 128-byte row -- never collide on a bank.
 __device__ __forceinline__ void store_chunk_swz(double* tile, int row, const double* Jp, const double* Jl, const double* r, double sc, bool masked) {
   double2* base = reinterpret_cast<double2*>(tile) + (size_t)row * 8;
   const int x = row & 7;
@@ -243,40 +249,51 @@ __device__ __forceinline__ void store_chunk_swz(double* tile, int row, const dou
   for (int a = 0; a < 8; a++) base[a ^ x] = v[a];
 }
 
-// ------------------------------------------------------------------------------------------ reprojection Jacobians, TMA-staged
-// Same arithmetic as reproj_jac_kernel, restructured around the memory system:
-//   * observations are pose-major, so the pose/camera entries a 256-observation tile needs are a short CONTIGUOUS range
-//     of the table: one 1-D TMA bulk copy stages them in shared memory (no per-thread 384-byte reloads);
-//   * each thread writes its 128-byte chunk into a (swizzled, bank-conflict-free) shared-memory image of the output tile,
-//     and one elected thread stores the whole 32 KB tile with a single TMA tensor store: full-line HBM writes, no LSU
-//     store traffic.  (Without a tensor map -- `tmap_ok == 0` -- the image is linear and goes out as a 1-D bulk copy.)
+// ------------------------------------------------------------------------------------------ reprojection Jacobians, fused
+// THE Jacobian-evaluation kernel.  One thread per observation, observations in POSE-major order, chunks stored POINT-major.
+//   * the pose/camera entries a 256-observation tile needs are a short contiguous range of the table: one 1-D TMA bulk copy
+//     stages them in shared memory;
+//   * every thread writes its 128-byte chunk into a swizzled shared-memory image of the tile (16-byte piece a of row r at
+//     a ^ (r & 7): conflict free), then each WARP scatters its own 32 rows to their point-major positions -- eight lanes per
+//     row, i.e. every store instruction writes four complete 128-byte lines;
+//   * the pose-side normal-equation sums H_pp = sum Jp^T Jp, g_p = sum Jp^T r of the rows (which no later kernel could form
+//     without gathering, now that the chunks are point-major) are taken from the same image with the fp64 tensor cores: per
+//     pair of rows one m8n8k4 product [Jp | r]^T [Jp | r], A and B fragments being the same register.  Warps that span a
+//     keyframe boundary run one masked pass per keyframe.  Warp partials are combined through shared memory (fixed order) and
+//     leave as one set of reductions per (tile, keyframe).
+// Only the final combine needs a block barrier: scatter and products read what the same warp wrote.
 constexpr int kJacMaxPc = 6;                       // staged pose/camera entries per tile
 constexpr int kJacMaxCls = 16;                     // calibration classes staged in shared memory
+constexpr int kJacAccSlots = 6;                    // keyframes per tile whose sums are combined on chip (more: direct reductions)
+constexpr int kJacWarps = kJacThreads / 32;
 constexpr int kJacTileBytes = kJacThreads * kChunk * 8;
-constexpr int kJacSmemBytes = kJacTileBytes + kJacMaxPc * (int)sizeof(PoseCam) + 16 + 1024;   // + slack to align the tile to 1 KB
+constexpr int kJacSmemBytes = kJacTileBytes + kJacMaxPc * (int)sizeof(PoseCam) + 16 + 128;
 
-__global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const __grid_constant__ CUtensorMap tmap, int tmap_ok,
-                                                                         const ObsRec* __restrict__ obs, int64_t n,
-                                                                         const PoseCam* __restrict__ pcam, int C,
-                                                                         const CalibClass* __restrict__ cls, int ncls,
-                                                                         const double* __restrict__ points, int apply_loss,
-                                                                         const uint2* __restrict__ tile_pc,
-                                                                         double* __restrict__ J, double* __restrict__ scalars) {
+__global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_fused_kernel(const ObsRec* __restrict__ obs, int64_t n,
+                                                                           const PoseCam* __restrict__ pcam, int C,
+                                                                           const CalibClass* __restrict__ cls, int ncls,
+                                                                           const double* __restrict__ points, int apply_loss,
+                                                                           const uint2* __restrict__ tile_pc,
+                                                                           const int32_t* __restrict__ f_of_pose,
+                                                                           double* __restrict__ J, double* __restrict__ pose_acc,
+                                                                           double* __restrict__ scalars) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ double red[33];
   __shared__ CalibClass cls_s[kJacMaxCls];
-  // the swizzled tile must sit on a 1 KB boundary of the shared-memory window
-  unsigned char* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
-  double* out_tile = reinterpret_cast<double*>(smem);
+  __shared__ double part_s[kJacWarps][2][64];      // per warp: the 8x8 products of its (at most two) keyframes
+  __shared__ int part_slot[kJacWarps][2];
+  __shared__ double wcost[kJacWarps], wfixed[kJacWarps];
+  unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
+  double* tile = reinterpret_cast<double*>(smem);
   PoseCam* pc_s = reinterpret_cast<PoseCam*>(smem + kJacTileBytes);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kJacTileBytes + kJacMaxPc * sizeof(PoseCam));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t i0 = (int64_t)blockIdx.x * kJacThreads;
   const int nt = (int)min((int64_t)kJacThreads, n - i0);
   const uint2 tp = tile_pc[blockIdx.x];  // first pose/camera entry of the tile, number of entries staged
   const int64_t i = i0 + threadIdx.x;
   const bool active = (int)threadIdx.x < nt;
   double2 uv = make_double2(0.0, 0.0);
-  uint4 id = make_uint4(0, 0, 0, 0);
+  uint4 id = make_uint4(0, 0, 0, 3u);
   if (active) {  // issue the record loads first: they head the longest dependency chain (record -> point)
     uv = reinterpret_cast<const double2*>(obs)[2 * i];
     id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];
@@ -293,36 +310,120 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_tma_kernel(const __
   if (active) {
     X[0] = points[3 * (size_t)id.y]; X[1] = points[3 * (size_t)id.y + 1]; X[2] = points[3 * (size_t)id.y + 2];
   }
-  const CalibClass cc = cls_s[id.z];
+  const CalibClass cc = cls_s[(id.w >> 16) & (kJacMaxCls - 1)];
+  const uint32_t pose0 = tp.x / (uint32_t)C;       // first keyframe of the tile
+  // accumulation slot of this row: keyframe index inside the tile, -1: no pose-side sums (inactive row, constant pose)
+  int slot = -1;
   mbar_wait(bar, 0);
-  if (active) {
-    const uint32_t pci = id.x * (uint32_t)C + ((id.w >> 8) & 0xffu);
-    const uint32_t rel = pci - tp.x;
+  {
     double r[2], Jp[12], Jl[6];
-    // two explicit paths so that the staged entries are read with shared-memory loads (a `cond ? smem : global`
-    // reference would compile to generic loads, tracked by the long scoreboard)
-    if (rel < tp.y) reproj_residual_jacobian(pc_s[rel], X, uv.x, uv.y, cc.mx, cc.my, r, Jp, Jl);
-    else reproj_residual_jacobian(pcam[pci], X, uv.x, uv.y, cc.mx, cc.my, r, Jp, Jl);
-    const double s = r[0] * r[0] + r[1] * r[1];
-    double sc = 1.0, c = 0.5 * s;
-    if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
-    const bool masked = (id.w & kObsMasked) != 0u;
-    if (!masked) { if ((id.w & 3u) == 3u) fixed = c; else cost = c; }
-    if (tmap_ok) store_chunk_swz(out_tile, (int)threadIdx.x, Jp, Jl, r, sc, masked);
-    else store_chunk(out_tile + (size_t)threadIdx.x * kChunk, Jp, Jl, r, sc, masked);
+    double sc = 1.0;
+    bool masked = true;
+    if (active) {
+      const uint32_t pci = id.x * (uint32_t)C + ((id.w >> 8) & 0xffu);
+      const uint32_t rel = pci - tp.x;
+      // two explicit paths so that the staged entries are read with shared-memory loads (a `cond ? smem : global`
+      // reference would compile to generic loads, tracked by the long scoreboard)
+      if (rel < tp.y) reproj_residual_jacobian(pc_s[rel], X, uv.x, uv.y, cc.mx, cc.my, r, Jp, Jl);
+      else reproj_residual_jacobian(pcam[pci], X, uv.x, uv.y, cc.mx, cc.my, r, Jp, Jl);
+      const double s = r[0] * r[0] + r[1] * r[1];
+      double c = 0.5 * s;
+      if (apply_loss && cc.huber > 0.0) c = huber(cc.huber, s, &sc);
+      masked = (id.w & kObsMasked) != 0u;
+      if (!masked) { if ((id.w & 3u) == 3u) fixed = c; else cost = c; }
+      if (!(id.w & 1u) && !masked) slot = (int)(id.x - pose0);
+    }
+    if (active) store_chunk_swz(tile, (int)threadIdx.x, Jp, Jl, r, sc, masked);
+    else {
+      double2* base = reinterpret_cast<double2*>(tile) + (size_t)threadIdx.x * 8;
+#pragma unroll
+      for (int a = 0; a < 8; a++) base[a] = make_double2(0.0, 0.0);
+    }
   }
-  fence_proxy_async_smem();
-  cost = block_sum_all<kJacThreads>(cost, red);     // contains __syncthreads: the tile image is complete after it
-  fixed = block_sum_all<kJacThreads>(fixed, red);
+  __syncwarp();
+  // ---- scatter the warp's 32 rows: eight lanes per row, four complete lines per store instruction
+  {
+    const int sub = lane >> 3, piece = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      const int rl = 4 * it + sub;                                   // row inside the warp
+      const uint32_t d = __shfl_sync(0xffffffffu, id.z, rl);
+      const bool act = __shfl_sync(0xffffffffu, (int)active, rl) != 0;
+      const int row = 32 * w + rl;
+      const double2 v = reinterpret_cast<const double2*>(tile)[(size_t)row * 8 + (piece ^ (row & 7))];
+      if (act) reinterpret_cast<double2*>(J)[(size_t)d * 8 + piece] = v;
+    }
+  }
+  // ---- pose-side sums of the warp's rows on the fp64 tensor cores
+  int nparts = 0;
+  {
+    const int a = lane >> 2, k = lane & 3;                           // fragment element [a][k]: parameter column a, residual row k
+    const int rr = k & 1;                                            // residual row inside the observation
+    // chunk [Jr 2x3 | Jl 2x3 | r 2 | pad]: columns 0-2 of Jp are -Jl, 3-5 are Jr, column 6 carries r (-> g_p), column 7 is zero
+    const int idx = a < 3 ? 6 + 3 * rr + a : (a < 6 ? 3 * rr + (a - 3) : 12 + rr);
+    const double sgn = a < 3 ? -1.0 : (a < 7 ? 1.0 : 0.0);
+    const int pc = idx >> 1, wi = idx & 1;
+    const int smin = __reduce_min_sync(0xffffffffu, slot < 0 ? 0x7fffffff : slot);
+    const int smax = __reduce_max_sync(0xffffffffu, slot);
+    for (int s = smin; s <= smax; s++) {
+      const uint32_t m = __ballot_sync(0xffffffffu, slot == s);
+      if (m == 0u) continue;
+      double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int rl = 2 * j + (k >> 1);
+        const int row = 32 * w + rl;
+        const double2 v2 = reinterpret_cast<const double2*>(tile)[(size_t)row * 8 + (pc ^ (row & 7))];
+        double v = wi ? v2.y : v2.x;
+        v = ((m >> rl) & 1u) ? sgn * v : 0.0;
+        dmma_m8n8k4(d0, d1, v, v);
+      }
+      if (s < kJacAccSlots && nparts < 2) {
+        part_s[w][nparts][8 * a + 2 * k] = d0; part_s[w][nparts][8 * a + 2 * k + 1] = d1;
+        if (lane == 0) part_slot[w][nparts] = s;
+        nparts++;
+      } else {
+        // more than two keyframes inside one warp, or more than kJacAccSlots in the tile: reduce straight into global memory
+        const int f = f_of_pose[pose0 + (uint32_t)s];
+        double* acc = pose_acc + (size_t)f * kPoseAcc;
+        const int c0 = 2 * k;
+        if (a < 6) {
+          if (c0 < 6) { red_add(&acc[6 * a + c0], d0); red_add(&acc[6 * a + c0 + 1], d1); }
+          else red_add(&acc[36 + a], d0);                            // column 6: g_p
+        }
+      }
+    }
+    if (lane == 0) { for (int q = nparts; q < 2; q++) part_slot[w][q] = -1; }
+  }
+  cost = warp_sum(cost); fixed = warp_sum(fixed);
+  if (lane == 0) { wcost[w] = cost; wfixed[w] = fixed; }
+  __syncthreads();
+  // ---- combine the warp partials per keyframe (fixed order) and reduce into the pose accumulators
+  for (int t = threadIdx.x; t < kJacAccSlots * 64; t += kJacThreads) {
+    const int s = t >> 6, e = t & 63;
+    const int a = e >> 3, c = e & 7;
+    if (a >= 6 || c >= 7) continue;
+    double sum = 0.0;
+    bool any = false;
+#pragma unroll
+    for (int ww = 0; ww < kJacWarps; ww++) {
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+        if (part_slot[ww][q] == s) { sum += part_s[ww][q][e]; any = true; }
+    }
+    if (!any) continue;
+    const int f = f_of_pose[pose0 + (uint32_t)s];
+    double* acc = pose_acc + (size_t)f * kPoseAcc;
+    red_add(c < 6 ? &acc[6 * a + c] : &acc[36 + a], sum);
+  }
   if (threadIdx.x == 0) {
-    if (tmap_ok) tma_store_2d(&tmap, 0, (int)i0, out_tile);     // rows beyond n are clipped by the tensor map
-    else tma_store_1d(J + (size_t)i0 * kChunk, out_tile, (uint32_t)nt * kChunk * 8);
-    if (cost != 0.0) atomicAdd(&scalars[SC_COST], cost);
-    if (fixed != 0.0) atomicAdd(&scalars[SC_FIXED], fixed);
-    tma_store_wait_read();
+    double cs = 0.0, fs = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < kJacWarps; ww++) { cs += wcost[ww]; fs += wfixed[ww]; }
+    if (cs != 0.0) atomicAdd(&scalars[SC_COST], cs);
+    if (fs != 0.0) atomicAdd(&scalars[SC_FIXED], fs);
   }
 }
-
 
 // Residual-only evaluation at the candidate point (cost only; nothing is stored).
 __global__ void __launch_bounds__(kJacThreads) reproj_cost_kernel(const ObsRec* __restrict__ obs, int64_t n,
@@ -336,7 +437,7 @@ __global__ void __launch_bounds__(kJacThreads) reproj_cost_kernel(const ObsRec* 
   if (i < n) {
     const double2 uv = reinterpret_cast<const double2*>(obs)[2 * i];
     const uint4 id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];
-    const CalibClass cc = cls[id.z];
+    const CalibClass cc = cls[id.w >> 16];
     const PoseCam& pc = pcam[(size_t)id.x * C + cc.cam];
     const double X[3] = {points[3 * (size_t)id.y], points[3 * (size_t)id.y + 1], points[3 * (size_t)id.y + 2]};
     double r[2];
@@ -356,16 +457,14 @@ __global__ void __launch_bounds__(kJacThreads) reproj_cost_kernel(const ObsRec* 
 }
 
 // ------------------------------------------------------------------------------------------ pose-side J^T J accumulation
-// One CTA per keyframe: the keyframe's Jacobian tile is contiguous (pose-major order).  Accumulates
-// H_pp = sum Jp^T Jp (6x6), g_p = sum Jp^T r and the column square norms with warp-shuffle reductions;
-// one set of atomics per CTA.
+// Fallback beside reproj_jac_kernel (the kernel without TMA staging / fused sums): one CTA per keyframe walks the keyframe's
+// pose-major records, gathers each chunk from its point-major position and accumulates H_pp, g_p with warp-shuffle
+// reductions; one set of reductions per CTA.
 constexpr int kPoseAccThreads = 256;
-__global__ void __launch_bounds__(kPoseAccThreads) pose_accum_kernel(const double* __restrict__ J,
-                                                                      const uint32_t* __restrict__ pose_ptr,
-                                                                      const int32_t* __restrict__ f_of_pose,
-                                                                      const uint32_t* __restrict__ su_ptr,
-                                                                      double* __restrict__ S_upper, double* __restrict__ gp,
-                                                                      double* __restrict__ hpp_diag) {
+__global__ void __launch_bounds__(kPoseAccThreads) pose_accum_gather_kernel(const ObsRec* __restrict__ obs, const double* __restrict__ J,
+                                                                             const uint32_t* __restrict__ pose_ptr,
+                                                                             const int32_t* __restrict__ f_of_pose,
+                                                                             double* __restrict__ pose_acc) {
   const int k = blockIdx.x;
   const int f = f_of_pose[k];
   if (f < 0) return;
@@ -377,7 +476,7 @@ __global__ void __launch_bounds__(kPoseAccThreads) pose_accum_kernel(const doubl
   for (uint32_t i = b0 + threadIdx.x; i < b1; i += kPoseAccThreads) {
     double jp[12], jl_[6];
     double2 r;
-    load_chunk(J + (size_t)i * kChunk, jp, jl_, r.x, r.y);
+    load_chunk(J + (size_t)obs[i].dst * kChunk, jp, jl_, r.x, r.y);
     int t = 0;
 #pragma unroll
     for (int a = 0; a < 6; a++) {
@@ -399,102 +498,32 @@ __global__ void __launch_bounds__(kPoseAccThreads) pose_accum_kernel(const doubl
     double s = 0;
 #pragma unroll
     for (int i = 0; i < kPoseAccThreads / 32; i++) s += red[threadIdx.x][i];
-    double* Sd = S_upper + (size_t)su_ptr[f] * 36;
+    double* A = pose_acc + (size_t)f * kPoseAcc;
     if (threadIdx.x < 21) {
       int a = 0, t = threadIdx.x;
       while (t >= 6 - a) { t -= 6 - a; a++; }
       const int b = a + t;
-      atomicAdd(&Sd[a * 6 + b], s);
-      if (a != b) atomicAdd(&Sd[b * 6 + a], s);
-      else atomicAdd(&hpp_diag[6 * f + a], s);
+      red_add(&A[a * 6 + b], s);
+      if (a != b) red_add(&A[b * 6 + a], s);
     } else {
-      atomicAdd(&gp[6 * f + (threadIdx.x - 21)], s);
+      red_add(&A[36 + (threadIdx.x - 21)], s);
     }
   }
 }
-
-// pose_accum_tma_kernel: the same reduction with the keyframe's Jacobian tile STAGED BY TMA.  The chunk array is viewed
-// through the tensor map of the Jacobian kernel ([n_obs x 128 B], 128-byte swizzle); a CTA walks its keyframe's contiguous
-// rows in boxes of 256, double-buffered: while the threads reduce box t out of shared memory (thread = row, the eight
-// 16-byte pieces at their swizzled positions: conflict free), the TMA unit is already fetching box t + 1 with full-line
-// reads.  Rows of the box that belong to the next keyframe are skipped; rows past the end of the array arrive zero-filled.
-constexpr int kPoseAccTmaSmem = 2 * kPoseAccThreads * kChunk * 8 + 1024 + 64;
-__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_addr(dst_smem)),
-               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_addr(bar)) : "memory");
-}
-__global__ void __launch_bounds__(kPoseAccThreads) pose_accum_tma_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                                          const uint32_t* __restrict__ pose_ptr,
-                                                                          const int32_t* __restrict__ f_of_pose,
-                                                                          const uint32_t* __restrict__ su_ptr,
-                                                                          double* __restrict__ S_upper, double* __restrict__ gp,
-                                                                          double* __restrict__ hpp_diag) {
-  extern __shared__ __align__(128) unsigned char pa_raw[];
-  const int k = blockIdx.x;
-  const int f = f_of_pose[k];
-  if (f < 0) return;
-  const uint32_t b0 = pose_ptr[k], b1 = pose_ptr[k + 1];
-  if (b0 == b1) return;
-  unsigned char* base = pa_raw + ((1024u - (smem_addr(pa_raw) & 1023u)) & 1023u);
-  constexpr int kBoxBytes = kPoseAccThreads * kChunk * 8;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 2 * kBoxBytes);
-  const int nbox = (int)((b1 - b0 + kPoseAccThreads - 1) / kPoseAccThreads);
-  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
-  __syncthreads();
-  if (threadIdx.x == 0) { mbar_expect_tx(&bar[0], kBoxBytes); tma_load_2d(base, &tmap, 0, (int)b0, &bar[0]); }
-  double acc[27];
-#pragma unroll
-  for (int a = 0; a < 27; a++) acc[a] = 0.0;
-  const int x = threadIdx.x & 7;
-  for (int t = 0; t < nbox; t++) {
-    if (t + 1 < nbox && threadIdx.x == 0) {
-      const int nb = (t + 1) & 1;
-      mbar_expect_tx(&bar[nb], kBoxBytes);
-      tma_load_2d(base + nb * kBoxBytes, &tmap, 0, (int)(b0 + (uint32_t)(t + 1) * kPoseAccThreads), &bar[nb]);
-    }
-    mbar_wait(&bar[t & 1], (uint32_t)((t >> 1) & 1));
-    const uint32_t row = b0 + (uint32_t)t * kPoseAccThreads + threadIdx.x;
-    if (row < b1) {
-      const double2* c = reinterpret_cast<const double2*>(base + (t & 1) * kBoxBytes) + (size_t)threadIdx.x * 8;
-      double raw[14], jp[12], jl[6], r[2];
-#pragma unroll
-      for (int a = 0; a < 7; a++) { const double2 v = c[a ^ x]; raw[2 * a] = v.x; raw[2 * a + 1] = v.y; }
-      decode_chunk(raw, jp, jl, r);
-      int q = 0;
-#pragma unroll
-      for (int a = 0; a < 6; a++) {
-#pragma unroll
-        for (int b = a; b < 6; b++) acc[q++] += jp[a] * jp[b] + jp[6 + a] * jp[6 + b];
-      }
-#pragma unroll
-      for (int a = 0; a < 6; a++) acc[21 + a] += jp[a] * r[0] + jp[6 + a] * r[1];
-    }
-    fence_proxy_async_smem();
-    __syncthreads();   // box t is consumed: its buffer may be refilled (by the load issued in iteration t + 1)
-  }
-  __shared__ double red[27][kPoseAccThreads / 32];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-#pragma unroll
-  for (int a = 0; a < 27; a++) {
-    const double v = warp_sum(acc[a]);
-    if (l == 0) red[a][w] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 27) {
-    double s = 0;
-#pragma unroll
-    for (int i = 0; i < kPoseAccThreads / 32; i++) s += red[threadIdx.x][i];
-    double* Sd = S_upper + (size_t)su_ptr[f] * 36;
-    if (threadIdx.x < 21) {
-      int a = 0, t = threadIdx.x;
-      while (t >= 6 - a) { t -= 6 - a; a++; }
-      const int b = a + t;
-      atomicAdd(&Sd[a * 6 + b], s);
-      if (a != b) atomicAdd(&Sd[b * 6 + a], s);
-      else atomicAdd(&hpp_diag[6 * f + a], s);
-    } else {
-      atomicAdd(&gp[6 * f + (threadIdx.x - 21)], s);
-    }
+// reduced system += pose-side sums of the reprojection blocks (one thread per entry)
+__global__ void pose_acc_add_kernel(int nf, const double* __restrict__ pose_acc, const uint32_t* __restrict__ su_ptr,
+                                    double* __restrict__ S_upper, double* __restrict__ gp, double* __restrict__ hpp_diag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nf * 42) return;
+  const int f = t / 42, e = t - 42 * f;
+  const double v = pose_acc[(size_t)f * kPoseAcc + e];
+  if (v == 0.0) return;
+  // reductions, not plain stores: the side-stream kernels (objects, priors, rel-pose) add into the same entries concurrently
+  if (e < 36) {
+    red_add(&S_upper[(size_t)su_ptr[f] * 36 + e], v);   // the diagonal block of row f is the first block of its upper row
+    if (e % 7 == 0) red_add(&hpp_diag[6 * f + e / 7], v);
+  } else {
+    red_add(&gp[6 * f + (e - 36)], v);
   }
 }
 
@@ -870,10 +899,6 @@ __global__ void __launch_bounds__(T, MINB) obj_schur_kernel(EArgs A, const uint3
 }
 
 
-// fp64 tensor-core product D (8x8) += A (8x4) B (4x8): lane holds A[lane/4][lane%4], B[lane%4][lane/4], D[lane/4][2 (lane%4) + {0,1}]
-__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 // ------------------------------------------------------------------------------------------ points: row-owner elimination
 // Two kernels replace the batched kernels above (kept selectable for A/B measurements):
@@ -908,7 +933,7 @@ __global__ void __launch_bounds__(256, 2) point_prep_kernel(EArgs A, const uint3
   for (int a = 0; a < 18; a++) W0[a] = 0.0;
   auto sweep = [&](const uint4 G, double* W) {
     for (uint32_t k = 0; k < G.w; k++) {
-      const uint32_t pos = k == 0 ? G.x : (G.w <= 2 ? G.y : A.pos[G.y + k]);
+      const uint32_t pos = G.x + k;   // a group's chunks are consecutive (point-major Jacobian array)
       double jp[12], jl[6];
       double2 rv;
       load_chunk(A.J + (size_t)pos * kChunk, jp, jl, rv.x, rv.y);
@@ -1300,7 +1325,7 @@ __global__ void __launch_bounds__(256) backsub_rows_kernel(EArgs A, const uint32
 #pragma unroll
     for (int a = 0; a < 6; a++) dp[a] = fi >= 0 ? dpose[6 * fi + a] : 0.0;
     for (uint32_t k = 0; k < G.w; k++) {
-      const uint32_t pos = k == 0 ? G.x : (G.w <= 2 ? G.y : A.pos[G.y + k]);
+      const uint32_t pos = G.x + k;   // a group's chunks are consecutive (point-major Jacobian array)
       double jp[12], jl[6];
       double2 rv;
       load_chunk(A.J + (size_t)pos * kChunk, jp, jl, rv.x, rv.y);

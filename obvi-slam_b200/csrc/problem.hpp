@@ -51,9 +51,11 @@ struct ObsRec {       // 32 B, one per reprojection observation, pose-major orde
   double ur, vr;      // rectified feature
   uint32_t pose;      // pose index
   uint32_t point;     // internal point index
-  uint32_t cls;       // calibration class (camera, sigma, huber)
-  uint32_t flags;     // bit0: pose constant, bit1: point constant, bits 8-15: camera index
+  uint32_t dst;       // position of this observation's Jacobian chunk: POINT-major (point, pose, camera) order
+  uint32_t flags;     // bit0: pose constant, bit1: point constant, bit2: masked, bits 8-15: camera index (valid when C <= 256),
+                      // bits 16-31: calibration class (camera, sigma, huber)
 };
+inline uint32_t obs_cls(const ObsRec& o) { return o.flags >> 16; }
 struct CalibClass { double mx, my, huber; int32_t cam; int32_t pad; };  // 32 B
 struct BBoxRec {      // one per bbox observation, object-major order
   double brect[4];
@@ -100,7 +102,7 @@ struct Structure {
   //   groups : per point, one record per run of observations taken from the same pose (stereo pair = one group)
   //   entries: per (reduced-matrix row a, column range [a + 5r, a + 5r + 5)): the (point, pose a) slots that contribute
   //   items  : <= kRowItemEnts consecutive entries of one (row, range) list = the work of one warp
-  struct RowGroup { uint32_t pos0, pos1, gs, cnt; };   // cnt <= 2: chunk positions; cnt > 2: pos1 = first list entry
+  struct RowGroup { uint32_t pos0, pos1, gs, cnt; };   // chunks pos0 .. pos0 + cnt - 1 of the point-major Jacobian array
   struct RowItem { uint32_t row, dlo, off, cnt; };
   struct PointRows {
     std::vector<uint32_t> grp_ptr;      // P + 1
@@ -332,6 +334,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
       }
     }
     for (int t = 0; t < nt; t++) for (const ClsKey& c : local_cls[t]) class_of(c.cam, c.sigma, c.huber);
+    if (S.classes.size() >= 65536) { err = "more than 65535 (camera, sigma, huber) calibration classes"; return false; }
     // segment starts, and the start of every chunk's share inside each segment
     S.pose_ptr.assign(S.K + 1, 0);
     for (int k = 0; k < S.K; k++) {
@@ -381,8 +384,8 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
           const int pt = (int)(uint32_t)kv[i].first;
           ObsRec& o = S.obs[b + i];
           o.ur = (f.px - c.intr[2]) / c.intr[0]; o.vr = (f.py - c.intr[3]) / c.intr[1];
-          o.pose = k; o.point = pt; o.cls = last_cls;
-          o.flags = (S.f_of_pose[k] < 0 ? 1u : 0u) | (S.point_const[pt] ? 2u : 0u) | ((uint32_t)f.cam << 8);
+          o.pose = k; o.point = pt; o.dst = 0;   // dst: filled once the point lists exist
+          o.flags = (S.f_of_pose[k] < 0 ? 1u : 0u) | (S.point_const[pt] ? 2u : 0u) | (((uint32_t)f.cam & 0xffu) << 8) | (last_cls << 16);
           S.obs_user[b + i] = n;
         }
       }
@@ -477,6 +480,11 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
   // list entries of one e-block are visited in obs order = (pose, camera): equal poses are adjacent
   build_elist(S.pts, S.P, [&](int64_t q) { return (int)S.obs[q].point; }, [&](int64_t q) { return (int)S.obs[q].pose; }, S.n_obs);
   build_elist(S.objs, S.O, [&](int64_t q) { return (int)S.bbox[q].obj; }, [&](int64_t q) { return (int)S.bbox[q].pose; }, S.n_bbox);
+  // The reprojection Jacobian chunks are stored POINT-major: entry d of the point lists (ordered by point, then pose, then
+  // camera) is chunk d, so every point's chunks are one contiguous range.  pts.pos keeps the pose-major record index of entry d
+  // on the host (masking, exports); the record carries its chunk position.
+#pragma omp parallel for schedule(static)
+  for (int64_t d = 0; d < S.n_obs; d++) S.obs[S.pts.pos[d]].dst = (uint32_t)d;
   for (Structure::EList* L : {&S.pts, &S.objs}) {
     const int ne = (int)L->nslots.size();
     const std::vector<uint8_t>& cst = (L == &S.pts) ? S.point_const : S.obj_const;
@@ -600,7 +608,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
         uint32_t d2 = d + 1;
         while (d2 < S.pts.ptr[e + 1] && S.pts.slot[d] != 0xFFFF && S.pts.slot[d2] == S.pts.slot[d]) d2++;
         Structure::RowGroup G;
-        G.cnt = d2 - d; G.pos0 = S.pts.pos[d]; G.pos1 = G.cnt == 2 ? S.pts.pos[d + 1] : (G.cnt > 2 ? d : 0u);
+        G.cnt = d2 - d; G.pos0 = d; G.pos1 = d + 1;   // chunks d .. d + cnt - 1 (point-major positions)
         G.gs = S.pts.slot[d] == 0xFFFF ? 0xFFFFFFFFu : dptr[e] + (uint32_t)(S.pts.f[d] - sf[0]);
         R.grp[w] = G; R.grp_f[w] = S.pts.f[d]; w++;
         d = d2;

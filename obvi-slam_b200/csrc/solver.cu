@@ -224,8 +224,7 @@ struct Solver {
   DBuf<uint8_t> pose_skip, point_skip, obj_skip;
   DBuf<uint2> jac_tile;  // per 256-observation tile: first pose/camera entry, entries staged by TMA
   int jac_mode = 1;  // 1: TMA-staged tile kernel (default), 0: plain loads / stores (OBVI_JAC=plain)
-  CUtensorMap jac_tmap;     // [n_obs x 128 B] view of J for the swizzled tile store of the Jacobian kernel
-  int jac_tmap_ok = 0;
+  DBuf<double> pose_acc;    // per variable pose: H_pp (36) | g_p (6) | spare (6) of the reprojection blocks, filled by the Jacobian kernel
   DBuf<BBoxRec> bbox;
   DBuf<UnaryRec> unary;
   DBuf<RelRec> rel;
@@ -332,8 +331,7 @@ struct Solver {
     if (const char* e = getenv("OBVI_PROFILE")) prof.on = std::string(e) == "1";
     if (const char* e = getenv("OBVI_DEBUG_BT_FAIL_RANK")) debug_bt_fail_rank = atoi(e);
     if (const char* e = getenv("OBVI_JAC")) jac_mode = std::string(e) == "plain" ? 0 : 1;
-    CUDA_OK(cudaFuncSetAttribute(reproj_jac_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes));
-    CUDA_OK(cudaFuncSetAttribute(pose_accum_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoseAccTmaSmem));
+    CUDA_OK(cudaFuncSetAttribute(reproj_jac_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes));
   }
 
   void upload_elist(EListDev& D, const Structure::EList& L, const std::vector<uint8_t>& cst, int NE, int maxs) {
@@ -364,12 +362,17 @@ struct Solver {
       for (int64_t t = 0; t < ntiles; t++) {
         const ObsRec& a = S.obs[t * kJacThreads];
         const ObsRec& b = S.obs[std::min<int64_t>(S.n_obs, (t + 1) * kJacThreads) - 1];
-        const uint32_t lo = a.pose * (uint32_t)S.C + (uint32_t)S.classes[a.cls].cam, hi = b.pose * (uint32_t)S.C + (uint32_t)S.classes[b.cls].cam;
+        const uint32_t lo = a.pose * (uint32_t)S.C + (uint32_t)S.classes[obs_cls(a)].cam, hi = b.pose * (uint32_t)S.C + (uint32_t)S.classes[obs_cls(b)].cam;
         tp[t] = make_uint2(lo, std::min<uint32_t>(hi - lo + 1, kJacMaxPc));
       }
       jac_tile.upload(tp, stream);
     }
     upload_elist(pts, S.pts, S.point_const, 3, 16);
+    {   // device view: entry d of the point lists IS chunk d (host pts.pos keeps the pose-major record index)
+      std::vector<uint32_t> ident(S.n_obs);
+      for (int64_t d = 0; d < S.n_obs; d++) ident[d] = (uint32_t)d;
+      pts.pos.upload(ident, stream);
+    }
     upload_elist(objs, S.objs, S.obj_const, 7, kObjMaxSlots);   // overflow areas for every object the split kernel cannot stage on chip
     {
       const Structure::PointRows& R = S.prow;
@@ -395,7 +398,7 @@ struct Solver {
     for (int b = 0; b < 3; b++) { poses[b].alloc((size_t)S.K * 6); points[b].alloc((size_t)S.P * 3); objects[b].alloc((size_t)S.O * 7); }
     pcam.alloc((size_t)S.K * std::max(S.C, 1)); pcam_cand.alloc((size_t)S.K * std::max(S.C, 1));
     J.alloc((size_t)S.n_obs * kChunk); Jb.alloc((size_t)S.n_bbox * kBBoxChunk);
-    encode_jac_tmap();
+    pose_acc.alloc((size_t)std::max(S.nf, 1) * kPoseAcc);
     unary_out.alloc(S.n_unary); rel_out.alloc(S.n_rel);
     const size_t nf6 = (size_t)S.nf * 6;
     // a sharded run all-reduces this buffer once per build; its tail carries the linearisation's scalars along
@@ -575,35 +578,23 @@ struct Solver {
     join();
     prof.end("lin: side join", pt2, stream);
   }
-  // the reprojection Jacobian-evaluation kernel (three revisions, selectable with OBVI_JAC = plain | tma | persistent)
-  // Tensor map of the chunk array for the Jacobian kernel's tile store (128-byte rows, 256-row boxes, 128-byte swizzle).
-  void encode_jac_tmap() {
-    jac_tmap_ok = 0;
-    std::memset(&jac_tmap, 0, sizeof(jac_tmap));
-    if (st.n_obs == 0 || getenv("OBVI_JAC_LINEAR")) return;
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) { cudaGetLastError(); return; }
-    const cuuint64_t gdim[2] = {(cuuint64_t)kChunk, (cuuint64_t)st.n_obs};
-    const cuuint64_t gstride[1] = {(cuuint64_t)kChunk * 8};
-    const cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)kJacThreads};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult rc = ((EncodeFn)fn)(&jac_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, J.p, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    jac_tmap_ok = rc == CUDA_SUCCESS;
-  }
+  // The reprojection Jacobian-evaluation kernel: chunks to their point-major positions + the pose-side sums into pose_acc
+  // (zeroed here).  Fused TMA-staged kernel by default; OBVI_JAC=plain (or more than 16 calibration classes / 256 cameras)
+  // selects the plain kernel followed by the gathering pose accumulation.
   void launch_jacobian(int apply_loss, const double* pts_dev) {
     const Structure& S = st;
-    const bool tma_ok = (int)S.classes.size() <= kJacMaxCls && S.C <= 256;
+    const bool fused_ok = (int)S.classes.size() <= kJacMaxCls && S.C <= 256;
     const int ntiles = nblk(S.n_obs, kJacThreads);
-    if (jac_mode >= 1 && tma_ok) {
-      reproj_jac_tma_kernel<<<ntiles, kJacThreads, kJacSmemBytes, stream>>>(jac_tmap, jac_tmap_ok, obs.p, S.n_obs, pcam.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss, jac_tile.p, J.p, scalars.p);
+    pose_acc.zero(stream);
+    if (jac_mode >= 1 && fused_ok) {
+      reproj_jac_fused_kernel<<<ntiles, kJacThreads, kJacSmemBytes, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, (int)S.classes.size(), pts_dev, apply_loss,
+                                                                              jac_tile.p, f_of_pose.p, J.p, pose_acc.p, scalars.p);
+      launches++;
     } else {
       reproj_jac_kernel<<<ntiles, kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam.p, S.C, classes.p, pts_dev, apply_loss, J.p, scalars.p);
+      if (S.nf) pose_accum_gather_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(obs.p, J.p, pose_ptr.p, f_of_pose.p, pose_acc.p);
+      launches += 2;
     }
-    launches++;
   }
   void launch_unary(int mode, int apply_loss, int buf, cudaStream_t strm) {
     const Structure& S = st;
@@ -636,9 +627,8 @@ struct Solver {
       launches += 2;
     } else if (S.O) { schur_eblock_kernel<7, 4, 128, 64, true><<<S.O, 128, 0, s2>>>(eargs(objs, Jb.p), lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p); launches++; }
     prof.end("zero", pt0, stream); pt0 = prof.begin(stream);
-    if (S.n_obs && S.nf) {
-      if (jac_tmap_ok && !getenv("OBVI_POSE_ACCUM_PLAIN")) pose_accum_tma_kernel<<<S.K, kPoseAccThreads, kPoseAccTmaSmem, stream>>>(jac_tmap, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
-      else pose_accum_kernel<<<S.K, kPoseAccThreads, 0, stream>>>(J.p, pose_ptr.p, f_of_pose.p, su_ptr.p, S_upper, gp, hpp_diag);
+    if (S.n_obs && S.nf) {   // pose-side sums of the reprojection blocks (formed by the Jacobian kernel, radius-independent)
+      pose_acc_add_kernel<<<nblk((int64_t)S.nf * 42, 256), 256, 0, stream>>>(S.nf, pose_acc.p, su_ptr.p, S_upper, gp, hpp_diag);
       launches++;
     }
     prof.end("pose_accum", pt0, stream); pt0 = prof.begin(stream);
@@ -1442,7 +1432,7 @@ int obvi_evaluate_factor_type(obvi_problem* p, int type, int apply_loss, double*
       const int64_t u = live_rank[S.obs_user[q]];
       if (u < 0) continue;   // removed in place
       double jp[12], jl[6], rr[2];
-      decode_chunk(&h[(size_t)q * kChunk], jp, jl, rr);
+      decode_chunk(&h[(size_t)S.obs[q].dst * kChunk], jp, jl, rr);
       if (J0) std::memcpy(J0 + 12 * u, jp, 96);
       if (J1) std::memcpy(J1 + 6 * u, jl, 48);
       if (r) std::memcpy(r + 2 * u, rr, 16);
@@ -1529,7 +1519,7 @@ int obvi_evaluate(obvi_problem* p, int apply_loss, double* cost, double* residua
     const uint64_t i = id_index(id);
     const double* src;
     switch (id_type(id)) {
-      case OBVI_FACTOR_REPROJECTION: src = &hJ[(size_t)inv_rp[i] * kChunk + kChunkR]; break;
+      case OBVI_FACTOR_REPROJECTION: src = &hJ[(size_t)S.obs[inv_rp[i]].dst * kChunk + kChunkR]; break;
       case OBVI_FACTOR_BBOX: src = &hB[(size_t)inv_bb[i] * kBBoxChunk + 52]; break;
       case OBVI_FACTOR_REL_POSE: src = hR[inv_rl[i]].r; break;
       default: src = hU[inv_un[i]].r; break;
@@ -1597,7 +1587,7 @@ int obvi_evaluate_jacobian(obvi_problem* p, int apply_loss, const obvi_factor_id
     double unaryJ[49], rp_jp[12], rp_jl[6], rp_r[2];
     switch (id_type(ids[n])) {
       case OBVI_FACTOR_REPROJECTION: {
-        decode_chunk(&hJ[(size_t)s.inv_rp[i] * kChunk], rp_jp, rp_jl, rp_r);
+        decode_chunk(&hJ[(size_t)S.obs[s.inv_rp[i]].dst * kChunk], rp_jp, rp_jl, rp_r);
         parts[np++] = {pb.reproj[i].pose, 6, rp_jp, 6, 0, 1.0}; parts[np++] = {pb.reproj[i].point, 3, rp_jl, 3, 0, 1.0}; r = rp_r; break; }
       case OBVI_FACTOR_BBOX: {
         const double* ch = &hB[(size_t)s.inv_bb[i] * kBBoxChunk];
@@ -1663,7 +1653,8 @@ int obvi_topk_outliers(obvi_problem* p, int type, double fraction, obvi_factor_i
       int64_t dead = c;
       for (int64_t q = 0; q < nb; q++) {
         const int64_t lr = live_rank[rp ? S.obs_user[q] : S.bbox_user[q]];
-        rank[q] = lr >= 0 ? (uint32_t)lr : (0x80000000u | (uint32_t)(dead++));
+        // indexed by CHUNK position (reprojection chunks are point-major; bbox chunks are in record order)
+        rank[rp ? S.obs[q].dst : (uint32_t)q] = lr >= 0 ? (uint32_t)lr : (0x80000000u | (uint32_t)(dead++));
       }
     }
     const int64_t n_dead = rp ? s.n_masked_rp : s.n_masked_bb;
