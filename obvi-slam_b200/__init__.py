@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libobvi_ba.so")
+LIB_PATH = os.environ.get("OBVI_LIB_PATH") or os.path.join(_HERE, "libobvi_ba.so")   # OBVI_LIB_PATH: A/B builds of the same library
 _LIB = None
 
 _d = C.POINTER(C.c_double)

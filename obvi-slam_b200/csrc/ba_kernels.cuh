@@ -198,16 +198,24 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+// Warp-level wait: ONE lane spins on the barrier, the others join it at a warp barrier (which also carries the acquired view
+// of the copied data to them): 31 fewer try_wait instructions per spin.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) { while (!mbar_try_wait(bar, parity)) {} }
+  __syncwarp();
 }
 // 1-D bulk copy global -> shared (TMA, completes on the mbarrier); size multiple of 16, 16-byte aligned
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -901,157 +909,262 @@ __global__ void __launch_bounds__(T, MINB) obj_schur_kernel(EArgs A, const uint3
 
 
 // ------------------------------------------------------------------------------------------ points: row-owner elimination
-// Two kernels replace the batched kernels above (kept selectable for A/B measurements):
-//   point_prep_kernel  - LPP lanes per point (8 by default; 16 -- one sweep even for the longest tracks -- measured slower),
-//                        a lane per pose group (the stereo pair of one keyframe): H_ll, g_l by xor-shuffle steps, damping, 3x3 inverse, and per (point, pose) slot the record
-//                        [W = sum Jp^T Jl (6x3) | Z = W Hinv (6x3) | Z g_l (6)] written to `WZ` (42 doubles per slot);
+// Two kernels eliminate the points:
+//   point_prep_kernel  - per point H_ll, g_l, damping, the 3x3 inverse Hinv and its Cholesky factor F (Hinv = F F^T); per
+//                        (point, keyframe) slot the record [U = (sum Jp^T Jl) F (6x3) | w = F^T g_l (3) | pad] written to `WZ`
+//                        (24 doubles = 192 bytes per slot).  With U the Schur update is SYMMETRIC, S_ab -= U_a U_b^T, and the
+//                        right-hand side b_a -= U_a w, so one 6x3 matrix per slot serves as both operands.
 //   schur_rows_kernel  - a warp per work item = (row a of the reduced matrix, 5 consecutive column offsets, <= 128 slots of
-//                        pose a): for every slot, A = Z_a, B = W_b^T of the point's slots at a + d, one DMMA per block pair,
+//                        pose a): for every slot, A = U_a, B = U_b^T of the point's slots at a + d, one DMMA per block pair,
 //                        the 6x6 accumulators live in REGISTERS for the whole item and are flushed once.
-// Compared with the batched kernel: no shared-memory accumulators (one LDG + one DMMA per block pair instead of
-// LDS.128 + DMMA + STS.128), no block barriers, lanes are never idle in the per-point phase.
-constexpr int kWZ = 42;
-struct RowGroupD { uint32_t pos0, pos1, gs, cnt; };
+// The Jacobian chunks are point-major, so a point's chunks are one contiguous range: point_prep and the back-substitution
+// stream them through shared memory with per-warp double-buffered TMA bulk copies (WarpChunkPipe below) -- every global-load
+// latency (list pointers, group records, chunks) is taken one batch ahead of its use.
+constexpr int kWZ = 24;
+constexpr int kWZw = 18;                  // offset of w in the slot record
+constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
+struct RowGroupD { uint32_t pos0; int32_t f; uint32_t gs, cnt; };   // chunks pos0 .. pos0 + cnt - 1, pose f index (-1 constant), slot
 struct RowItemD { uint32_t row, dlo, off, cnt; };
 
-template <int LPP>
-__global__ void __launch_bounds__(256, 2) point_prep_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr,
-                                                          const uint4* __restrict__ grp, const uint8_t* __restrict__ regular,
-                                                          LMParams lm, double* __restrict__ WZ, double* __restrict__ scalars) {
-  __shared__ double s_gmax[8];
-  const int e = blockIdx.x * (256 / LPP) + threadIdx.x / LPP;
-  const int sub = threadIdx.x % LPP;
-  const bool act = e < A.ne && regular[e];
-  uint32_t g0 = 0, g1 = 0;
-  if (act) { g0 = grp_ptr[e]; g1 = grp_ptr[e + 1]; }
-  double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-  // the lane's FIRST group keeps its W in registers across the reduction (the common case: <= 8 groups per point, so
-  // every lane has at most one); further groups (gi + 8, ...) park W in the record and reload it for the Z pass
-  double W0[18];
-  uint32_t gs0 = 0xFFFFFFFFu;
+constexpr int kPipeWarps = 8;             // warps per CTA of the streaming point kernels (one CTA per SM)
+constexpr int kStageChunks = 96;          // chunks per stage: 12 KB; a batch = 4 consecutive points (~80 chunks on average)
+constexpr int kPipeSmem = kPipeWarps * 2 * kStageChunks * kChunk * 8 + 128;
+static_assert(kPipeSmem <= 227 * 1024, "stages must fit the shared memory of one SM");
+
+// Tables of one batch (points 4 b .. 4 b + 3), spread over the lanes: lane j < 5 holds chunk-list pointer and group pointer of
+// point 4 b + j, lane j < 4 the `regular` flag.
+struct PipeInfo { uint32_t cptr, gptr, reg; };
+__device__ __forceinline__ PipeInfo pipe_load_info(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ grp_ptr,
+                                                   const uint8_t* __restrict__ regular, int b, int ne, int lane) {
+  PipeInfo r{0u, 0u, 0u};
+  const int e = 4 * b + lane;
+  if (lane < 5) { const int ec = min(e, ne); r.cptr = ptr[ec]; r.gptr = grp_ptr[ec]; }
+  if (lane < 4 && e < ne) r.reg = regular[e];
+  return r;
+}
+// Stage layout of a batch: the chunk ranges of its regular points back to back, in point order; a point whose range does
+// not fit into what is left of the stage is not staged (its lanes read global memory).  Same arithmetic on both sides.
+struct PipeLayout { uint32_t p[5]; uint32_t off[4]; bool staged[4]; };
+struct PipeMine { uint32_t p, off; bool staged; };   // the entries of the lane's own point (selected without dynamic indexing)
+__device__ __forceinline__ PipeMine pipe_mine(const PipeLayout& L, int pt) {
+  PipeMine m;
+  m.p = pt == 0 ? L.p[0] : (pt == 1 ? L.p[1] : (pt == 2 ? L.p[2] : L.p[3]));
+  m.off = pt == 0 ? L.off[0] : (pt == 1 ? L.off[1] : (pt == 2 ? L.off[2] : L.off[3]));
+  m.staged = pt == 0 ? L.staged[0] : (pt == 1 ? L.staged[1] : (pt == 2 ? L.staged[2] : L.staged[3]));
+  return m;
+}
+__device__ __forceinline__ PipeLayout pipe_layout(const PipeInfo& I) {
+  PipeLayout L;
 #pragma unroll
-  for (int a = 0; a < 18; a++) W0[a] = 0.0;
-  auto sweep = [&](const uint4 G, double* W) {
-    for (uint32_t k = 0; k < G.w; k++) {
-      const uint32_t pos = G.x + k;   // a group's chunks are consecutive (point-major Jacobian array)
-      double jp[12], jl[6];
-      double2 rv;
-      load_chunk(A.J + (size_t)pos * kChunk, jp, jl, rv.x, rv.y);
-      int t = 0;
+  for (int j = 0; j < 5; j++) L.p[j] = __shfl_sync(0xffffffffu, I.cptr, j);
+  uint32_t off = 0;
 #pragma unroll
-      for (int a = 0; a < 3; a++) {
-        g[a] += jl[a] * rv.x + jl[3 + a] * rv.y;
-#pragma unroll
-        for (int b = a; b < 3; b++) H[t++] += jl[a] * jl[b] + jl[3 + a] * jl[3 + b];
-      }
-      if (G.z != 0xFFFFFFFFu) {
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-          for (int c = 0; c < 3; c++) W[3 * a + c] += jp[a] * jl[c] + jp[6 + a] * jl[3 + c];
-      }
-    }
-  };
-  if (g0 + sub < g1) {
-    const uint4 G = grp[g0 + sub];
-    gs0 = G.z;
-    sweep(G, W0);
+  for (int j = 0; j < 4; j++) {
+    const uint32_t rg = __shfl_sync(0xffffffffu, I.reg, j);
+    const uint32_t cnt = L.p[j + 1] - L.p[j];
+    L.staged[j] = rg != 0u && cnt != 0u && off + cnt <= (uint32_t)kStageChunks;
+    L.off[j] = off;
+    if (L.staged[j]) off += cnt;
   }
-  for (uint32_t gi = g0 + sub + LPP; gi < g1; gi += LPP) {
-    const uint4 G = grp[gi];
-    double W[18];
+  return L;
+}
+__device__ __forceinline__ void pipe_issue(const PipeLayout& L, const double* __restrict__ J, double* stage, uint64_t* bar, int lane) {
+  if (lane == 0) {
+    uint32_t bytes = 0;
 #pragma unroll
-    for (int a = 0; a < 18; a++) W[a] = 0.0;
-    sweep(G, W);
-    if (G.z != 0xFFFFFFFFu) {
-      double2* out = reinterpret_cast<double2*>(WZ + (size_t)G.z * kWZ);
+    for (int j = 0; j < 4; j++) if (L.staged[j]) bytes += (L.p[j + 1] - L.p[j]) * (uint32_t)(kChunk * 8);
+    mbar_expect_tx(bar, bytes);
 #pragma unroll
-      for (int a = 0; a < 9; a++) out[a] = make_double2(W[2 * a], W[2 * a + 1]);
-    }
+    for (int j = 0; j < 4; j++)
+      if (L.staged[j]) tma_load_1d(stage + (size_t)L.off[j] * kChunk, J + (size_t)L.p[j] * kChunk, (L.p[j + 1] - L.p[j]) * (uint32_t)(kChunk * 8), bar);
   }
-#pragma unroll
-  for (int d = 1; d < LPP; d <<= 1) {
-#pragma unroll
-    for (int a = 0; a < 6; a++) H[a] += __shfl_xor_sync(0xffffffffu, H[a], d);
-#pragma unroll
-    for (int a = 0; a < 3; a++) g[a] += __shfl_xor_sync(0xffffffffu, g[a], d);
-  }
+}
+// 3x3 lower Cholesky factor F of an SPD matrix given row-major (F F^T = A); tiny negative pivots from rounding clamp to 0
+__device__ __forceinline__ void chol3(const double* A, double* F /* f00 f10 f11 f20 f21 f22 */) {
+  F[0] = sqrt(fmax(A[0], 0.0));
+  const double i0 = F[0] > 0.0 ? 1.0 / F[0] : 0.0;
+  F[1] = A[3] * i0; F[3] = A[6] * i0;
+  F[2] = sqrt(fmax(A[4] - F[1] * F[1], 0.0));
+  const double i1 = F[2] > 0.0 ? 1.0 / F[2] : 0.0;
+  F[4] = (A[7] - F[3] * F[1]) * i1;
+  F[5] = sqrt(fmax(A[8] - F[3] * F[3] - F[4] * F[4], 0.0));
+}
+
+__global__ void __launch_bounds__(32 * kPipeWarps, 1) point_prep_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr,
+                                                                         const uint4* __restrict__ grp, const uint8_t* __restrict__ regular,
+                                                                         LMParams lm, double* __restrict__ WZ, double* __restrict__ scalars) {
+  extern __shared__ __align__(128) unsigned char pipe_raw[];
+  __shared__ uint64_t bars[kPipeWarps][2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int pt = lane >> 3, sub = lane & 7;
+  unsigned char* base = pipe_raw + ((128u - (smem_addr(pipe_raw) & 127u)) & 127u);
+  double* stage0 = reinterpret_cast<double*>(base) + (size_t)(2 * w) * kStageChunks * kChunk;
+  double* stage1 = stage0 + (size_t)kStageChunks * kChunk;
+  if (lane == 0) { mbar_init(&bars[w][0], 1); mbar_init(&bars[w][1], 1); }
+  __syncwarp();
+  const int nb = (A.ne + 3) / 4;
+  const int W = gridDim.x * kPipeWarps;
+  int b = blockIdx.x * kPipeWarps + w;
   double gmax = 0.0;
-  if (act) {
-    if (A.prior_H) {
+  int nfail = 0;
+  if (b >= nb) return;
+  // prologue: batch b staged, tables of batch b + W requested
+  PipeInfo Icur = pipe_load_info(A.ptr, grp_ptr, regular, b, A.ne, lane);
+  PipeLayout Lcur = pipe_layout(Icur);
+  pipe_issue(Lcur, A.J, stage0, &bars[w][0], lane);
+  PipeInfo Inext = pipe_load_info(A.ptr, grp_ptr, regular, min(b + W, nb), A.ne, lane);
+  // group records of this lane for the current batch (groups sub and sub + 8 of its point), fetched one batch ahead
+  auto load_groups = [&](const PipeInfo& I, uint4& G0, uint4& G1) {
+    const uint32_t g0 = __shfl_sync(0xffffffffu, I.gptr, pt), g1 = __shfl_sync(0xffffffffu, I.gptr, pt + 1);
+    G0 = make_uint4(0u, 0u, kNoSlot, 0u); G1 = G0;
+    if (g0 + sub < g1) G0 = grp[g0 + sub];
+    if (g0 + sub + 8 < g1) G1 = grp[g0 + sub + 8];
+  };
+  uint4 G0, G1, G0n = make_uint4(0u, 0u, kNoSlot, 0u), G1n = G0n;
+  load_groups(Icur, G0, G1);
+  for (int it = 0; b < nb; b += W, it++) {
+    const int cur = it & 1;
+    const bool more = b + W < nb;
+    PipeLayout Lnext = Lcur;
+    if (more) {   // stage the next batch (its tables arrived during the previous iteration) and request the one after
+      Lnext = pipe_layout(Inext);
+      fence_proxy_async_smem();
+      __syncwarp();
+      pipe_issue(Lnext, A.J, cur ? stage0 : stage1, cur ? &bars[w][0] : &bars[w][1], lane);
+      load_groups(Inext, G0n, G1n);
+    }
+    PipeInfo Iafter = pipe_load_info(A.ptr, grp_ptr, regular, min(b + 2 * W, nb), A.ne, lane);
+    const int e = 4 * b + pt;
+    const uint32_t reg_pt = __shfl_sync(0xffffffffu, Icur.reg, pt);   // (outside the && below: every lane must take part in the shuffle)
+    const bool act = e < A.ne && reg_pt != 0u;
+    // Inactive lanes (points past the end, points left to the generic kernels) run the SAME code on zero groups and skip the
+    // stores, so that the warp stays converged through the shuffles and warp barriers of the iteration.
+    const uint32_t g0 = __shfl_sync(0xffffffffu, Icur.gptr, pt);
+    const uint32_t g1s = __shfl_sync(0xffffffffu, Icur.gptr, pt + 1);
+    const uint32_t g1 = act ? g1s : g0;
+    if (!act) { G0.w = 0u; G1.w = 0u; }
+    // per-point data that does not depend on the chunks: requested before the wait
+    double s[3] = {1.0, 1.0, 1.0};
+    if (act && !lm.compute_scale) { s[0] = A.escale[(size_t)e * 3]; s[1] = A.escale[(size_t)e * 3 + 1]; s[2] = A.escale[(size_t)e * 3 + 2]; }
+    const PipeMine M = pipe_mine(Lcur, pt);
+    // chunk `pos` of a staged point sits at cbase + pos * kChunk (derived from the shared-memory pointer only, so that the
+    // staged path compiles to shared-memory loads)
+    const double* cbase = (cur ? stage1 : stage0) + ((ptrdiff_t)M.off - (ptrdiff_t)M.p) * kChunk;
+    // The choice between the shared-memory path and the global one is made PER WARP (uniform), so that the staged path keeps
+    // shared-memory addressing (LDS) without lane-divergent copies of the sweeps.
+    const bool staged = __all_sync(0xffffffffu, M.staged || !act);
+    const double* gbase = M.staged ? cbase : A.J;          // mixed warp (a point did not fit into the stage): generic addressing
+    mbar_wait_warp(cur ? &bars[w][1] : &bars[w][0], (uint32_t)((it >> 1) & 1));
+    double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    auto sweep_hg = [&](const double* cb, const uint4 G) {
+      for (uint32_t k = 0; k < G.w; k++) {
+        double jp[12], jl[6];
+        double2 rv;
+        load_chunk(cb + (size_t)(G.x + k) * kChunk, jp, jl, rv.x, rv.y);
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          g[a] += jl[a] * rv.x + jl[3 + a] * rv.y;
+#pragma unroll
+          for (int c = a; c < 3; c++) H[t++] += jl[a] * jl[c] + jl[3 + a] * jl[3 + c];
+        }
+      }
+    };
+    auto all_groups = [&](auto&& fn) {   // fn (record) for every group of this lane: the two prefetched ones, then the rare rest
+      if (G0.w) fn(G0);
+      if (G1.w) fn(G1);
+      for (uint32_t gi = g0 + sub + 16; gi < g1; gi += 8) fn(grp[gi]);
+    };
+    if (staged) all_groups([&](const uint4 G) { sweep_hg(cbase, G); });
+    else all_groups([&](const uint4 G) { sweep_hg(gbase, G); });
+    __syncwarp();
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+#pragma unroll
+      for (int a = 0; a < 6; a++) H[a] += __shfl_xor_sync(0xffffffffu, H[a], d);
+#pragma unroll
+      for (int a = 0; a < 3; a++) g[a] += __shfl_xor_sync(0xffffffffu, g[a], d);
+    }
+    if (act && A.prior_H) {
       const double* ph = A.prior_H + (size_t)e * 9;
       H[0] += ph[0]; H[1] += ph[1]; H[2] += ph[2]; H[3] += ph[4]; H[4] += ph[5]; H[5] += ph[8];
 #pragma unroll
       for (int a = 0; a < 3; a++) g[a] += A.prior_g[(size_t)e * 3 + a];
     }
-    double s[3];
     const double hd[3] = {H[0], H[3], H[5]};
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-      s[a] = lm.compute_scale ? 1.0 / (1.0 + sqrt(hd[a])) : A.escale[(size_t)e * 3 + a];
+      if (lm.compute_scale) s[a] = 1.0 / (1.0 + sqrt(hd[a]));
       gmax = fmax(gmax, fabs(g[a]));
     }
-    double Hs[9], hinv[9];
+    double Hs[9], hinv[9], F[6];
     Hs[0] = s[0] * H[0] * s[0]; Hs[1] = Hs[3] = s[0] * H[1] * s[1]; Hs[2] = Hs[6] = s[0] * H[2] * s[2];
     Hs[4] = s[1] * H[3] * s[1]; Hs[5] = Hs[7] = s[1] * H[4] * s[2]; Hs[8] = s[2] * H[5] * s[2];
 #pragma unroll
     for (int a = 0; a < 3; a++) Hs[4 * a] += fmin(fmax(Hs[4 * a], lm.min_diag), lm.max_diag) * lm.inv_radius;
     const bool ok = spd_inverse3_cofactor(Hs, hinv);
     if (!ok) {
-      if (sub == 0) atomicAdd(&scalars[SC_FAIL], 1.0);
 #pragma unroll
       for (int a = 0; a < 9; a++) hinv[a] = 0.0;
     } else {
 #pragma unroll
       for (int a = 0; a < 3; a++)
 #pragma unroll
-        for (int b = 0; b < 3; b++) hinv[3 * a + b] *= s[a] * s[b];
-      if (sub == 0) {
-        if (lm.compute_scale) { A.escale[(size_t)e * 3] = s[0]; A.escale[(size_t)e * 3 + 1] = s[1]; A.escale[(size_t)e * 3 + 2] = s[2]; }
-#pragma unroll
-        for (int a = 0; a < 9; a++) A.einv[(size_t)e * 9 + a] = hinv[a];
-#pragma unroll
-        for (int a = 0; a < 3; a++) A.eg[(size_t)e * 3 + a] = g[a];
-      }
+        for (int c = 0; c < 3; c++) hinv[3 * a + c] *= s[a] * s[c];
     }
-    auto emit = [&](uint32_t gs, const double* W, bool store_w) {
-      double2* rec = reinterpret_cast<double2*>(WZ + (size_t)gs * kWZ);
-      double Z[18], zg[6];
+    if (act && sub == 0) {
+      if (!ok) nfail++;
+      if (lm.compute_scale && ok) { A.escale[(size_t)e * 3] = s[0]; A.escale[(size_t)e * 3 + 1] = s[1]; A.escale[(size_t)e * 3 + 2] = s[2]; }
+#pragma unroll
+      for (int a = 0; a < 9; a++) A.einv[(size_t)e * 9 + a] = hinv[a];
+#pragma unroll
+      for (int a = 0; a < 3; a++) A.eg[(size_t)e * 3 + a] = g[a];
+    }
+    chol3(hinv, F);
+    const double wv[3] = {F[0] * g[0] + F[1] * g[1] + F[3] * g[2], F[2] * g[1] + F[4] * g[2], F[5] * g[2]};   // F^T g
+    auto emit = [&](const double* cb, const uint4 G) {
+      double Wm[18];
+#pragma unroll
+      for (int a = 0; a < 18; a++) Wm[a] = 0.0;
+      for (uint32_t k = 0; k < G.w; k++) {
+        double jp[12], jl[6];
+        double2 rv;
+        load_chunk(cb + (size_t)(G.x + k) * kChunk, jp, jl, rv.x, rv.y);
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) Wm[3 * a + c] += jp[a] * jl[c] + jp[6 + a] * jl[3 + c];
+      }
+      double U[18];
 #pragma unroll
       for (int a = 0; a < 6; a++) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) Z[3 * a + c] = W[3 * a] * hinv[c] + W[3 * a + 1] * hinv[3 + c] + W[3 * a + 2] * hinv[6 + c];
-        zg[a] = Z[3 * a] * g[0] + Z[3 * a + 1] * g[1] + Z[3 * a + 2] * g[2];
+        U[3 * a] = Wm[3 * a] * F[0] + Wm[3 * a + 1] * F[1] + Wm[3 * a + 2] * F[3];
+        U[3 * a + 1] = Wm[3 * a + 1] * F[2] + Wm[3 * a + 2] * F[4];
+        U[3 * a + 2] = Wm[3 * a + 2] * F[5];
       }
-      if (store_w) {
+      if (G.z != kNoSlot) {
+        double2* rec = reinterpret_cast<double2*>(WZ + (size_t)G.z * kWZ);
 #pragma unroll
-        for (int a = 0; a < 9; a++) rec[a] = make_double2(W[2 * a], W[2 * a + 1]);
+        for (int a = 0; a < 9; a++) rec[a] = make_double2(U[2 * a], U[2 * a + 1]);
+        rec[9] = make_double2(wv[0], wv[1]);
+        rec[10] = make_double2(wv[2], 0.0);
       }
-#pragma unroll
-      for (int a = 0; a < 9; a++) rec[9 + a] = make_double2(Z[2 * a], Z[2 * a + 1]);
-#pragma unroll
-      for (int a = 0; a < 3; a++) rec[18 + a] = make_double2(zg[2 * a], zg[2 * a + 1]);
     };
-    if (gs0 != 0xFFFFFFFFu) emit(gs0, W0, true);
-    for (uint32_t gi = g0 + sub + LPP; gi < g1; gi += LPP) {
-      const uint32_t gs = grp[gi].z;
-      if (gs == 0xFFFFFFFFu) continue;
-      const double2* rec = reinterpret_cast<const double2*>(WZ + (size_t)gs * kWZ);
-      double W[18];
-#pragma unroll
-      for (int a = 0; a < 9; a++) { const double2 v = rec[a]; W[2 * a] = v.x; W[2 * a + 1] = v.y; }
-      emit(gs, W, false);
-    }
+    if (staged) all_groups([&](const uint4 G) { emit(cbase, G); });
+    else all_groups([&](const uint4 G) { emit(gbase, G); });
+    __syncwarp();
+    Icur = Inext; Inext = Iafter; Lcur = Lnext; G0 = G0n; G1 = G1n;
   }
-#pragma unroll
-  for (int d = LPP; d < 32; d <<= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, d));
-  if ((threadIdx.x & 31) == 0) s_gmax[threadIdx.x >> 5] = gmax;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double mx = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) mx = fmax(mx, s_gmax[i]);
-    if (mx > 0.0) atomic_max_nonneg(&scalars[SC_GMAX], mx);
+  __syncwarp();
+  gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 16));
+  gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 8));
+  gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 4));
+  gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 2));
+  gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, 1));
+  nfail = __reduce_add_sync(0xffffffffu, nfail);
+  if (lane == 0) {
+    if (gmax > 0.0) atomic_max_nonneg(&scalars[SC_GMAX], gmax);
+    if (nfail) atomicAdd(&scalars[SC_FAIL], (double)nfail);
   }
 }
 
@@ -1066,34 +1179,35 @@ __global__ void __launch_bounds__(32 * kRowWarps) schur_rows_kernel(const uint4*
   const uint4 it = items[item];
   const int frow = lane >> 2, fk = lane & 3;
   const bool fvalid = frow < 6 && fk < 3;
-  const int off = 3 * frow + fk;
   double2 acc[5];
 #pragma unroll
   for (int j = 0; j < 5; j++) acc[j] = make_double2(0.0, 0.0);
-  double accb = 0.0;
   const uint32_t* ep = ent + it.z;
   const bool first_range = it.y == 0;
-  // Software pipeline: the operands of entry i + 1 are in flight while the tensor-core products of entry i issue (two
-  // register sets, loop unrolled by two); entry descriptors are fetched 32 at a time (one per lane) and broadcast with
-  // a shuffle.  Only the k = 3 column of the A fragment has to be zero: rows / columns 6-7 of C are never flushed, so
-  // the B fragment is loaded without a validity predicate from a clamped (always finite) element.  Slots are dense, so
-  // column j of the range is the record (dlo + j) slots after the row's own.
-  struct Ops { double a, b[5], zb; uint32_t n; };
-  const int offb = 3 * (frow < 6 ? frow : 5) + (fk < 3 ? fk : 2);
+  // Fragment element of this lane inside a slot record: U[frow][fk] for the 6x3 block; fragment row 6 reads w[fk] (column 6
+  // of the B operand of the DIAGONAL pair: C[.][6] = U_a w, the right-hand side contribution); everything else is clamped to
+  // a finite element and multiplied by a zero of the A operand (k = 3 column) or lands in rows / columns 6-7 that are never
+  // flushed.  Slots are dense, so column j of the range is the record (dlo + j) slots after the row's own.
+  const int offb = frow < 6 ? 3 * frow + (fk < 3 ? fk : 2) : (frow == 6 ? kWZw + (fk < 3 ? fk : 2) : 0);
   const double* WZb = WZ + (size_t)it.y * kWZ + offb;
+  struct Ops { double a, b[5]; uint32_t n; };
   auto load_ops = [&](uint32_t e, Ops& o) {
     const uint32_t gs = e & 0x7ffffffu;
     o.n = e >> 27;
-    const double* za = WZ + (size_t)gs * kWZ;
     const double* zb = WZb + (size_t)gs * kWZ;
-    o.a = fvalid ? za[18 + off] : 0.0;
+    if (first_range) {
+      o.b[0] = zb[0];                       // the diagonal pair: A and B come from the same record
+      o.a = fk < 3 && frow < 6 ? o.b[0] : 0.0;
+    } else {
+      const double av = WZ[(size_t)gs * kWZ + offb];
+      o.a = fk < 3 && frow < 6 ? av : 0.0;
+      o.b[0] = zb[0];
+    }
 #pragma unroll
-    for (int j = 0; j < 5; j++)
+    for (int j = 1; j < 5; j++)
       if ((uint32_t)j < o.n) o.b[j] = zb[j * kWZ];
-    if (first_range) o.zb = lane < 6 ? za[36 + lane] : 0.0;
   };
   auto consume = [&](const Ops& o) {
-    if (first_range) accb += o.zb;
 #pragma unroll
     for (int j = 0; j < 5; j++)
       if ((uint32_t)j < o.n) dmma_m8n8k4(acc[j].x, acc[j].y, o.a, o.b[j]);
@@ -1126,7 +1240,8 @@ __global__ void __launch_bounds__(32 * kRowWarps) schur_rows_kernel(const uint4*
       if (acc[j].y != 0.0) atomicAdd(C + 1, -acc[j].y);
     }
   }
-  if (first_range && lane < 6 && accb != 0.0) atomicAdd(&b_schur[6 * it.x + lane], -accb);
+  // column 6 of the diagonal product: lanes with fk == 3 hold C[frow][6]
+  if (first_range && fk == 3 && frow < 6 && acc[0].x != 0.0) atomicAdd(&b_schur[6 * it.x + frow], -acc[0].x);
 }
 
 // Back-substitution for one e-block + its share of the model cost change and of the candidate point:
@@ -1300,83 +1415,139 @@ __global__ void __launch_bounds__(128) backsub_points_kernel(EArgs A, int n_e, c
   }
 }
 
-// Single-pass back-substitution for the points the row-owner path handles (8 lanes per point, a lane per pose group).
+// Single-pass back-substitution for the points the row-owner path handles (8 lanes per point, a lane per pose group; the
+// chunks streamed through shared memory like in point_prep_kernel).
 // With a = Jp delta_p per observation, the point's share of the model cost change expands to
 //   sum m (r + m/2),  m = a + Jl delta_e   =   sum a.(r + a/2)  +  delta_e.(g_l + t)  +  delta_e^T H_ll delta_e / 2
 // with t = sum Jl^T a, g_l = sum Jl^T r, H_ll = sum Jl^T Jl, so one sweep over the Jacobian chunks is enough (the generic
 // kernel above sweeps twice: once for t, once for m after delta_e is known).
-template <int LPP>
-__global__ void __launch_bounds__(256) backsub_rows_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr, const uint4* __restrict__ grp,
-                                                            const int32_t* __restrict__ grp_f, const uint8_t* __restrict__ regular,
-                                                            const double* __restrict__ dpose, const double* __restrict__ x,
-                                                            double* __restrict__ x_cand, double* __restrict__ delta_e,
-                                                            double* __restrict__ scalars) {
-  __shared__ double s_mc[8], s_s2[8];
-  const int e = blockIdx.x * (256 / LPP) + threadIdx.x / LPP;
-  const int sub = threadIdx.x % LPP;
-  const bool act = e < A.ne && regular[e];
-  uint32_t g0 = 0, g1 = 0;
-  if (act) { g0 = grp_ptr[e]; g1 = grp_ptr[e + 1]; }
-  double H[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0}, t[3] = {0, 0, 0}, sa = 0.0;
-  for (uint32_t gi = g0 + sub; gi < g1; gi += LPP) {
-    const uint4 G = grp[gi];
-    const int fi = grp_f[gi];
-    double dp[6];
+__global__ void __launch_bounds__(32 * kPipeWarps, 1) backsub_rows_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr, const uint4* __restrict__ grp,
+                                                                           const uint8_t* __restrict__ regular,
+                                                                           const double* __restrict__ dpose, const double* __restrict__ x,
+                                                                           double* __restrict__ x_cand, double* __restrict__ delta_e,
+                                                                           double* __restrict__ scalars) {
+  extern __shared__ __align__(128) unsigned char pipe_raw[];
+  __shared__ uint64_t bars[kPipeWarps][2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int pt = lane >> 3, sub = lane & 7;
+  unsigned char* base = pipe_raw + ((128u - (smem_addr(pipe_raw) & 127u)) & 127u);
+  double* stage0 = reinterpret_cast<double*>(base) + (size_t)(2 * w) * kStageChunks * kChunk;
+  double* stage1 = stage0 + (size_t)kStageChunks * kChunk;
+  if (lane == 0) { mbar_init(&bars[w][0], 1); mbar_init(&bars[w][1], 1); }
+  __syncwarp();
+  const int nb = (A.ne + 3) / 4;
+  const int W = gridDim.x * kPipeWarps;
+  int b = blockIdx.x * kPipeWarps + w;
+  if (b >= nb) return;
+  double mc_acc = 0.0, s2_acc = 0.0;
+  PipeInfo Icur = pipe_load_info(A.ptr, grp_ptr, regular, b, A.ne, lane);
+  PipeLayout Lcur = pipe_layout(Icur);
+  pipe_issue(Lcur, A.J, stage0, &bars[w][0], lane);
+  PipeInfo Inext = pipe_load_info(A.ptr, grp_ptr, regular, min(b + W, nb), A.ne, lane);
+  auto load_groups = [&](const PipeInfo& I, uint4& G0, uint4& G1) {
+    const uint32_t g0 = __shfl_sync(0xffffffffu, I.gptr, pt), g1 = __shfl_sync(0xffffffffu, I.gptr, pt + 1);
+    G0 = make_uint4(0u, 0xFFFFFFFFu, kNoSlot, 0u); G1 = G0;
+    if (g0 + sub < g1) G0 = grp[g0 + sub];
+    if (g0 + sub + 8 < g1) G1 = grp[g0 + sub + 8];
+  };
+  uint4 G0, G1, G0n = make_uint4(0u, 0u, kNoSlot, 0u), G1n = G0n;
+  load_groups(Icur, G0, G1);
+  for (int it = 0; b < nb; b += W, it++) {
+    const int cur = it & 1;
+    const bool more = b + W < nb;
+    PipeLayout Lnext = Lcur;
+    if (more) {
+      Lnext = pipe_layout(Inext);
+      fence_proxy_async_smem();
+      __syncwarp();
+      pipe_issue(Lnext, A.J, cur ? stage0 : stage1, cur ? &bars[w][0] : &bars[w][1], lane);
+      load_groups(Inext, G0n, G1n);
+    }
+    PipeInfo Iafter = pipe_load_info(A.ptr, grp_ptr, regular, min(b + 2 * W, nb), A.ne, lane);
+    const int e = 4 * b + pt;
+    const uint32_t reg_pt = __shfl_sync(0xffffffffu, Icur.reg, pt);   // (outside the && below: every lane must take part in the shuffle)
+    const bool act = e < A.ne && reg_pt != 0u;
+    const uint32_t g0 = __shfl_sync(0xffffffffu, Icur.gptr, pt), g1 = __shfl_sync(0xffffffffu, Icur.gptr, pt + 1);
+    // pose steps of the two prefetched groups + the point's inverse / gradient: requested before the wait
+    double dp0[6], dp1[6];
 #pragma unroll
-    for (int a = 0; a < 6; a++) dp[a] = fi >= 0 ? dpose[6 * fi + a] : 0.0;
-    for (uint32_t k = 0; k < G.w; k++) {
-      const uint32_t pos = G.x + k;   // a group's chunks are consecutive (point-major Jacobian array)
-      double jp[12], jl[6];
-      double2 rv;
-      load_chunk(A.J + (size_t)pos * kChunk, jp, jl, rv.x, rv.y);
-      const double a0 = jp[0] * dp[0] + jp[1] * dp[1] + jp[2] * dp[2] + jp[3] * dp[3] + jp[4] * dp[4] + jp[5] * dp[5];
-      const double a1 = jp[6] * dp[0] + jp[7] * dp[1] + jp[8] * dp[2] + jp[9] * dp[3] + jp[10] * dp[4] + jp[11] * dp[5];
-      sa += a0 * (rv.x + 0.5 * a0) + a1 * (rv.y + 0.5 * a1);
-      int q = 0;
+    for (int a = 0; a < 6; a++) {
+      dp0[a] = (act && G0.w && (int)G0.y >= 0) ? dpose[6 * (size_t)G0.y + a] : 0.0;
+      dp1[a] = (act && G1.w && (int)G1.y >= 0) ? dpose[6 * (size_t)G1.y + a] : 0.0;
+    }
+    double hinv[9], eg[3];
+    if (act && sub == 0) {
+#pragma unroll
+      for (int a = 0; a < 9; a++) hinv[a] = A.einv[(size_t)e * 9 + a];
+#pragma unroll
+      for (int a = 0; a < 3; a++) eg[a] = A.eg[(size_t)e * 3 + a];
+    }
+    const PipeMine M = pipe_mine(Lcur, pt);
+    const double* cbase = (cur ? stage1 : stage0) + ((ptrdiff_t)M.off - (ptrdiff_t)M.p) * kChunk;
+    mbar_wait_warp(cur ? &bars[w][1] : &bars[w][0], (uint32_t)((it >> 1) & 1));
+    double H[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0}, t[3] = {0, 0, 0}, sa = 0.0;
+    auto sweep = [&](const double* cb, const uint4 G, const double* dp) {
+      for (uint32_t k = 0; k < G.w; k++) {
+        double jp[12], jl[6];
+        double2 rv;
+        load_chunk(cb + (size_t)(G.x + k) * kChunk, jp, jl, rv.x, rv.y);
+        const double a0 = jp[0] * dp[0] + jp[1] * dp[1] + jp[2] * dp[2] + jp[3] * dp[3] + jp[4] * dp[4] + jp[5] * dp[5];
+        const double a1 = jp[6] * dp[0] + jp[7] * dp[1] + jp[8] * dp[2] + jp[9] * dp[3] + jp[10] * dp[4] + jp[11] * dp[5];
+        sa += a0 * (rv.x + 0.5 * a0) + a1 * (rv.y + 0.5 * a1);
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          t[a] += jl[a] * a0 + jl[3 + a] * a1;
+          gl[a] += jl[a] * rv.x + jl[3 + a] * rv.y;
+#pragma unroll
+          for (int c = a; c < 3; c++) H[q++] += jl[a] * jl[c] + jl[3 + a] * jl[3 + c];
+        }
+      }
+    };
+    auto rest = [&](const double* cb) {   // groups beyond the two prefetched ones (tracks over more than 16 keyframes)
+      for (uint32_t gi = g0 + sub + 16; gi < g1; gi += 8) {
+        const uint4 G = grp[gi];
+        double dp[6];
+#pragma unroll
+        for (int a = 0; a < 6; a++) dp[a] = (int)G.y >= 0 ? dpose[6 * (size_t)G.y + a] : 0.0;
+        sweep(cb, G, dp);
+      }
+    };
+    const bool staged = __all_sync(0xffffffffu, M.staged || !act);   // per-warp choice, see point_prep_kernel
+    const double* gbase = M.staged ? cbase : A.J;
+    if (staged) { if (act) { if (G0.w) sweep(cbase, G0, dp0); if (G1.w) sweep(cbase, G1, dp1); rest(cbase); } }
+    else { if (act) { if (G0.w) sweep(gbase, G0, dp0); if (G1.w) sweep(gbase, G1, dp1); rest(gbase); } }
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+#pragma unroll
+      for (int a = 0; a < 6; a++) H[a] += __shfl_xor_sync(0xffffffffu, H[a], d);
+#pragma unroll
+      for (int a = 0; a < 3; a++) { gl[a] += __shfl_xor_sync(0xffffffffu, gl[a], d); t[a] += __shfl_xor_sync(0xffffffffu, t[a], d); }
+      sa += __shfl_xor_sync(0xffffffffu, sa, d);
+    }
+    if (act && sub == 0) {
+      double u[3], de[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) u[a] = t[a] + eg[a];
 #pragma unroll
       for (int a = 0; a < 3; a++) {
-        t[a] += jl[a] * a0 + jl[3 + a] * a1;
-        gl[a] += jl[a] * rv.x + jl[3 + a] * rv.y;
-#pragma unroll
-        for (int b = a; b < 3; b++) H[q++] += jl[a] * jl[b] + jl[3 + a] * jl[3 + b];
+        de[a] = -(hinv[3 * a] * u[0] + hinv[3 * a + 1] * u[1] + hinv[3 * a + 2] * u[2]);
+        delta_e[(size_t)e * 3 + a] = de[a];
+        x_cand[(size_t)e * 3 + a] = x[(size_t)e * 3 + a] + de[a];
+        s2_acc += de[a] * de[a];
       }
+      const double hd0 = H[0] * de[0] + H[1] * de[1] + H[2] * de[2];
+      const double hd1 = H[1] * de[0] + H[3] * de[1] + H[4] * de[2];
+      const double hd2 = H[2] * de[0] + H[4] * de[1] + H[5] * de[2];
+      mc_acc += sa + de[0] * (gl[0] + t[0] + 0.5 * hd0) + de[1] * (gl[1] + t[1] + 0.5 * hd1) + de[2] * (gl[2] + t[2] + 0.5 * hd2);
     }
+    __syncwarp();
+    Icur = Inext; Inext = Iafter; Lcur = Lnext; G0 = G0n; G1 = G1n;
   }
-#pragma unroll
-  for (int d = 1; d < LPP; d <<= 1) {
-#pragma unroll
-    for (int a = 0; a < 6; a++) H[a] += __shfl_xor_sync(0xffffffffu, H[a], d);
-#pragma unroll
-    for (int a = 0; a < 3; a++) { gl[a] += __shfl_xor_sync(0xffffffffu, gl[a], d); t[a] += __shfl_xor_sync(0xffffffffu, t[a], d); }
-    sa += __shfl_xor_sync(0xffffffffu, sa, d);
-  }
-  double mc = 0.0, s2 = 0.0;
-  if (act && sub == 0) {
-    const double* hinv = A.einv + (size_t)e * 9;
-    double u[3], de[3];
-#pragma unroll
-    for (int a = 0; a < 3; a++) u[a] = t[a] + A.eg[(size_t)e * 3 + a];
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      de[a] = -(hinv[3 * a] * u[0] + hinv[3 * a + 1] * u[1] + hinv[3 * a + 2] * u[2]);
-      delta_e[(size_t)e * 3 + a] = de[a];
-      x_cand[(size_t)e * 3 + a] = x[(size_t)e * 3 + a] + de[a];
-      s2 += de[a] * de[a];
-    }
-    const double hd0 = H[0] * de[0] + H[1] * de[1] + H[2] * de[2];
-    const double hd1 = H[1] * de[0] + H[3] * de[1] + H[4] * de[2];
-    const double hd2 = H[2] * de[0] + H[4] * de[1] + H[5] * de[2];
-    mc = sa + de[0] * (gl[0] + t[0] + 0.5 * hd0) + de[1] * (gl[1] + t[1] + 0.5 * hd1) + de[2] * (gl[2] + t[2] + 0.5 * hd2);
-  }
-  mc = warp_sum(mc); s2 = warp_sum(s2);
-  if ((threadIdx.x & 31) == 0) { s_mc[threadIdx.x >> 5] = mc; s_s2[threadIdx.x >> 5] = s2; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double m = 0.0, s = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { m += s_mc[i]; s += s_s2[i]; }
-    if (m != 0.0) atomicAdd(&scalars[SC_MODEL], m);
-    if (s != 0.0) atomicAdd(&scalars[SC_STEP2], s);
+  mc_acc = warp_sum(mc_acc); s2_acc = warp_sum(s2_acc);
+  if (lane == 0) {
+    if (mc_acc != 0.0) atomicAdd(&scalars[SC_MODEL], mc_acc);
+    if (s2_acc != 0.0) atomicAdd(&scalars[SC_STEP2], s2_acc);
   }
 }
 

@@ -102,7 +102,7 @@ struct Structure {
   //   groups : per point, one record per run of observations taken from the same pose (stereo pair = one group)
   //   entries: per (reduced-matrix row a, column range [a + 5r, a + 5r + 5)): the (point, pose a) slots that contribute
   //   items  : <= kRowItemEnts consecutive entries of one (row, range) list = the work of one warp
-  struct RowGroup { uint32_t pos0, pos1, gs, cnt; };   // chunks pos0 .. pos0 + cnt - 1 of the point-major Jacobian array
+  struct RowGroup { uint32_t pos0, pos1, gs, cnt; };   // chunks pos0 .. pos0 + cnt - 1 of the point-major Jacobian array; pos1 = f index of the pose (int32, -1 constant)
   struct RowItem { uint32_t row, dlo, off, cnt; };
   struct PointRows {
     std::vector<uint32_t> grp_ptr;      // P + 1
@@ -608,7 +608,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
         uint32_t d2 = d + 1;
         while (d2 < S.pts.ptr[e + 1] && S.pts.slot[d] != 0xFFFF && S.pts.slot[d2] == S.pts.slot[d]) d2++;
         Structure::RowGroup G;
-        G.cnt = d2 - d; G.pos0 = d; G.pos1 = d + 1;   // chunks d .. d + cnt - 1 (point-major positions)
+        G.cnt = d2 - d; G.pos0 = d; G.pos1 = (uint32_t)S.pts.f[d];   // chunks d .. d + cnt - 1 (point-major positions); pos1 = f index of the pose
         G.gs = S.pts.slot[d] == 0xFFFF ? 0xFFFFFFFFu : dptr[e] + (uint32_t)(S.pts.f[d] - sf[0]);
         R.grp[w] = G; R.grp_f[w] = S.pts.f[d]; w++;
         d = d2;

@@ -214,6 +214,7 @@ struct Solver {
   // communicator
   std::shared_ptr<Comm> comm;
   int rank = 0, world = 1;
+  int debug_skip = 0;            // OBVI_DEBUG_SKIP bit mask: 1 point_prep, 2 schur_rows, 4 backsub_rows (hang bisection only; results are garbage)
   int debug_bt_fail_rank = -1;   // OBVI_DEBUG_BT_FAIL_RANK: this rank reports a failed factorisation (tests of the fallback path)
   // device structure
   DBuf<Camera> cams;
@@ -235,7 +236,6 @@ struct Solver {
   DBuf<uint32_t> pr_ent;
   DBuf<Structure::RowItem> pr_items;
   DBuf<uint8_t> pr_regular;
-  DBuf<int32_t> pr_grp_f;
   DBuf<double> WZ;
   int n_row_items = 0, n_row_fallback = 0;
   // in-place removal of reprojection / bbox blocks (two-phase outlier exclusion without a structure rebuild)
@@ -270,7 +270,6 @@ struct Solver {
   DBuf<unsigned int> rs_u32;  // [4 reduction counters | nsb arrival counters | nsb z epochs]
   bool defer_sync = true;        // OBVI_DEFER_SYNC=0: two host synchronisations per accepted LM iteration instead of one
   bool obj_split = true;      // OBVI_OBJ_SPLIT=0: one-kernel object elimination (254 registers; kept for A/B runs and tests)
-  int lanes_per_point = 8;   // OBVI_LPP=16: sixteen lanes per point in point_prep / backsub_rows (measured slower: 359 / 200 us vs 329 / 165)
   bool bt_v1 = false;   // OBVI_BT=v1: first-generation factorisation kernels (scalar-pivot Gauss-Jordan, FMA GEMM)
   // The factorisation is reused across LM iterations while it still preconditions well: it is redone when the
   // trust-region radius moved by more than 2x since it was computed or the last PCG needed more than
@@ -325,13 +324,15 @@ struct Solver {
     if (const char* e = getenv("OBVI_REFACTOR_RATIO")) kRefactorRatio = std::max(1.0, atof(e));
     if (const char* e = getenv("OBVI_DEFER_SYNC")) defer_sync = std::string(e) != "0";
     if (const char* e = getenv("OBVI_OBJ_SPLIT")) obj_split = std::string(e) != "0";
-    if (const char* e = getenv("OBVI_LPP")) lanes_per_point = std::string(e) == "16" ? 16 : 8;
     if (const char* e = getenv("OBVI_PCG")) pcg_resident = std::string(e) != "grid";
     CUDA_OK(cudaFuncSetAttribute(pcg_bt_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentSmem));
     if (const char* e = getenv("OBVI_PROFILE")) prof.on = std::string(e) == "1";
     if (const char* e = getenv("OBVI_DEBUG_BT_FAIL_RANK")) debug_bt_fail_rank = atoi(e);
+    if (const char* e = getenv("OBVI_DEBUG_SKIP")) debug_skip = atoi(e);
     if (const char* e = getenv("OBVI_JAC")) jac_mode = std::string(e) == "plain" ? 0 : 1;
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes));
+    CUDA_OK(cudaFuncSetAttribute(point_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem));
+    CUDA_OK(cudaFuncSetAttribute(backsub_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem));
   }
 
   void upload_elist(EListDev& D, const Structure::EList& L, const std::vector<uint8_t>& cst, int NE, int maxs) {
@@ -377,7 +378,7 @@ struct Solver {
     {
       const Structure::PointRows& R = S.prow;
       n_row_items = (int)R.items.size(); n_row_fallback = (int)R.fallback.size();
-      pr_grp_ptr.upload(R.grp_ptr, stream); pr_grp.upload(R.grp, stream); pr_grp_f.upload(R.grp_f, stream); pr_regular.upload(R.regular, stream);
+      pr_grp_ptr.upload(R.grp_ptr, stream); pr_grp.upload(R.grp, stream); pr_regular.upload(R.regular, stream);
       pr_ent.upload(R.ent, stream); pr_items.upload(R.items, stream); pr_rowblk.upload(R.rowblk, stream); pr_fallback.upload(R.fallback, stream);
       WZ.alloc((size_t)std::max<int64_t>(R.n_slots, 1) * kWZ); WZ.zero(stream);   // gap slots stay zero
     }
@@ -539,6 +540,8 @@ struct Solver {
 
   // ---- kernel sequences -------------------------------------------------------------------------------
   static int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
+  // persistent streaming point kernels: one CTA of kPipeWarps warps per SM, a warp per batch of 4 points
+  int pipe_grid(int npoints) const { return std::max(1, std::min(num_sms, nblk(nblk(npoints, 4), kPipeWarps))); }
   EArgs eargs(EListDev& D, const double* Jp) {
     EArgs a;
     a.ptr = D.ptr.p; a.pos = D.pos.p; a.f = D.f.p; a.slot = D.slot.p; a.pair_ptr = D.pair_ptr.p; a.nslots = D.nslots.p;
@@ -633,10 +636,9 @@ struct Solver {
     }
     prof.end("pose_accum", pt0, stream); pt0 = prof.begin(stream);
     {
-      if (S.P && lanes_per_point == 8) { point_prep_kernel<8><<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
-      else if (S.P) { point_prep_kernel<16><<<nblk(S.P, 16), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
+      if (S.P && !(debug_skip & 1)) { point_prep_kernel<<<pipe_grid(S.P), 32 * kPipeWarps, kPipeSmem, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
       prof.end("point_prep", pt0, stream); pt0 = prof.begin(stream);
-      if (n_row_items) { schur_rows_kernel<<<nblk(n_row_items, kRowWarps), 32 * kRowWarps, 0, stream>>>(reinterpret_cast<const uint4*>(pr_items.p), n_row_items, pr_ent.p, WZ.p, pr_rowblk.p, kRowSpan, S_upper, b_schur); launches++; }
+      if (n_row_items && !(debug_skip & 2)) { schur_rows_kernel<<<nblk(n_row_items, kRowWarps), 32 * kRowWarps, 0, stream>>>(reinterpret_cast<const uint4*>(pr_items.p), n_row_items, pr_ent.p, WZ.p, pr_rowblk.p, kRowSpan, S_upper, b_schur); launches++; }
       if (n_row_fallback) {
         EArgs a = eargs(pts, J.p); a.elist = pr_fallback.p;
         schur_eblock_kernel<3, 2, 32, 16, false><<<n_row_fallback, 32, 0, stream>>>(a, lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p);
@@ -722,8 +724,7 @@ struct Solver {
     if (S.nf) { pose_step_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(S.nf, pose_of_f.p, pscale.p, y.p, poses[cur].p, poses[cand].p, dpose.p, rank == 0, scalars.p); launches++; }
     fork();
     if (S.P) {
-      if (lanes_per_point == 8) backsub_rows_kernel<8><<<nblk(S.P, 32), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_grp_f.p, pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
-      else backsub_rows_kernel<16><<<nblk(S.P, 16), 256, 0, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_grp_f.p, pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
+      if (!(debug_skip & 4)) backsub_rows_kernel<<<pipe_grid(S.P), 32 * kPipeWarps, kPipeSmem, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
       launches++;
       if (n_row_fallback) {   // points outside the row-owner path: generic kernel on the fallback list
         EArgs a = eargs(pts, J.p); a.elist = pr_fallback.p;
