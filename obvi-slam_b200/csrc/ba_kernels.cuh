@@ -267,28 +267,28 @@ __device__ __forceinline__ void store_chunk_swz(double* tile, int row, const dou
 //   * the pose-side normal-equation sums H_pp = sum Jp^T Jp, g_p = sum Jp^T r of the rows (which no later kernel could form
 //     without gathering, now that the chunks are point-major) are taken from the same image with the fp64 tensor cores: per
 //     pair of rows one m8n8k4 product [Jp | r]^T [Jp | r], A and B fragments being the same register.  Warps that span a
-//     keyframe boundary run one masked pass per keyframe.  Warp partials are combined through shared memory (fixed order) and
-//     leave as one set of reductions per (tile, keyframe).
-// Only the final combine needs a block barrier: scatter and products read what the same warp wrote.
+//     keyframe boundary run one masked pass per keyframe; every (warp, keyframe) product leaves as 42 fire-and-forget
+//     reductions (combining the warps of a tile in shared memory first cost more instructions than it saved).
+// Only the cost sum needs a block barrier: scatter and products read what the same warp wrote.
 constexpr int kJacMaxPc = 6;                       // staged pose/camera entries per tile
 constexpr int kJacMaxCls = 16;                     // calibration classes staged in shared memory
-constexpr int kJacAccSlots = 6;                    // keyframes per tile whose sums are combined on chip (more: direct reductions)
 constexpr int kJacWarps = kJacThreads / 32;
 constexpr int kJacTileBytes = kJacThreads * kChunk * 8;
 constexpr int kJacSmemBytes = kJacTileBytes + kJacMaxPc * (int)sizeof(PoseCam) + 16 + 128;
 
-__global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_fused_kernel(const ObsRec* __restrict__ obs, int64_t n,
+#ifndef OBVI_JAC_MINB
+#define OBVI_JAC_MINB 4
+#endif
+__global__ void __launch_bounds__(kJacThreads, OBVI_JAC_MINB) reproj_jac_fused_kernel(const ObsRec* __restrict__ obs, int64_t n,
                                                                            const PoseCam* __restrict__ pcam, int C,
                                                                            const CalibClass* __restrict__ cls, int ncls,
                                                                            const double* __restrict__ points, int apply_loss,
-                                                                           const uint2* __restrict__ tile_pc,
+                                                                           const uint4* __restrict__ tile_pc,
                                                                            const int32_t* __restrict__ f_of_pose,
                                                                            double* __restrict__ J, double* __restrict__ pose_acc,
                                                                            double* __restrict__ scalars) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ CalibClass cls_s[kJacMaxCls];
-  __shared__ double part_s[kJacWarps][2][64];      // per warp: the 8x8 products of its (at most two) keyframes
-  __shared__ int part_slot[kJacWarps][2];
   __shared__ double wcost[kJacWarps], wfixed[kJacWarps];
   unsigned char* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
   double* tile = reinterpret_cast<double*>(smem);
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_fused_kernel(const 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t i0 = (int64_t)blockIdx.x * kJacThreads;
   const int nt = (int)min((int64_t)kJacThreads, n - i0);
-  const uint2 tp = tile_pc[blockIdx.x];  // first pose/camera entry of the tile, number of entries staged
+  const uint4 tp = tile_pc[blockIdx.x];  // first pose/camera entry of the tile, number of entries staged, first keyframe
   const int64_t i = i0 + threadIdx.x;
   const bool active = (int)threadIdx.x < nt;
   double2 uv = make_double2(0.0, 0.0);
@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_fused_kernel(const 
     X[0] = points[3 * (size_t)id.y]; X[1] = points[3 * (size_t)id.y + 1]; X[2] = points[3 * (size_t)id.y + 2];
   }
   const CalibClass cc = cls_s[(id.w >> 16) & (kJacMaxCls - 1)];
-  const uint32_t pose0 = tp.x / (uint32_t)C;       // first keyframe of the tile
-  // accumulation slot of this row: keyframe index inside the tile, -1: no pose-side sums (inactive row, constant pose)
+  const uint32_t pose0 = tp.z;
+  // accumulation slot of this row: keyframe index inside the tile, -1: no pose-side sums (inactive row, constant pose, masked)
   int slot = -1;
   mbar_wait(bar, 0);
   {
@@ -356,14 +356,12 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_fused_kernel(const 
     for (int it = 0; it < 8; it++) {
       const int rl = 4 * it + sub;                                   // row inside the warp
       const uint32_t d = __shfl_sync(0xffffffffu, id.z, rl);
-      const bool act = __shfl_sync(0xffffffffu, (int)active, rl) != 0;
       const int row = 32 * w + rl;
       const double2 v = reinterpret_cast<const double2*>(tile)[(size_t)row * 8 + (piece ^ (row & 7))];
-      if (act) reinterpret_cast<double2*>(J)[(size_t)d * 8 + piece] = v;
+      if (row < nt) reinterpret_cast<double2*>(J)[(size_t)d * 8 + piece] = v;
     }
   }
-  // ---- pose-side sums of the warp's rows on the fp64 tensor cores
-  int nparts = 0;
+  // ---- pose-side sums of the warp's rows on the fp64 tensor cores; one set of reductions per (warp, keyframe)
   {
     const int a = lane >> 2, k = lane & 3;                           // fragment element [a][k]: parameter column a, residual row k
     const int rr = k & 1;                                            // residual row inside the observation
@@ -381,49 +379,22 @@ __global__ void __launch_bounds__(kJacThreads, 4) reproj_jac_fused_kernel(const 
       for (int j = 0; j < 16; j++) {
         const int rl = 2 * j + (k >> 1);
         const int row = 32 * w + rl;
-        const double2 v2 = reinterpret_cast<const double2*>(tile)[(size_t)row * 8 + (pc ^ (row & 7))];
-        double v = wi ? v2.y : v2.x;
+        double v = tile[(size_t)row * kChunk + 2 * (pc ^ (row & 7)) + wi];
         v = ((m >> rl) & 1u) ? sgn * v : 0.0;
         dmma_m8n8k4(d0, d1, v, v);
       }
-      if (s < kJacAccSlots && nparts < 2) {
-        part_s[w][nparts][8 * a + 2 * k] = d0; part_s[w][nparts][8 * a + 2 * k + 1] = d1;
-        if (lane == 0) part_slot[w][nparts] = s;
-        nparts++;
-      } else {
-        // more than two keyframes inside one warp, or more than kJacAccSlots in the tile: reduce straight into global memory
-        const int f = f_of_pose[pose0 + (uint32_t)s];
-        double* acc = pose_acc + (size_t)f * kPoseAcc;
-        const int c0 = 2 * k;
-        if (a < 6) {
-          if (c0 < 6) { red_add(&acc[6 * a + c0], d0); red_add(&acc[6 * a + c0 + 1], d1); }
-          else red_add(&acc[36 + a], d0);                            // column 6: g_p
-        }
+      const int f = f_of_pose[pose0 + (uint32_t)s];
+      double* acc = pose_acc + (size_t)f * kPoseAcc;
+      const int c0 = 2 * k;
+      if (a < 6) {
+        if (c0 < 6) { red_add(&acc[6 * a + c0], d0); red_add(&acc[6 * a + c0 + 1], d1); }
+        else red_add(&acc[36 + a], d0);                              // column 6: g_p
       }
     }
-    if (lane == 0) { for (int q = nparts; q < 2; q++) part_slot[w][q] = -1; }
   }
   cost = warp_sum(cost); fixed = warp_sum(fixed);
   if (lane == 0) { wcost[w] = cost; wfixed[w] = fixed; }
   __syncthreads();
-  // ---- combine the warp partials per keyframe (fixed order) and reduce into the pose accumulators
-  for (int t = threadIdx.x; t < kJacAccSlots * 64; t += kJacThreads) {
-    const int s = t >> 6, e = t & 63;
-    const int a = e >> 3, c = e & 7;
-    if (a >= 6 || c >= 7) continue;
-    double sum = 0.0;
-    bool any = false;
-#pragma unroll
-    for (int ww = 0; ww < kJacWarps; ww++) {
-#pragma unroll
-      for (int q = 0; q < 2; q++)
-        if (part_slot[ww][q] == s) { sum += part_s[ww][q][e]; any = true; }
-    }
-    if (!any) continue;
-    const int f = f_of_pose[pose0 + (uint32_t)s];
-    double* acc = pose_acc + (size_t)f * kPoseAcc;
-    red_add(c < 6 ? &acc[6 * a + c] : &acc[36 + a], sum);
-  }
   if (threadIdx.x == 0) {
     double cs = 0.0, fs = 0.0;
 #pragma unroll
@@ -1190,27 +1161,26 @@ __global__ void __launch_bounds__(32 * kRowWarps) schur_rows_kernel(const uint4*
   // flushed.  Slots are dense, so column j of the range is the record (dlo + j) slots after the row's own.
   const int offb = frow < 6 ? 3 * frow + (fk < 3 ? fk : 2) : (frow == 6 ? kWZw + (fk < 3 ? fk : 2) : 0);
   const double* WZb = WZ + (size_t)it.y * kWZ + offb;
+  // (the A operand is kept RAW here and masked in consume (): a select next to the load would make the fetch of entry i + 1
+  //  wait for its own data and defeat the two-entry software pipeline)
   struct Ops { double a, b[5]; uint32_t n; };
+  const bool avalid = fk < 3 && frow < 6;
   auto load_ops = [&](uint32_t e, Ops& o) {
     const uint32_t gs = e & 0x7ffffffu;
     o.n = e >> 27;
     const double* zb = WZb + (size_t)gs * kWZ;
-    if (first_range) {
-      o.b[0] = zb[0];                       // the diagonal pair: A and B come from the same record
-      o.a = fk < 3 && frow < 6 ? o.b[0] : 0.0;
-    } else {
-      const double av = WZ[(size_t)gs * kWZ + offb];
-      o.a = fk < 3 && frow < 6 ? av : 0.0;
-      o.b[0] = zb[0];
-    }
+    o.b[0] = zb[0];
+    if (!first_range) o.a = WZ[(size_t)gs * kWZ + offb];   // first range: the diagonal pair, A and B come from the same record
 #pragma unroll
     for (int j = 1; j < 5; j++)
       if ((uint32_t)j < o.n) o.b[j] = zb[j * kWZ];
   };
   auto consume = [&](const Ops& o) {
+    const double araw = first_range ? o.b[0] : o.a;
+    const double a = avalid ? araw : 0.0;
 #pragma unroll
     for (int j = 0; j < 5; j++)
-      if ((uint32_t)j < o.n) dmma_m8n8k4(acc[j].x, acc[j].y, o.a, o.b[j]);
+      if ((uint32_t)j < o.n) dmma_m8n8k4(acc[j].x, acc[j].y, a, o.b[j]);
   };
   Ops o0, o1;
   uint32_t mine = 0u;

@@ -223,7 +223,7 @@ struct Solver {
   DBuf<uint32_t> pose_ptr, su_ptr, sf_ptr, sf_col, sf_src;
   DBuf<int32_t> f_of_pose, pose_of_f;
   DBuf<uint8_t> pose_skip, point_skip, obj_skip;
-  DBuf<uint2> jac_tile;  // per 256-observation tile: first pose/camera entry, entries staged by TMA
+  DBuf<uint4> jac_tile;  // per 256-observation tile: first pose/camera entry, entries staged by TMA, first keyframe
   int jac_mode = 1;  // 1: TMA-staged tile kernel (default), 0: plain loads / stores (OBVI_JAC=plain)
   DBuf<double> pose_acc;    // per variable pose: H_pp (36) | g_p (6) | spare (6) of the reprojection blocks, filled by the Jacobian kernel
   DBuf<BBoxRec> bbox;
@@ -359,12 +359,12 @@ struct Solver {
     bbox.upload(S.bbox, stream); unary.upload(S.unary, stream); rel.upload(S.rel, stream);
     {
       const int64_t ntiles = (S.n_obs + kJacThreads - 1) / kJacThreads;
-      std::vector<uint2> tp(ntiles);
+      std::vector<uint4> tp(ntiles);
       for (int64_t t = 0; t < ntiles; t++) {
         const ObsRec& a = S.obs[t * kJacThreads];
         const ObsRec& b = S.obs[std::min<int64_t>(S.n_obs, (t + 1) * kJacThreads) - 1];
         const uint32_t lo = a.pose * (uint32_t)S.C + (uint32_t)S.classes[obs_cls(a)].cam, hi = b.pose * (uint32_t)S.C + (uint32_t)S.classes[obs_cls(b)].cam;
-        tp[t] = make_uint2(lo, std::min<uint32_t>(hi - lo + 1, kJacMaxPc));
+        tp[t] = make_uint4(lo, std::min<uint32_t>(hi - lo + 1, kJacMaxPc), a.pose, 0u);
       }
       jac_tile.upload(tp, stream);
     }
