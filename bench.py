@@ -29,7 +29,7 @@ WORKLOAD = dict(workload="C3: 2000 keyframes / 200k points / 500 objects, full r
                 l2="working set per iteration (0.09 GB observations + 0.36 GB Jacobian chunks) exceeds the 126 MB L2: no flush needed")
 
 
-JAC_KERNEL = "reproj_jac_tma_kernel (reprojection residual + Jacobian evaluation)"
+JAC_KERNEL = "reproj_jac_fused_kernel (reprojection residual + Jacobian evaluation, point-major scatter, fused pose-side sums)"
 TRAFFIC_FILE = "r02_jacobian_traffic.json"
 
 _JSON_OUT = None

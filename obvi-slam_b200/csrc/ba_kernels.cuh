@@ -1182,21 +1182,31 @@ __global__ void __launch_bounds__(32 * kRowWarps) schur_rows_kernel(const uint4*
     for (int j = 0; j < 5; j++)
       if ((uint32_t)j < o.n) dmma_m8n8k4(acc[j].x, acc[j].y, a, o.b[j]);
   };
-  Ops o0, o1;
+  // Software pipeline, kRowDepth entries deep (2: measured 541 / 638 / 699 us for depth 2 / 3 / 4 on C3 -- occupancy hides the
+  // load latency better than a deeper per-warp pipeline at 78 / 94 registers): the operands of entries i + 1 .. are in flight while the
+  // tensor-core products of entry i issue (register sets, loop unrolled by kRowDepth); entry descriptors are fetched 32 at a
+  // time (one per lane) and broadcast with a shuffle.
+#ifndef OBVI_ROW_DEPTH
+#define OBVI_ROW_DEPTH 2
+#endif
+  constexpr int kRowDepth = OBVI_ROW_DEPTH;
+  Ops o[kRowDepth];
   uint32_t mine = 0u;
-  auto fetch = [&](uint32_t i, Ops& o) {   // i < it.w
+  auto fetch = [&](uint32_t i, Ops& op) {   // i < it.w
     if ((i & 31u) == 0u) { mine = 0u; if (i + lane < it.w) mine = ep[i + lane]; }
-    load_ops(__shfl_sync(0xffffffffu, mine, (int)(i & 31u)), o);
+    load_ops(__shfl_sync(0xffffffffu, mine, (int)(i & 31u)), op);
   };
-  fetch(0, o0);
-  uint32_t i = 0;
-  for (; i + 2 <= it.w; i += 2) {
-    fetch(i + 1, o1);
-    consume(o0);
-    if (i + 2 < it.w) fetch(i + 2, o0);
-    consume(o1);
+#pragma unroll
+  for (int q = 0; q < kRowDepth - 1; q++)
+    if ((uint32_t)q < it.w) fetch(q, o[q]);
+  for (uint32_t i = 0; i < it.w; i += kRowDepth) {
+#pragma unroll
+    for (int q = 0; q < kRowDepth; q++) {
+      // slot q is consumed now; the slot consumed last ((q + kRowDepth - 1) % kRowDepth) is refilled with entry i + q + kRowDepth - 1
+      if (i + q + kRowDepth - 1 < it.w) fetch(i + q + kRowDepth - 1, o[(q + kRowDepth - 1) % kRowDepth]);
+      if (i + q < it.w) consume(o[q]);
+    }
   }
-  if (i < it.w) consume(o0);
   if (fvalid) {
     const uint32_t* rb = rowblk + (size_t)it.x * row_span + it.y;
     const int coff = 6 * frow + 2 * fk;

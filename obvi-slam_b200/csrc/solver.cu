@@ -276,7 +276,9 @@ struct Solver {
   // kRefactorPcgIters iterations.  (A stale preconditioner changes the PCG iteration count, never its answer.)
   double bt_radius = -1.0;
   int last_pcg_iters = 0;
-  int kRefactorPcgIters = 8;   // OBVI_REFACTOR_ITERS
+  int bt_fresh_iters = 0;        // PCG iterations of the first solve after the current factorisation (0: not seen yet)
+  bool bt_fresh_pending = false;
+  int kRefactorPcgIters = 3;   // OBVI_REFACTOR_ITERS: refactor once the PCG needs this many iterations more than with a fresh factorisation
   double kRefactorRatio = 2.0; // OBVI_REFACTOR_RATIO
   int64_t bt_factorizations = 0;
   double* h_scalars = nullptr;  // pinned
@@ -663,8 +665,13 @@ struct Solver {
       launches++;
       if (!use_bt) { minv_kernel<<<nblk(S.nf, 64), 64, 0, stream>>>(S.nf, sf_ptr.p, sf_col.p, Sf.p, Minv.p, scalars.p); launches++; }
       prof.end("finish", pt0, stream); pt0 = prof.begin(stream);
-      const bool stale = bt_radius <= 0.0 || lm.radius > kRefactorRatio * bt_radius || lm.radius * kRefactorRatio < bt_radius || last_pcg_iters > kRefactorPcgIters;
-      if (stale) { factor_bt(); bt_radius = lm.radius; bt_factorizations++; prof.end("factor_bt", pt0, stream); }
+      // redo the factorisation when the radius moved by more than kRefactorRatio since it was computed, or when the last PCG
+      // needed clearly more iterations than the first one after that factorisation did (bt_fresh_iters: what a FRESH
+      // preconditioner achieves on this problem -- an absolute threshold refactors every iteration on graphs whose fresh count
+      // already sits at it)
+      const bool worn = bt_fresh_iters > 0 ? last_pcg_iters >= bt_fresh_iters + kRefactorPcgIters : last_pcg_iters > 3 * kRefactorPcgIters;
+      const bool stale = bt_radius <= 0.0 || lm.radius > kRefactorRatio * bt_radius || lm.radius * kRefactorRatio < bt_radius || worn;
+      if (stale) { factor_bt(); bt_radius = lm.radius; bt_factorizations++; bt_fresh_iters = 0; bt_fresh_pending = true; prof.end("factor_bt", pt0, stream); }
     }
   }
   void solve_reduced(const obvi_solver_options& o, bool force_jacobi = false) {
@@ -864,7 +871,7 @@ int Solver::object_covariances(int64_t n_pairs, double* const* obj_a, double* co
   gather_params();
   LMParams lm;
   lm.radius = std::numeric_limits<double>::infinity(); lm.inv_radius = 0.0; lm.min_diag = 1e-6; lm.max_diag = 1e32; lm.compute_scale = 1;
-  bt_radius = -1.0; last_pcg_iters = 0;
+  bt_radius = -1.0; last_pcg_iters = 0; bt_fresh_iters = 0; bt_fresh_pending = false;
   linearize(1);
   build_reduced(lm);
   fetch_scalars(0);
@@ -940,7 +947,7 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
   sum->num_residual_blocks_reduced = (int32_t)S.num_residual_blocks_reduced;
   sum->num_residuals_reduced = (int32_t)S.num_residuals_reduced;
   gather_params();
-  bt_radius = -1.0; last_pcg_iters = 0;
+  bt_radius = -1.0; last_pcg_iters = 0; bt_fresh_iters = 0; bt_fresh_pending = false;
 
   int n_log = 0;
   int user_stop = 0;   // first non-zero return of the iteration callback: 1 abort, 2 terminate successfully
@@ -1046,6 +1053,7 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
     const int pcg_it = (int)h_scalars[SC_PCG_IT];
     pcg_total += pcg_it;
     last_pcg_iters = pcg_it;
+    if (bt_fresh_pending) { bt_fresh_iters = pcg_it; bt_fresh_pending = false; }
     const double model_change = -h_scalars[SC_MODEL];
     bool valid = !build_failed && h_scalars[SC_FAIL] == 0.0 && h_scalars[SC_PCG_BREAK] == 0.0 && std::isfinite(model_change) &&
                  std::isfinite(h_scalars[SC_STEP2]) && model_change > 0.0;
