@@ -112,11 +112,25 @@ def measured_peak_gbs():
 
 def host_cores():
     """Host threads this process may use.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, so the count is taken
-    from the affinity mask and handed to the oracle explicitly (it calls omp_set_num_threads, oracle/ba_oracle.cpp)."""
+    from the affinity mask -- capped by the cgroup CPU quota when one is set (a container that shows 24 CPUs but is allowed 6
+    CPU-seconds per second runs 24 OpenMP threads far slower than 6) -- and handed to the oracle explicitly (it calls
+    omp_set_num_threads, oracle/ba_oracle.cpp)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]          # cgroup v2
+        if quota != "max":
+            n = max(1, min(n, -(-int(quota) // int(period))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())   # v1
+            if q > 0:
+                n = max(1, min(n, -(-q // per)))
+        except Exception:
+            pass
+    return n
 
 
 def cpu_leg(g, iters, threads=None, tolerances=False):

@@ -241,6 +241,9 @@ int obvi_comm_init(obvi_problem* p, const void* unique_id_128_bytes, int rank, i
  * thread, all making the same sequence of obvi_solve / obvi_evaluate calls.  It exists so that the sharded code path can be
  * run and checked on a single-GPU box (NCCL refuses two ranks on one device); the multi-process path is obvi_comm_init. */
 int obvi_comm_init_local(obvi_problem** handles, int world_size);
+/* Share the communicator (and rank / world size) of `src` with another problem handle on the same device: the reference solves
+ * hundreds of windows per session (offline_problem_runner.h:100-270); the communicator is created once. */
+int obvi_comm_attach(obvi_problem* p, const obvi_problem* src);
 
 /* ---- measurement hook (bench.py): times `reps` back-to-back launches of the reprojection Jacobian-evaluation
  *      kernel at the current host values with CUDA events on the solver's stream (after 3 warm-up launches) and

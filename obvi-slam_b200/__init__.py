@@ -132,6 +132,7 @@ def lib():
         "obvi_comm_unique_id": ([vp], C.c_int),
         "obvi_comm_init": ([vp, vp, C.c_int, C.c_int], C.c_int),
         "obvi_comm_init_local": ([C.POINTER(vp), C.c_int], C.c_int),
+        "obvi_comm_attach": ([vp, vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here means the library does not export what obvi_ba.h declares
@@ -148,7 +149,7 @@ EXPORTED_SYMBOLS = [
     "obvi_factor_add_shape_prior", "obvi_factor_add_ltm_prior", "obvi_factor_add_rel_pose", "obvi_factor_add_param_prior",
     "obvi_factor_remove", "obvi_num_factors", "obvi_num_structure_builds", "obvi_residual_blocks", "obvi_solver_options_init", "obvi_solve",
     "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_evaluate_jacobian", "obvi_object_covariances", "obvi_profile_jacobian", "obvi_debug_partition", "obvi_debug_structure_hash", "obvi_comm_unique_id",
-    "obvi_comm_init", "obvi_comm_init_local",
+    "obvi_comm_init", "obvi_comm_init_local", "obvi_comm_attach",
 ]
 
 
@@ -404,6 +405,10 @@ class Problem:
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._ck(self._lib.obvi_comm_init(self._h, buf, rank, world))
+
+    def comm_attach(self, src):
+        """Use the communicator of problem `src` (same device)."""
+        self._ck(self._lib.obvi_comm_attach(self._h, src._h))
 
     @staticmethod
     def comm_init_local(problems):

@@ -1854,6 +1854,15 @@ int obvi_comm_init(obvi_problem* p, const void* uid, int rank, int world) {
   API_END(p)
 }
 
+// Share the communicator of `src` (set up with obvi_comm_init / obvi_comm_init_local) with another problem handle of the same
+// process and device: a schedule solves hundreds of problems one after the other, a communicator is created once.
+int obvi_comm_attach(obvi_problem* p, const obvi_problem* src) {
+  if (!p || !src || !src->s.comm) return OBVI_ERR_INVALID_ARGUMENT;
+  if (p->s.pb.device != src->s.pb.device) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "obvi_comm_attach: the two problems live on different devices");
+  p->s.comm = src->s.comm; p->s.rank = src->s.rank; p->s.world = src->s.world; p->s.pb.dirty = true;
+  return OBVI_OK;
+}
+
 // Join `world` problem handles of THIS process into one sharded solve (handle i becomes rank i).  Every handle must then
 // be driven by its own host thread, all of them making the same sequence of collective calls (obvi_solve, obvi_evaluate).
 int obvi_comm_init_local(obvi_problem** handles, int world) {

@@ -114,12 +114,19 @@ def build_scope(g, start, nxt, p: ScheduleParams, *, include_visual=True, includ
     in_win = lambda f: (f >= start) & (f <= nxt)
     # visual factors in the window, features with enough observations inside it
     if include_visual and len(rp["pose"]):
-        m = in_win(rp["pose"])
-        cnt = np.bincount(rp["point"][m], minlength=len(g.points))
-        m &= cnt[rp["point"]] >= p.min_low_level_feature_observations
+        if getattr(g, "_rp_sorted", None) is None:          # observations in pose order: a window is one slice
+            g._rp_sorted = bool(np.all(np.diff(rp["pose"]) >= 0))
+        if g._rp_sorted:
+            lo, hi = np.searchsorted(rp["pose"], [start, nxt + 1])
+            cnt = np.bincount(rp["point"][lo:hi], minlength=len(g.points))
+            rp_idx = lo + np.nonzero(cnt[rp["point"][lo:hi]] >= p.min_low_level_feature_observations)[0]
+        else:
+            m = in_win(rp["pose"])
+            cnt = np.bincount(rp["point"][m], minlength=len(g.points))
+            m &= cnt[rp["point"]] >= p.min_low_level_feature_observations
+            rp_idx = np.nonzero(m)[0]
     else:
-        m = np.zeros(len(rp["pose"]), bool)
-    rp_idx = np.nonzero(m)[0]
+        rp_idx = np.zeros(0, np.int64)
     # rel-pose factors: only for window frames with too few feature observations (both ends inside the window)
     if relpose_mode == "starved":
         per_frame = np.bincount(rp["pose"][rp_idx], minlength=len(g.poses)) if len(rp_idx) else np.zeros(len(g.poses), np.int64)
@@ -264,6 +271,7 @@ def run_schedule(g, backend, p: ScheduleParams, max_frame=None, log=None):
         sub, maps = build_scope(g, start, nxt, p)
         before = sub.poses.copy()
         snap = (sub.poses.copy(), sub.points.copy(), sub.objects.copy())
+        backend.kind = tag
         costs = backend.two_phase(sub, ph1.as_dict(), ph2.as_dict(), p.feature_outlier_percentage) if p.two_phase else backend.solve(sub, ph1.as_dict())
         if p.allow_reversion_after_detecting_jumps and not poses_stable(before, sub.poses, p):
             sub.poses[:], sub.points[:], sub.objects[:] = snap
@@ -278,6 +286,7 @@ def run_schedule(g, backend, p: ScheduleParams, max_frame=None, log=None):
         nc = p.poses_prior_to_window_to_keep_constant
         sub, maps = build_scope(g, max(0, nxt - nc), nxt, p, n_const=nc)
         if not sub.const_pose.all():
+            backend.kind = "tracking"
             c = backend.solve(sub, p.pre_pgo_tracking.as_dict()); write_back(g, sub, maps)
             out.append(dict(frame=nxt, start=int(maps["pose"][0]), kind="tracking", costs=c))
         # PGO with objects: rel-pose factor on every consecutive pair from the CURRENT estimates
@@ -293,6 +302,7 @@ def run_schedule(g, backend, p: ScheduleParams, max_frame=None, log=None):
         Rm = synth.rotvec_to_mat(rel[:, 3:6])
         sub.relpose = dict(p1=np.arange(k - 1), p2=np.arange(1, k), t=np.ascontiguousarray(rel[:, :3]), Rm=Rm,
                            cov=synth.odom_cov(rel[:, :3], Rm, k=p.pgo_cov_multiplier), huber=p.pgo_huber)
+        backend.kind = "pgo"
         c = backend.solve(sub, (p.final_pgo if final else p.pgo).as_dict()); write_back(g, sub, maps)
         out.append(dict(frame=nxt, start=0, kind="pgo", costs=c, n_bbox=len(maps["bb"])))
         if rel_pts is not None:   # re-anchor every point to its first-observing pose (:238-283)
@@ -302,6 +312,7 @@ def run_schedule(g, backend, p: ScheduleParams, max_frame=None, log=None):
         if p.enable_visual_feats_only_opt_post_pgo:   # points-only BA (:285-353)
             sub, maps = build_scope(g, 0, nxt, p, include_objects=False, fix_poses=True, relpose_mode="none")
             if len(sub.points):
+                backend.kind = "points_only"
                 c = backend.solve(sub, p.post_pgo_vf_adjustment.as_dict()); write_back(g, sub, maps)
                 out.append(dict(frame=nxt, start=0, kind="points_only", costs=c, n_reproj=len(maps["rp"])))
         if log:
@@ -322,3 +333,102 @@ def run_schedule(g, backend, p: ScheduleParams, max_frame=None, log=None):
         iteration(window_start(nxt, max_frame, p), nxt, False)
     iteration(0, max_frame, True)     # final refinement (offline_problem_runner.h:232-241)
     return out
+
+
+class ShardedGpuBackend(GpuBackend):
+    """GpuBackend for `world` ranks (one process per GPU): the large solves of the schedule -- kinds listed in `sharded_kinds`
+    with at least `min_obs` reprojection + bounding-box blocks -- are sharded over the ranks (e-blocks dealt to ranks, one NCCL
+    all-reduce of the reduced system per build, obvi_comm_*); everything else (local windows: too small to shard) is
+    solved by rank 0 alone.  After every solve rank 0's parameter blocks are broadcast, so all ranks hold bit-identical state
+    and take identical schedule decisions (windows are sequentially dependent: nothing runs concurrently).
+
+    `dist` is torch.distributed (initialised, NCCL); `template` a Problem on this rank's device whose communicator
+    (obvi_comm_init) the per-solve problems attach to."""
+
+    def __init__(self, ob, device, dist, template, sharded_kinds=("pgo", "points_only", "gba", "final"), min_obs=200_000):
+        super().__init__(ob, device)
+        self.dist, self.template, self.sharded_kinds, self.min_obs = dist, template, set(sharded_kinds), min_obs
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.kind = None
+        self.stats.update(sharded_solves=0, rank0_solves=0)
+
+    def _bcast(self, sub):
+        import torch
+        for arr in (sub.poses, sub.points, sub.objects):
+            if arr.size:
+                t = torch.from_numpy(arr).cuda()
+                self.dist.broadcast(t, 0)
+                arr[...] = t.cpu().numpy()
+
+    def _sharded(self, sub):
+        return self.world > 1 and self.kind in self.sharded_kinds and len(sub.reproj["pose"]) + len(sub.bbox["obj"]) >= self.min_obs
+
+    def _problem(self, sub, sharded):
+        p = self.ob.problem_from_graph(sub, device=self.device)
+        if sharded:
+            p.comm_attach(self.template)
+        return p
+
+    def solve(self, sub, opts):
+        t = time.time()
+        sharded = self._sharded(sub)
+        cost = [0.0]
+        if sharded or self.rank == 0:
+            p = self._problem(sub, sharded)
+            s = self._acc(p.solve(**opts))
+            cost = [s.final_cost]
+            self.stats["structure_builds"] += p.num_structure_builds()
+            self.stats["sharded_solves" if sharded else "rank0_solves"] += 1
+        if self.world > 1:
+            self._bcast(sub)
+            cost = self._bcast_scalars(cost)
+        self.stats["wall_s"] += time.time() - t
+        return cost
+
+    def _bcast_scalars(self, vals):
+        import torch
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        self.dist.broadcast(t, 0)
+        return t.tolist()
+
+    def two_phase(self, sub, opts1, opts2, frac):
+        t = time.time()
+        sharded = self._sharded(sub)
+        x0 = (sub.poses.copy(), sub.points.copy(), sub.objects.copy())
+        costs = [0.0, 0.0]
+        if not sharded:
+            if self.rank == 0:
+                costs = GpuBackend.two_phase(self, sub, opts1, opts2, frac)
+                self.stats["rank0_solves"] += 2
+            if self.world > 1:
+                self._bcast(sub)
+                costs = self._bcast_scalars(costs)
+            return costs
+        import torch
+        p = self._problem(sub, True)
+        s1 = self._acc(p.solve(**opts1))
+        # outlier ranking needs the residuals of the WHOLE graph in order of addition: rank 0 ranks on an unsharded problem at the
+        # phase-I solution and broadcasts the indices (the ranking itself is the device top-k of obvi_topk_outliers)
+        n_rp, n_bb = len(sub.reproj["pose"]), len(sub.bbox["obj"])
+        if self.rank == 0:
+            q = self.ob.problem_from_graph(sub, device=self.device)
+            out_rp = q.topk_outliers(self.ob.FACTOR_REPROJECTION, frac) if n_rp else np.zeros(0, np.uint64)
+            out_bb = q.topk_outliers(self.ob.FACTOR_BBOX, frac) if n_bb else np.zeros(0, np.uint64)
+            # factor ids are (type << 56 | index in order of addition): the same on every rank
+            idx = np.concatenate([np.asarray(out_rp, np.uint64), np.asarray(out_bb, np.uint64)]).astype(np.int64)
+            n = torch.tensor([len(idx)], dtype=torch.int64, device="cuda")
+        else:
+            n = torch.zeros(1, dtype=torch.int64, device="cuda")
+        self.dist.broadcast(n, 0)
+        buf = torch.from_numpy(idx).cuda() if self.rank == 0 else torch.zeros(int(n.item()), dtype=torch.int64, device="cuda")
+        if int(n.item()):
+            self.dist.broadcast(buf, 0)
+        for fid in buf.cpu().numpy().astype(np.uint64):
+            p.remove_residual_block(int(fid))
+        sub.poses[:], sub.points[:], sub.objects[:] = x0
+        s2 = self._acc(p.solve(**opts2))
+        self.stats["structure_builds"] += p.num_structure_builds(); self.stats["excluded"] += int(n.item())
+        self.stats["sharded_solves"] += 2
+        self._bcast(sub)      # (already identical on every rank after the merged write-back; keeps the invariant explicit)
+        self.stats["wall_s"] += time.time() - t
+        return [s1.final_cost, s2.final_cost]

@@ -231,7 +231,7 @@ def _fill_points(rng, K, P, R_gt, t_gt, min_parallax_deg, n_starved):
 def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_poses=1,
                sigma_px=1.5, outlier_frac=0.05, min_point_obs=5, min_obj_obs=10, ltm_frac=0.0,
                pose_noise=True, min_parallax_deg=1.0, symmetric_priors=False, min_bbox_px=30.0, max_obj_kf=40,
-               fill=False, starved_every=20):
+               fill=False, starved_every=20, noise_seed=None):
     """Build S(K, P, O, seed).
 
     relpose: "starved" -> rel-pose factors only into feature-starved keyframes (reference rule,
@@ -250,8 +250,13 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
              feature-starved keyframes drop); objects are drawn 8x and the first O seen from >= max_obj_kf keyframes by
              both cameras are kept.  Without it the gates simply thin the graph (the round-1 "C3-gated" workload).
     starved_every: every n-th keyframe keeps at most 30 feature observations (and so gets a relative-pose factor).
+    noise_seed: separate seed for everything that is MEASUREMENT or INITIALISATION noise (pixel noise, outliers, bounding-box
+             noise, odometry drift, initial point / object errors).  Sessions built with the same `seed` and different
+             `noise_seed`s revisit the same trajectory, points and objects with independent measurements: the multi-session
+             (long-term-map) workload of BASELINE config 5.
     """
     rng = np.random.default_rng(seed)
+    rng_n = rng if noise_seed is None else np.random.default_rng(noise_seed)
     g = FactorGraph()
     g.cams = [dict(intr=INTR, R=R_EXTR.copy(), t=T_EXTR[c].copy()) for c in range(2)]
 
@@ -329,9 +334,9 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
     good = cnt[obs_point] >= min_point_obs
     obs_pose, obs_point, obs_cam, obs_px = obs_pose[good], obs_point[good], obs_cam[good], obs_px[good]
     n_obs = len(obs_pose)
-    obs_px = obs_px + rng.normal(0.0, 1.0, (n_obs, 2))
-    outl = rng.random(n_obs) < outlier_frac
-    obs_px[outl] += rng.uniform(-50.0, 50.0, (int(outl.sum()), 2))
+    obs_px = obs_px + rng_n.normal(0.0, 1.0, (n_obs, 2))
+    outl = rng_n.random(n_obs) < outlier_frac
+    obs_px[outl] += rng_n.uniform(-50.0, 50.0, (int(outl.sum()), 2))
     # canonical order: by pose, camera, point
     order = np.lexsort((obs_point, obs_cam, obs_pose))
     g.reproj = dict(pose=obs_pose[order].astype(np.int64), point=obs_point[order].astype(np.int64),
@@ -389,7 +394,7 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
                 # (q13+sqrt, q13-sqrt, ...)/q33 which equals that order for q33 < 0.
                 lo_x, hi_x = np.minimum(px[:, 0], px[:, 1]), np.maximum(px[:, 0], px[:, 1])
                 lo_y, hi_y = np.minimum(px[:, 2], px[:, 3]), np.maximum(px[:, 2], px[:, 3])
-                c4 = np.stack([lo_x, hi_x, lo_y, hi_y], -1) + rng.normal(0.0, 10.0, (len(sel), 4))
+                c4 = np.stack([lo_x, hi_x, lo_y, hi_y], -1) + rng_n.normal(0.0, 10.0, (len(sel), 4))
                 c4 = np.stack([np.clip(c4[:, 0], 0, IMG_W - 1), np.clip(c4[:, 1], 0, IMG_W - 1),
                                np.clip(c4[:, 2], 0, IMG_H - 1), np.clip(c4[:, 3], 0, IMG_H - 1)], -1)
                 cov = np.zeros((len(sel), 4, 4))
@@ -421,8 +426,8 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
         R_i[0], t_i[0] = R_gt[0], t_gt[0]
         dR = np.einsum("nji,njk->nik", R_gt[:-1], R_gt[1:])
         dt = np.einsum("nji,nj->ni", R_gt[:-1], t_gt[1:] - t_gt[:-1])
-        nR = rotvec_to_mat(rng.normal(0.0, np.deg2rad(0.03), (K - 1, 3)))
-        nt = dt * (1.0 + rng.normal(0.0, 0.002, (K - 1, 3)))
+        nR = rotvec_to_mat(rng_n.normal(0.0, np.deg2rad(0.03), (K - 1, 3)))
+        nt = dt * (1.0 + rng_n.normal(0.0, 0.002, (K - 1, 3)))
         for i in range(K - 1):
             R_i[i + 1] = R_i[i] @ dR[i] @ nR[i]
             t_i[i + 1] = t_i[i] + R_i[i] @ nt[i]
@@ -435,16 +440,16 @@ def make_graph(K, P, O, seed=0, *, objects_on=True, relpose="starved", n_const_p
     # them -- the map is locally consistent, as after triangulation from the current pose estimates
     X_loc = np.einsum("nji,nj->ni", R_gt[anchor], X_gt - t_gt[anchor])
     X0 = np.einsum("nij,nj->ni", R_i[anchor], X_loc) + t_i[anchor]
-    g.points = np.ascontiguousarray(X0 + rng.normal(0.0, 0.1, (P, 3)))
+    g.points = np.ascontiguousarray(X0 + rng_n.normal(0.0, 0.1, (P, 3)))
     g.points_gt = X_gt
     obj0 = obj_gt.copy()
     if O > 0:
         c_loc = np.einsum("nji,nj->ni", R_gt[okf], obj_gt[:, 0:3] - t_gt[okf])
         obj0[:, 0:3] = np.einsum("nij,nj->ni", R_i[okf], c_loc) + t_i[okf]
         obj0[:, 3] += mat_to_rotvec(np.einsum("nij,nkj->nik", R_i[okf], R_gt[okf]))[:, 2]
-        obj0[:, 0:3] += rng.normal(0.0, 0.3, (O, 3))
-        obj0[:, 3] += rng.normal(0.0, 0.2, O)
-        obj0[:, 4:7] *= 1.0 + rng.uniform(-0.2, 0.2, (O, 3))
+        obj0[:, 0:3] += rng_n.normal(0.0, 0.3, (O, 3))
+        obj0[:, 3] += rng_n.normal(0.0, 0.2, O)
+        obj0[:, 4:7] *= 1.0 + rng_n.uniform(-0.2, 0.2, (O, 3))
     g.objects = np.ascontiguousarray(obj0)
     g.objects_gt = obj_gt
 
