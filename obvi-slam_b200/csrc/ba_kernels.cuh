@@ -897,10 +897,12 @@ constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 struct RowGroupD { uint32_t pos0; int32_t f; uint32_t gs, cnt; };   // chunks pos0 .. pos0 + cnt - 1, pose f index (-1 constant), slot
 struct RowItemD { uint32_t row, dlo, off, cnt; };
 
-constexpr int kPipeWarps = 8;             // warps per CTA of the streaming point kernels (one CTA per SM)
+// Two shapes of the per-warp pipeline fill the shared memory of an SM (one CTA per SM either way):
+//   <8 warps, 2 stages>  : every warp double-buffers (its next batch lands while it computes the current one);
+//   <16 warps, 1 stage>  : twice the warps, each waits for its own copy -- the other 15 cover the wait.
 constexpr int kStageChunks = 96;          // chunks per stage: 12 KB; a batch = 4 consecutive points (~80 chunks on average)
-constexpr int kPipeSmem = kPipeWarps * 2 * kStageChunks * kChunk * 8 + 128;
-static_assert(kPipeSmem <= 227 * 1024, "stages must fit the shared memory of one SM");
+constexpr int pipe_smem(int warps, int stages) { return warps * stages * kStageChunks * kChunk * 8 + 128; }
+static_assert(pipe_smem(8, 2) <= 227 * 1024 && pipe_smem(16, 1) <= 227 * 1024, "stages must fit the shared memory of one SM");
 
 // Tables of one batch (points 4 b .. 4 b + 3), spread over the lanes: lane j < 5 holds chunk-list pointer and group pointer of
 // point 4 b + j, lane j < 4 the `regular` flag.
@@ -961,21 +963,22 @@ __device__ __forceinline__ void chol3(const double* A, double* F /* f00 f10 f11 
   F[5] = sqrt(fmax(A[8] - F[3] * F[3] - F[4] * F[4], 0.0));
 }
 
-__global__ void __launch_bounds__(32 * kPipeWarps, 1) point_prep_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr,
+template <int WARPS, int STAGES>
+__global__ void __launch_bounds__(32 * WARPS, 1) point_prep_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr,
                                                                          const uint4* __restrict__ grp, const uint8_t* __restrict__ regular,
                                                                          LMParams lm, double* __restrict__ WZ, double* __restrict__ scalars) {
   extern __shared__ __align__(128) unsigned char pipe_raw[];
-  __shared__ uint64_t bars[kPipeWarps][2];
+  __shared__ uint64_t bars[WARPS][2];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int pt = lane >> 3, sub = lane & 7;
   unsigned char* base = pipe_raw + ((128u - (smem_addr(pipe_raw) & 127u)) & 127u);
-  double* stage0 = reinterpret_cast<double*>(base) + (size_t)(2 * w) * kStageChunks * kChunk;
-  double* stage1 = stage0 + (size_t)kStageChunks * kChunk;
+  double* stage0 = reinterpret_cast<double*>(base) + (size_t)(STAGES * w) * kStageChunks * kChunk;
+  double* stage1 = STAGES == 2 ? stage0 + (size_t)kStageChunks * kChunk : stage0;
   if (lane == 0) { mbar_init(&bars[w][0], 1); mbar_init(&bars[w][1], 1); }
   __syncwarp();
   const int nb = (A.ne + 3) / 4;
-  const int W = gridDim.x * kPipeWarps;
-  int b = blockIdx.x * kPipeWarps + w;
+  const int W = gridDim.x * WARPS;
+  int b = blockIdx.x * WARPS + w;
   double gmax = 0.0;
   int nfail = 0;
   if (b >= nb) return;
@@ -994,16 +997,16 @@ __global__ void __launch_bounds__(32 * kPipeWarps, 1) point_prep_kernel(EArgs A,
   uint4 G0, G1, G0n = make_uint4(0u, 0u, kNoSlot, 0u), G1n = G0n;
   load_groups(Icur, G0, G1);
   for (int it = 0; b < nb; b += W, it++) {
-    const int cur = it & 1;
+    const int cur = STAGES == 2 ? (it & 1) : 0;
     const bool more = b + W < nb;
     PipeLayout Lnext = Lcur;
-    if (more) {   // stage the next batch (its tables arrived during the previous iteration) and request the one after
-      Lnext = pipe_layout(Inext);
+    if (more) Lnext = pipe_layout(Inext);
+    if (STAGES == 2 && more) {   // stage the next batch (its tables arrived during the previous iteration) and request the one after
       fence_proxy_async_smem();
       __syncwarp();
       pipe_issue(Lnext, A.J, cur ? stage0 : stage1, cur ? &bars[w][0] : &bars[w][1], lane);
-      load_groups(Inext, G0n, G1n);
     }
+    if (more) load_groups(Inext, G0n, G1n);
     PipeInfo Iafter = pipe_load_info(A.ptr, grp_ptr, regular, min(b + 2 * W, nb), A.ne, lane);
     const int e = 4 * b + pt;
     const uint32_t reg_pt = __shfl_sync(0xffffffffu, Icur.reg, pt);   // (outside the && below: every lane must take part in the shuffle)
@@ -1025,7 +1028,7 @@ __global__ void __launch_bounds__(32 * kPipeWarps, 1) point_prep_kernel(EArgs A,
     // shared-memory addressing (LDS) without lane-divergent copies of the sweeps.
     const bool staged = __all_sync(0xffffffffu, M.staged || !act);
     const double* gbase = M.staged ? cbase : A.J;          // mixed warp (a point did not fit into the stage): generic addressing
-    mbar_wait_warp(cur ? &bars[w][1] : &bars[w][0], (uint32_t)((it >> 1) & 1));
+    mbar_wait_warp(cur ? &bars[w][1] : &bars[w][0], (uint32_t)(STAGES == 2 ? ((it >> 1) & 1) : (it & 1)));
     double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
     auto sweep_hg = [&](const double* cb, const uint4 G) {
       for (uint32_t k = 0; k < G.w; k++) {
@@ -1124,6 +1127,10 @@ __global__ void __launch_bounds__(32 * kPipeWarps, 1) point_prep_kernel(EArgs A,
     if (staged) all_groups([&](const uint4 G) { emit(cbase, G); });
     else all_groups([&](const uint4 G) { emit(gbase, G); });
     __syncwarp();
+    if (STAGES == 1 && more) {     // single stage: the next batch is requested once this one has been consumed
+      fence_proxy_async_smem();
+      pipe_issue(Lnext, A.J, stage0, &bars[w][0], lane);
+    }
     Icur = Inext; Inext = Iafter; Lcur = Lnext; G0 = G0n; G1 = G1n;
   }
   __syncwarp();
@@ -1401,23 +1408,24 @@ __global__ void __launch_bounds__(128) backsub_points_kernel(EArgs A, int n_e, c
 //   sum m (r + m/2),  m = a + Jl delta_e   =   sum a.(r + a/2)  +  delta_e.(g_l + t)  +  delta_e^T H_ll delta_e / 2
 // with t = sum Jl^T a, g_l = sum Jl^T r, H_ll = sum Jl^T Jl, so one sweep over the Jacobian chunks is enough (the generic
 // kernel above sweeps twice: once for t, once for m after delta_e is known).
-__global__ void __launch_bounds__(32 * kPipeWarps, 1) backsub_rows_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr, const uint4* __restrict__ grp,
+template <int WARPS, int STAGES>
+__global__ void __launch_bounds__(32 * WARPS, 1) backsub_rows_kernel(EArgs A, const uint32_t* __restrict__ grp_ptr, const uint4* __restrict__ grp,
                                                                            const uint8_t* __restrict__ regular,
                                                                            const double* __restrict__ dpose, const double* __restrict__ x,
                                                                            double* __restrict__ x_cand, double* __restrict__ delta_e,
                                                                            double* __restrict__ scalars) {
   extern __shared__ __align__(128) unsigned char pipe_raw[];
-  __shared__ uint64_t bars[kPipeWarps][2];
+  __shared__ uint64_t bars[WARPS][2];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int pt = lane >> 3, sub = lane & 7;
   unsigned char* base = pipe_raw + ((128u - (smem_addr(pipe_raw) & 127u)) & 127u);
-  double* stage0 = reinterpret_cast<double*>(base) + (size_t)(2 * w) * kStageChunks * kChunk;
-  double* stage1 = stage0 + (size_t)kStageChunks * kChunk;
+  double* stage0 = reinterpret_cast<double*>(base) + (size_t)(STAGES * w) * kStageChunks * kChunk;
+  double* stage1 = STAGES == 2 ? stage0 + (size_t)kStageChunks * kChunk : stage0;
   if (lane == 0) { mbar_init(&bars[w][0], 1); mbar_init(&bars[w][1], 1); }
   __syncwarp();
   const int nb = (A.ne + 3) / 4;
-  const int W = gridDim.x * kPipeWarps;
-  int b = blockIdx.x * kPipeWarps + w;
+  const int W = gridDim.x * WARPS;
+  int b = blockIdx.x * WARPS + w;
   if (b >= nb) return;
   double mc_acc = 0.0, s2_acc = 0.0;
   PipeInfo Icur = pipe_load_info(A.ptr, grp_ptr, regular, b, A.ne, lane);
@@ -1433,16 +1441,16 @@ __global__ void __launch_bounds__(32 * kPipeWarps, 1) backsub_rows_kernel(EArgs 
   uint4 G0, G1, G0n = make_uint4(0u, 0u, kNoSlot, 0u), G1n = G0n;
   load_groups(Icur, G0, G1);
   for (int it = 0; b < nb; b += W, it++) {
-    const int cur = it & 1;
+    const int cur = STAGES == 2 ? (it & 1) : 0;
     const bool more = b + W < nb;
     PipeLayout Lnext = Lcur;
-    if (more) {
-      Lnext = pipe_layout(Inext);
+    if (more) Lnext = pipe_layout(Inext);
+    if (STAGES == 2 && more) {
       fence_proxy_async_smem();
       __syncwarp();
       pipe_issue(Lnext, A.J, cur ? stage0 : stage1, cur ? &bars[w][0] : &bars[w][1], lane);
-      load_groups(Inext, G0n, G1n);
     }
+    if (more) load_groups(Inext, G0n, G1n);
     PipeInfo Iafter = pipe_load_info(A.ptr, grp_ptr, regular, min(b + 2 * W, nb), A.ne, lane);
     const int e = 4 * b + pt;
     const uint32_t reg_pt = __shfl_sync(0xffffffffu, Icur.reg, pt);   // (outside the && below: every lane must take part in the shuffle)
@@ -1464,7 +1472,7 @@ __global__ void __launch_bounds__(32 * kPipeWarps, 1) backsub_rows_kernel(EArgs 
     }
     const PipeMine M = pipe_mine(Lcur, pt);
     const double* cbase = (cur ? stage1 : stage0) + ((ptrdiff_t)M.off - (ptrdiff_t)M.p) * kChunk;
-    mbar_wait_warp(cur ? &bars[w][1] : &bars[w][0], (uint32_t)((it >> 1) & 1));
+    mbar_wait_warp(cur ? &bars[w][1] : &bars[w][0], (uint32_t)(STAGES == 2 ? ((it >> 1) & 1) : (it & 1)));
     double H[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0}, t[3] = {0, 0, 0}, sa = 0.0;
     auto sweep = [&](const double* cb, const uint4 G, const double* dp) {
       for (uint32_t k = 0; k < G.w; k++) {
@@ -1522,6 +1530,10 @@ __global__ void __launch_bounds__(32 * kPipeWarps, 1) backsub_rows_kernel(EArgs 
       mc_acc += sa + de[0] * (gl[0] + t[0] + 0.5 * hd0) + de[1] * (gl[1] + t[1] + 0.5 * hd1) + de[2] * (gl[2] + t[2] + 0.5 * hd2);
     }
     __syncwarp();
+    if (STAGES == 1 && more) {     // single stage: the next batch is requested once this one has been consumed
+      fence_proxy_async_smem();
+      pipe_issue(Lnext, A.J, stage0, &bars[w][0], lane);
+    }
     Icur = Inext; Inext = Iafter; Lcur = Lnext; G0 = G0n; G1 = G1n;
   }
   mc_acc = warp_sum(mc_acc); s2_acc = warp_sum(s2_acc);

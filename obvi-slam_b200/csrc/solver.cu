@@ -333,8 +333,11 @@ struct Solver {
     if (const char* e = getenv("OBVI_DEBUG_SKIP")) debug_skip = atoi(e);
     if (const char* e = getenv("OBVI_JAC")) jac_mode = std::string(e) == "plain" ? 0 : 1;
     CUDA_OK(cudaFuncSetAttribute(reproj_jac_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kJacSmemBytes));
-    CUDA_OK(cudaFuncSetAttribute(point_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem));
-    CUDA_OK(cudaFuncSetAttribute(backsub_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem));
+    CUDA_OK(cudaFuncSetAttribute(point_prep_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(8, 2)));
+    CUDA_OK(cudaFuncSetAttribute(backsub_rows_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(8, 2)));
+    CUDA_OK(cudaFuncSetAttribute(point_prep_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(16, 1)));
+    CUDA_OK(cudaFuncSetAttribute(backsub_rows_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(16, 1)));
+    if (const char* e = getenv("OBVI_PIPE")) pipe_warps = std::string(e) == "16" ? 16 : 8;
   }
 
   void upload_elist(EListDev& D, const Structure::EList& L, const std::vector<uint8_t>& cst, int NE, int maxs) {
@@ -543,7 +546,8 @@ struct Solver {
   // ---- kernel sequences -------------------------------------------------------------------------------
   static int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
   // persistent streaming point kernels: one CTA of kPipeWarps warps per SM, a warp per batch of 4 points
-  int pipe_grid(int npoints) const { return std::max(1, std::min(num_sms, nblk(nblk(npoints, 4), kPipeWarps))); }
+  int pipe_grid(int npoints) const { return std::max(1, std::min(num_sms, nblk(nblk(npoints, 4), pipe_warps))); }
+  int pipe_warps = 8;    // OBVI_PIPE=16: sixteen single-stage warps per SM instead of eight double-buffered ones
   EArgs eargs(EListDev& D, const double* Jp) {
     EArgs a;
     a.ptr = D.ptr.p; a.pos = D.pos.p; a.f = D.f.p; a.slot = D.slot.p; a.pair_ptr = D.pair_ptr.p; a.nslots = D.nslots.p;
@@ -638,7 +642,11 @@ struct Solver {
     }
     prof.end("pose_accum", pt0, stream); pt0 = prof.begin(stream);
     {
-      if (S.P && !(debug_skip & 1)) { point_prep_kernel<<<pipe_grid(S.P), 32 * kPipeWarps, kPipeSmem, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p); launches++; }
+      if (S.P && !(debug_skip & 1)) {
+        if (pipe_warps == 16) point_prep_kernel<16, 1><<<pipe_grid(S.P), 32 * 16, pipe_smem(16, 1), stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p);
+        else point_prep_kernel<8, 2><<<pipe_grid(S.P), 32 * 8, pipe_smem(8, 2), stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p);
+        launches++;
+      }
       prof.end("point_prep", pt0, stream); pt0 = prof.begin(stream);
       if (n_row_items && !(debug_skip & 2)) { schur_rows_kernel<<<nblk(n_row_items, kRowWarps), 32 * kRowWarps, 0, stream>>>(reinterpret_cast<const uint4*>(pr_items.p), n_row_items, pr_ent.p, WZ.p, pr_rowblk.p, kRowSpan, S_upper, b_schur); launches++; }
       if (n_row_fallback) {
@@ -731,7 +739,10 @@ struct Solver {
     if (S.nf) { pose_step_kernel<<<nblk((int64_t)S.nf * 6, 256), 256, 0, stream>>>(S.nf, pose_of_f.p, pscale.p, y.p, poses[cur].p, poses[cand].p, dpose.p, rank == 0, scalars.p); launches++; }
     fork();
     if (S.P) {
-      if (!(debug_skip & 4)) backsub_rows_kernel<<<pipe_grid(S.P), 32 * kPipeWarps, kPipeSmem, stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
+      if (!(debug_skip & 4)) {
+        if (pipe_warps == 16) backsub_rows_kernel<16, 1><<<pipe_grid(S.P), 32 * 16, pipe_smem(16, 1), stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
+        else backsub_rows_kernel<8, 2><<<pipe_grid(S.P), 32 * 8, pipe_smem(8, 2), stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
+      }
       launches++;
       if (n_row_fallback) {   // points outside the row-owner path: generic kernel on the fallback list
         EArgs a = eargs(pts, J.p); a.elist = pr_fallback.p;
