@@ -198,6 +198,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -885,9 +888,10 @@ __global__ void __launch_bounds__(T, MINB) obj_schur_kernel(EArgs A, const uint3
 //                        (point, keyframe) slot the record [U = (sum Jp^T Jl) F (6x3) | w = F^T g_l (3) | pad] written to `WZ`
 //                        (24 doubles = 192 bytes per slot).  With U the Schur update is SYMMETRIC, S_ab -= U_a U_b^T, and the
 //                        right-hand side b_a -= U_a w, so one 6x3 matrix per slot serves as both operands.
-//   schur_rows_kernel  - a warp per work item = (row a of the reduced matrix, 5 consecutive column offsets, <= 128 slots of
-//                        pose a): for every slot, A = U_a, B = U_b^T of the point's slots at a + d, one DMMA per block pair,
-//                        the 6x6 accumulators live in REGISTERS for the whole item and are flushed once.
+//   schur_rows_kernel  - a warp per work item = (rows 2m and 2m + 1 of the reduced matrix, 5 consecutive column offsets,
+//                        <= 128 points with a slot in either row): per point six slot records are loaded and feed up to ten
+//                        DMMAs (A = U_row, B = U_col^T, one per block pair); the 2 x 5 6x6 accumulators live in REGISTERS
+//                        for the whole item and are flushed once.
 // The Jacobian chunks are point-major, so a point's chunks are one contiguous range: point_prep and the back-substitution
 // stream them through shared memory with per-warp double-buffered TMA bulk copies (WarpChunkPipe below) -- every global-load
 // latency (list pointers, group records, chunks) is taken one batch ahead of its use.
@@ -1147,89 +1151,136 @@ __global__ void __launch_bounds__(32 * WARPS, 1) point_prep_kernel(EArgs A, cons
 }
 
 constexpr int kRowWarps = 4;
-__global__ void __launch_bounds__(32 * kRowWarps) schur_rows_kernel(const uint4* __restrict__ items, int n_items,
+constexpr int kRowRec = 8;                      // records per ring stage: 6 column records + 2 row records
+// A warp per work item.  Rows fa = 2 it.x and fb = fa + 1; accA[j] = sum U_fa U_(fa + dlo + j)^T, accB[j] = sum U_fb U_(fb + dlo + j)^T
+// over the item's points.  The operands are STAGED by the copy engine: per entry one 1-D bulk copy brings the point's (up
+// to) six consecutive slot records into a per-warp ring in shared memory (plus the two row records for ranges past the
+// first), and the lanes read their fragment element from the ring -- no global-load latency is left on the DMMA chain.
+// The ring has two halves of H entries, one mbarrier each; a half is refilled in ONE step by H lanes in parallel -- every
+// lane already holds the descriptor of "its" entry (entry k lives in lane k % 32), computes that entry's addresses and
+// issues its copies -- so the serial per-entry cost on the consuming side is a shuffle, eight LDS and the products.
+// The products of an entry are selected by ONE warp-uniform switch on the number of records (a C++ `if` or a predicate
+// around mma.sync costs four register moves and a WARPSYNC per product: 207 instructions per entry of at most ten
+// products, measured); a missing row multiplies by a zero A operand instead.
+#ifndef OBVI_ROW_MINB
+#define OBVI_ROW_MINB 6
+#endif
+template <int H>
+__global__ void __launch_bounds__(32 * kRowWarps, OBVI_ROW_MINB) schur_rows_kernel(const uint4* __restrict__ items, int n_items,
                                                                      const uint32_t* __restrict__ ent, const double* __restrict__ WZ,
                                                                      const uint32_t* __restrict__ rowblk, int row_span,
                                                                      double* __restrict__ S_upper, double* __restrict__ b_schur) {
-  const int item = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  static_assert(H == 2 || H == 4 || H == 8, "a half of the ring is refilled by H lanes of one 32-entry chunk");
+  extern __shared__ __align__(128) unsigned char rows_smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kRowWarps + w;
   if (item >= n_items) return;
-  const int lane = threadIdx.x & 31;
+  constexpr int kStage = kRowRec * kWZ;          // doubles per entry
+  double* ring = reinterpret_cast<double*>(rows_smem) + (size_t)w * 2 * H * kStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rows_smem + (size_t)kRowWarps * 2 * H * kStage * 8) + w * 2;
+  if (lane == 0) { mbar_init(&bars[0], H); mbar_init(&bars[1], H); }
+  // records of a stage that an entry does not copy keep what an earlier entry left there (finite, times a zero A operand);
+  // before the first entry that must not be a NaN pattern
+  for (int q = lane; q < 2 * H * kStage; q += 32) ring[q] = 0.0;
+  fence_proxy_async_smem();
+  __syncwarp();
   const uint4 it = items[item];
   const int frow = lane >> 2, fk = lane & 3;
   const bool fvalid = frow < 6 && fk < 3;
-  double2 acc[5];
+  double2 accA[5], accB[5];
 #pragma unroll
-  for (int j = 0; j < 5; j++) acc[j] = make_double2(0.0, 0.0);
+  for (int j = 0; j < 5; j++) { accA[j] = make_double2(0.0, 0.0); accB[j] = make_double2(0.0, 0.0); }
   const uint32_t* ep = ent + it.z;
+  const uint32_t cnt = it.w;
   const bool first_range = it.y == 0;
   // Fragment element of this lane inside a slot record: U[frow][fk] for the 6x3 block; fragment row 6 reads w[fk] (column 6
   // of the B operand of the DIAGONAL pair: C[.][6] = U_a w, the right-hand side contribution); everything else is clamped to
   // a finite element and multiplied by a zero of the A operand (k = 3 column) or lands in rows / columns 6-7 that are never
-  // flushed.  Slots are dense, so column j of the range is the record (dlo + j) slots after the row's own.
+  // flushed.  Slots are dense, so with g the slot of row fa, column j of row fa is record g + dlo + j and column j of row fb is
+  // record g + dlo + j + 1: six records serve both rows.
   const int offb = frow < 6 ? 3 * frow + (fk < 3 ? fk : 2) : (frow == 6 ? kWZw + (fk < 3 ? fk : 2) : 0);
-  const double* WZb = WZ + (size_t)it.y * kWZ + offb;
-  // (the A operand is kept RAW here and masked in consume (): a select next to the load would make the fetch of entry i + 1
-  //  wait for its own data and defeat the two-entry software pipeline)
-  struct Ops { double a, b[5]; uint32_t n; };
-  const bool avalid = fk < 3 && frow < 6;
-  auto load_ops = [&](uint32_t e, Ops& o) {
-    const uint32_t gs = e & 0x7ffffffu;
-    o.n = e >> 27;
-    const double* zb = WZb + (size_t)gs * kWZ;
-    o.b[0] = zb[0];
-    if (!first_range) o.a = WZ[(size_t)gs * kWZ + offb];   // first range: the diagonal pair, A and B come from the same record
-#pragma unroll
-    for (int j = 1; j < 5; j++)
-      if ((uint32_t)j < o.n) o.b[j] = zb[j * kWZ];
-  };
-  auto consume = [&](const Ops& o) {
-    const double araw = first_range ? o.b[0] : o.a;
-    const double a = avalid ? araw : 0.0;
-#pragma unroll
-    for (int j = 0; j < 5; j++)
-      if ((uint32_t)j < o.n) dmma_m8n8k4(acc[j].x, acc[j].y, a, o.b[j]);
-  };
-  // Software pipeline, kRowDepth entries deep (2: measured 541 / 638 / 699 us for depth 2 / 3 / 4 on C3 -- occupancy hides the
-  // load latency better than a deeper per-warp pipeline at 78 / 94 registers): the operands of entries i + 1 .. are in flight while the
-  // tensor-core products of entry i issue (register sets, loop unrolled by kRowDepth); entry descriptors are fetched 32 at a
-  // time (one per lane) and broadcast with a shuffle.
-#ifndef OBVI_ROW_DEPTH
-#define OBVI_ROW_DEPTH 2
-#endif
-  constexpr int kRowDepth = OBVI_ROW_DEPTH;
-  Ops o[kRowDepth];
-  uint32_t mine = 0u;
-  auto fetch = [&](uint32_t i, Ops& op) {   // i < it.w
-    if ((i & 31u) == 0u) { mine = 0u; if (i + lane < it.w) mine = ep[i + lane]; }
-    load_ops(__shfl_sync(0xffffffffu, mine, (int)(i & 31u)), op);
-  };
-#pragma unroll
-  for (int q = 0; q < kRowDepth - 1; q++)
-    if ((uint32_t)q < it.w) fetch(q, o[q]);
-  for (uint32_t i = 0; i < it.w; i += kRowDepth) {
-#pragma unroll
-    for (int q = 0; q < kRowDepth; q++) {
-      // slot q is consumed now; the slot consumed last ((q + kRowDepth - 1) % kRowDepth) is refilled with entry i + q + kRowDepth - 1
-      if (i + q + kRowDepth - 1 < it.w) fetch(i + q + kRowDepth - 1, o[(q + kRowDepth - 1) % kRowDepth]);
-      if (i + q < it.w) consume(o[q]);
+  // entry descriptors: entries c0 + lane (e_lo) and c0 + 32 + lane (e_hi)
+  uint32_t e_lo = lane < cnt ? ep[lane] : 0u, e_hi = 32u + lane < cnt ? ep[32 + lane] : 0u, c0 = 0u;
+  auto refill = [&](uint32_t i0, int half) {                 // entries i0 .. i0 + H - 1 (i0 a multiple of H) -> stages of `half`
+    const uint32_t q = ((uint32_t)lane - i0) & 31u;
+    if (q < (uint32_t)H) {
+      const uint32_t k = i0 + q;
+      if (k < cnt) {
+        const uint32_t e = (k - c0) < 32u ? e_lo : e_hi;
+        const size_t g1 = e & 0x3ffffffu;                   // g + 1 (g = -1 when the very first point starts on an odd row)
+        const uint32_t nl = (e >> 26) & 7u, va = (e >> 29) & 1u, vb = (e >> 30) & 1u;
+        const uint32_t j0 = 1u - va;
+        double* st = ring + (size_t)(half * H + q) * kStage;
+        const uint32_t bytes_b = (nl - j0) * (uint32_t)(kWZ * 8);
+        const uint32_t na = first_range ? 0u : va + vb;
+        mbar_expect_tx(&bars[half], bytes_b + na * (uint32_t)(kWZ * 8));
+        tma_load_1d(st + j0 * kWZ, WZ + (g1 - 1 + it.y + j0) * kWZ, bytes_b, &bars[half]);
+        if (na) tma_load_1d(st + (6 + j0) * kWZ, WZ + (g1 - 1 + j0) * kWZ, na * (uint32_t)(kWZ * 8), &bars[half]);
+      } else {
+        mbar_arrive(&bars[half]);
+      }
     }
+  };
+  refill(0u, 0);
+  if ((uint32_t)H < cnt) refill((uint32_t)H, 1);
+  int half = 0; uint32_t ph = 0u;
+  for (uint32_t i0 = 0; i0 < cnt; i0 += H) {
+    if (i0 - c0 == 32u) { c0 += 32u; e_lo = e_hi; e_hi = c0 + 32u + lane < cnt ? ep[c0 + 32u + lane] : 0u; }
+    mbar_wait_warp(&bars[half], ph);
+    const uint32_t qn = min((uint32_t)H, cnt - i0);
+#pragma unroll 1
+    for (uint32_t q = 0; q < qn; q++) {
+      const uint32_t k = i0 + q;
+      const uint32_t e = __shfl_sync(0xffffffffu, (k - c0) < 32u ? e_lo : e_hi, (int)(k & 31u));
+      const double* st = ring + (size_t)(half * H + q) * kStage + offb;
+      double b[6];
+#pragma unroll
+      for (int j = 0; j < 6; j++) b[j] = st[j * kWZ];
+      double aA = first_range ? b[0] : st[6 * kWZ], aB = first_range ? b[1] : st[7 * kWZ];
+      aA = (fvalid && (e & (1u << 29))) ? aA : 0.0;
+      aB = (fvalid && (e & (1u << 30))) ? aB : 0.0;
+      switch ((e >> 26) & 7u) {
+        case 6: dmma_m8n8k4(accB[4].x, accB[4].y, aB, b[5]);
+        case 5: dmma_m8n8k4(accA[4].x, accA[4].y, aA, b[4]); dmma_m8n8k4(accB[3].x, accB[3].y, aB, b[4]);
+        case 4: dmma_m8n8k4(accA[3].x, accA[3].y, aA, b[3]); dmma_m8n8k4(accB[2].x, accB[2].y, aB, b[3]);
+        case 3: dmma_m8n8k4(accA[2].x, accA[2].y, aA, b[2]); dmma_m8n8k4(accB[1].x, accB[1].y, aB, b[2]);
+        case 2: dmma_m8n8k4(accA[1].x, accA[1].y, aA, b[1]); dmma_m8n8k4(accB[0].x, accB[0].y, aB, b[1]);
+        default: dmma_m8n8k4(accA[0].x, accA[0].y, aA, b[0]);
+      }
+    }
+    // The half is free once the products above have ISSUED (their operands are in registers), which program order
+    // guarantees for the whole warp: the refill needs no barrier of its own.
+    __syncwarp();
+    if (i0 + 2 * H < cnt) refill(i0 + 2 * H, half);
+    half ^= 1; if (half == 0) ph ^= 1u;
   }
+  const uint32_t fa = 2u * it.x;
   if (fvalid) {
-    const uint32_t* rb = rowblk + (size_t)it.x * row_span + it.y;
+    const uint32_t* rb = rowblk + (size_t)fa * row_span + it.y;      // rowblk holds 2 ceil(nf / 2) rows: fb's row always exists
     const int coff = 6 * frow + 2 * fk;
 #pragma unroll
     for (int j = 0; j < 5; j++) {
       if ((int)it.y + j >= row_span) break;
-      const uint32_t blk = rb[j];
-      if (blk == 0xFFFFFFFFu) continue;
-      double* C = S_upper + (size_t)blk * 36 + coff;
-      if (acc[j].x != 0.0) atomicAdd(C, -acc[j].x);
-      if (acc[j].y != 0.0) atomicAdd(C + 1, -acc[j].y);
+      const uint32_t blkA = rb[j], blkB = rb[row_span + j];
+      if (blkA != 0xFFFFFFFFu) {
+        double* C = S_upper + (size_t)blkA * 36 + coff;
+        if (accA[j].x != 0.0) atomicAdd(C, -accA[j].x);
+        if (accA[j].y != 0.0) atomicAdd(C + 1, -accA[j].y);
+      }
+      if (blkB != 0xFFFFFFFFu) {
+        double* C = S_upper + (size_t)blkB * 36 + coff;
+        if (accB[j].x != 0.0) atomicAdd(C, -accB[j].x);
+        if (accB[j].y != 0.0) atomicAdd(C + 1, -accB[j].y);
+      }
     }
   }
-  // column 6 of the diagonal product: lanes with fk == 3 hold C[frow][6]
-  if (first_range && fk == 3 && frow < 6 && acc[0].x != 0.0) atomicAdd(&b_schur[6 * it.x + frow], -acc[0].x);
+  // column 6 of the diagonal products: lanes with fk == 3 hold C[frow][6]
+  if (first_range && fk == 3 && frow < 6) {
+    if (accA[0].x != 0.0) atomicAdd(&b_schur[6 * fa + frow], -accA[0].x);
+    if (accB[0].x != 0.0) atomicAdd(&b_schur[6 * (fa + 1) + frow], -accB[0].x);
+  }
 }
+constexpr size_t rows_smem_bytes(int H) { return (size_t)kRowWarps * (2 * H * kRowRec * kWZ * 8 + 16); }
 
 // Back-substitution for one e-block + its share of the model cost change and of the candidate point:
 //   delta_e = -Hinv (g_e + sum_obs Je^T (Jp delta_p)),  model += sum m (r + m/2), m = Jp delta_p + Je delta_e

@@ -100,18 +100,19 @@ struct Structure {
   // Row-owner point elimination (point_prep_kernel + schur_rows_kernel).  A point is "regular" when its variable poses
   // span fewer than kRowSpan consecutive f indices; every other point goes to the generic per-e-block kernel.
   //   groups : per point, one record per run of observations taken from the same pose (stereo pair = one group)
-  //   entries: per (reduced-matrix row a, column range [a + 5r, a + 5r + 5)): the (point, pose a) slots that contribute
-  //   items  : <= kRowItemEnts consecutive entries of one (row, range) list = the work of one warp
+  //   entries: per (PAIR of reduced-matrix rows (2m, 2m + 1), range of five column offsets): the points with a slot in
+  //            either row (layout at row_pair_entries in build_structure)
+  //   items  : <= kRowItemEnts consecutive entries of one (row pair, range) list = the work of one warp
   struct RowGroup { uint32_t pos0, pos1, gs, cnt; };   // chunks pos0 .. pos0 + cnt - 1 of the point-major Jacobian array; pos1 = f index of the pose (int32, -1 constant)
-  struct RowItem { uint32_t row, dlo, off, cnt; };
+  struct RowItem { uint32_t row, dlo, off, cnt; };     // row = pair index m
   struct PointRows {
     std::vector<uint32_t> grp_ptr;      // P + 1
     std::vector<RowGroup> grp;
     std::vector<int32_t> grp_f;         // f index of the group's pose (-1 constant)
     std::vector<uint8_t> regular;       // P
-    std::vector<uint32_t> ent;          // slot | columns in this range (1..5) << 27
+    std::vector<uint32_t> ent;          // (slot of row 2m) + 1 | records << 26 | row flags << 29
     std::vector<RowItem> items;
-    std::vector<uint32_t> rowblk;       // nf * kRowSpan: S_upper block of (a, a + d) or 0xFFFFFFFF
+    std::vector<uint32_t> rowblk;       // 2 ceil(nf / 2) * kRowSpan: S_upper block of (a, a + d) or 0xFFFFFFFF
     std::vector<uint32_t> fallback;
     int64_t n_slots = 0;
   } prow;
@@ -564,7 +565,29 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     Structure::PointRows& R = S.prow;
     R.regular.assign(S.P, 0); R.grp_ptr.assign(S.P + 1, 0);
     constexpr int kRanges = (kRowSpan + 4) / 5;
-    std::vector<uint32_t> cnt((size_t)nf * kRanges + 1, 0);
+    const int npair = (nf + 1) / 2;
+    std::vector<uint32_t> cnt((size_t)npair * kRanges + 1, 0);
+    // Entries of one point: for every PAIR of reduced-matrix rows (fa, fb) = (2m, 2m + 1) the point has a slot in, and every
+    // range r of five column offsets, one entry = (g + 1) | nl << 26 | va << 29 | vb << 30 with g the (dense) slot of row fa,
+    // nl <= 6 the number of the point's records from g + 5r on, va / vb whether the point has the row at all.  Row fa takes
+    // the products with records g + 5r + k, k < min(nl, 5), row fb those with k = 1 .. nl - 1: six operand records for up to
+    // ten 6x6 products.  Gap poses inside a track own no row.
+    auto row_pair_entries = [](const int32_t* sf, int ns, uint32_t d0, auto&& emit) {
+      if (ns == 0) return;
+      const int f0 = sf[0], f1 = sf[ns - 1];
+      uint32_t present = 0;
+      for (int a = 0; a < ns; a++) present |= 1u << (sf[a] - f0);
+      for (int m = f0 >> 1; 2 * m <= f1; m++) {
+        const int fa = 2 * m, fb = fa + 1;
+        const bool va = fa >= f0 && ((present >> (fa - f0)) & 1u), vb = fb <= f1 && ((present >> (fb - f0)) & 1u);
+        for (int r = 0; r < kRanges; r++) {
+          const int nA = va ? std::max(0, std::min(5, f1 - fa - 5 * r + 1)) : 0, nB = vb ? std::max(0, std::min(5, f1 - fb - 5 * r + 1)) : 0;
+          if (!nA && !nB) break;
+          const int nl = std::max(nA, nB ? nB + 1 : 0);      // records g + 5r + k, k < nl, are this point's
+          emit(m, r, (uint32_t)((int64_t)d0 + (fa - f0) + 1) | ((uint32_t)nl << 26) | ((uint32_t)(nA > 0) << 29) | ((uint32_t)(nB > 0) << 30));
+        }
+      }
+    };
     std::vector<uint32_t> dptr(S.P + 1, 0);
     std::vector<uint8_t> pt_has_prior(S.P, 0);
     for (const UnaryRec& u : S.unary) if (u.kind == 1) pt_has_prior[u.idx] = 1;
@@ -587,10 +610,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
         ngs++; d = d2;
       }
       ngs_of[e] = ngs;
-      for (int a = 0; a < ns; a++) {
-        const int ncol = sf[ns - 1] - sf[a] + 1;
-        for (int r = 0; 5 * r < ncol; r++) __atomic_fetch_add(&cnt[(size_t)sf[a] * kRanges + r + 1], 1u, __ATOMIC_RELAXED);
-      }
+      row_pair_entries(sf, ns, 0u, [&](int m, int r, uint32_t) { __atomic_fetch_add(&cnt[(size_t)m * kRanges + r + 1], 1u, __ATOMIC_RELAXED); });
     }
     for (int e = 0; e < S.P; e++) {
       R.grp_ptr[e + 1] = R.grp_ptr[e] + ngs_of[e]; dptr[e + 1] = dptr[e] + span_of[e];
@@ -615,24 +635,20 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
       }
     }
     R.n_slots = dptr[S.P];
-    if (R.n_slots >= (1ll << 27)) { err = "too many point slots for the row-owner elimination"; return false; }
+    if (R.n_slots >= (1ll << 26) - 1) { err = "too many point slots for the row-owner elimination"; return false; }
     for (size_t i = 0; i + 1 < cnt.size(); i++) cnt[i + 1] += cnt[i];
     R.ent.resize(cnt.back());
     std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
     for (int e = 0; e < S.P; e++) {
       if (!R.regular[e]) continue;
       const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]]; const int ns = S.pts.nslots[e];
-      for (int a = 0; a < ns; a++) {
-        const int ncol = sf[ns - 1] - sf[a] + 1;
-        const uint32_t gs = dptr[e] + (uint32_t)(sf[a] - sf[0]);
-        for (int r = 0; 5 * r < ncol; r++) R.ent[cur[(size_t)sf[a] * kRanges + r]++] = gs | ((uint32_t)std::min(5, ncol - 5 * r) << 27);
-      }
+      row_pair_entries(sf, ns, dptr[e], [&](int m, int r, uint32_t ent) { R.ent[cur[(size_t)m * kRanges + r]++] = ent; });
     }
-    for (int a = 0; a < nf; a++) for (int r = 0; r < kRanges; r++) {
-      const uint32_t b0 = cnt[(size_t)a * kRanges + r], b1 = cnt[(size_t)a * kRanges + r + 1];
-      for (uint32_t o = b0; o < b1; o += kRowItemEnts) R.items.push_back({(uint32_t)a, (uint32_t)(5 * r), o, std::min<uint32_t>(kRowItemEnts, b1 - o)});
+    for (int m = 0; m < npair; m++) for (int r = 0; r < kRanges; r++) {
+      const uint32_t b0 = cnt[(size_t)m * kRanges + r], b1 = cnt[(size_t)m * kRanges + r + 1];
+      for (uint32_t o = b0; o < b1; o += kRowItemEnts) R.items.push_back({(uint32_t)m, (uint32_t)(5 * r), o, std::min<uint32_t>(kRowItemEnts, b1 - o)});
     }
-    R.rowblk.assign((size_t)nf * kRowSpan, 0xFFFFFFFFu);
+    R.rowblk.assign((size_t)(2 * npair) * kRowSpan, 0xFFFFFFFFu);   // (an odd nf leaves one all-empty row behind the last pair)
     for (int a = 0; a < nf; a++) for (int d = 0; d < kRowSpan && a + d < nf; d++)
       if ((bits[(size_t)a * W + ((a + d) >> 6)] >> ((a + d) & 63)) & 1) R.rowblk[(size_t)a * kRowSpan + d] = blk_of(a, a + d);
   }

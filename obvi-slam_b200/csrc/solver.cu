@@ -338,6 +338,9 @@ struct Solver {
     CUDA_OK(cudaFuncSetAttribute(point_prep_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(16, 1)));
     CUDA_OK(cudaFuncSetAttribute(backsub_rows_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem(16, 1)));
     if (const char* e = getenv("OBVI_PIPE")) pipe_warps = std::string(e) == "16" ? 16 : 8;
+    if (const char* e = getenv("OBVI_ROW_STAGES")) row_stages = atoi(e);
+    CUDA_OK(cudaFuncSetAttribute(schur_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes(8)));
+    CUDA_OK(cudaFuncSetAttribute(schur_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, rows_smem_bytes(4)));
   }
 
   void upload_elist(EListDev& D, const Structure::EList& L, const std::vector<uint8_t>& cst, int NE, int maxs) {
@@ -547,6 +550,7 @@ struct Solver {
   static int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
   // persistent streaming point kernels: one CTA of kPipeWarps warps per SM, a warp per batch of 4 points
   int pipe_grid(int npoints) const { return std::max(1, std::min(num_sms, nblk(nblk(npoints, 4), pipe_warps))); }
+  int row_stages = 2;    // entries per half of the operand ring of schur_rows_kernel (OBVI_ROW_STAGES = 2 / 4 / 8)
   int pipe_warps = 8;    // OBVI_PIPE=16: sixteen single-stage warps per SM instead of eight double-buffered ones
   EArgs eargs(EListDev& D, const double* Jp) {
     EArgs a;
@@ -648,7 +652,15 @@ struct Solver {
         launches++;
       }
       prof.end("point_prep", pt0, stream); pt0 = prof.begin(stream);
-      if (n_row_items && !(debug_skip & 2)) { schur_rows_kernel<<<nblk(n_row_items, kRowWarps), 32 * kRowWarps, 0, stream>>>(reinterpret_cast<const uint4*>(pr_items.p), n_row_items, pr_ent.p, WZ.p, pr_rowblk.p, kRowSpan, S_upper, b_schur); launches++; }
+      if (n_row_items && !(debug_skip & 2)) {
+        const uint4* items = reinterpret_cast<const uint4*>(pr_items.p);
+        const int g = nblk(n_row_items, kRowWarps), t = 32 * kRowWarps;
+        // measured on C3 (in situ): 477 / 495 / 686 us for H = 2 / 4 / 8 -- resident warps count for more than ring depth
+        if (row_stages == 4) schur_rows_kernel<4><<<g, t, rows_smem_bytes(4), stream>>>(items, n_row_items, pr_ent.p, WZ.p, pr_rowblk.p, kRowSpan, S_upper, b_schur);
+        else if (row_stages == 8) schur_rows_kernel<8><<<g, t, rows_smem_bytes(8), stream>>>(items, n_row_items, pr_ent.p, WZ.p, pr_rowblk.p, kRowSpan, S_upper, b_schur);
+        else schur_rows_kernel<2><<<g, t, rows_smem_bytes(2), stream>>>(items, n_row_items, pr_ent.p, WZ.p, pr_rowblk.p, kRowSpan, S_upper, b_schur);
+        launches++;
+      }
       if (n_row_fallback) {
         EArgs a = eargs(pts, J.p); a.elist = pr_fallback.p;
         schur_eblock_kernel<3, 2, 32, 16, false><<<n_row_fallback, 32, 0, stream>>>(a, lm, su_ptr.p, S_upper, gp, hpp_diag, b_schur, scalars.p);
