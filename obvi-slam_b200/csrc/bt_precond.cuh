@@ -876,4 +876,260 @@ __global__ void __launch_bounds__(kPcgThreads, 1) pcg_bt_resident_kernel(int nf,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// The same resident PCG with FLAG-IN-DATA hand-offs.  Everything one CTA hands to another -- the forward contributions of
+// the elimination tree, the published z blocks, the search direction p read by the neighbours' S p products, the partial
+// sums of the grid-wide reductions -- travels as 16-byte words {lo32, tag, hi32, tag}: the consumer polls the DATA until
+// both tags carry the expected value.  A hand-off is then one store and one (polled) load through L2; the version above
+// pays atomics into an accumulator, a __threadfence, a release on a separate counter, an acquire spin on it and only then
+// the load of the data -- about 3 us a hop against 1.2 us, on a critical path of 2 log2(nsb) hops per preconditioner
+// application plus four reductions per iteration.  Tags increase monotonically (tag0 advances with every launch), so no
+// buffer is cleared between uses; each 8-byte half validates itself, so the scheme does not depend on a 16-byte store
+// being single-copy atomic.  The reductions add the per-CTA partials in a fixed order: the solve is run-to-run
+// deterministic for a given S.  r, p and y live in the registers of the owning threads.
+struct LLSync {
+  uint4* red;               // [4][nsb] rotating reduction slots
+  uint4* u;                 // [nsb][kLLSlots][96] forward contributions: slot 2 l + side (side 0: source on the left)
+  uint4* z;                 // [nsb][96] published z blocks
+  uint4* p;                 // [6 nf] search direction
+  unsigned int tag0;        // first tag of this launch minus one
+};
+constexpr int kLLSlots = 16;  // 2 * (levels <= 8)
+__device__ __forceinline__ void ll_store(uint4* a, double v, unsigned int tag) {
+  const unsigned int lo = (unsigned int)__double2loint(v), hi = (unsigned int)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 ll_peek(const uint4* a) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ll_load(const uint4* a, unsigned int tag) {
+  uint4 v;
+  do { v = ll_peek(a); } while (v.y != tag || v.w != tag);
+  return __hiloint2double((int)v.z, (int)v.x);
+}
+
+__global__ void __launch_bounds__(kPcgThreads, 1) pcg_bt_ll_kernel(int nf, const uint32_t* __restrict__ sf_ptr,
+                                                                    const uint32_t* __restrict__ sf_col,
+                                                                    const double* __restrict__ Sf, const double* __restrict__ rhs,
+                                                                    BtApply P, LLSync Y, double* __restrict__ y, int max_iter,
+                                                                    double tol, double* __restrict__ scalars) {
+  extern __shared__ __align__(16) double rsm[];
+  double* sD = rsm;                       // Dinv_i
+  double* sA = rsm + kB * kLdR;           // GaT_i
+  double* sC = rsm + 2 * kB * kLdR;       // GcT_i
+  double* part = rsm + 3 * kB * kLdR;     // [5][96] partial sums
+  double* sw = part + 5 * kB;             // w_i
+  double* sz = sw + kB;                   // z_i
+  double* sv1 = sz + kB;                  // z_a  (or q on its way to the owner threads)
+  double* sv2 = sv1 + kB;                 // z_c
+  __shared__ double red[kPcgThreads / 32], red2[kPcgThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  const int I = blockIdx.x, nsb = P.nsb, nCTA = gridDim.x;
+  const int n = 6 * nf;
+  const int row0 = I * kB;
+  const int my = row0 + tid;              // this thread's vector entry (tid < 96)
+  const bool own = tid < kB && my < n;
+
+  // ---- tree position of this block
+  int lev = 0;                            // elimination level (root: nlev)
+  if (I == 0) lev = P.nlev; else while (((I >> lev) & 1) == 0) lev++;
+  const int sstep = 1 << lev;
+  const int na = I == 0 ? -1 : I - sstep;
+  int nc = -1;
+  if (I != 0) { const int k = I >> lev, nl = (nsb + sstep - 1) >> lev; if (k + 1 < nl) nc = I + sstep; }
+  unsigned int umask = 0;                 // slots of u_I that receive a contribution before I is eliminated
+  for (int l = 0; l < lev; l++) {
+    const int s = 1 << l, k = I >> l, nl = (nsb + s - 1) >> l;
+    if (k >= 1) umask |= 1u << (2 * l);
+    if (k + 1 < nl) umask |= 1u << (2 * l + 1);
+  }
+
+  // ---- factors -> shared memory (once per solve)
+  for (int t = tid; t < kBB; t += kPcgThreads) {
+    const int rr_ = t / kB, cc = t - rr_ * kB;
+    sD[rr_ * kLdR + cc] = P.Dinv[(size_t)I * kBB + t];
+    sA[rr_ * kLdR + cc] = P.GaT[(size_t)I * kBB + t];
+    sC[rr_ * kLdR + cc] = P.GcT[(size_t)I * kBB + t];
+  }
+
+  unsigned int seq = 0;                   // grid-wide reduction sequence number (same in every CTA)
+  // sum `v` over the grid; everybody gets the total (partials added in CTA order)
+  auto grid_sum = [&](double v) -> double {
+    v = warp_sum(v);
+    if (lane == 0) red[wib] = v;
+    __syncthreads();
+    const unsigned int tag = Y.tag0 + seq + 1u;
+    uint4* slot = Y.red + (size_t)(seq & 3u) * nsb;
+    if (tid == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < kPcgThreads / 32; i++) s += red[i];
+      ll_store(slot + I, s, tag);
+    }
+    double t = tid < nCTA ? ll_load(slot + tid, tag) : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) red2[wib] = t;
+    __syncthreads();
+    double tot = 0.0;
+    for (int i = 0; i < (nCTA + 31) / 32; i++) tot += red2[i];
+    seq++;
+    return tot;
+  };
+
+  unsigned int epoch = 0;
+  // z_I = (T^-1 r)_I for every block, dataflow over the elimination tree; `rv` is the owner thread's residual entry.
+  // Returns this thread's share of r . z.
+  auto apply = [&](double rv) -> double {
+    epoch++;
+    const unsigned int tag = Y.tag0 + epoch;
+    // forward: gather the neighbours' pushes, w_I = r_I - u_I
+    if (umask) {
+      if (tid < 5 * kB) {
+        const int row = tid % kB, grp = tid / kB;
+        const uint4* base = Y.u + ((size_t)I * kLLSlots) * kB + row;
+        uint4 raw[4]; bool need[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int sl = grp + 5 * q;
+          need[q] = sl < kLLSlots && ((umask >> sl) & 1u);
+          if (need[q]) raw[q] = ll_peek(base + (size_t)sl * kB);
+        }
+        double a = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (!need[q]) continue;
+          while (raw[q].y != tag || raw[q].w != tag) raw[q] = ll_peek(base + (size_t)(grp + 5 * q) * kB);
+          a += __hiloint2double((int)raw[q].z, (int)raw[q].x);
+        }
+        part[grp * kB + row] = a;
+      }
+      __syncthreads();
+    }
+    if (tid < kB) {
+      double uv = 0.0;
+      if (umask) uv = part[tid] + part[kB + tid] + part[2 * kB + tid] + part[3 * kB + tid] + part[4 * kB + tid];
+      sw[tid] = (my < n ? rv : 0.0) - uv;
+    }
+    __syncthreads();
+    if (I != 0) {
+      // push GaT_I w_I to the left survivor, GcT_I w_I to the right one: thread (row, quarter) sums 24 columns, the four
+      // quarters of a row sit in adjacent lanes
+      if (tid < 4 * kB) {
+        const int row = tid >> 2, pt = tid & 3;
+        const int c0 = pt * 24;
+        double a = 0.0, c = 0.0;
+#pragma unroll 8
+        for (int cc = c0; cc < c0 + 24; cc++) { const double wv = sw[cc]; a += sA[row * kLdR + cc] * wv; c += sC[row * kLdR + cc] * wv; }
+        a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+        c += __shfl_xor_sync(0xffffffffu, c, 1); c += __shfl_xor_sync(0xffffffffu, c, 2);
+        // I is the RIGHT neighbour of na (side 1) and the LEFT neighbour of nc (side 0)
+        if (pt == 0 && na >= 0) ll_store(Y.u + ((size_t)na * kLLSlots + 2 * lev + 1) * kB + row, a, tag);
+        if (pt == 1 && nc >= 0) ll_store(Y.u + ((size_t)nc * kLLSlots + 2 * lev) * kB + row, c, tag);
+      }
+      // backward: z of the two survivors
+      if (tid < kB) sv1[tid] = na >= 0 ? ll_load(Y.z + (size_t)na * kB + tid, tag) : 0.0;
+      else if (tid < 2 * kB) sv2[tid - kB] = nc >= 0 ? ll_load(Y.z + (size_t)nc * kB + (tid - kB), tag) : 0.0;
+      __syncthreads();
+    }
+    // z_I[c] = sum_r Dinv[r][c] w[r] - GaT[r][c] za[r] - GcT[r][c] zc[r]   (thread (c, part) sums 20 rows)
+    if (tid < 5 * kB) {
+      const int col = tid % kB, pt = tid / kB;
+      const int r0 = pt * 20, r1 = min(r0 + 20, kB);
+      double a = 0.0;
+      if (I != 0) {
+        for (int rr_ = r0; rr_ < r1; rr_++) a += sD[rr_ * kLdR + col] * sw[rr_] - sA[rr_ * kLdR + col] * sv1[rr_] - sC[rr_ * kLdR + col] * sv2[rr_];
+      } else {
+        for (int rr_ = r0; rr_ < r1; rr_++) a += sD[rr_ * kLdR + col] * sw[rr_];
+      }
+      part[pt * kB + col] = a;
+    }
+    __syncthreads();
+    double rz = 0.0;
+    if (tid < kB) {
+      const double zv = part[tid] + part[kB + tid] + part[2 * kB + tid] + part[3 * kB + tid] + part[4 * kB + tid];
+      sz[tid] = zv;
+      ll_store(Y.z + (size_t)row0 + tid, zv, tag);
+      if (my < n) rz = rv * zv;
+    }
+    return rz;
+  };
+
+  // ---- initial residual
+  double rown = 0.0, pown = 0.0, yown = 0.0;
+  if (tid < kB && my < n) rown = rhs[my];
+  __syncthreads();
+  const double bb = grid_sum(rown * rown);
+  int it = 0, brk = 0;
+  double rr = bb;
+  if (((volatile double*)scalars)[SC_BT_FAIL] != 0.0) brk = 2;  // factorisation failed: the host falls back to block-Jacobi
+  if (bb > 0.0 && brk == 0) {
+    double rho = grid_sum(apply(rown));
+    if (own) { pown = sz[tid]; ll_store(Y.p + my, pown, Y.tag0 + 1u); }
+    while (it < max_iter) {
+      const unsigned int ptag = Y.tag0 + (unsigned int)it + 1u;
+      // q_I = (S p)_I: one warp per pose row of this super-block
+      double qv = 0.0;                    // lanes 0..5 of warp w hold q for pose 16 I + w
+      {
+        const int i = I * kSbPoses + wib;
+        if (i < nf) {
+          const uint32_t p0 = sf_ptr[i], nb = sf_ptr[i + 1] - p0;
+          const uint32_t len = nb * 6;
+          const double* row = Sf + (size_t)p0 * 36;
+          double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+          for (uint32_t e0 = lane; e0 < len; e0 += 128) {
+            uint32_t ee[4]; double xv[4], sv[4][6]; uint4 raw[4]; const uint4* xa[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              ee[u] = e0 + 32 * u;
+              const bool in = ee[u] < len;
+              const uint32_t e = in ? ee[u] : 0u;
+              const uint32_t k = e / 6, c = e - 6 * k;
+              xa[u] = Y.p + (6 * (size_t)sf_col[p0 + k] + c);
+              raw[u] = ll_peek(xa[u]);
+#pragma unroll
+              for (int a = 0; a < 6; a++) sv[u][a] = in ? row[a * len + e] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              while (raw[u].y != ptag || raw[u].w != ptag) raw[u] = ll_peek(xa[u]);
+              xv[u] = ee[u] < len ? __hiloint2double((int)raw[u].z, (int)raw[u].x) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              a0 += sv[u][0] * xv[u]; a1 += sv[u][1] * xv[u]; a2 += sv[u][2] * xv[u];
+              a3 += sv[u][3] * xv[u]; a4 += sv[u][4] * xv[u]; a5 += sv[u][5] * xv[u];
+            }
+          }
+          a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4); a5 = warp_sum(a5);
+          if (lane < 6) qv = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : lane == 3 ? a3 : lane == 4 ? a4 : a5;
+        }
+      }
+      // q travels through shared memory to the owner threads (tid < 96)
+      if (lane < 6) sv1[6 * wib + lane] = qv;
+      __syncthreads();
+      const double qown = own ? sv1[tid] : 0.0;
+      const double pqs = grid_sum(qown * pown);
+      if (!(pqs > 0.0)) { brk = 1; break; }
+      const double alpha = rho / pqs;
+      if (own) { yown += alpha * pown; rown -= alpha * qown; }
+      rr = grid_sum(own ? rown * rown : 0.0);
+      it++;
+      if (rr <= tol * tol * bb) break;
+      const double rho_new = grid_sum(apply(rown));
+      const double beta = rho_new / rho;
+      rho = rho_new;
+      if (own) { pown = sz[tid] + beta * pown; ll_store(Y.p + my, pown, Y.tag0 + (unsigned int)it + 1u); }
+    }
+  }
+  if (own) y[my] = yown;
+  if (I == 0 && tid == 0) {
+    scalars[SC_PCG_IT] = (double)it;
+    scalars[SC_PCG_RES] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+    scalars[SC_PCG_BB] = bb;
+    scalars[SC_PCG_BREAK] = (double)brk;
+  }
+}
+
 }  // namespace obvi

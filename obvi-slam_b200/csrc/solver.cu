@@ -267,6 +267,9 @@ struct Solver {
   bool pcg_resident = true;  // OBVI_PCG=grid: the grid-barrier PCG kernel instead of the shared-memory-resident dataflow one
   bool resident_ok = false;
   DBuf<double> rs_dbl;        // [16 reduction slots | nsb * 96 forward accumulators]
+  DBuf<uint4> ll_buf;         // flag-in-data hand-off words of pcg_bt_ll_kernel: [4 nsb reductions | nsb x 16 x 96 pushes | nsb x 96 z | nsb x 96 p]
+  unsigned int ll_tag = 0;    // last tag handed out (tags only grow, the buffer is cleared when they would wrap)
+  bool pcg_ll = true;         // OBVI_PCG=flags: the resident kernel with counter / flag hand-offs
   DBuf<unsigned int> rs_u32;  // [4 reduction counters | nsb arrival counters | nsb z epochs]
   bool defer_sync = true;        // OBVI_DEFER_SYNC=0: two host synchronisations per accepted LM iteration instead of one
   bool obj_split = true;      // OBVI_OBJ_SPLIT=0: one-kernel object elimination (254 registers; kept for A/B runs and tests)
@@ -326,7 +329,8 @@ struct Solver {
     if (const char* e = getenv("OBVI_REFACTOR_RATIO")) kRefactorRatio = std::max(1.0, atof(e));
     if (const char* e = getenv("OBVI_DEFER_SYNC")) defer_sync = std::string(e) != "0";
     if (const char* e = getenv("OBVI_OBJ_SPLIT")) obj_split = std::string(e) != "0";
-    if (const char* e = getenv("OBVI_PCG")) pcg_resident = std::string(e) != "grid";
+    if (const char* e = getenv("OBVI_PCG")) { pcg_resident = std::string(e) != "grid"; pcg_ll = std::string(e) != "flags"; }
+    CUDA_OK(cudaFuncSetAttribute(pcg_bt_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentSmem));
     CUDA_OK(cudaFuncSetAttribute(pcg_bt_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentSmem));
     if (const char* e = getenv("OBVI_PROFILE")) prof.on = std::string(e) == "1";
     if (const char* e = getenv("OBVI_DEBUG_BT_FAIL_RANK")) debug_bt_fail_rank = atoi(e);
@@ -433,6 +437,9 @@ struct Solver {
       CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_bt_resident_kernel, kPcgThreads, kResidentSmem));
       resident_ok = pcg_resident && per_sm >= 1 && nsb <= num_sms * per_sm;
       rs_dbl.alloc(16 + (size_t)nsb * kB); rs_u32.alloc(4 + 2 * (size_t)nsb);
+      static_assert(kLLSlots >= 2 * 8, "levels of the elimination tree");
+      if (nlev > kLLSlots / 2) resident_ok = false;
+      ll_buf.alloc(4 * (size_t)nsb + (size_t)nsb * kLLSlots * kB + 2 * (size_t)nsb * kB); ll_buf.zero(stream); ll_tag = 0;
     }
     bt_D.alloc((size_t)nsb * kBB); bt_Dinv.alloc((size_t)nsb * kBB); bt_GaT.alloc((size_t)nsb * kBB); bt_GcT.alloc((size_t)nsb * kBB);
     bt_w.alloc((size_t)nsb * kB); bt_z.alloc((size_t)nsb * kB);
@@ -699,6 +706,22 @@ struct Solver {
     if (!S.nf) return;
     int nf = S.nf, max_iter = o.pcg_max_iterations;
     double tol = o.pcg_relative_tolerance;
+    if (use_bt && !force_jacobi && resident_ok && pcg_ll) {
+      BtApply P; P.nsb = nsb; P.nlev = nlev; P.Dinv = bt_Dinv.p; P.GaT = bt_GaT.p; P.GcT = bt_GcT.p; P.w = bt_w.p; P.z = bt_z.p;
+      // tags of one launch: reductions use tag0 + 1 .. tag0 + 3 max_iter + 3, applications and p fewer
+      const unsigned int span = 4u * (unsigned int)std::max(max_iter, 1) + 16u;
+      if (ll_tag > 0xFFFFFFFFu - 2u * span) { ll_buf.zero(stream); ll_tag = 0; }
+      LLSync Y; Y.red = ll_buf.p; Y.u = Y.red + 4 * (size_t)nsb; Y.z = Y.u + (size_t)nsb * kLLSlots * kB; Y.p = Y.z + (size_t)nsb * kB; Y.tag0 = ll_tag;
+      ll_tag += span;
+      const uint32_t *a1 = sf_ptr.p, *a2 = sf_col.p;
+      const double *a3 = Sf.p, *a4 = rhs.p;
+      double *a6 = y.p, *a14 = scalars.p;
+      void* args[] = {&nf, &a1, &a2, &a3, &a4, &P, &Y, &a6, &max_iter, &tol, &a14};
+      CUDA_OK(cudaLaunchCooperativeKernel((void*)pcg_bt_ll_kernel, dim3(nsb), dim3(kPcgThreads), args, kResidentSmem, stream));
+      launches++;
+      share_solution();
+      return;
+    }
     if (use_bt && !force_jacobi && resident_ok) {
       BtApply P; P.nsb = nsb; P.nlev = nlev; P.Dinv = bt_Dinv.p; P.GaT = bt_GaT.p; P.GcT = bt_GcT.p; P.w = bt_w.p; P.z = bt_z.p;
       ResidentSync Y; Y.red_val = rs_dbl.p; Y.u = rs_dbl.p + 16; Y.red_cnt = rs_u32.p; Y.cnt_w = rs_u32.p + 4; Y.ready_z = rs_u32.p + 4 + nsb;
