@@ -109,6 +109,9 @@ int obvi_factor_add_param_prior(obvi_problem* p, double* block, int param_idx, d
                                 double huber, obvi_factor_id* id);
 /* Problem::RemoveResidualBlock (object_pose_graph_optimizer.h:1105-1155). */
 int obvi_factor_remove(obvi_problem* p, obvi_factor_id id);
+/* The same for n blocks in one call (the excluded-factor list between the two phases of a window holds ~10 % of its
+ * residual blocks, offline_problem_runner.h:752-833); stops at the first unknown id, earlier ones stay removed. */
+int obvi_factor_remove_batch(obvi_problem* p, const obvi_factor_id* ids, int64_t n);
 int64_t obvi_num_factors(const obvi_problem* p);
 /* How often the flat device layout was rebuilt from the host container.  Removing reprojection / bounding-box blocks of
  * an already solved problem (the outlier exclusion between the two phases, offline_problem_runner.h:752-833) is done in

@@ -116,6 +116,7 @@ def lib():
         "obvi_factor_add_rel_pose": ([vp, vp, vp, _d, _d, _d, dbl, u64p], C.c_int),
         "obvi_factor_add_param_prior": ([vp, vp, C.c_int, dbl, dbl, dbl, u64p], C.c_int),
         "obvi_factor_remove": ([vp, C.c_uint64], C.c_int),
+        "obvi_factor_remove_batch": ([vp, u64p, i64], C.c_int),
         "obvi_num_factors": ([vp], i64),
         "obvi_num_structure_builds": ([vp], i64),
         "obvi_residual_blocks": ([vp, u64p, i32p, i32p, i64, C.POINTER(i64)], C.c_int),
@@ -147,7 +148,7 @@ EXPORTED_SYMBOLS = [
     "obvi_param_add_array", "obvi_param_remove", "obvi_param_set_constant", "obvi_param_is_constant", "obvi_camera_add",
     "obvi_factor_add_reproj", "obvi_factor_add_reproj_batch", "obvi_factor_add_bbox", "obvi_factor_add_bbox_batch",
     "obvi_factor_add_shape_prior", "obvi_factor_add_ltm_prior", "obvi_factor_add_rel_pose", "obvi_factor_add_param_prior",
-    "obvi_factor_remove", "obvi_num_factors", "obvi_num_structure_builds", "obvi_residual_blocks", "obvi_solver_options_init", "obvi_solve",
+    "obvi_factor_remove", "obvi_factor_remove_batch", "obvi_num_factors", "obvi_num_structure_builds", "obvi_residual_blocks", "obvi_solver_options_init", "obvi_solve",
     "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_evaluate_jacobian", "obvi_object_covariances", "obvi_profile_jacobian", "obvi_debug_partition", "obvi_debug_structure_hash", "obvi_comm_unique_id",
     "obvi_comm_init", "obvi_comm_init_local", "obvi_comm_attach",
 ]
@@ -284,6 +285,10 @@ class Problem:
 
     def remove_residual_block(self, fid):
         self._ck(self._lib.obvi_factor_remove(self._h, C.c_uint64(int(fid))))
+
+    def remove_residual_blocks(self, fids):
+        ids = np.ascontiguousarray(fids, dtype=np.uint64)
+        self._ck(self._lib.obvi_factor_remove_batch(self._h, ids.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int64(len(ids))))
 
     def num_residual_blocks(self):
         return int(self._lib.obvi_num_factors(self._h))

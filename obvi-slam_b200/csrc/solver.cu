@@ -1414,6 +1414,14 @@ int obvi_factor_remove(obvi_problem* p, obvi_factor_id id) {
   if (!((t == OBVI_FACTOR_REPROJECTION || t == OBVI_FACTOR_BBOX) && p->s.mask_factor(t, i))) pb.dirty = true;
   return OBVI_OK;
 }
+int obvi_factor_remove_batch(obvi_problem* p, const obvi_factor_id* ids, int64_t n) {
+  if (!p || (n > 0 && !ids) || n < 0) return OBVI_ERR_INVALID_ARGUMENT;
+  for (int64_t k = 0; k < n; k++) {
+    const int rc = obvi_factor_remove(p, ids[k]);
+    if (rc != OBVI_OK) return rc;             // blocks before k stay removed, like a loop of single calls
+  }
+  return OBVI_OK;
+}
 int64_t obvi_num_factors(const obvi_problem* p) { return p ? p->s.pb.n_live : 0; }
 int64_t obvi_num_structure_builds(const obvi_problem* p) { return p ? p->s.structure_builds : 0; }
 

@@ -227,8 +227,7 @@ class GpuBackend:
             out += list(p.topk_outliers(self.ob.FACTOR_REPROJECTION, frac))
         if len(sub.bbox["obj"]):
             out += list(p.topk_outliers(self.ob.FACTOR_BBOX, frac))
-        for fid in out:
-            p.remove_residual_block(fid)
+        p.remove_residual_blocks(out)
         sub.poses[:], sub.points[:], sub.objects[:] = x0        # setValuesFromAnotherPoseGraph
         s2 = self._acc(p.solve(**opts2))
         self.stats["structure_builds"] += p.num_structure_builds(); self.stats["excluded"] += len(out)
@@ -423,8 +422,7 @@ class ShardedGpuBackend(GpuBackend):
         buf = torch.from_numpy(idx).cuda() if self.rank == 0 else torch.zeros(int(n.item()), dtype=torch.int64, device="cuda")
         if int(n.item()):
             self.dist.broadcast(buf, 0)
-        for fid in buf.cpu().numpy().astype(np.uint64):
-            p.remove_residual_block(int(fid))
+        p.remove_residual_blocks(buf.cpu().numpy().astype(np.uint64))
         sub.poses[:], sub.points[:], sub.objects[:] = x0
         s2 = self._acc(p.solve(**opts2))
         self.stats["structure_builds"] += p.num_structure_builds(); self.stats["excluded"] += int(n.item())

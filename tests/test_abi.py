@@ -18,7 +18,7 @@ def declared_symbols():
 def test_library_exports_every_declared_symbol(ob):
     lib = ob.lib()
     names = declared_symbols()
-    assert len(names) >= 28
+    assert len(names) >= 29
     for n in names:
         assert hasattr(lib, n), f"libobvi_ba.so does not export {n}"
     assert set(ob.EXPORTED_SYMBOLS) <= set(names)
@@ -65,6 +65,15 @@ def test_problem_bookkeeping_host_only(ob):
     with pytest.raises(ob.ObviError):
         p.remove_residual_block(ids[2])
     assert p.num_residual_blocks() == 9 and ids[2] not in p.residual_blocks()[0]
+    # the batch call removes like a loop of single calls and stops at the first unknown id
+    extra = [p.add_reprojection(poses[0], pts[1], cam, (1.0 + k, 2.0), 1.5, 1.0) for k in range(3)]
+    assert p.num_residual_blocks() == 12
+    p.remove_residual_blocks(extra[:2])
+    assert p.num_residual_blocks() == 10
+    with pytest.raises(ob.ObviError):
+        p.remove_residual_blocks([extra[2], extra[0]])
+    assert p.num_residual_blocks() == 9 and extra[2] not in p.residual_blocks()[0]
+    p.remove_residual_blocks([])
     assert not p.is_parameter_block_constant(poses[0])
     p.set_parameter_block_constant(poses[0])
     assert p.is_parameter_block_constant(poses[0])
