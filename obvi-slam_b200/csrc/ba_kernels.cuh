@@ -407,28 +407,38 @@ __global__ void __launch_bounds__(kJacThreads, OBVI_JAC_MINB) reproj_jac_fused_k
   }
 }
 
-// Residual-only evaluation at the candidate point (cost only; nothing is stored).
+// Residual-only evaluation at the candidate point (cost only; nothing is stored).  kCostPer consecutive tiles of 256 records
+// per CTA: the record loads of all of them are issued before the first gather, and the two block reductions + atomics are
+// paid once per kCostPer * 256 observations.
+constexpr int kCostPer = 4;
 __global__ void __launch_bounds__(kJacThreads) reproj_cost_kernel(const ObsRec* __restrict__ obs, int64_t n,
                                                                    const PoseCam* __restrict__ pcam, int C,
                                                                    const CalibClass* __restrict__ cls,
                                                                    const double* __restrict__ points,
                                                                    double* __restrict__ scalars) {
   __shared__ double red[33];
-  const int64_t i = (int64_t)blockIdx.x * kJacThreads + threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.x * (kJacThreads * kCostPer) + threadIdx.x;
   double cost = 0.0, fixed = 0.0;
-  if (i < n) {
-    const double2 uv = reinterpret_cast<const double2*>(obs)[2 * i];
-    const uint4 id = reinterpret_cast<const uint4*>(obs)[2 * i + 1];
-    const CalibClass cc = cls[id.w >> 16];
-    const PoseCam& pc = pcam[(size_t)id.x * C + cc.cam];
-    const double X[3] = {points[3 * (size_t)id.y], points[3 * (size_t)id.y + 1], points[3 * (size_t)id.y + 2]};
+  double2 uv[kCostPer]; uint4 id[kCostPer];
+#pragma unroll
+  for (int k = 0; k < kCostPer; k++) {
+    const int64_t i = i0 + (int64_t)k * kJacThreads;
+    if (i < n) { uv[k] = reinterpret_cast<const double2*>(obs)[2 * i]; id[k] = reinterpret_cast<const uint4*>(obs)[2 * i + 1]; }
+  }
+#pragma unroll
+  for (int k = 0; k < kCostPer; k++) {
+    const int64_t i = i0 + (int64_t)k * kJacThreads;
+    if (i >= n) continue;
+    const CalibClass cc = cls[id[k].w >> 16];
+    const PoseCam& pc = pcam[(size_t)id[k].x * C + cc.cam];
+    const double X[3] = {points[3 * (size_t)id[k].y], points[3 * (size_t)id[k].y + 1], points[3 * (size_t)id[k].y + 2]};
     double r[2];
-    reproj_residual(pc, X, uv.x, uv.y, cc.mx, cc.my, r);
+    reproj_residual(pc, X, uv[k].x, uv[k].y, cc.mx, cc.my, r);
     const double s = r[0] * r[0] + r[1] * r[1];
     double sc, c = 0.5 * s;
     if (cc.huber > 0.0) c = huber(cc.huber, s, &sc);
-    if (id.w & kObsMasked) c = 0.0;
-    if ((id.w & 3u) == 3u) fixed = c; else cost = c;
+    if (id[k].w & kObsMasked) c = 0.0;
+    if ((id[k].w & 3u) == 3u) fixed += c; else cost += c;
   }
   cost = block_sum_all<kJacThreads>(cost, red);
   fixed = block_sum_all<kJacThreads>(fixed, red);
@@ -913,10 +923,12 @@ static_assert(pipe_smem(8, 2) <= 227 * 1024 && pipe_smem(16, 1) <= 227 * 1024, "
 struct PipeInfo { uint32_t cptr, gptr, reg; };
 __device__ __forceinline__ PipeInfo pipe_load_info(const uint32_t* __restrict__ ptr, const uint32_t* __restrict__ grp_ptr,
                                                    const uint8_t* __restrict__ regular, int b, int ne, int lane) {
-  PipeInfo r{0u, 0u, 0u};
-  const int e = 4 * b + lane;
-  if (lane < 5) { const int ec = min(e, ne); r.cptr = ptr[ec]; r.gptr = grp_ptr[ec]; }
-  if (lane < 4 && e < ne) r.reg = regular[e];
+  // Every lane loads (clamped indices, the values of lanes >= 5 are never used): a predicated load into registers that were
+  // first set to a default makes the compiler re-initialise them AFTER the load on some paths, and that write waits for the
+  // load -- the prefetch then costs a full global-memory latency per batch (measured: 16 % of point_prep's stall samples).
+  PipeInfo r;
+  const int ec = min(4 * b + lane, ne);
+  r.cptr = ptr[ec]; r.gptr = grp_ptr[ec]; r.reg = regular[min(ec, ne - 1)];
   return r;
 }
 // Stage layout of a batch: the chunk ranges of its regular points back to back, in point order; a point whose range does
@@ -992,14 +1004,17 @@ __global__ void __launch_bounds__(32 * WARPS, 1) point_prep_kernel(EArgs A, cons
   pipe_issue(Lcur, A.J, stage0, &bars[w][0], lane);
   PipeInfo Inext = pipe_load_info(A.ptr, grp_ptr, regular, min(b + W, nb), A.ne, lane);
   // group records of this lane for the current batch (groups sub and sub + 8 of its point), fetched one batch ahead
+  // (unconditional loads at clamped indices, see pipe_load_info; records past the point's range are dropped where used)
+  const uint32_t ngrp = grp_ptr[A.ne];
+  if (ngrp == 0u) return;                 // no regular point
   auto load_groups = [&](const PipeInfo& I, uint4& G0, uint4& G1) {
-    const uint32_t g0 = __shfl_sync(0xffffffffu, I.gptr, pt), g1 = __shfl_sync(0xffffffffu, I.gptr, pt + 1);
-    G0 = make_uint4(0u, 0u, kNoSlot, 0u); G1 = G0;
-    if (g0 + sub < g1) G0 = grp[g0 + sub];
-    if (g0 + sub + 8 < g1) G1 = grp[g0 + sub + 8];
+    const uint32_t g0 = __shfl_sync(0xffffffffu, I.gptr, pt);
+    G0 = grp[min(g0 + sub, ngrp - 1u)];
+    G1 = grp[min(g0 + sub + 8u, ngrp - 1u)];
   };
-  uint4 G0, G1, G0n = make_uint4(0u, 0u, kNoSlot, 0u), G1n = G0n;
+  uint4 G0, G1, G0n, G1n;
   load_groups(Icur, G0, G1);
+  G0n = G0; G1n = G1;
   for (int it = 0; b < nb; b += W, it++) {
     const int cur = STAGES == 2 ? (it & 1) : 0;
     const bool more = b + W < nb;
@@ -1020,7 +1035,8 @@ __global__ void __launch_bounds__(32 * WARPS, 1) point_prep_kernel(EArgs A, cons
     const uint32_t g0 = __shfl_sync(0xffffffffu, Icur.gptr, pt);
     const uint32_t g1s = __shfl_sync(0xffffffffu, Icur.gptr, pt + 1);
     const uint32_t g1 = act ? g1s : g0;
-    if (!act) { G0.w = 0u; G1.w = 0u; }
+    if (!(g0 + sub < g1)) G0 = make_uint4(0u, 0u, kNoSlot, 0u);
+    if (!(g0 + sub + 8u < g1)) G1 = make_uint4(0u, 0u, kNoSlot, 0u);
     // per-point data that does not depend on the chunks: requested before the wait
     double s[3] = {1.0, 1.0, 1.0};
     if (act && !lm.compute_scale) { s[0] = A.escale[(size_t)e * 3]; s[1] = A.escale[(size_t)e * 3 + 1]; s[2] = A.escale[(size_t)e * 3 + 2]; }
@@ -1483,14 +1499,16 @@ __global__ void __launch_bounds__(32 * WARPS, 1) backsub_rows_kernel(EArgs A, co
   PipeLayout Lcur = pipe_layout(Icur);
   pipe_issue(Lcur, A.J, stage0, &bars[w][0], lane);
   PipeInfo Inext = pipe_load_info(A.ptr, grp_ptr, regular, min(b + W, nb), A.ne, lane);
+  const uint32_t ngrp = grp_ptr[A.ne];
+  if (ngrp == 0u) return;                 // no regular point
   auto load_groups = [&](const PipeInfo& I, uint4& G0, uint4& G1) {
-    const uint32_t g0 = __shfl_sync(0xffffffffu, I.gptr, pt), g1 = __shfl_sync(0xffffffffu, I.gptr, pt + 1);
-    G0 = make_uint4(0u, 0xFFFFFFFFu, kNoSlot, 0u); G1 = G0;
-    if (g0 + sub < g1) G0 = grp[g0 + sub];
-    if (g0 + sub + 8 < g1) G1 = grp[g0 + sub + 8];
+    const uint32_t g0 = __shfl_sync(0xffffffffu, I.gptr, pt);
+    G0 = grp[min(g0 + sub, ngrp - 1u)];
+    G1 = grp[min(g0 + sub + 8u, ngrp - 1u)];
   };
-  uint4 G0, G1, G0n = make_uint4(0u, 0u, kNoSlot, 0u), G1n = G0n;
+  uint4 G0, G1, G0n, G1n;
   load_groups(Icur, G0, G1);
+  G0n = G0; G1n = G1;
   for (int it = 0; b < nb; b += W, it++) {
     const int cur = STAGES == 2 ? (it & 1) : 0;
     const bool more = b + W < nb;
@@ -1507,6 +1525,8 @@ __global__ void __launch_bounds__(32 * WARPS, 1) backsub_rows_kernel(EArgs A, co
     const uint32_t reg_pt = __shfl_sync(0xffffffffu, Icur.reg, pt);   // (outside the && below: every lane must take part in the shuffle)
     const bool act = e < A.ne && reg_pt != 0u;
     const uint32_t g0 = __shfl_sync(0xffffffffu, Icur.gptr, pt), g1 = __shfl_sync(0xffffffffu, Icur.gptr, pt + 1);
+    if (!(act && g0 + sub < g1)) G0 = make_uint4(0u, 0xFFFFFFFFu, kNoSlot, 0u);
+    if (!(act && g0 + sub + 8u < g1)) G1 = make_uint4(0u, 0xFFFFFFFFu, kNoSlot, 0u);
     // pose steps of the two prefetched groups + the point's inverse / gradient: requested before the wait
     double dp0[6], dp1[6];
 #pragma unroll

@@ -796,7 +796,7 @@ struct Solver {
     zero_scalars(SC_CAND, 2);
     if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cand].p, S.K, cams.p, S.C, 0, pcam_cand.p); launches++; }
     fork();
-    if (S.n_obs) { reproj_cost_kernel<<<nblk(S.n_obs, kJacThreads), kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam_cand.p, S.C, classes.p, points[cand].p, scalars.p); launches++; }
+    if (S.n_obs) { reproj_cost_kernel<<<nblk(S.n_obs, kJacThreads * kCostPer), kJacThreads, 0, stream>>>(obs.p, S.n_obs, pcam_cand.p, S.C, classes.p, points[cand].p, scalars.p); launches++; }
     CUDA_OK(cudaStreamWaitEvent(s3, ev_fork, 0));
     if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, s2>>>(bbox.p, S.n_bbox, pcam_cand.p, S.C, objects[cand].p, 1, 1, Jb.p, scalars.p); launches++; }
     if (S.n_unary) launch_unary(3, 1, cand, s3);
