@@ -644,9 +644,14 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
       const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]]; const int ns = S.pts.nslots[e];
       row_pair_entries(sf, ns, dptr[e], [&](int m, int r, uint32_t ent) { R.ent[cur[(size_t)m * kRanges + r]++] = ent; });
     }
+    // A warp walks its item's entries one after the other, so a small problem gets SHORT items (the longest item is the
+    // kernel's run time: 54 us for the 128-entry items of a 50-keyframe window) and a large one the full kRowItemEnts, which
+    // amortise the flush of the 2 x 5 accumulators: aim at ~4096 items, 16 <= entries per item <= kRowItemEnts.
+    uint32_t item_ents = 16;
+    while (item_ents < (uint32_t)kRowItemEnts && (uint64_t)item_ents * 4096u < R.ent.size()) item_ents *= 2;
     for (int m = 0; m < npair; m++) for (int r = 0; r < kRanges; r++) {
       const uint32_t b0 = cnt[(size_t)m * kRanges + r], b1 = cnt[(size_t)m * kRanges + r + 1];
-      for (uint32_t o = b0; o < b1; o += kRowItemEnts) R.items.push_back({(uint32_t)m, (uint32_t)(5 * r), o, std::min<uint32_t>(kRowItemEnts, b1 - o)});
+      for (uint32_t o = b0; o < b1; o += item_ents) R.items.push_back({(uint32_t)m, (uint32_t)(5 * r), o, std::min<uint32_t>(item_ents, b1 - o)});
     }
     R.rowblk.assign((size_t)(2 * npair) * kRowSpan, 0xFFFFFFFFu);   // (an odd nf leaves one all-empty row behind the last pair)
     for (int a = 0; a < nf; a++) for (int d = 0; d < kRowSpan && a + d < nf; d++)
