@@ -1239,6 +1239,7 @@ __global__ void __launch_bounds__(32 * kRowWarps, OBVI_ROW_MINB) schur_rows_kern
   };
   refill(0u, 0);
   if ((uint32_t)H < cnt) refill((uint32_t)H, 1);
+  const uint32_t maskA = fvalid ? (1u << 29) : 0u, maskB = fvalid ? (1u << 30) : 0u;   // row flag of the entry AND a real fragment element
   int half = 0; uint32_t ph = 0u;
   for (uint32_t i0 = 0; i0 < cnt; i0 += H) {
     if (i0 - c0 == 32u) { c0 += 32u; e_lo = e_hi; e_hi = c0 + 32u + lane < cnt ? ep[c0 + 32u + lane] : 0u; }
@@ -1253,8 +1254,8 @@ __global__ void __launch_bounds__(32 * kRowWarps, OBVI_ROW_MINB) schur_rows_kern
 #pragma unroll
       for (int j = 0; j < 6; j++) b[j] = st[j * kWZ];
       double aA = first_range ? b[0] : st[6 * kWZ], aB = first_range ? b[1] : st[7 * kWZ];
-      aA = (fvalid && (e & (1u << 29))) ? aA : 0.0;
-      aB = (fvalid && (e & (1u << 30))) ? aB : 0.0;
+      aA = (e & maskA) ? aA : 0.0;
+      aB = (e & maskB) ? aB : 0.0;
       switch ((e >> 26) & 7u) {
         case 6: dmma_m8n8k4(accB[4].x, accB[4].y, aB, b[5]);
         case 5: dmma_m8n8k4(accA[4].x, accA[4].y, aA, b[4]); dmma_m8n8k4(accB[3].x, accB[3].y, aB, b[4]);
