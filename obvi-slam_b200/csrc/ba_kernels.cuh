@@ -548,6 +548,7 @@ struct EArgs {
   const uint32_t* overflow_off;  // per e-block offset (in doubles) into overflow, valid when nslots > MAXS
   const uint32_t* elist;         // optional: process e-block elist[blockIdx.x] instead of blockIdx.x
   int ne;
+  int batch_begin = 0;      // streaming point kernels: first batch (4 points) that holds a regular point of this rank
 };
 
 // One CTA (T threads) per e-block.  Phase A: H_ee, g_e (shuffle reductions), damping, inverse.
@@ -992,9 +993,9 @@ __global__ void __launch_bounds__(32 * WARPS, 1) point_prep_kernel(EArgs A, cons
   double* stage1 = STAGES == 2 ? stage0 + (size_t)kStageChunks * kChunk : stage0;
   if (lane == 0) { mbar_init(&bars[w][0], 1); mbar_init(&bars[w][1], 1); }
   __syncwarp();
-  const int nb = (A.ne + 3) / 4;
+  const int nb = (A.ne + 3) / 4;          // (A.ne stops at the last regular point of this rank, batch_begin starts at its first one)
   const int W = gridDim.x * WARPS;
-  int b = blockIdx.x * WARPS + w;
+  int b = A.batch_begin + blockIdx.x * WARPS + w;
   double gmax = 0.0;
   int nfail = 0;
   if (b >= nb) return;
@@ -1491,9 +1492,9 @@ __global__ void __launch_bounds__(32 * WARPS, 1) backsub_rows_kernel(EArgs A, co
   double* stage1 = STAGES == 2 ? stage0 + (size_t)kStageChunks * kChunk : stage0;
   if (lane == 0) { mbar_init(&bars[w][0], 1); mbar_init(&bars[w][1], 1); }
   __syncwarp();
-  const int nb = (A.ne + 3) / 4;
+  const int nb = (A.ne + 3) / 4;          // (A.ne stops at the last regular point of this rank, batch_begin starts at its first one)
   const int W = gridDim.x * WARPS;
-  int b = blockIdx.x * WARPS + w;
+  int b = A.batch_begin + blockIdx.x * WARPS + w;
   if (b >= nb) return;
   double mc_acc = 0.0, s2_acc = 0.0;
   PipeInfo Icur = pipe_load_info(A.ptr, grp_ptr, regular, b, A.ne, lane);

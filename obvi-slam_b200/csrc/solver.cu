@@ -236,6 +236,7 @@ struct Solver {
   DBuf<uint32_t> pr_ent;
   DBuf<Structure::RowItem> pr_items;
   DBuf<uint8_t> pr_regular;
+  int pr_batch_begin = 0, pr_batch_end = 0;
   DBuf<double> WZ;
   int n_row_items = 0, n_row_fallback = 0;
   // in-place removal of reprojection / bbox blocks (two-phase outlier exclusion without a structure rebuild)
@@ -391,6 +392,11 @@ struct Solver {
       const Structure::PointRows& R = S.prow;
       n_row_items = (int)R.items.size(); n_row_fallback = (int)R.fallback.size();
       pr_grp_ptr.upload(R.grp_ptr, stream); pr_grp.upload(R.grp, stream); pr_regular.upload(R.regular, stream);
+      {   // batches of four points between the first and the last regular point of this rank
+        int first = -1, last = -1;
+        for (int e = 0; e < (int)R.regular.size(); e++) if (R.regular[e]) { if (first < 0) first = e; last = e; }
+        pr_batch_begin = first < 0 ? 0 : first / 4; pr_batch_end = first < 0 ? 0 : last / 4 + 1;
+      }
       pr_ent.upload(R.ent, stream); pr_items.upload(R.items, stream); pr_rowblk.upload(R.rowblk, stream); pr_fallback.upload(R.fallback, stream);
       WZ.alloc((size_t)std::max<int64_t>(R.n_slots, 1) * kWZ); WZ.zero(stream);   // gap slots stay zero
     }
@@ -556,7 +562,8 @@ struct Solver {
   // ---- kernel sequences -------------------------------------------------------------------------------
   static int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
   // persistent streaming point kernels: one CTA of kPipeWarps warps per SM, a warp per batch of 4 points
-  int pipe_grid(int npoints) const { return std::max(1, std::min(num_sms, nblk(nblk(npoints, 4), pipe_warps))); }
+  int pipe_grid() const { return std::max(1, std::min(num_sms, nblk(pr_batch_end - pr_batch_begin, pipe_warps))); }
+  EArgs pipe_args() { EArgs a = eargs(pts, J.p); a.batch_begin = pr_batch_begin; a.ne = std::min(a.ne, 4 * pr_batch_end); return a; }
   int row_stages = 2;    // entries per half of the operand ring of schur_rows_kernel (OBVI_ROW_STAGES = 2 / 4 / 8)
   int pipe_warps = 8;    // OBVI_PIPE=16: sixteen single-stage warps per SM instead of eight double-buffered ones
   EArgs eargs(EListDev& D, const double* Jp) {
@@ -654,8 +661,8 @@ struct Solver {
     prof.end("pose_accum", pt0, stream); pt0 = prof.begin(stream);
     {
       if (S.P && !(debug_skip & 1)) {
-        if (pipe_warps == 16) point_prep_kernel<16, 1><<<pipe_grid(S.P), 32 * 16, pipe_smem(16, 1), stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p);
-        else point_prep_kernel<8, 2><<<pipe_grid(S.P), 32 * 8, pipe_smem(8, 2), stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p);
+        if (pipe_warps == 16) point_prep_kernel<16, 1><<<pipe_grid(), 32 * 16, pipe_smem(16, 1), stream>>>(pipe_args(), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p);
+        else point_prep_kernel<8, 2><<<pipe_grid(), 32 * 8, pipe_smem(8, 2), stream>>>(pipe_args(), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, lm, WZ.p, scalars.p);
         launches++;
       }
       prof.end("point_prep", pt0, stream); pt0 = prof.begin(stream);
@@ -775,8 +782,8 @@ struct Solver {
     fork();
     if (S.P) {
       if (!(debug_skip & 4)) {
-        if (pipe_warps == 16) backsub_rows_kernel<16, 1><<<pipe_grid(S.P), 32 * 16, pipe_smem(16, 1), stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
-        else backsub_rows_kernel<8, 2><<<pipe_grid(S.P), 32 * 8, pipe_smem(8, 2), stream>>>(eargs(pts, J.p), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
+        if (pipe_warps == 16) backsub_rows_kernel<16, 1><<<pipe_grid(), 32 * 16, pipe_smem(16, 1), stream>>>(pipe_args(), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
+        else backsub_rows_kernel<8, 2><<<pipe_grid(), 32 * 8, pipe_smem(8, 2), stream>>>(pipe_args(), pr_grp_ptr.p, reinterpret_cast<const uint4*>(pr_grp.p), pr_regular.p, dpose.p, points[cur].p, points[cand].p, pts.delta.p, scalars.p);
       }
       launches++;
       if (n_row_fallback) {   // points outside the row-owner path: generic kernel on the fallback list
