@@ -579,20 +579,22 @@ struct Solver {
   void zero_scalars(int first, int count) { CUDA_OK(cudaMemsetAsync(scalars.p + first, 0, count * sizeof(double), stream)); }
 
   // residuals + Jacobians at the current point
-  void linearize(int apply_loss) {
+  // defer_side: the caller runs build_reduced () next, which takes the side streams back (the loop's case).  The side kernels
+  // (bounding boxes, priors, rel-pose, |x|) are placed BEHIND the Jacobian kernel -- beside it they took SMs from the
+  // bandwidth-bound kernel (230 us in situ against 184 alone) -- and then run under the point elimination, whose persistent
+  // CTAs leave most of an SM's threads and registers free.
+  bool side_pending = false;
+  void linearize(int apply_loss, bool defer_side = false) {
     const Structure& S = st;
     const size_t pt0 = prof.begin(stream);
     stage0_local = world > 1;
     zero_scalars(SC_COST, 3);
     if (S.K * S.C > 0) { pose_cam_kernel<<<nblk((int64_t)S.K * S.C, 128), 128, 0, stream>>>(poses[cur].p, S.K, cams.p, S.C, 1, pcam.p); launches++; }
-    fork();
     prof.end("lin: pose_cam", pt0, stream);
-    // The Jacobian kernel is enqueued FIRST: linearize () usually follows a host synchronisation, so every API call made
-    // before this launch is time the device sits idle.  The side kernels wait on the fork event only and, coming from
-    // high-priority streams, are placed as soon as the first Jacobian CTAs retire.
     const size_t pt1 = prof.begin(stream);
     if (S.n_obs) launch_jacobian(apply_loss, points[cur].p);
     prof.end("lin: jacobian", pt1, stream);
+    fork();
     CUDA_OK(cudaStreamWaitEvent(s3, ev_fork, 0));
     if (S.n_bbox) { bbox_kernel<<<nblk(S.n_bbox, 64), 64, 0, s2>>>(bbox.p, S.n_bbox, pcam.p, S.C, objects[cur].p, 0, apply_loss, Jb.p, scalars.p); launches++; }
     if (S.n_unary) { launch_unary(0, apply_loss, cur, s3); }
@@ -601,7 +603,10 @@ struct Solver {
     if (S.P) { xnorm_kernel<<<nblk((int64_t)S.P * 3, 256), 256, 0, s3>>>(points[cur].p, point_skip.p, S.P, 3, scalars.p); launches++; }
     if (S.O) { xnorm_kernel<<<nblk((int64_t)S.O * 7, 256), 256, 0, s3>>>(objects[cur].p, obj_skip.p, S.O, 7, scalars.p); launches++; }
     const size_t pt2 = prof.begin(stream);
-    CUDA_OK(cudaEventRecord(ev_join3, s3)); CUDA_OK(cudaStreamWaitEvent(stream, ev_join3, 0));
+    CUDA_OK(cudaEventRecord(ev_join3, s3));
+    // unary factors on points are re-run on the MAIN stream at the start of build_reduced (): no deferral then
+    if (defer_side && !(S.n_unary && pts.has_prior)) { side_pending = true; return; }
+    CUDA_OK(cudaStreamWaitEvent(stream, ev_join3, 0));
     join();
     prof.end("lin: side join", pt2, stream);
   }
@@ -644,6 +649,7 @@ struct Solver {
     // unary factors on points feed the point elimination: keep them on the main stream in that case
     if (S.n_unary && pts.has_prior) launch_unary(1, 1, cur, stream);
     fork();
+    if (side_pending) CUDA_OK(cudaStreamWaitEvent(s2, ev_join3, 0));   // s2 reads what linearize ()'s kernels on s3 wrote (unary_out, rel_out)
     // side stream: priors, rel-pose and the object elimination (all accumulate with atomics); enqueued first, high priority
     if (S.n_unary && !pts.has_prior) launch_unary(1, 1, cur, s2);
     if (S.n_rel) { relpose_kernel<<<nblk(S.n_rel, 64), 64, 0, s2>>>(rel.p, S.n_rel, 1, 1, poses[cur].p, rel_out.p, S_upper, gp, hpp_diag, dpose.p, scalars.p); launches++; }
@@ -682,6 +688,7 @@ struct Solver {
       }
     }
     prof.end("schur_points", pt0, stream); pt0 = prof.begin(stream);
+    if (side_pending) { CUDA_OK(cudaStreamWaitEvent(stream, ev_join3, 0)); side_pending = false; }   // s3 of a deferred linearize ()
     join();
     prof.end("join(objects,rel)", pt0, stream); pt0 = prof.begin(stream);
     if (world > 1) {
@@ -1027,7 +1034,7 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
   CUDA_OK(cudaEventRecord(ev[6], stream));
   // ---- iteration 0
   CUDA_OK(cudaEventRecord(ev[0], stream));
-  linearize(1);
+  linearize(1, true);
   CUDA_OK(cudaEventRecord(ev[1], stream));
   build_reduced(lm);
   CUDA_OK(cudaEventRecord(ev[2], stream));
@@ -1147,7 +1154,7 @@ int Solver::solve(const obvi_solver_options& o, obvi_summary* sum, obvi_iteratio
       lm.radius = std::min(o.max_trust_region_radius, lm.radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
       decrease = 2.0;
       CUDA_OK(cudaEventRecord(ev[0], stream));
-      linearize(1);
+      linearize(1, true);
       CUDA_OK(cudaEventRecord(ev[1], stream));
       build_reduced(lm);
       CUDA_OK(cudaEventRecord(ev[5], stream));
