@@ -138,16 +138,86 @@ struct LocalComm : Comm {
   }
 };
 
+// ---- device-memory cache --------------------------------------------------------------------------------
+// The reference's schedule builds one problem per window (4069 solves at BASELINE config 4): ~100 device buffers each,
+// and cudaMalloc / cudaFree cost 0.1 - 1 ms apiece (cudaFree also synchronises the device).  Freed blocks are kept per
+// device and handed to the next request of about that size (<= 25 % larger).  A block may come back while work that used it
+// is still in flight on another problem's stream, so the first reuse after any release synchronises the device once.
+// OBVI_NO_CACHE=1 turns it off; OBVI_CACHE_MB caps the cached bytes (default 8192).
+struct DevCache {
+  std::mutex mu;
+  std::multimap<size_t, void*> blocks;
+  size_t cached = 0, limit = (size_t)8192 << 20;
+  bool dirty = false, off = false;
+  DevCache() {
+    if (const char* e = getenv("OBVI_NO_CACHE")) off = std::string(e) == "1";
+    if (const char* e = getenv("OBVI_CACHE_MB")) limit = (size_t)std::max(0, atoi(e)) << 20;
+  }
+  static DevCache& get() {
+    static DevCache c[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return c[dev & 63];
+  }
+  void* take(size_t bytes, size_t& got) {
+    if (off) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = blocks.lower_bound(bytes);
+    if (it == blocks.end() || it->first > bytes + bytes / 4 + 4096) return nullptr;
+    void* p = it->second; got = it->first; cached -= got; blocks.erase(it);
+    if (dirty) { cudaDeviceSynchronize(); dirty = false; }
+    return p;
+  }
+  void give(void* p, size_t bytes) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!off && cached + bytes <= limit) {
+        // a recycled block reads as zeros, like the fresh pages cudaMalloc hands out (ordered before the reuse by the
+        // device synchronisation in take ())
+        cudaMemsetAsync(p, 0, bytes, 0);
+        blocks.emplace(bytes, p); cached += bytes; dirty = true;
+        return;
+      }
+    }
+    cudaFree(p);
+  }
+};
+// pinned host blocks of one size (the per-problem scalar read-back buffer): cudaMallocHost costs ~1 ms
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<void*> blocks;
+  size_t bytes = 0;
+  static PinnedPool& get() { static PinnedPool p; return p; }
+  void* take(size_t n) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (bytes == n && !blocks.empty()) { void* p = blocks.back(); blocks.pop_back(); return p; }
+    }
+    void* p = nullptr;
+    CUDA_OK(cudaMallocHost(&p, n));
+    return p;
+  }
+  void give(void* p, size_t n) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (bytes == 0) bytes = n;
+    if (bytes == n && blocks.size() < 64) blocks.push_back(p); else cudaFreeHost(p);
+  }
+};
+
 // ---- small RAII device buffer ---------------------------------------------------------------------------
 template <class T>
 struct DBuf {
   T* p = nullptr;
-  size_t n = 0;
+  size_t n = 0;          // elements requested
+  size_t cap = 0;        // bytes of the block behind p
   void alloc(size_t count) {
-    if (count <= n && p) return;
+    if (p && count * sizeof(T) <= cap) { n = std::max(n, count); return; }
     free();
     if (count == 0) count = 1;
-    CUDA_OK(cudaMalloc((void**)&p, count * sizeof(T)));
+    const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    void* q = DevCache::get().take(bytes, cap);
+    if (!q) { CUDA_OK(cudaMalloc(&q, bytes)); cap = bytes; }
+    p = (T*)q;
     n = count;
   }
   void upload(const std::vector<T>& v, cudaStream_t s) {
@@ -155,7 +225,7 @@ struct DBuf {
     if (!v.empty()) CUDA_OK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
   }
   void zero(cudaStream_t s) { if (p) CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
-  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void free() { if (p) DevCache::get().give(p, cap); p = nullptr; n = 0; cap = 0; }
   ~DBuf() { free(); }
 };
 
@@ -290,7 +360,7 @@ struct Solver {
   int64_t launches = 0;
 
   ~Solver() {
-    if (h_scalars) cudaFreeHost(h_scalars);
+    if (h_scalars) PinnedPool::get().give(h_scalars, SC_COUNT * sizeof(double));
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
@@ -302,10 +372,19 @@ struct Solver {
 
   void init_device() {
     CUDA_OK(cudaSetDevice(pb.device));
-    cudaDeviceProp prop;
-    CUDA_OK(cudaGetDeviceProperties(&prop, pb.device));
-    if (prop.major < 10) throw std::runtime_error(std::string("obvi_ba is built for sm_100a (B200); found ") + prop.name);
-    num_sms = prop.multiProcessorCount;
+    {   // (cudaGetDeviceProperties takes about a millisecond: asked once per device, not once per problem)
+      static std::mutex mu;
+      static std::map<int, std::pair<int, int>> seen;     // device -> (compute capability major, SM count)
+      std::lock_guard<std::mutex> lk(mu);
+      auto it = seen.find(pb.device);
+      if (it == seen.end()) {
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, pb.device));
+        if (prop.major < 10) throw std::runtime_error(std::string("obvi_ba is built for sm_100a (B200); found ") + prop.name);
+        it = seen.emplace(pb.device, std::make_pair(prop.major, prop.multiProcessorCount)).first;
+      }
+      num_sms = it->second.second;
+    }
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     // the side streams carry the small latency-bound kernels (objects, priors, rel-pose): highest priority, so that their
     // few CTAs are placed as soon as a slot frees up instead of queueing behind the grid of a big point kernel
@@ -317,7 +396,7 @@ struct Solver {
     CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
-    CUDA_OK(cudaMallocHost((void**)&h_scalars, SC_COUNT * sizeof(double)));
+    h_scalars = (double*)PinnedPool::get().take(SC_COUNT * sizeof(double));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pcg_blocks_per_sm, pcg_kernel, kPcgThreads, 0));
     if (pcg_blocks_per_sm < 1) throw std::runtime_error("pcg_kernel cannot be made resident");
     CUDA_OK(cudaFuncSetAttribute(bt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBB * 8));
