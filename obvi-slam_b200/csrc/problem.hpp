@@ -366,7 +366,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     {
       std::vector<std::pair<uint64_t, uint32_t>> kv;
       uint32_t last_cls = 0; int last_cam = -1; double last_sigma = 0, last_huber = 0;
-#pragma omp for schedule(dynamic, 16)
+#pragma omp for schedule(dynamic, 1)     // (a 50-keyframe window has 50 segments of ~2000 records: chunks of 16 kept 4 threads busy)
       for (int k = 0; k < S.K; k++) {
         const uint32_t b = S.pose_ptr[k], e = S.pose_ptr[k + 1];
         kv.resize(e - b);
@@ -445,13 +445,38 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
   auto setbit = [&](int i, int j) { bits[(size_t)i * W + (j >> 6)] |= 1ull << (j & 63); };
   for (int i = 0; i < nf; i++) setbit(i, i);
 
-  auto build_elist = [&](Structure::EList& L, int ne, auto entry_e, auto entry_pose, int64_t n_entries) {
+  // regular(e): the e-block is eliminated by the row-owner kernels, which never read its slot-pair table (12.5 M entries at C3)
+  auto build_elist = [&](Structure::EList& L, int ne, auto entry_e, auto entry_pose, int64_t n_entries, auto regular) {
     L.ptr.assign(ne + 1, 0);
-    for (int64_t q = 0; q < n_entries; q++) L.ptr[entry_e(q) + 1]++;
-    for (int e = 0; e < ne; e++) L.ptr[e + 1] += L.ptr[e];
     L.pos.resize(n_entries); L.f.resize(n_entries); L.slot.resize(n_entries);
-    std::vector<uint32_t> cur(L.ptr.begin(), L.ptr.end() - 1);
-    for (int64_t q = 0; q < n_entries; q++) { const uint32_t d = cur[entry_e(q)]++; L.pos[d] = (uint32_t)q; L.f[d] = S.f_of_pose[entry_pose(q)]; }
+    int nt = 1;
+#ifdef _OPENMP
+    nt = std::max(1, omp_get_max_threads());
+#endif
+    nt = (int)std::min<int64_t>(nt, std::max<int64_t>(1, n_entries / 65536));
+    if (nt > 1) {
+      // stable counting sort by e-block with one histogram per thread (contiguous chunks of the entries, chunk t's share
+      // of an e-block's range follows chunk t - 1's: the order a serial pass produces)
+      std::vector<std::vector<uint32_t>> hist(nt, std::vector<uint32_t>(ne, 0));
+      auto chunk = [&](int t, int64_t& b, int64_t& e) { b = n_entries * t / nt; e = n_entries * (t + 1) / nt; };
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+      for (int t = 0; t < nt; t++) { int64_t b, e; chunk(t, b, e); std::vector<uint32_t>& h = hist[t]; for (int64_t q = b; q < e; q++) h[entry_e(q)]++; }
+      for (int e = 0; e < ne; e++) {
+        uint32_t acc = L.ptr[e];
+        for (int t = 0; t < nt; t++) { const uint32_t c = hist[t][e]; hist[t][e] = acc; acc += c; }
+        L.ptr[e + 1] = acc;
+      }
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+      for (int t = 0; t < nt; t++) {
+        int64_t b, e; chunk(t, b, e); std::vector<uint32_t>& cur = hist[t];
+        for (int64_t q = b; q < e; q++) { const uint32_t d = cur[entry_e(q)]++; L.pos[d] = (uint32_t)q; L.f[d] = S.f_of_pose[entry_pose(q)]; }
+      }
+    } else {
+      for (int64_t q = 0; q < n_entries; q++) L.ptr[entry_e(q) + 1]++;
+      for (int e = 0; e < ne; e++) L.ptr[e + 1] += L.ptr[e];
+      std::vector<uint32_t> cur(L.ptr.begin(), L.ptr.end() - 1);
+      for (int64_t q = 0; q < n_entries; q++) { const uint32_t d = cur[entry_e(q)]++; L.pos[d] = (uint32_t)q; L.f[d] = S.f_of_pose[entry_pose(q)]; }
+    }
     L.nslots.assign(ne, 0); L.pair_ptr.assign(ne + 1, 0); L.slot_ptr.assign(ne + 1, 0);
     int max_slots = L.max_slots;
 #pragma omp parallel for schedule(static, 1024) reduction(max : max_slots)
@@ -466,21 +491,28 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
       max_slots = std::max(max_slots, ns);
     }
     L.max_slots = max_slots;
-    for (int e = 0; e < ne; e++) {
-      const int ns = L.nslots[e];
-      L.pair_ptr[e + 1] = L.pair_ptr[e] + (uint32_t)(ns * (ns + 1) / 2);
-      L.slot_ptr[e + 1] = L.slot_ptr[e] + ns;
-    }
+    for (int e = 0; e < ne; e++) L.slot_ptr[e + 1] = L.slot_ptr[e] + L.nslots[e];
     L.slot_f.resize(L.slot_ptr[ne]);
 #pragma omp parallel for schedule(static, 1024)
     for (int e = 0; e < ne; e++) {
       uint32_t w = L.slot_ptr[e]; int lastf = -1;
       for (uint32_t d = L.ptr[e]; d < L.ptr[e + 1]; d++) if (L.f[d] >= 0 && L.f[d] != lastf) { L.slot_f[w++] = L.f[d]; lastf = L.f[d]; }
     }
+    for (int e = 0; e < ne; e++) {
+      const int ns = L.nslots[e];
+      L.pair_ptr[e + 1] = L.pair_ptr[e] + (regular(e) ? 0u : (uint32_t)(ns * (ns + 1) / 2));
+    }
+  };
+  // a point goes to the row-owner kernels when it has observations, is variable and its variable poses span < kRowSpan f indices
+  auto point_regular = [&](int e) {
+    if (S.pts.ptr[e] == S.pts.ptr[e + 1] || S.point_const[e]) return false;
+    const int ns = S.pts.nslots[e];
+    const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]];
+    return !(ns > 0 && sf[ns - 1] - sf[0] >= kRowSpan);
   };
   // list entries of one e-block are visited in obs order = (pose, camera): equal poses are adjacent
-  build_elist(S.pts, S.P, [&](int64_t q) { return (int)S.obs[q].point; }, [&](int64_t q) { return (int)S.obs[q].pose; }, S.n_obs);
-  build_elist(S.objs, S.O, [&](int64_t q) { return (int)S.bbox[q].obj; }, [&](int64_t q) { return (int)S.bbox[q].pose; }, S.n_bbox);
+  build_elist(S.pts, S.P, [&](int64_t q) { return (int)S.obs[q].point; }, [&](int64_t q) { return (int)S.obs[q].pose; }, S.n_obs, point_regular);
+  build_elist(S.objs, S.O, [&](int64_t q) { return (int)S.bbox[q].obj; }, [&](int64_t q) { return (int)S.bbox[q].pose; }, S.n_bbox, [](int) { return false; });
   // The reprojection Jacobian chunks are stored POINT-major: entry d of the point lists (ordered by point, then pose, then
   // camera) is chunk d, so every point's chunks are one contiguous range.  pts.pos keeps the pose-major record index of entry d
   // on the host (masking, exports); the record carries its chunk position.
@@ -553,6 +585,7 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     const std::vector<uint8_t>& cst = (L == &S.pts) ? S.point_const : S.obj_const;
 #pragma omp parallel for schedule(static, 1024)
     for (int e = 0; e < ne; e++) {
+      if (L->pair_ptr[e] == L->pair_ptr[e + 1]) continue;       // no table: a regular point (or no slots)
       const int32_t* sf = &L->slot_f[L->slot_ptr[e]]; const int ns = L->nslots[e];
       uint32_t w = L->pair_ptr[e];
       for (int a = 0; a < ns; a++) for (int b = a; b < ns; b++) L->pair_blk[w++] = cst[e] ? 0u : blk_of(sf[a], sf[b]);
@@ -598,9 +631,8 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     for (int e = 0; e < S.P; e++) {
       // constant points with observations (they still carry model-cost terms) and prior-only points keep the generic kernels
       if (S.pts.ptr[e] == S.pts.ptr[e + 1]) { if (!S.point_const[e] && pt_has_prior[e]) kind[e] = 1; continue; }
-      if (S.point_const[e]) { kind[e] = 1; continue; }
+      if (!point_regular(e)) { kind[e] = 1; continue; }     // constant, or a track over >= kRowSpan f indices
       const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]]; const int ns = S.pts.nslots[e];
-      if (ns > 0 && sf[ns - 1] - sf[0] >= kRowSpan) { kind[e] = 1; continue; }
       kind[e] = 2;
       span_of[e] = ns ? (uint32_t)(sf[ns - 1] - sf[0] + 1) : 0u;
       uint32_t ngs = 0;
@@ -610,7 +642,6 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
         ngs++; d = d2;
       }
       ngs_of[e] = ngs;
-      row_pair_entries(sf, ns, 0u, [&](int m, int r, uint32_t) { __atomic_fetch_add(&cnt[(size_t)m * kRanges + r + 1], 1u, __ATOMIC_RELAXED); });
     }
     for (int e = 0; e < S.P; e++) {
       R.grp_ptr[e + 1] = R.grp_ptr[e] + ngs_of[e]; dptr[e + 1] = dptr[e] + span_of[e];
@@ -636,13 +667,39 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
     }
     R.n_slots = dptr[S.P];
     if (R.n_slots >= (1ll << 26) - 1) { err = "too many point slots for the row-owner elimination"; return false; }
-    for (size_t i = 0; i + 1 < cnt.size(); i++) cnt[i + 1] += cnt[i];
-    R.ent.resize(cnt.back());
-    std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
-    for (int e = 0; e < S.P; e++) {
-      if (!R.regular[e]) continue;
-      const int32_t* sf = &S.pts.slot_f[S.pts.slot_ptr[e]]; const int ns = S.pts.nslots[e];
-      row_pair_entries(sf, ns, dptr[e], [&](int m, int r, uint32_t ent) { R.ent[cur[(size_t)m * kRanges + r]++] = ent; });
+    // entries: counting sort by (row pair, range), points in order inside a list; one histogram per thread over a
+    // contiguous chunk of the points (chunk t's share of a list follows chunk t - 1's: the serial order)
+    {
+      int nt = 1;
+#ifdef _OPENMP
+      nt = std::max(1, omp_get_max_threads());
+#endif
+      nt = std::min(nt, std::max(1, S.P / 4096));
+      const size_t nl = (size_t)npair * kRanges;
+      std::vector<std::vector<uint32_t>> hist(nt, std::vector<uint32_t>(nl, 0));
+      auto chunk = [&](int t, int& b, int& e) { b = (int)((int64_t)S.P * t / nt); e = (int)((int64_t)S.P * (t + 1) / nt); };
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+      for (int t = 0; t < nt; t++) {
+        int b, e2; chunk(t, b, e2); std::vector<uint32_t>& h = hist[t];
+        for (int e = b; e < e2; e++) {
+          if (kind[e] != 2) continue;
+          row_pair_entries(&S.pts.slot_f[S.pts.slot_ptr[e]], S.pts.nslots[e], 0u, [&](int m, int r, uint32_t) { h[(size_t)m * kRanges + r]++; });
+        }
+      }
+      for (size_t l = 0; l < nl; l++) {
+        uint32_t acc = cnt[l];
+        for (int t = 0; t < nt; t++) { const uint32_t c = hist[t][l]; hist[t][l] = acc; acc += c; }
+        cnt[l + 1] = acc;
+      }
+      R.ent.resize(cnt.back());
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+      for (int t = 0; t < nt; t++) {
+        int b, e2; chunk(t, b, e2); std::vector<uint32_t>& cur = hist[t];
+        for (int e = b; e < e2; e++) {
+          if (kind[e] != 2) continue;
+          row_pair_entries(&S.pts.slot_f[S.pts.slot_ptr[e]], S.pts.nslots[e], dptr[e], [&](int m, int r, uint32_t ent) { R.ent[cur[(size_t)m * kRanges + r]++] = ent; });
+        }
+      }
     }
     // A warp walks its item's entries one after the other, so a small problem gets SHORT items (the longest item is the
     // kernel's run time: 54 us for the 128-entry items of a 50-keyframe window) and a large one the full kRowItemEnts, which
