@@ -258,6 +258,10 @@ int obvi_profile_jacobian(obvi_problem* p, int reps, double* seconds_per_launch,
 /* Host-only inspection of how the structure build shards the graph for (rank, world_size); stats has 12 entries
  * (see solver.cu).  Used by the CPU-side multi-process tests. */
 int obvi_debug_partition(obvi_problem* p, int rank, int world_size, int64_t* stats);
+/* Host-only: the row-pair work lists of the point elimination built for (rank, world_size); stats has 8 entries: entries,
+ * work items, 6x6 products the entries select (must equal the number of (keyframe a <= keyframe b) pairs over all regular
+ * points), dense slots, regular points, points left to the generic kernels, entries covered by items, longest item. */
+int obvi_debug_row_products(obvi_problem* p, int rank, int world_size, int64_t* stats);
 /* Host-only: FNV-1a hash over every array of the structure built for (rank, world_size) -- the exact bytes the solver would
  * upload.  Lets a change of the (host) structure build be checked bit for bit without a GPU. */
 int obvi_debug_structure_hash(obvi_problem* p, int rank, int world_size, uint64_t* hash);

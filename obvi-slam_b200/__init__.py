@@ -130,6 +130,7 @@ def lib():
         "obvi_profile_jacobian": ([vp, C.c_int, _d, C.POINTER(i64), C.POINTER(i64)], C.c_int),
         "obvi_debug_partition": ([vp, C.c_int, C.c_int, C.POINTER(i64)], C.c_int),
         "obvi_debug_structure_hash": ([vp, C.c_int, C.c_int, C.POINTER(C.c_uint64)], C.c_int),
+        "obvi_debug_row_products": ([vp, C.c_int, C.c_int, C.POINTER(C.c_int64)], C.c_int),
         "obvi_comm_unique_id": ([vp], C.c_int),
         "obvi_comm_init": ([vp, vp, C.c_int, C.c_int], C.c_int),
         "obvi_comm_init_local": ([C.POINTER(vp), C.c_int], C.c_int),
@@ -149,7 +150,7 @@ EXPORTED_SYMBOLS = [
     "obvi_factor_add_reproj", "obvi_factor_add_reproj_batch", "obvi_factor_add_bbox", "obvi_factor_add_bbox_batch",
     "obvi_factor_add_shape_prior", "obvi_factor_add_ltm_prior", "obvi_factor_add_rel_pose", "obvi_factor_add_param_prior",
     "obvi_factor_remove", "obvi_factor_remove_batch", "obvi_num_factors", "obvi_num_structure_builds", "obvi_residual_blocks", "obvi_solver_options_init", "obvi_solve",
-    "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_evaluate_jacobian", "obvi_object_covariances", "obvi_profile_jacobian", "obvi_debug_partition", "obvi_debug_structure_hash", "obvi_comm_unique_id",
+    "obvi_evaluate", "obvi_evaluate_factor_type", "obvi_topk_outliers", "obvi_evaluate_jacobian", "obvi_object_covariances", "obvi_profile_jacobian", "obvi_debug_partition", "obvi_debug_row_products", "obvi_debug_structure_hash", "obvi_comm_unique_id",
     "obvi_comm_init", "obvi_comm_init_local", "obvi_comm_attach",
 ]
 
@@ -390,6 +391,13 @@ class Problem:
         self._ck(self._lib.obvi_debug_partition(self._h, rank, world, st))
         keys = ["n_obs", "n_bbox", "n_unary", "n_rel", "nf", "n_upper", "points_here", "objects_here", "point_batches",
                 "structure_checksum", "num_parameters_reduced", "num_residual_blocks_reduced"]
+        return dict(zip(keys, list(st)))
+
+    def debug_row_products(self, rank=0, world=1):
+        """Host-only: the row-pair work lists of the point elimination; see obvi_debug_row_products."""
+        st = (C.c_int64 * 8)()
+        self._ck(self._lib.obvi_debug_row_products(self._h, rank, world, st))
+        keys = ["entries", "items", "products", "dense_slots", "regular_points", "fallback_points", "entries_in_items", "longest_item"]
         return dict(zip(keys, list(st)))
 
     def debug_structure_hash(self, rank=0, world=1):

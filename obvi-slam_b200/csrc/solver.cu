@@ -1935,6 +1935,29 @@ int obvi_debug_partition(obvi_problem* p, int rank, int world, int64_t* stats) {
   }
 }
 
+int obvi_debug_row_products(obvi_problem* p, int rank, int world, int64_t* stats) {
+  if (!p || !stats || world < 1 || rank < 0 || rank >= world) return OBVI_ERR_INVALID_ARGUMENT;
+  try {
+    Structure S;
+    std::string err;
+    if (!build_structure(p->s.pb, S, rank, world, err)) return fail(p, OBVI_ERR_INVALID_ARGUMENT, err.c_str());
+    const Structure::PointRows& R = S.prow;
+    int64_t products = 0, in_items = 0, regular = 0, max_item = 0;
+    for (uint32_t e : R.ent) {
+      const int nl = (int)((e >> 26) & 7u), va = (int)((e >> 29) & 1u), vb = (int)((e >> 30) & 1u);
+      products += (va ? std::min(nl, 5) : 0) + (vb ? nl - 1 : 0);      // what schur_rows_kernel's switch accumulates with a non-zero A operand
+    }
+    for (const Structure::RowItem& it : R.items) { in_items += it.cnt; max_item = std::max<int64_t>(max_item, it.cnt); }
+    for (uint8_t r : R.regular) regular += r;
+    const int64_t v[8] = {(int64_t)R.ent.size(), (int64_t)R.items.size(), products, R.n_slots, regular, (int64_t)R.fallback.size(), in_items, max_item};
+    std::memcpy(stats, v, sizeof(v));
+    return OBVI_OK;
+  } catch (const std::exception& e) {
+    p->s.pb.error = e.what();
+    return OBVI_ERR_INVALID_ARGUMENT;
+  }
+}
+
 int obvi_debug_structure_hash(obvi_problem* p, int rank, int world, uint64_t* hash) {
   if (!p || !hash || world < 1 || rank < 0 || rank >= world) return OBVI_ERR_INVALID_ARGUMENT;
   try {
