@@ -193,11 +193,21 @@ class Problem {
     if (cost || residuals) {
       int64_t n = 0;
       double c = 0;
-      if (obvi_evaluate(handle_, loss, &c, nullptr, 0, residuals ? &n : nullptr) != OBVI_OK) { last_error_ = obvi_last_error(handle_); return false; }
-      if (residuals) {
+      if (!residuals) {
+        if (obvi_evaluate(handle_, loss, &c, nullptr, 0, nullptr) != OBVI_OK) { last_error_ = obvi_last_error(handle_); return false; }
+      } else {
+        // ONE evaluation: the length of the residual vector is known here (sum of the blocks' residual counts), so the sizing
+        // call of the C ABI -- a second full linearisation -- is not needed.
         // obvi_evaluate concatenates in order of addition; reorder when the caller lists the blocks differently
+        {
+          std::vector<ResidualBlockId> live;
+          GetResidualBlocks(&live);
+          for (ResidualBlockId rb : live) n += rb->cost->num_residuals();
+        }
         std::vector<double> all(n, 0.0);
-        if (obvi_evaluate(handle_, loss, &c, all.data(), n, &n) != OBVI_OK) { last_error_ = obvi_last_error(handle_); return false; }
+        int64_t got = 0;
+        if (obvi_evaluate(handle_, loss, &c, all.data(), n, &got) != OBVI_OK) { last_error_ = obvi_last_error(handle_); return false; }
+        if (got != n) { last_error_ = "Evaluate: residual count mismatch between the shim and the backend"; return false; }
         if (!subset) { *residuals = all; }
         else {
           std::vector<ResidualBlockId> order;
