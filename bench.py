@@ -138,14 +138,14 @@ _THREADS = {}
 
 def pick_threads(g):
     """Thread count for the CPU restatement, MEASURED: one LM iteration of this graph with host_cores(), half and a quarter of
-    it, the fastest wins.  On the multi-GPU boxes the visible core count (24) is not what the process gets -- 24 OpenMP
+    it (and 32 / 16 on boxes with more cores than that), the fastest wins.  On the multi-GPU boxes the visible core count (24) is not what the process gets -- 24 OpenMP
     threads ran the solve 20x slower than 16 threads on the single-GPU box, with no cgroup quota to read -- so the count is
     not trusted, it is timed (a few seconds).  The timings travel in the JSON line (cpu_baseline.threads_tried)."""
     key = id(g)
     if key not in _THREADS:
         n = host_cores()
         tried = {}
-        for t in sorted({n, max(1, n // 2), max(1, n // 4)}, reverse=True):
+        for t in sorted({n, max(1, n // 2), max(1, n // 4), min(n, 32), min(n, 16)}, reverse=True):
             tried[t] = cpu_leg(g, 1, threads=t)[2]
             if len(tried) > 1 and tried[t] > 1.5 * min(tried.values()):
                 break                                   # getting slower with fewer threads: stop
