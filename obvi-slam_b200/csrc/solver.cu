@@ -168,6 +168,12 @@ struct DevCache {
     if (dirty) { cudaDeviceSynchronize(); dirty = false; }
     return p;
   }
+  void release_all() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (dirty) { cudaDeviceSynchronize(); dirty = false; }
+    for (auto& b : blocks) cudaFree(b.second);
+    blocks.clear(); cached = 0;
+  }
   void give(void* p, size_t bytes) {
     {
       std::lock_guard<std::mutex> lk(mu);
@@ -216,7 +222,14 @@ struct DBuf {
     if (count == 0) count = 1;
     const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
     void* q = DevCache::get().take(bytes, cap);
-    if (!q) { CUDA_OK(cudaMalloc(&q, bytes)); cap = bytes; }
+    if (!q) {
+      if (cudaMalloc(&q, bytes) != cudaSuccess) {       // out of memory with blocks parked in the cache: release them and retry
+        (void)cudaGetLastError();
+        DevCache::get().release_all();
+        CUDA_OK(cudaMalloc(&q, bytes));
+      }
+      cap = bytes;
+    }
     p = (T*)q;
     n = count;
   }
