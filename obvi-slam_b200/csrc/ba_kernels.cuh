@@ -448,6 +448,13 @@ __global__ void __launch_bounds__(kJacThreads) reproj_cost_kernel(const ObsRec* 
   }
 }
 
+// Residual export (Problem::Evaluate): the two residuals of every chunk, packed -- 16 instead of 128 bytes per observation
+// cross PCIe.
+__global__ void extract_residuals_kernel(const double* __restrict__ J, int64_t n, double2* __restrict__ out) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) out[q] = *reinterpret_cast<const double2*>(J + q * kChunk + kChunkR);
+}
+
 // ------------------------------------------------------------------------------------------ pose-side J^T J accumulation
 // Fallback beside reproj_jac_kernel (the kernel without TMA staging / fused sums): one CTA per keyframe walks the keyframe's
 // pose-major records, gathers each chunk from its point-major position and accumulates H_pp, g_p with warp-shuffle

@@ -1670,9 +1670,14 @@ int obvi_evaluate(obvi_problem* p, int apply_loss, double* cost, double* residua
   if (s.world > 1) return fail(p, OBVI_ERR_INVALID_ARGUMENT, "residual export is single-rank only");
   const Structure& S = s.st;
   // per-type residuals in internal order -> per factor index
-  std::vector<double> hJ((size_t)S.n_obs * kChunk), hB((size_t)S.n_bbox * kBBoxChunk);
+  std::vector<double> hJ((size_t)S.n_obs * 2), hB((size_t)S.n_bbox * kBBoxChunk);     // hJ: the packed residuals, by chunk position
   std::vector<RelOut> hR(S.n_rel); std::vector<UnaryOut> hU(S.n_unary);
-  if (S.n_obs) CUDA_OK(cudaMemcpy(hJ.data(), s.J.p, hJ.size() * 8, cudaMemcpyDeviceToHost));
+  if (S.n_obs) {
+    DBuf<double> packed; packed.alloc((size_t)S.n_obs * 2);
+    extract_residuals_kernel<<<Solver::nblk(S.n_obs, 256), 256, 0, s.stream>>>(s.J.p, S.n_obs, reinterpret_cast<double2*>(packed.p));
+    CUDA_OK(cudaMemcpyAsync(hJ.data(), packed.p, hJ.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_OK(cudaStreamSynchronize(s.stream));
+  }
   if (S.n_bbox) CUDA_OK(cudaMemcpy(hB.data(), s.Jb.p, hB.size() * 8, cudaMemcpyDeviceToHost));
   if (S.n_rel) CUDA_OK(cudaMemcpy(hR.data(), s.rel_out.p, hR.size() * sizeof(RelOut), cudaMemcpyDeviceToHost));
   if (S.n_unary) CUDA_OK(cudaMemcpy(hU.data(), s.unary_out.p, hU.size() * sizeof(UnaryOut), cudaMemcpyDeviceToHost));
@@ -1688,7 +1693,7 @@ int obvi_evaluate(obvi_problem* p, int apply_loss, double* cost, double* residua
     const uint64_t i = id_index(id);
     const double* src;
     switch (id_type(id)) {
-      case OBVI_FACTOR_REPROJECTION: src = &hJ[(size_t)S.obs[inv_rp[i]].dst * kChunk + kChunkR]; break;
+      case OBVI_FACTOR_REPROJECTION: src = &hJ[(size_t)S.obs[inv_rp[i]].dst * 2]; break;
       case OBVI_FACTOR_BBOX: src = &hB[(size_t)inv_bb[i] * kBBoxChunk + 52]; break;
       case OBVI_FACTOR_REL_POSE: src = hR[inv_rl[i]].r; break;
       default: src = hU[inv_un[i]].r; break;
