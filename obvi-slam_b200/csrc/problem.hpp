@@ -250,9 +250,16 @@ inline bool build_structure(const Problem& pb, Structure& S, int rank, int world
       int32_t seen = __atomic_load_n(&first[f.point], __ATOMIC_RELAXED);
       while (k < seen && !__atomic_compare_exchange_n(&first[f.point], &seen, k, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
     }
+    // stable counting sort of the used 3-blocks by first observing pose (bucket K: never observed)
     std::vector<int32_t> ids;
-    for (int b = 0; b < nb; b++) if (used[b] && pb.blocks[b].size == 3) ids.push_back(b);
-    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return first[a] < first[b]; });
+    {
+      std::vector<uint32_t> start(S.K + 2, 0);
+      auto bucket = [&](int b) { return first[b] == INT32_MAX ? S.K : first[b]; };
+      for (int b = 0; b < nb; b++) if (used[b] && pb.blocks[b].size == 3) start[bucket(b) + 1]++;
+      for (int k = 0; k <= S.K; k++) start[k + 1] += start[k];
+      ids.resize(start[S.K + 1]);
+      for (int b = 0; b < nb; b++) if (used[b] && pb.blocks[b].size == 3) ids[start[bucket(b)]++] = b;
+    }
     S.P = (int)ids.size();
     S.point_block = ids;
     S.point_const.resize(S.P);
