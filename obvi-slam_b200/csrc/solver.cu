@@ -620,6 +620,7 @@ struct Solver {
     const Structure& S = st;
     h_poses.resize((size_t)S.K * 6); h_points.resize((size_t)S.P * 3); h_objects.resize((size_t)S.O * 7);
     for (int k = 0; k < S.K; k++) std::memcpy(&h_poses[6 * (size_t)k], pb.blocks[S.pose_block[k]].host, 48);
+#pragma omp parallel for schedule(static) if (S.P > 32768)
     for (int i = 0; i < S.P; i++) std::memcpy(&h_points[3 * (size_t)i], pb.blocks[S.point_block[i]].host, 24);
     for (int i = 0; i < S.O; i++) std::memcpy(&h_objects[7 * (size_t)i], pb.blocks[S.obj_block[i]].host, 56);
     if (S.K) CUDA_OK(cudaMemcpyAsync(poses[0].p, h_poses.data(), h_poses.size() * 8, cudaMemcpyHostToDevice, stream));
@@ -646,6 +647,7 @@ struct Solver {
     if (S.O) CUDA_OK(cudaMemcpyAsync(h_objects.data(), objects[buf].p, h_objects.size() * 8, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
     for (int k = 0; k < S.K; k++) if (S.f_of_pose[k] >= 0) std::memcpy(pb.blocks[S.pose_block[k]].host, &h_poses[6 * (size_t)k], 48);
+#pragma omp parallel for schedule(static) if (S.P > 32768)
     for (int i = 0; i < S.P; i++) if (!S.point_const[i]) std::memcpy(pb.blocks[S.point_block[i]].host, &h_points[3 * (size_t)i], 24);
     for (int i = 0; i < S.O; i++) if (!S.obj_const[i]) std::memcpy(pb.blocks[S.obj_block[i]].host, &h_objects[7 * (size_t)i], 56);
   }
